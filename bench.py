@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py -- WKV6 fwd+bwd tokens/s at the RWKV-6 1B6 shape (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+A "step" is one forward + backward pass of the WKV6 operator over one batch of synthetic input
+(B=8, T=4096, H=32, N=64, bf16) per GPU, through the reference-shaped Python surface
+(RUN_CUDA_RWKV6 -> C ABI -> sm_100a kernels).  N > 1 is launched by torchrun, one rank per GPU;
+the batch dimension is sharded, there is no data-path collective (weak scaling).
+
+Prints ONE JSON line (rank 0).  `value` = device-resident throughput; `e2e` = same metric with host
+buffers (pinned) copied in and results copied out inside the timed region; `roofline` = achieved
+algorithmic HBM bytes/s of the dominant kernel over the measured copy bandwidth
+(MEASURED_PEAKS.json); `cpu_baseline` = the oracle's C port (oracle/wkv6_oracle.c, the reference
+kernels' arithmetic on host cores) on a bounded sample; `reference_cuda` = the reference's own CUDA
+kernels (oracle/_ref) timed on the same GPU and inputs, when they were built.
+`--impl reference` times the reference's CPU implementation of the path (the oracle port, all host
+threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "WKV6 fwd+bwd tokens/s (1B6 shape)"
+UNIT = "tokens/s"
+B, T, H, N = 8, 4096, 32, 64
+C = H * N
+BYTES_FWD = 10     # r,k,v,w read + y written, bf16                      
+BYTES_BWD = 18     # r,k,v,w,gy read + gr,gk,gv,gw written, bf16
+CPU_SAMPLE = dict(B=1, T=4096, H=32)   # 1/8 of one step's batch
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def config(n_gpus):
+    return {"workload": f"WKV6 op fwd+bwd, B={B} T={T} H={H} N={N} per GPU (RWKV-x060 World 1B6 shape), "
+                        "w ~ time_decay range U(-6,-1)+0.3N(0,1), synthetic randn r/k/v/gy",
+            "global_batch": B * n_gpus, "seq_len": T, "heads": H, "head_size": N,
+            "parallelism": f"batch-sharded x{n_gpus}, no data-path collective",
+            "l2": "inputs (6 x 134 MB per step) are larger than the 126 MB L2; no explicit flush"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons through NVML while the timed region runs."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
+                     "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80, "sync_boost": 0x10,
+                     "applications_clocks": 0x2}
+            while not self._stop_evt.is_set():
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for k, b in names.items():
+                    if bits & b:
+                        self.reasons.add(k)
+                time.sleep(0.01)
+        except Exception as e:  # no NVML: report that instead of inventing numbers
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        return {"sm_mhz": statistics.median(self.samples) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+def run_cpu(steps, warmup, budget_s=20.0):
+    """The oracle's C port on host cores, on CPU_SAMPLE: up to `steps` runs of the sample, stopping
+    early once `budget_s` seconds of CPU work are spent.  Returns (tokens/s, cores, s/run, runs)."""
+    from oracle import c_oracle
+    from rwkv_lm_ext_b200.synthetic import make_inputs
+    s = CPU_SAMPLE
+    r, k, v, w, u, gy = (t.float() for t in make_inputs(s["B"], s["T"], s["H"], seed=0, decay="model"))
+    cores = c_oracle.num_threads()
+    for _ in range(warmup):
+        c_oracle.forward(r[:, :256], k[:, :256], v[:, :256], w[:, :256], u)
+        c_oracle.backward(r[:, :256], k[:, :256], v[:, :256], w[:, :256], u, gy[:, :256])
+    ts = []
+    while len(ts) < steps and (not ts or sum(ts) < budget_s):
+        t0 = time.perf_counter()
+        c_oracle.forward(r, k, v, w, u)
+        c_oracle.backward(r, k, v, w, u, gy)
+        ts.append(time.perf_counter() - t0)
+    sec = sum(ts) / len(ts)
+    return s["B"] * s["T"] / sec, cores, sec, len(ts)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--kernel-impl", default="auto", choices=["auto", "simt", "tc"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        val, cores, sec, steps = run_cpu(max(1, args.steps), min(args.warmup, 1), budget_s=30.0)
+        sample = (f"fwd+bwd on B={CPU_SAMPLE['B']} T={CPU_SAMPLE['T']} H={CPU_SAMPLE['H']} "
+                  f"(1/8 of one step's batch), mean of {steps} runs, {sec:.2f} s each, {cores} threads")
+        line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+                "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3 * (B / CPU_SAMPLE["B"]),
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                "data": "synthetic", "config": config(args.gpus),
+                "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    import rwkv_lm_ext_b200 as M
+    from rwkv_lm_ext_b200.synthetic import make_inputs
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    M.load()
+    M.set_impl(args.kernel_impl)
+
+    # synthetic inputs, created on the host (pinned) so the e2e leg has real host buffers
+    host = [t.pin_memory() for t in make_inputs(B, T, H, seed=rank, decay="model")]
+    r, k, v, w, u, gy = (t.to(dev, non_blocking=True) for t in host)
+    torch.cuda.synchronize()
+
+    def step(r, k, v, w, u, gy, ev=None):
+        leaves = [t.requires_grad_(True) for t in (r, k, v, w, u)]
+        if ev:
+            ev[0].record()
+        y = M.RUN_CUDA_RWKV6(B, T, C, H, *leaves)
+        if ev:
+            ev[1].record()
+        y.backward(gy)
+        if ev:
+            ev[2].record()
+        grads = [t.grad for t in leaves]
+        for t in leaves:
+            t.grad = None
+        return y, grads
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step(r, k, v, w, u, gy)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    launches0 = M.launch_count()
+    t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t_start.record()
+    for i in range(args.steps):
+        step(r, k, v, w, u, gy, evs[i])
+    t_end.record()
+    barrier()
+    clocks = sampler.stop()
+    launches = M.launch_count() - launches0
+    ms = t_start.elapsed_time(t_end) / args.steps
+    fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
+    bwd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+    if world > 1:
+        tms = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = world * B * T / (ms * 1e-3)
+
+    # ---- end to end: host buffers in, results out, inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        outs_host = [torch.empty(B, T, C, dtype=torch.bfloat16).pin_memory() for _ in range(5)]
+        gu_host = torch.empty(H, N, dtype=torch.bfloat16).pin_memory()
+        h2d = sum(t.numel() * t.element_size() for t in host)
+        d2h = sum(t.numel() * t.element_size() for t in outs_host) + gu_host.numel() * 2
+
+        def e2e_step():
+            dv = [t.to(dev, non_blocking=True) for t in host]
+            y, grads = step(*dv)
+            for dst, src in zip(outs_host, [y] + grads[:4]):
+                dst.copy_(src, non_blocking=True)
+            gu_host.copy_(grads[4], non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        ksteps = max(3, min(args.steps, 10))
+        a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(ksteps):
+            e2e_step()
+        b_.record()
+        barrier()
+        ems = a.elapsed_time(b_) / ksteps
+        if world > 1:
+            tms = torch.tensor([ems], device=dev, dtype=torch.float64)
+            dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+            ems = float(tms.item())
+        e2e = {"value": world * B * T / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "ms_per_step": ems, "steps": ksteps,
+               "api": "rwkv_lm_ext_b200.RUN_CUDA_RWKV6 + .backward, pinned host tensors"}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    peak, peak_src = peaks()
+    elems = B * T * C
+    dom_is_bwd = bwd_ms >= fwd_ms
+    dom_ms = bwd_ms if dom_is_bwd else fwd_ms
+    dom_bytes = elems * (BYTES_BWD if dom_is_bwd else BYTES_FWD)
+    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    impl_name = {0: "auto", 1: "simt", 2: "tc"}[M.load().wkv6b200_get_impl()]
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src,
+                "kernel": ("wkv6 backward" if dom_is_bwd else "wkv6 forward") + f" ({impl_name})",
+                "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
+                "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
+                "step_frac": elems * (BYTES_FWD + BYTES_BWD) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config(world),
+            "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline}
+    if e2e:
+        line["e2e"] = e2e
+
+    # ---- the reference's own CUDA kernels on the same inputs (not part of the contract; context)
+    try:
+        from oracle import ref_cuda
+        if world == 1 and ref_cuda.available("wkv6"):
+            def ref_step():
+                y, ew = ref_cuda.wkv6_forward(r, k, v, w, u)
+                return ref_cuda.wkv6_backward(r, k, v, ew, u, gy)
+            ref_step()
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(3):
+                ref_step()
+            b_.record()
+            torch.cuda.synchronize()
+            rms = a.elapsed_time(b_) / 3
+            line["reference_cuda"] = {"value": B * T / (rms * 1e-3), "unit": UNIT, "ms_per_step": rms,
+                                      "what": "reference cuda/wkv6_cuda.cu (oracle/_ref) incl. its fp32 ew pre-pass, same GPU"}
+    except Exception as e:
+        line["reference_cuda"] = {"unavailable": f"{type(e).__name__}: {e}"}
+
+    if world == 1 and not args.no_cpu_baseline:
+        val, cores, sec, runs = run_cpu(1000, 1, budget_s=12.0)
+        line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": f"fwd+bwd on B={CPU_SAMPLE['B']} T={CPU_SAMPLE['T']} H={CPU_SAMPLE['H']} "
+                                          f"(1/8 of one step's batch), mean of {runs} runs of {sec:.2f} s, {cores} threads"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,183 @@
+/* wkv6_b200.h -- C ABI of the B200-native WKV6 hot path (libwkv6_b200.so).
+ *
+ * Drop-in boundary for yynil/RWKV_LM_EXT.  Every entry point replaces one launcher the
+ * reference's pybind modules bind (file:line cited per function).  Plain pointers and sizes only:
+ * no torch types.  All pointers are DEVICE pointers unless marked "host".  Every function
+ *   - returns 0 on success, a negative WKV6_E* code otherwise (wkv6b200_last_error() has text);
+ *   - is asynchronous: work is enqueued on `stream` (a cudaStream_t; NULL = legacy default
+ *     stream, which is what the reference's bare <<<>>> launches use, cuda/wkv6_cuda.cu:233);
+ *   - never allocates device memory: the caller owns every buffer, including the workspace
+ *     (size from the matching *_workspace_bytes) -- the reference wrappers likewise pre-allocate all
+ *     outputs with torch.empty (src/model.py:211,225-230).
+ *
+ * Layout contract (identical to the reference): r,k,v,w,y,gy,g* are [B,T,C] contiguous,
+ * C = H*64 (head size is fixed at 64 like -D_N_=64, src/model.py:189); u is [H,64];
+ * states are [.,H,64(value j),64(key i)] (cuda/wkv6state_cuda.cu:15,24).
+ */
+#ifndef WKV6_B200_H
+#define WKV6_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* exported symbol (the library is built with -fvisibility=hidden) */
+#if defined(__GNUC__)
+#define WKV6_API __attribute__((visibility("default")))
+#else
+#define WKV6_API
+#endif
+
+#define WKV6_HEAD_SIZE 64
+
+/* error codes */
+#define WKV6_OK            0
+#define WKV6_EINVAL       -1   /* bad shape / null pointer / C != H*64 */
+#define WKV6_EWORKSPACE   -2   /* workspace too small */
+#define WKV6_ECUDA        -3   /* CUDA runtime / driver error (text in wkv6b200_last_error) */
+#define WKV6_EUNSUPPORTED -4   /* the selected implementation cannot run this shape */
+
+/* element types of r,k,v,u,y for the inference entry (cuda/rwkv6_op.cpp:12-34) */
+#define WKV6_BF16 0
+#define WKV6_FP16 1
+#define WKV6_FP32 2
+
+/* implementation selector, see wkv6b200_set_impl */
+#define WKV6_IMPL_AUTO 0       /* tensor-core chunked kernels where the shape allows, else SIMT */
+#define WKV6_IMPL_SIMT 1       /* exact fp32 step recurrence on CUDA cores (all shapes)          */
+#define WKV6_IMPL_TC   2       /* tcgen05/TMA chunked kernels only; WKV6_EUNSUPPORTED otherwise  */
+
+WKV6_API int         wkv6b200_abi_version(void);
+WKV6_API const char *wkv6b200_last_error(void);              /* host string, thread-local */
+WKV6_API int         wkv6b200_set_impl(int impl);            /* returns the previous value */
+WKV6_API int         wkv6b200_get_impl(void);
+/* number of kernels this library launched since process start (bench.py's gpu_launches) */
+WKV6_API uint64_t    wkv6b200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * (a1/a2) wkv6 -- replaces cuda_forward / cuda_backward of cuda/wkv6_cuda.cu:229-242, bound by
+ * cuda/wkv6_op.cpp:8-22 as forward(B,T,C,H,r,k,v,w,u,y) / backward(...,gy,gr,gk,gv,gw,gu).
+ * r,k,v,u,y,gy,gr,gk,gv,gw,gu: bf16.  ew: fp32 [B,T,C] = -exp(w) (src/model.py:210).
+ * gu: [B,C] per-batch partials (the wrapper sums over B, src/model.py:232).
+ * gw[:,0] and gw[:,T-1] are exact zeros (cuda/wkv6_cuda.cu:201,226).
+ * ------------------------------------------------------------------------------------------ */
+WKV6_API int wkv6_forward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                 const float *ew, const void *u, void *y, void *stream);
+WKV6_API size_t wkv6_backward_workspace_bytes(int B, int T, int C, int H);
+WKV6_API int wkv6_backward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                  const float *ew, const void *u, const void *gy, void *gr, void *gk, void *gv,
+                  void *gw, void *gu, void *workspace, size_t workspace_bytes, void *stream);
+
+/* Same operator taking the raw bf16 decay logits w (what RUN_CUDA_RWKV6 receives,
+ * src/model.py:235) so the host wrapper can skip the three fp32 elementwise passes that build
+ * `ew`.  gw is d/d(raw w) in both forms. */
+WKV6_API int wkv6_forward_raww(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                      const void *w, const void *u, void *y, void *stream);
+WKV6_API int wkv6_backward_raww(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                       const void *w, const void *u, const void *gy, void *gr, void *gk, void *gv,
+                       void *gw, void *gu, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (a3) wkv6state -- cuda/wkv6state_cuda.cu:298-311 bound by cuda/wkv6state_op.cpp:8-21.
+ * w: raw bf16 logits.  s: bf16 [H,64,64], shared by the batch, read-only.
+ * gs: bf16 [B,H,64,64] per-batch partials (wrapper sums over B, src/model.py:182).
+ * Gradients are those of the mathematical operator (fp64-autograd parity); the reference
+ * kernel_backward_111 mis-indexes `s` (cuda/wkv6state_cuda.cu:79,91) -- not reproduced.
+ * ------------------------------------------------------------------------------------------ */
+WKV6_API int wkv6state_forward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                      const void *w, const void *u, const void *s, void *y, void *stream);
+WKV6_API int wkv6state_backward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                       const void *w, const void *u, const void *s, const void *gy, void *gr,
+                       void *gk, void *gv, void *gw, void *gu, void *gs, void *workspace,
+                       size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (a4) wkv6infctx -- cuda/wkv6infctx_cuda.cu:298-311 bound by cuda/wkv6infctx_op.cpp:8-22.
+ * s: bf16 [B,H,64,64]; forward OVERWRITES it with the final state (cuda/wkv6infctx_cuda.cu:65-67).
+ * backward takes the INITIAL state (the reference wrapper hands its kernel the mutated tensor,
+ * src/model.py:104-106 -- a defect; the host wrapper here keeps a copy of the initial state).
+ * wkv6infctx_forward_f32state: same with an fp32 state that is carried without the bf16 round trip.
+ * ------------------------------------------------------------------------------------------ */
+WKV6_API int wkv6infctx_forward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                       const void *w, const void *u, void *s, void *y, void *stream);
+WKV6_API int wkv6infctx_forward_f32state(int B, int T, int C, int H, const void *r, const void *k,
+                                const void *v, const void *w, const void *u, float *s, void *y,
+                                void *stream);
+WKV6_API int wkv6infctx_backward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                        const void *w, const void *u, const void *s_initial, const void *gy,
+                        void *gr, void *gk, void *gv, void *gw, void *gu, void *gs,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (a5) wkv6_bi -- cuda/wkv6_bi_cuda.cu:363-376 bound by cuda/wkv6_bi_op.cpp:8-21.
+ * mask: int32 [B,T].  p[b] = first t with mask==0, or T-1.  y[t>p] = 0 (reference: unwritten).
+ * ew: fp32 -exp(w).  Backward = gradient of this forward.
+ * ------------------------------------------------------------------------------------------ */
+WKV6_API int wkv6_bi_forward(int B, int T, int C, int H, const int *mask, const void *r, const void *k,
+                    const void *v, const float *ew, const void *u, void *y, void *stream);
+WKV6_API int wkv6_bi_backward(int B, int T, int C, int H, const int *mask, const void *r, const void *k,
+                     const void *v, const float *ew, const void *u, const void *gy, void *gr,
+                     void *gk, void *gv, void *gw, void *gu, void *workspace,
+                     size_t workspace_bytes, void *stream);
+WKV6_API int wkv6_bi_forward_raww(int B, int T, int C, int H, const int *mask, const void *r,
+                         const void *k, const void *v, const void *w, const void *u, void *y,
+                         void *stream);
+WKV6_API int wkv6_bi_backward_raww(int B, int T, int C, int H, const int *mask, const void *r,
+                          const void *k, const void *v, const void *w, const void *u,
+                          const void *gy, void *gr, void *gk, void *gv, void *gw, void *gu,
+                          void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * (a6) rwkv6 inference -- cuda/rwkv6.cu:73-87 bound by cuda/rwkv6_op.cpp:12-34
+ * (forward_bf16 / forward_fp16 / forward_fp32).  state: fp32 [B,H,64,64] in and out (the
+ * reference is only correct for B = 1, cuda/rwkv6.cu:17; here every batch row has its own state).
+ * w_decay: fp32 [B,T,C] = exp(-exp(w)) (src/model_run.py:64).  dtype: WKV6_BF16/FP16/FP32.
+ * ------------------------------------------------------------------------------------------ */
+WKV6_API int rwkv6_forward(int dtype, int B, int T, int C, int H, float *state, const void *r,
+                  const void *k, const void *v, const float *w_decay, const void *u, void *y,
+                  void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Memory-bound neighbours of the recurrence.
+ * ------------------------------------------------------------------------------------------ */
+/* (a9) pos[b] = first t with idx[b,t]==token_id, 0 if absent
+ * (== torch.eq(idx,id).int().argmax(-1), src/model_ext.py:209,1765); idx int64 [B,T]; pos int64 [B]. */
+WKV6_API int eos_index_i64(int B, int T, const int64_t *idx, int64_t token_id, int64_t *pos, void *stream);
+/* out[b,:] = x[b,pos[b],:]  (src/model_ext.py:210-211); x bf16 [B,T,D], out bf16 [B,D]. */
+WKV6_API int gather_rows_bf16(int B, int T, int D, const void *x, const int64_t *pos, void *out,
+                     void *stream);
+/* (a10) pooling (src/model_ext.py:1708-1738, src/model_run.py:777-797).
+ * kind: 0 weightedmean, 1 lasttoken, 2 avg.  variant: 0 train (L = actual_len), 1 infer
+ * (L = actual_len + 1).  x bf16 [B,T,D]; actual_len int64 [B]; out_f32 fp32 [B,D] (the host
+ * wrapper casts to bf16 where the reference does). */
+WKV6_API int pooling_bf16(int kind, int variant, int B, int T, int D, const void *x,
+                 const int64_t *actual_len, float *out_f32, void *stream);
+/* (a12) mask = (idx != pad) & (idx != emb) as int32; rev_idx[b] = [len-1..0, len..T-1],
+ * len = sum(mask[b]) (src/model_ext.py:398-417). */
+WKV6_API int create_mask_rev_idx(int B, int T, const int64_t *idx, int64_t emb_id, int64_t pad_id,
+                        int32_t *mask, int64_t *rev_idx, void *stream);
+/* out[b,t,:] = x[b,rev_idx[b,t],:]  (reverse_x, src/model_ext.py:418-419); bf16 [B,T,D]. */
+WKV6_API int gather_tokens_bf16(int B, int T, int D, const void *x, const int64_t *rev_idx, void *out,
+                       void *stream);
+
+/* (a7) token-shift + ddlerp of RWKV_Tmix_x060.jit_func (src/model.py:437-449), mixing stage:
+ * given x [B,T,C], the five data-dependent coefficients m [5,B,T,C] (output of the rank-R LoRA
+ * bmm) and maa [5,C], writes xw,xk,xv,xr,xg = x + (shift(x)-x)*(maa_n + m_n) into out [5,B,T,C].
+ * shift_state: NULL (zero pad) or bf16 [B,C] (infctx, src/model.py:738-745).  All bf16. */
+WKV6_API int tmix_ddlerp_mix_bf16(int B, int T, int C, const void *x, const void *shift_state,
+                         const void *maa, const void *m, void *out, void *stream);
+/* xxx = x + (shift(x)-x)*maa_x  (src/model.py:439-441), the LoRA input.  bf16. */
+WKV6_API int tmix_shift_lerp_bf16(int B, int T, int C, const void *x, const void *shift_state,
+                         const void *maa_x, void *out, void *stream);
+/* (a8) GroupNorm(H groups, eps) * g  of jit_func_2 (src/model.py:461-467), fwd only.
+ * y,g,out bf16 [B*T,C]; ln_w, ln_b bf16 [C]. */
+WKV6_API int groupnorm_gate_bf16(int BT, int C, int H, float eps, const void *y, const void *g,
+                        const void *ln_w, const void *ln_b, void *out, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WKV6_B200_H */

@@ -1,0 +1,98 @@
+"""ctypes loader of libwkv6_b200.so (the C ABI declared in include/wkv6_b200.h).
+
+There is NO fallback: if the library is missing and cannot be built, importing any operator fails
+loudly.  Nothing here imports ``oracle/``.
+"""
+import ctypes
+import os
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "libwkv6_b200.so")
+
+c_p, c_i, c_sz, c_i64, c_f = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_int64, ctypes.c_float
+
+# name -> (restype, argtypes); mirrors include/wkv6_b200.h one to one
+_BTCH = [c_i, c_i, c_i, c_i]
+SIGNATURES = {
+    "wkv6b200_abi_version": (c_i, []),
+    "wkv6b200_last_error": (ctypes.c_char_p, []),
+    "wkv6b200_set_impl": (c_i, [c_i]),
+    "wkv6b200_get_impl": (c_i, []),
+    "wkv6b200_launch_count": (ctypes.c_uint64, []),
+    "wkv6_forward": (c_i, _BTCH + [c_p] * 7),
+    "wkv6_forward_raww": (c_i, _BTCH + [c_p] * 7),
+    "wkv6_backward_workspace_bytes": (c_sz, _BTCH),
+    "wkv6_backward": (c_i, _BTCH + [c_p] * 12 + [c_sz, c_p]),
+    "wkv6_backward_raww": (c_i, _BTCH + [c_p] * 12 + [c_sz, c_p]),
+    "wkv6state_forward": (c_i, _BTCH + [c_p] * 8),
+    "wkv6state_backward": (c_i, _BTCH + [c_p] * 14 + [c_sz, c_p]),
+    "wkv6infctx_forward": (c_i, _BTCH + [c_p] * 8),
+    "wkv6infctx_forward_f32state": (c_i, _BTCH + [c_p] * 8),
+    "wkv6infctx_backward": (c_i, _BTCH + [c_p] * 14 + [c_sz, c_p]),
+    "wkv6_bi_forward": (c_i, _BTCH + [c_p] * 8),
+    "wkv6_bi_forward_raww": (c_i, _BTCH + [c_p] * 8),
+    "wkv6_bi_backward": (c_i, _BTCH + [c_p] * 13 + [c_sz, c_p]),
+    "wkv6_bi_backward_raww": (c_i, _BTCH + [c_p] * 13 + [c_sz, c_p]),
+    "rwkv6_forward": (c_i, [c_i] + _BTCH + [c_p] * 8),
+    "eos_index_i64": (c_i, [c_i, c_i, c_p, c_i64, c_p, c_p]),
+    "gather_rows_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "pooling_bf16": (c_i, [c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "create_mask_rev_idx": (c_i, [c_i, c_i, c_p, c_i64, c_i64, c_p, c_p, c_p]),
+    "gather_tokens_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "tmix_ddlerp_mix_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "tmix_shift_lerp_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "groupnorm_gate_bf16": (c_i, [c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_p]),
+}
+
+_lib = None
+
+
+class Wkv6B200Error(RuntimeError):
+    pass
+
+
+def load(build_if_missing: bool = True):
+    """Return the loaded library; raise if it is not there (never falls back to anything else)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        if build_if_missing and os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):
+            from .build import build_library
+            build_library()
+        else:
+            raise Wkv6B200Error(f"{LIB_PATH} is missing: run `python -m rwkv_lm_ext_b200.build` "
+                                "(there is no CPU or eager fallback)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here = header and library disagree
+        fn.restype, fn.argtypes = res, args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().wkv6b200_last_error().decode(errors="replace")
+        raise Wkv6B200Error(f"{what} failed with code {rc}: {msg}")
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream_of(t):
+    import torch
+    return torch.cuda.current_stream(t.device).cuda_stream
+
+
+def launch_count() -> int:
+    return int(load().wkv6b200_launch_count())
+
+
+IMPL = {"auto": 0, "simt": 1, "tc": 2}
+
+
+def set_impl(name: str) -> str:
+    prev = load().wkv6b200_set_impl(IMPL[name])
+    return {v: k for k, v in IMPL.items()}[prev]

@@ -1,0 +1,222 @@
+// extern "C" entry points of libwkv6_b200.so -- see include/wkv6_b200.h for the contract.
+#include <atomic>
+#include <cstdarg>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace wkv6 {
+
+static thread_local char g_err[512] = "";
+static std::atomic<int> g_impl{-1};
+static std::atomic<uint64_t> g_launches{0};
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+static int current_impl() {
+    int v = g_impl.load();
+    if (v < 0) {
+        const char *e = getenv("WKV6_B200_IMPL");   // "simt" | "tc" | "auto"
+        v = WKV6_IMPL_AUTO;
+        if (e && !strcmp(e, "simt")) v = WKV6_IMPL_SIMT;
+        if (e && !strcmp(e, "tc")) v = WKV6_IMPL_TC;
+        g_impl.store(v);
+    }
+    return v;
+}
+
+static int check_shape(int B, int T, int C, int H) {
+    if (B < 0 || T < 0 || H <= 0 || C != H * N) {
+        set_error("bad shape B=%d T=%d C=%d H=%d (need C == H*%d)", B, T, C, H, N);
+        return WKV6_EINVAL;
+    }
+    return WKV6_OK;
+}
+#define REQUIRE_PTRS(...)                                                        \
+    do {                                                                         \
+        const void *_p[] = {__VA_ARGS__};                                        \
+        for (size_t _i = 0; _i < sizeof(_p) / sizeof(_p[0]); _i++)               \
+            if (!_p[_i]) { set_error("%s: null pointer argument #%zu", __func__, _i); return WKV6_EINVAL; } \
+    } while (0)
+
+static int dispatch_forward(const Args &a) {
+    const int impl = current_impl();
+    if (impl != WKV6_IMPL_SIMT && tc_forward_supported(a)) return tc_forward(a);
+    if (impl == WKV6_IMPL_TC) { set_error("tensor-core forward does not support this call"); return WKV6_EUNSUPPORTED; }
+    return simt_forward(a);
+}
+static int dispatch_backward(const Args &a) {
+    const int impl = current_impl();
+    if (impl == WKV6_IMPL_TC) { set_error("tensor-core backward not available"); return WKV6_EUNSUPPORTED; }
+    return simt_backward(a);
+}
+
+}  // namespace wkv6
+
+using namespace wkv6;
+
+extern "C" {
+
+int wkv6b200_abi_version(void) { return 1; }
+const char *wkv6b200_last_error(void) { return g_err; }
+int wkv6b200_set_impl(int impl) {
+    int prev = current_impl();
+    g_impl.store(impl);
+    return prev;
+}
+int wkv6b200_get_impl(void) { return current_impl(); }
+uint64_t wkv6b200_launch_count(void) { return g_launches.load(); }
+
+// ------------------------------------------------------------------------------------ wkv6
+static int wkv6_fwd_common(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                           const void *w, int w_kind, const void *u, void *y, const int *mask, void *stream) {
+    if (int rc = check_shape(B, T, C, H)) return rc;
+    if ((size_t)B * T == 0) return WKV6_OK;
+    REQUIRE_PTRS(r, k, v, w, u, y);
+    Args a;
+    a.B = B; a.T = T; a.H = H; a.r = r; a.k = k; a.v = v; a.w = w; a.w_kind = w_kind; a.u = u; a.y = y;
+    a.mask = mask; a.stream = (cudaStream_t)stream;
+    return dispatch_forward(a);
+}
+static int wkv6_bwd_common(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                           const void *w, int w_kind, const void *u, const void *s0, long long s0_bstride,
+                           const void *gy, void *gr, void *gk, void *gv, void *gw, void *gu, void *gs,
+                           const int *mask, void *ws, size_t ws_bytes, void *stream) {
+    if (int rc = check_shape(B, T, C, H)) return rc;
+    if ((size_t)B * T == 0) return WKV6_OK;
+    REQUIRE_PTRS(r, k, v, w, u, gy, gr, gk, gv, gw, gu);
+    Args a;
+    a.B = B; a.T = T; a.H = H; a.r = r; a.k = k; a.v = v; a.w = w; a.w_kind = w_kind; a.u = u;
+    a.s0 = s0; a.s0_bstride = s0_bstride; a.gy = gy; a.gr = gr; a.gk = gk; a.gv = gv; a.gw = gw;
+    a.gu = gu; a.gs = gs; a.mask = mask; a.workspace = ws; a.workspace_bytes = ws_bytes;
+    a.stream = (cudaStream_t)stream;
+    return dispatch_backward(a);
+}
+
+int wkv6_forward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                 const float *ew, const void *u, void *y, void *stream) {
+    return wkv6_fwd_common(B, T, C, H, r, k, v, ew, W_LOG_F32, u, y, nullptr, stream);
+}
+int wkv6_forward_raww(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                      const void *w, const void *u, void *y, void *stream) {
+    return wkv6_fwd_common(B, T, C, H, r, k, v, w, W_RAW_BF16, u, y, nullptr, stream);
+}
+size_t wkv6_backward_workspace_bytes(int B, int T, int C, int H) {
+    (void)C;
+    return simt_backward_workspace_bytes(B, T, H);
+}
+int wkv6_backward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                  const float *ew, const void *u, const void *gy, void *gr, void *gk, void *gv,
+                  void *gw, void *gu, void *workspace, size_t workspace_bytes, void *stream) {
+    return wkv6_bwd_common(B, T, C, H, r, k, v, ew, W_LOG_F32, u, nullptr, 0, gy, gr, gk, gv, gw, gu,
+                           nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+int wkv6_backward_raww(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                       const void *w, const void *u, const void *gy, void *gr, void *gk, void *gv,
+                       void *gw, void *gu, void *workspace, size_t workspace_bytes, void *stream) {
+    return wkv6_bwd_common(B, T, C, H, r, k, v, w, W_RAW_BF16, u, nullptr, 0, gy, gr, gk, gv, gw, gu,
+                           nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+
+// ------------------------------------------------------------------------------- wkv6state
+int wkv6state_forward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                      const void *w, const void *u, const void *s, void *y, void *stream) {
+    if (int rc = check_shape(B, T, C, H)) return rc;
+    if ((size_t)B * T == 0) return WKV6_OK;
+    REQUIRE_PTRS(r, k, v, w, u, s, y);
+    Args a;
+    a.B = B; a.T = T; a.H = H; a.r = r; a.k = k; a.v = v; a.w = w; a.w_kind = W_RAW_BF16; a.u = u;
+    a.s0 = s; a.s0_bstride = 0; a.y = y; a.stream = (cudaStream_t)stream;
+    return dispatch_forward(a);
+}
+int wkv6state_backward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                       const void *w, const void *u, const void *s, const void *gy, void *gr,
+                       void *gk, void *gv, void *gw, void *gu, void *gs, void *workspace,
+                       size_t workspace_bytes, void *stream) {
+    REQUIRE_PTRS(s, gs);
+    return wkv6_bwd_common(B, T, C, H, r, k, v, w, W_RAW_BF16, u, s, 0, gy, gr, gk, gv, gw, gu, gs,
+                           nullptr, workspace, workspace_bytes, stream);
+}
+
+// ------------------------------------------------------------------------------ wkv6infctx
+static int infctx_fwd(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                      const void *w, const void *u, void *s, int f32, void *y, void *stream) {
+    if (int rc = check_shape(B, T, C, H)) return rc;
+    if ((size_t)B * T == 0) return WKV6_OK;
+    REQUIRE_PTRS(r, k, v, w, u, s, y);
+    Args a;
+    a.B = B; a.T = T; a.H = H; a.r = r; a.k = k; a.v = v; a.w = w; a.w_kind = W_RAW_BF16; a.u = u;
+    a.s0 = s; a.s0_f32 = f32; a.s0_bstride = (long long)H * N * N; a.sT = s; a.sT_f32 = f32;
+    a.y = y; a.stream = (cudaStream_t)stream;
+    return dispatch_forward(a);
+}
+int wkv6infctx_forward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                       const void *w, const void *u, void *s, void *y, void *stream) {
+    return infctx_fwd(B, T, C, H, r, k, v, w, u, s, 0, y, stream);
+}
+int wkv6infctx_forward_f32state(int B, int T, int C, int H, const void *r, const void *k,
+                                const void *v, const void *w, const void *u, float *s, void *y,
+                                void *stream) {
+    return infctx_fwd(B, T, C, H, r, k, v, w, u, s, 1, y, stream);
+}
+int wkv6infctx_backward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                        const void *w, const void *u, const void *s_initial, const void *gy,
+                        void *gr, void *gk, void *gv, void *gw, void *gu, void *gs,
+                        void *workspace, size_t workspace_bytes, void *stream) {
+    REQUIRE_PTRS(s_initial, gs);
+    return wkv6_bwd_common(B, T, C, H, r, k, v, w, W_RAW_BF16, u, s_initial, (long long)H * N * N, gy,
+                           gr, gk, gv, gw, gu, gs, nullptr, workspace, workspace_bytes, stream);
+}
+
+// --------------------------------------------------------------------------------- wkv6_bi
+int wkv6_bi_forward(int B, int T, int C, int H, const int *mask, const void *r, const void *k,
+                    const void *v, const float *ew, const void *u, void *y, void *stream) {
+    REQUIRE_PTRS(mask);
+    return wkv6_fwd_common(B, T, C, H, r, k, v, ew, W_LOG_F32, u, y, mask, stream);
+}
+int wkv6_bi_forward_raww(int B, int T, int C, int H, const int *mask, const void *r,
+                         const void *k, const void *v, const void *w, const void *u, void *y,
+                         void *stream) {
+    REQUIRE_PTRS(mask);
+    return wkv6_fwd_common(B, T, C, H, r, k, v, w, W_RAW_BF16, u, y, mask, stream);
+}
+int wkv6_bi_backward(int B, int T, int C, int H, const int *mask, const void *r, const void *k,
+                     const void *v, const float *ew, const void *u, const void *gy, void *gr,
+                     void *gk, void *gv, void *gw, void *gu, void *workspace,
+                     size_t workspace_bytes, void *stream) {
+    REQUIRE_PTRS(mask);
+    return wkv6_bwd_common(B, T, C, H, r, k, v, ew, W_LOG_F32, u, nullptr, 0, gy, gr, gk, gv, gw, gu,
+                           nullptr, mask, workspace, workspace_bytes, stream);
+}
+int wkv6_bi_backward_raww(int B, int T, int C, int H, const int *mask, const void *r,
+                          const void *k, const void *v, const void *w, const void *u,
+                          const void *gy, void *gr, void *gk, void *gv, void *gw, void *gu,
+                          void *workspace, size_t workspace_bytes, void *stream) {
+    REQUIRE_PTRS(mask);
+    return wkv6_bwd_common(B, T, C, H, r, k, v, w, W_RAW_BF16, u, nullptr, 0, gy, gr, gk, gv, gw, gu,
+                           nullptr, mask, workspace, workspace_bytes, stream);
+}
+
+// ------------------------------------------------------------------------- rwkv6 inference
+int rwkv6_forward(int dtype, int B, int T, int C, int H, float *state, const void *r,
+                  const void *k, const void *v, const float *w_decay, const void *u, void *y,
+                  void *stream) {
+    if (int rc = check_shape(B, T, C, H)) return rc;
+    if (dtype < WKV6_BF16 || dtype > WKV6_FP32) { set_error("bad dtype %d", dtype); return WKV6_EINVAL; }
+    if ((size_t)B * T == 0) return WKV6_OK;
+    REQUIRE_PTRS(state, r, k, v, w_decay, u, y);
+    Args a;
+    a.B = B; a.T = T; a.H = H; a.io_dtype = dtype; a.r = r; a.k = k; a.v = v; a.w = w_decay;
+    a.w_kind = W_DECAY_F32; a.u = u; a.s0 = state; a.s0_f32 = 1; a.s0_bstride = (long long)H * N * N;
+    a.sT = state; a.sT_f32 = 1; a.y = y; a.stream = (cudaStream_t)stream;
+    return dispatch_forward(a);
+}
+
+}  // extern "C"

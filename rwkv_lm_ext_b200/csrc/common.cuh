@@ -1,0 +1,88 @@
+// Shared declarations of libwkv6_b200.so (sm_100a only).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/wkv6_b200.h"
+
+namespace wkv6 {
+
+constexpr int N = WKV6_HEAD_SIZE;  // head size, fixed like the reference's -D_N_=64
+
+// how the decay tensor is encoded at the boundary
+enum WKind : int {
+    W_RAW_BF16 = 0,   // raw logits w, bf16           (wkv6state / wkv6infctx / RUN_CUDA_RWKV6)
+    W_LOG_F32 = 1,    // l = -exp(w), fp32            (wkv6 / wkv6_bi native entry, src/model.py:210)
+    W_DECAY_F32 = 2,  // d = exp(-exp(w)), fp32       (rwkv6 inference entry, src/model_run.py:64)
+};
+
+// One generic description of a WKV6 call; every C-ABI entry point fills one of these.
+struct Args {
+    int B = 0, T = 0, H = 0;
+    int io_dtype = WKV6_BF16;         // element type of r,k,v,u,y,(gy,g*)
+    const void *r = nullptr, *k = nullptr, *v = nullptr, *u = nullptr;
+    const void *w = nullptr;
+    int w_kind = W_RAW_BF16;
+    // initial state: nullptr (zero) | bf16/fp32 [.,H,64(value),64(key)], batch stride 0 or H*64*64
+    const void *s0 = nullptr;
+    int s0_f32 = 0;
+    long long s0_bstride = 0;
+    // final state out (may alias s0): nullptr | bf16/fp32 [B,H,64,64]
+    void *sT = nullptr;
+    int sT_f32 = 0;
+    void *y = nullptr;
+    // bidirectional (wkv6_bi): mask int32 [B,T]; nullptr = plain causal op
+    const int *mask = nullptr;
+    // backward only
+    const void *gy = nullptr;
+    void *gr = nullptr, *gk = nullptr, *gv = nullptr, *gw = nullptr, *gu = nullptr, *gs = nullptr;
+    void *workspace = nullptr;
+    size_t workspace_bytes = 0;
+    cudaStream_t stream = nullptr;
+};
+
+// implementations (each returns a WKV6_* code)
+int simt_forward(const Args &a);
+int simt_backward(const Args &a);
+size_t simt_backward_workspace_bytes(int B, int T, int H);
+
+int tc_forward(const Args &a);            // tcgen05 / TMA chunked forward
+bool tc_forward_supported(const Args &a);
+
+void set_error(const char *fmt, ...);
+void count_launch(int n = 1);
+
+#define WKV6_CUDA_CHECK(expr)                                                            \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            ::wkv6::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),    \
+                              __FILE__, __LINE__);                                       \
+            return WKV6_ECUDA;                                                           \
+        }                                                                                \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+template <typename T> __device__ __forceinline__ float to_f32(T x);
+template <> __device__ __forceinline__ float to_f32<__nv_bfloat16>(__nv_bfloat16 x) { return __bfloat162float(x); }
+template <> __device__ __forceinline__ float to_f32<__half>(__half x) { return __half2float(x); }
+template <> __device__ __forceinline__ float to_f32<float>(float x) { return x; }
+
+template <typename T> __device__ __forceinline__ T from_f32(float x);
+template <> __device__ __forceinline__ __nv_bfloat16 from_f32<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+template <> __device__ __forceinline__ __half from_f32<__half>(float x) { return __float2half_rn(x); }
+template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }
+
+// log-decay l = log d (<= 0) from whatever the boundary carries
+template <int WK> __device__ __forceinline__ float load_logdecay(const void *w, size_t idx) {
+    if (WK == W_RAW_BF16) return -__expf(__bfloat162float(((const __nv_bfloat16 *)w)[idx]));
+    if (WK == W_LOG_F32) return ((const float *)w)[idx];
+    return __logf(fmaxf(((const float *)w)[idx], 1e-38f));
+}
+
+}  // namespace wkv6

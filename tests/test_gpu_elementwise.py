@@ -1,0 +1,141 @@
+"""Memory-bound neighbours of the recurrence on the GPU against the oracle / torch expressions.
+Integer results are bit-exact.  `pytest -m gpu`."""
+import pytest
+import torch
+
+from tests.util import assert_bf16_close, load_golden, relrms
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def M():
+    import rwkv_lm_ext_b200 as M
+    M.load()
+    return M
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import wkv6_oracle
+    return wkv6_oracle
+
+
+def test_golden_mask_rev_idx_eos(M):
+    c = load_golden("mask_rev_idx")
+    idx = c["idx"].to(DEV)
+    mask, rev = M.create_mask_and_rev_idx(idx, emb_id=1, pad_id=0)
+    assert mask.dtype == torch.int32 and torch.equal(mask.cpu(), c["mask"])
+    assert rev.dtype == torch.int64 and torch.equal(rev.cpu(), c["rev_idx"])
+    assert torch.equal(M.eos_index(idx, 1).cpu(), c["eos_pos"])
+
+
+@pytest.mark.parametrize("B,T", [(1, 1), (3, 7), (64, 512), (5, 4096), (2, 100000)])
+def test_eos_index_bit_exact(M, B, T):
+    g = torch.Generator().manual_seed(T)
+    idx = torch.randint(2, 65536, (B, T), generator=g)
+    for b in range(B):
+        if b % 3 == 0:
+            idx[b, T - 1] = 1                       # eos last
+        elif b % 3 == 1:
+            idx[b, int(torch.randint(0, T, (1,), generator=g))] = 1
+            idx[b, T // 2] = 1                      # duplicates: first wins
+        # else: absent -> 0
+    want = torch.eq(idx, 1).int().argmax(-1)
+    got = M.eos_index(idx.to(DEV), 1)
+    assert got.dtype == torch.int64 and torch.equal(got.cpu(), want)
+
+
+def test_gather_and_reverse_bit_exact(M):
+    g = torch.Generator().manual_seed(0)
+    B, T, D = 7, 33, 768
+    x = torch.randn(B, T, D, generator=g).bfloat16().to(DEV)
+    idx = torch.randint(2, 100, (B, T), generator=g)
+    idx[:, -1] = 1
+    idx[2, 5] = 1
+    idx[2, 6:] = 0
+    idx = idx.to(DEV)
+    rows, pos = M.eos_gather(x, idx, 1)
+    assert torch.equal(rows, x[torch.arange(B, device=DEV), pos])
+    mask, rev = M.create_mask_and_rev_idx(idx)
+    want = torch.gather(x, 1, rev.unsqueeze(-1).expand(-1, -1, D))
+    got = M.reverse_x(x, rev)
+    assert torch.equal(got, want)
+    assert torch.equal(M.reverse_x(got, rev), x)        # the permutation is an involution
+    # odd D falls back to scalar copies
+    x2 = torch.randn(2, 5, 13, generator=g).bfloat16().to(DEV)
+    p2 = torch.tensor([4, 0], device=DEV)
+    assert torch.equal(M.gather_rows(x2, p2), x2[torch.arange(2, device=DEV), p2])
+
+
+def test_pooling_golden_and_random(M, O):
+    c = load_golden("pooling")
+    x = c["x"].bfloat16().to(DEV)
+    L = c["actual_len"].to(DEV)
+    for variant, kinds in (("train", ("weightedmean", "lasttoken", "avg")), ("infer", ("weightedmean", "lasttoken"))):
+        for kind in kinds:
+            got = M.pooling(x, L, kind, variant)
+            ref = c[f"{variant}_{kind}"]
+            if kind == "lasttoken":
+                assert torch.equal(got.float().cpu(), ref)
+            elif variant == "train":
+                assert_bf16_close(got, ref, f"pool {variant} {kind}")
+            else:
+                assert relrms(got, ref) < 1e-6
+    g = torch.Generator().manual_seed(1)
+    B, T, D = 16, 512, 2048
+    x = torch.randn(B, T, D, generator=g).bfloat16()
+    L = torch.randint(1, T, (B,), generator=g)
+    L[0] = T - 1
+    for kind in ("weightedmean", "avg"):
+        ref = O.pooling(x, L, kind, "train")
+        assert_bf16_close(M.pooling(x.to(DEV), L.to(DEV), kind, "train"), ref.float(), kind)
+    ref = O.pooling(x, L, "weightedmean", "infer")
+    assert relrms(M.pooling(x.to(DEV), L.to(DEV), "weightedmean", "infer"), ref) < 1e-6
+
+
+def test_ddlerp_matches_eager_bf16_chain(M, O):
+    """Bit-exact against the reference's eager bf16 op chain (src/model.py:437-448) run by torch on
+    the same device, and close to the fp64 oracle."""
+    g = torch.Generator().manual_seed(2)
+    B, T, C, R = 2, 37, 256, 32
+    x = torch.randn(B, T, C, generator=g).bfloat16().to(DEV)
+    maa_x = torch.rand(C, generator=g).bfloat16().to(DEV)
+    maa = torch.rand(5, C, generator=g).bfloat16().to(DEV)
+    w1 = (torch.randn(C, 5 * R, generator=g) * 0.05).bfloat16().to(DEV)
+    w2 = (torch.randn(5, R, C, generator=g) * 0.05).bfloat16().to(DEV)
+    shift = torch.nn.ZeroPad2d((0, 0, 1, -1))
+    xx = shift(x) - x
+    xxx_ref = x + xx * maa_x
+    assert torch.equal(M.tmix_shift_lerp(x, maa_x), xxx_ref)
+    m = torch.bmm(torch.tanh(xxx_ref @ w1).view(B * T, 5, -1).transpose(0, 1), w2).view(5, B, T, C)
+    want = torch.stack([x + xx * (maa[n] + m[n]) for n in range(5)])
+    got = M.tmix_ddlerp_mix(x, maa, m)
+    assert torch.equal(got, want)
+    ref = O.tmix_ddlerp(x.cpu(), maa_x.cpu(), maa.cpu(), w1.cpu(), w2.cpu())
+    for n in range(5):
+        assert_bf16_close(got[n], ref[n], f"ddlerp {n}", relrms_tol=2e-2)
+    # infctx variant: previous token comes from shift_state (src/model.py:738-745)
+    st = torch.randn(B, C, generator=g).bfloat16().to(DEV)
+    xx2 = torch.cat([st.unsqueeze(1), x[:, :-1]], 1) - x
+    assert torch.equal(M.tmix_shift_lerp(x, maa_x, st), x + xx2 * maa_x)
+
+
+def test_groupnorm_gate(M, O):
+    g = torch.Generator().manual_seed(3)
+    B, T, H = 3, 21, 4
+    C = H * 64
+    y = (torch.randn(B, T, C, generator=g) * 3).bfloat16()
+    gate = torch.randn(B, T, C, generator=g).bfloat16()
+    lw = torch.rand(C, generator=g).bfloat16()
+    lb = (torch.randn(C, generator=g) * 0.1).bfloat16()
+    eps = 1e-5 * 8 ** 2
+    ref = O.groupnorm_gate(y, gate, lw, lb, H, eps)
+    got = M.groupnorm_gate(y.to(DEV), gate.to(DEV), lw.to(DEV), lb.to(DEV), H, eps)
+    assert_bf16_close(got, ref, "gn*gate")
+    ln = torch.nn.GroupNorm(H, C, eps=eps).to(DEV).bfloat16()
+    ln.weight.data.copy_(lw)
+    ln.bias.data.copy_(lb)
+    eager = ln(y.to(DEV).view(B * T, C)).view(B, T, C) * gate.to(DEV)
+    assert relrms(got, eager) < 4e-3

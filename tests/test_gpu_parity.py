@@ -1,0 +1,284 @@
+"""Parity of the CUDA path (through the C ABI / the reference-shaped Python surface) against the
+oracle.  Needs a B200: run with `pytest -m gpu`.  Tolerances are in tests/util.py."""
+import os
+
+import pytest
+import torch
+
+from tests.util import (STATE_RELRMS, assert_bf16_close, load_golden, make_inputs, relrms)
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda"
+
+
+@pytest.fixture(scope="module")
+def M():
+    import rwkv_lm_ext_b200 as M
+    M.load()
+    return M
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import wkv6_oracle
+    return wkv6_oracle
+
+
+def _impls(M):
+    # every forward test runs on both implementations once the tensor-core one exists
+    return ["simt", "auto"]
+
+
+def _run_fwd_bwd(M, r, k, v, w, u, gy):
+    B, T, C = r.shape
+    H = u.shape[0]
+    leaves = [t.detach().clone().to(DEV).requires_grad_(True) for t in (r, k, v, w, u)]
+    y = M.RUN_CUDA_RWKV6(B, T, C, H, *leaves)
+    y.backward(gy.to(DEV))
+    return y.detach(), [t.grad for t in leaves]
+
+
+# ---------------------------------------------------------------------------------------------
+# golden fixtures produced by the reference itself
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+@pytest.mark.parametrize("name", ["wkv6_2x10x256_randn", "wkv6_2x150x128_decay"])
+def test_golden_forward_backward(M, name, impl):
+    c = load_golden(name)
+    M.set_impl(impl)
+    try:
+        bf = lambda t: t.bfloat16()
+        y, grads = _run_fwd_bwd(M, bf(c["r"]), bf(c["k"]), bf(c["v"]), bf(c["w"]), bf(c["u"]), bf(c["gy"]))
+    finally:
+        M.set_impl("auto")
+    assert_bf16_close(y, c["y_run_rwkv6_forward"], f"{name} y vs run_rwkv6_forward")
+    # the author's own bar (tests/test_cpu.py:290)
+    assert torch.allclose(y.float().cpu(), c["y_run_rwkv6_forward"], atol=1e-2 + 2 ** -7 * c["y_run_rwkv6_forward"].abs().max().item())
+    for g, key in zip(grads, ("gr", "gk", "gv", "gw", "gu")):
+        assert_bf16_close(g, c[key], f"{name} {key}")
+
+
+def test_golden_initial_state(M):
+    c = load_golden("wkv6state_2x70x128")
+    bf = lambda t: t.bfloat16().to(DEV)
+    B, T, C = c["r"].shape
+    H = 2
+    s_vk = c["s0_kv"].transpose(-1, -2).contiguous()
+    leaves = [bf(c[n]).requires_grad_(True) for n in ("r", "k", "v", "w", "u")]
+    s = bf(s_vk).requires_grad_(True)
+    s_work = s.clone()
+    y, s_out = M.RUN_CUDA_RWKV6_STATE(B, T, C, H, *leaves, s_work)
+    y.backward(bf(c["gy"]))
+    assert_bf16_close(y, c["y_fla"], "state y")
+    for t, key in zip(leaves, ("gr", "gk", "gv", "gw", "gu")):
+        assert_bf16_close(t.grad, c[key], f"state {key}")
+    assert_bf16_close(s.grad.transpose(-1, -2), c["gs_kv"], "state gs")
+
+
+# ---------------------------------------------------------------------------------------------
+# wkv6 forward / backward against the fp64 oracle, shapes around every tile boundary
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("impl", ["simt", "auto"])
+@pytest.mark.parametrize("decay", ["randn", "model"])
+@pytest.mark.parametrize("B,T,H", [(1, 1, 1), (2, 2, 1), (1, 15, 2), (2, 16, 1), (1, 17, 1), (1, 63, 2),
+                                   (2, 64, 2), (1, 65, 1), (1, 130, 3), (1, 257, 1)])
+def test_wkv6_vs_oracle(M, O, B, T, H, decay, impl):
+    r, k, v, w, u, gy = make_inputs(B, T, H, seed=B * 1000 + T, decay=decay)
+    ref = O.wkv6_backward(r, k, v, w, u, gy)
+    M.set_impl(impl)
+    try:
+        y, grads = _run_fwd_bwd(M, r, k, v, w, u, gy)
+    finally:
+        M.set_impl("auto")
+    assert_bf16_close(y, ref["y"], "y")
+    for g, key in zip(grads, ("gr", "gk", "gv", "gw", "gu")):
+        assert_bf16_close(g, ref[key], key)
+    # exact zeros at the edges like cuda/wkv6_cuda.cu:201,226
+    assert grads[3][:, 0].abs().max().item() == 0.0
+    assert grads[3][:, -1].abs().max().item() == 0.0
+
+
+def test_native_surface_matches_python_surface(M):
+    """cuda/wkv6_op.cpp signatures (fp32 ew = -exp(w), caller-allocated outputs)."""
+    B, T, H = 2, 70, 2
+    C = H * 64
+    r, k, v, w, u, gy = make_inputs(B, T, H, seed=5, decay="model", device=DEV)
+    ew = (-torch.exp(w.float())).contiguous()
+    y = torch.empty_like(r)
+    M.wkv6_cuda.forward(B, T, C, H, r, k, v, ew, u, y)
+    gr, gk, gv, gw = (torch.empty_like(r) for _ in range(4))
+    gu = torch.empty(B, C, device=DEV, dtype=torch.bfloat16)
+    M.wkv6_cuda.backward(B, T, C, H, r, k, v, ew, u, gy, gr, gk, gv, gw, gu)
+    y2, grads = _run_fwd_bwd(M, r, k, v, w, u, gy)
+    # same kernels, decay read in fp32 instead of recomputed from bf16 w: near-identical
+    assert relrms(y, y2) < 2e-3
+    for a, b in zip((gr, gk, gv, gw, gu.sum(0).view(H, 64)), grads):
+        assert relrms(a, b) < 5e-3
+
+
+# ---------------------------------------------------------------------------------------------
+# state variants
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("T", [1, 33, 64, 100])
+def test_wkv6state_vs_oracle(M, O, T):
+    B, H = 2, 2
+    C = H * 64
+    r, k, v, w, u, gy = make_inputs(B, T, H, seed=T, decay="model")
+    s = (torch.randn(H, 64, 64, generator=torch.Generator().manual_seed(T)) * 0.5).bfloat16()
+    ref = O.wkv6_backward(r, k, v, w, u, gy, s=s, s_layout="state")
+    leaves = [t.clone().to(DEV).requires_grad_(True) for t in (r, k, v, w, u, s)]
+    os.environ["RWKV_TRAIN_TYPE"] = "states"
+    try:
+        y = M.RUN_CUDA_RWKV6_STATE(B, T, C, H, *leaves)
+    finally:
+        os.environ.pop("RWKV_TRAIN_TYPE")
+    assert isinstance(y, torch.Tensor)
+    y.backward(gy.to(DEV))
+    assert_bf16_close(y, ref["y"], "y")
+    for t, key in zip(leaves, ("gr", "gk", "gv", "gw", "gu", "gs")):
+        assert_bf16_close(t.grad, ref[key], key)
+    assert leaves[3].grad[:, -1].abs().max().item() == 0.0
+    if T > 1:
+        assert leaves[3].grad[:, 0].abs().max().item() > 0.0      # real value at t = 0 (cuda/wkv6state_cuda.cu:254)
+
+
+def test_wkv6infctx_in_place_state_and_chain(M, O):
+    B, T, H = 2, 96, 2
+    C = H * 64
+    r, k, v, w, u, gy = make_inputs(B, T, H, seed=77, decay="model")
+    s0 = (torch.randn(B, H, 64, 64, generator=torch.Generator().manual_seed(1)) * 0.5).bfloat16()
+    y_ref, s_ref = O.wkv6infctx_forward(r, k, v, w, u, s0)
+    dv = lambda t: t.clone().to(DEV)
+    # one call, bf16 state written back in place (cuda/wkv6infctx_cuda.cu:65-67)
+    s = dv(s0)
+    y, s_ret = M.RUN_CUDA_RWKV6_STATE(B, T, C, H, dv(r), dv(k), dv(v), dv(w), dv(u), s)
+    assert s_ret.data_ptr() == s.data_ptr()
+    assert_bf16_close(y, y_ref, "infctx y")
+    assert_bf16_close(s, s_ref, "infctx final state (bf16)")
+    # chain of chunks with an fp32 carried state == one long call, fp32 tolerance
+    sf = dv(s0).float()
+    ys = []
+    for a in range(0, T, 32):
+        sl = slice(a, a + 32)
+        yc, sf = M.RUN_CUDA_RWKV6_STATE(B, 32, C, H, dv(r[:, sl]).contiguous(), dv(k[:, sl]).contiguous(),
+                                        dv(v[:, sl]).contiguous(), dv(w[:, sl]).contiguous(), dv(u), sf)
+        ys.append(yc)
+    assert_bf16_close(torch.cat(ys, 1), y_ref, "infctx chained y")
+    assert relrms(sf, s_ref) < STATE_RELRMS
+    # gradient w.r.t. the INITIAL state (the reference kernel sees the final one: a defect)
+    ref = O.wkv6_backward(r, k, v, w, u, gy, s=s0, s_layout="infctx")
+    leaves = [dv(t).requires_grad_(True) for t in (r, k, v, w, u)]
+    s_leaf = dv(s0).requires_grad_(True)
+    y2, _ = M.RUN_CUDA_RWKV6_STATE(B, T, C, H, *leaves, s_leaf.clone())
+    y2.backward(dv(gy))
+    for t, key in zip(leaves + [s_leaf], ("gr", "gk", "gv", "gw", "gu", "gs")):
+        assert_bf16_close(t.grad, ref[key], f"infctx {key}")
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
+def test_rwkv6_inference_op(M, O, dtype):
+    T, H = 50, 3
+    C = H * 64
+    r, k, v, w, u, _ = make_inputs(1, T, H, seed=9, decay="model")
+    cast = lambda t: t.float().to(dtype)
+    r, k, v, w, u = (cast(t[0]) if t.dim() == 3 else cast(t) for t in (r, k, v, w, u))
+    st0 = torch.randn(H, 64, 64, generator=torch.Generator().manual_seed(2)) * 0.3
+    decay = torch.exp(-torch.exp(w.float()))
+    y_ref, s_ref = O.rwkv6_inference_forward(st0, r, k, v, decay, u)
+    st = st0.clone().to(DEV)
+    y, st_ret = M.RUN_RWKV_6(1, T, C, H, st, r.to(DEV), k.to(DEV), v.to(DEV), w.to(DEV), u.to(DEV))
+    assert st_ret.data_ptr() == st.data_ptr() and tuple(y.shape) == (1, T, C) and y.dtype == dtype
+    if dtype == torch.float32:
+        assert relrms(y[0], y_ref) < 1e-5
+    else:
+        assert_bf16_close(y[0], y_ref, "inference y")
+    assert relrms(st, s_ref) < STATE_RELRMS
+
+
+# ---------------------------------------------------------------------------------------------
+# bidirectional op
+# ---------------------------------------------------------------------------------------------
+def test_wkv6_bi_vs_oracle(M, O):
+    B, T, H = 4, 64, 2
+    C = H * 64
+    r, k, v, w, u, gy = make_inputs(B, T, H, seed=21, decay="randn")
+    mask = torch.ones(B, T, dtype=torch.int32)
+    mask[0, 60:] = 0          # cuda/wkv6_bi.py:66-67 smoke masks
+    mask[1, 40:] = 0
+    mask[2, 0:] = 0           # empty row: p = 0
+    ref = O.wkv6_bi_backward(mask, r, k, v, w, u, gy)
+    leaves = [t.clone().to(DEV).requires_grad_(True) for t in (r, k, v, w, u)]
+    y = M.RUN_CUDA_RWKV6_BI(B, T, C, H, mask.to(DEV), *leaves)
+    y.backward(gy.to(DEV))
+    assert_bf16_close(y, ref["y"], "bi y")
+    assert y[0, 61:].abs().max().item() == 0.0 and y[1, 41:].abs().max().item() == 0.0
+    for t, key in zip(leaves, ("gr", "gk", "gv", "gw", "gu")):
+        assert_bf16_close(t.grad, ref[key], f"bi {key}")
+
+
+# ---------------------------------------------------------------------------------------------
+# against the reference's own CUDA kernels (oracle/_ref, built from /root/reference/cuda/*.cu)
+# ---------------------------------------------------------------------------------------------
+def test_against_reference_cuda_kernels(M):
+    from oracle import ref_cuda
+    if not ref_cuda.available("wkv6"):
+        pytest.skip("oracle/_ref not built (make -C oracle ref)")
+    B, T, H = 2, 512, 4
+    r, k, v, w, u, gy = make_inputs(B, T, H, seed=3, decay="model", device=DEV)
+    y_ref, ew = ref_cuda.wkv6_forward(r, k, v, w, u)
+    g_ref = ref_cuda.wkv6_backward(r, k, v, ew, u, gy)
+    torch.cuda.synchronize()
+    y, grads = _run_fwd_bwd(M, r, k, v, w, u, gy)
+    assert_bf16_close(y, y_ref.float(), "y vs reference CUDA", relrms_tol=6e-3)
+    for a, b, key in zip(grads, g_ref, ("gr", "gk", "gv", "gw", "gu")):
+        assert_bf16_close(a, b.float(), f"{key} vs reference CUDA", relrms_tol=8e-3)
+
+
+# ---------------------------------------------------------------------------------------------
+# long sequences: C oracle (fp32, multi-threaded) at T = 4096, and size-independent properties at
+# BASELINE.json's full shape
+# ---------------------------------------------------------------------------------------------
+def test_long_sequence_vs_c_oracle(M):
+    from oracle import c_oracle
+    B, T, H = 1, 4096, 2
+    r, k, v, w, u, gy = make_inputs(B, T, H, seed=4096, decay="model")
+    y_ref = c_oracle.forward(r, k, v, w, u)
+    g_ref = c_oracle.backward(r, k, v, w, u, gy)
+    y, grads = _run_fwd_bwd(M, r, k, v, w, u, gy)
+    assert_bf16_close(y, y_ref, "T=4096 y")
+    for a, key in zip(grads[:4], ("gr", "gk", "gv", "gw")):
+        assert_bf16_close(a, g_ref[key], f"T=4096 {key}")
+    assert_bf16_close(grads[4], g_ref["gu"].sum(0).view(H, 64), "T=4096 gu")
+
+
+def test_full_shape_properties(M):
+    """B=8, T=4096, H=32 (BASELINE.json configs[1]): too big for the oracle, so check
+    (1) split-and-carry == one call, (2) batch rows are independent, (3) SIMT == AUTO."""
+    B, T, H = 8, 4096, 32
+    C = H * 64
+    r, k, v, w, u, _ = make_inputs(B, T, H, seed=1, decay="model", device=DEV)
+    y = M.RUN_CUDA_RWKV6(B, T, C, H, r, k, v, w, u)
+    assert torch.isfinite(y.float()).all()
+    # (1) two halves chained through an fp32 state
+    s = torch.zeros(B, H, 64, 64, device=DEV)
+    h = T // 2
+    ya, s = M.RUN_CUDA_RWKV6_STATE(B, h, C, H, *(t[:, :h].contiguous() for t in (r, k, v, w)), u, s)
+    yb, s = M.RUN_CUDA_RWKV6_STATE(B, h, C, H, *(t[:, h:].contiguous() for t in (r, k, v, w)), u, s)
+    assert relrms(torch.cat([ya, yb], 1), y) < 3e-3
+    # (2) row 3 alone gives the same numbers
+    y3 = M.RUN_CUDA_RWKV6(1, T, C, H, *(t[3:4].contiguous() for t in (r, k, v, w)), u)
+    assert relrms(y3, y[3:4]) < 1e-6
+    # (3) implementations agree
+    M.set_impl("simt")
+    try:
+        ys = M.RUN_CUDA_RWKV6(B, T, C, H, r, k, v, w, u)
+    finally:
+        M.set_impl("auto")
+    assert relrms(y, ys) < 6e-3
+
+
+def test_empty_inputs(M):
+    z = torch.empty(0, 8, 64, device=DEV, dtype=torch.bfloat16)
+    u = torch.zeros(1, 64, device=DEV, dtype=torch.bfloat16)
+    assert M.RUN_CUDA_RWKV6(0, 8, 64, 1, z, z, z, z, u).shape == (0, 8, 64)
