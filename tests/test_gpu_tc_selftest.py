@@ -1,0 +1,36 @@
+"""tcgen05 / TMA / TMEM building blocks: one 64xNx64 MMA per operand layout against torch.matmul.
+`pytest -m gpu`."""
+import ctypes
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("manual", [0, 4])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("N,boff", [(64, 0), (16, 0), (16, 8)])
+def test_mma_layouts(a_mn, b_mn, manual, N, boff):
+    if boff and b_mn:
+        pytest.skip("row offset is a K-major B case")
+    from rwkv_lm_ext_b200 import _lib
+    lib = _lib.load()
+    fn = lib.wkv6b200_tc_selftest
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    g = torch.Generator().manual_seed(a_mn * 2 + b_mn + N)
+    A = torch.randn(64, 64, generator=g).bfloat16().cuda()
+    B = torch.randn(64, 64, generator=g).bfloat16().cuda()
+    D = torch.full((64, 64), float("nan"), device="cuda")
+    flags = a_mn | (b_mn << 1) | manual | boff
+    _lib.check(fn(flags, N, A.data_ptr(), B.data_ptr(), D.data_ptr(), torch.cuda.current_stream().cuda_stream), "selftest")
+    torch.cuda.synchronize()
+    Am = (A.t() if a_mn else A).float()                  # [M, K]
+    Bm = (B.t() if b_mn else B).float()                  # [N, K]
+    if boff:
+        Bm = Bm[16:]
+    want = Am @ Bm[:N].t()
+    got = D[:, :N]
+    err = (got - want).abs().max().item()
+    assert err < 1e-3 * max(1.0, want.abs().max().item()), f"flags={flags} N={N}: max err {err}\n{got[:4,:4]}\n{want[:4,:4]}"
