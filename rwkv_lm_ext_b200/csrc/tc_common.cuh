@@ -43,19 +43,26 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t by
 }
 __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
     uint32_t ok;
+    // the last operand is a suspend-time hint (ns): the hardware may park the thread instead of
+    // returning immediately, so a waiting warp does not steal issue slots from working warps
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)
         : "memory");
     return ok != 0;
 }
 // Bounded wait: a protocol bug traps (error returned to the host) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it)
-        if (it > (1u << 26)) __trap();
+        if (it > (1u << 20)) __trap();
+}
+// named barrier among a subset of the CTA's warps (hardware-blocking, no spinning)
+template <int ID, int NTHREADS_>
+__device__ __forceinline__ void named_bar_sync() {
+    asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NTHREADS_) : "memory");
 }
 
 // generic-proxy writes (st.shared) -> visible to the async proxy (TMA / tcgen05 operand reads)

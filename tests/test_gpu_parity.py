@@ -112,7 +112,7 @@ def test_native_surface_matches_python_surface(M):
     M.wkv6_cuda.backward(B, T, C, H, r, k, v, ew, u, gy, gr, gk, gv, gw, gu)
     y2, grads = _run_fwd_bwd(M, r, k, v, w, u, gy)
     # same kernels, decay read in fp32 instead of recomputed from bf16 w: near-identical
-    assert relrms(y, y2) < 2e-3
+    assert relrms(y, y2) < 6e-3      # tcgen05 path rounds scaled operands to bf16
     for a, b in zip((gr, gk, gv, gw, gu.sum(0).view(H, 64)), grads):
         assert relrms(a, b) < 5e-3
 
