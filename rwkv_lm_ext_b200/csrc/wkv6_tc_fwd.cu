@@ -53,7 +53,7 @@ constexpr uint32_t OFF_RT = 61440, OFF_P = OFF_RT;   // P is written after the M
 constexpr uint32_t OFF_RH = 69632, OFF_KH = 77824, OFF_KL = 86016, OFF_SB = 94208;
 constexpr uint32_t OFF_TILES_END = 102400;
 struct Extra {
-    float elam[64];
+    alignas(16) float elam[64];
     float diagu[64];
     float2 htot[8][32];       // per half-block (8 rows) decay totals, [half-block][channel pair]
     float dg[4][16][16];      // hazard route: exact diagonal blocks of A, [block][s][t]
@@ -61,7 +61,7 @@ struct Extra {
     uint32_t tmem_base;
     int hz[2];
 };
-constexpr uint32_t SMEM_BYTES = OFF_TILES_END + sizeof(Extra) + 1024;
+constexpr uint32_t SMEM_BYTES = OFF_TILES_END + sizeof(Extra);
 
 constexpr uint32_t TM_A = 0, TM_Y = 64, TM_S = 128, TM_COLS = 256;
 
@@ -99,9 +99,11 @@ __device__ __forceinline__ uint4 pack8(const uint32_t *v) {
 __global__ void __launch_bounds__(NTHREADS, 2)
 wkv6_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_k,
                    const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_w, Params p) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *sm = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    // dynamic shared memory is the only shared memory of this kernel, so it starts 1024-aligned
+    // (checked below); indexing it directly keeps every access in the shared address space (LDS/STS)
+    extern __shared__ __align__(1024) uint8_t sm[];
     Extra &ex = *reinterpret_cast<Extra *>(sm + OFF_TILES_END);
+    if ((smem_u32(sm) & 1023u) != 0) __trap();
     const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
     const int T = p.T, C = p.H * 64;
     const int NC = (T + L - 1) / L;
@@ -390,8 +392,9 @@ wkv6_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_const
             tc_fence_after();
             const bool hazard = ex.hz[par] != 0;
             // ---- A^T (lanes = s, columns = t)  ->  P[t][s] bf16, strictly lower + diag(u) term
-            const float dgu = ex.diagu[row];
+            //      P[t][s = row] lives at byte t*128 + ((s/8) ^ (t%8))*16 + (s%8)*2 of the swizzled tile
             const uint32_t pcol = ((uint32_t)(row >> 3) << 4), pin = (uint32_t)(row & 7) * 2;
+            uint8_t *pbase = sm + OFF_P + pin;
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
                 tmem_ld32(tmem_addr(tmem, tlane, TM_A + 32 * hh), v);
@@ -400,17 +403,18 @@ wkv6_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_const
 #pragma unroll
                     for (int cc = 0; cc < 32; cc++) {
                         const int t = 32 * hh + cc;
-                        float x = 0.f;
-                        if (t > row) {
-                            x = __uint_as_float(v[cc]);
-                            if (hazard && (t >> 4) == (row >> 4)) x = ex.dg[row >> 4][row & 15][t & 15];
-                        } else if (t == row) {
-                            x = dgu;
-                        }
-                        // P[t][s = row]: byte offset t*128 + ((s/8) ^ (t%8))*16 + (s%8)*2
-                        *reinterpret_cast<bf16 *>(sm + OFF_P + t * 128 + (pcol ^ ((uint32_t)(t & 7) << 4)) + pin) =
-                            __float2bfloat16_rn(x);
+                        const float x = (t > row) ? __uint_as_float(v[cc]) : 0.f;
+                        *reinterpret_cast<bf16 *>(pbase + t * 128 + (pcol ^ ((uint32_t)(t & 7) << 4))) = __float2bfloat16_rn(x);
                     }
+                }
+            }
+            if (act) {
+                *reinterpret_cast<bf16 *>(pbase + row * 128 + (pcol ^ ((uint32_t)(row & 7) << 4))) = __float2bfloat16_rn(ex.diagu[row]);
+                if (hazard) {
+                    const int qb = row & ~15;
+                    for (int t = row + 1; t < qb + 16; t++)
+                        *reinterpret_cast<bf16 *>(pbase + t * 128 + (pcol ^ ((uint32_t)(t & 7) << 4))) =
+                            __float2bfloat16_rn(ex.dg[row >> 4][row & 15][t & 15]);
                 }
             }
             // ---- decay the state: S[j][i] *= exp(Lam_i)
@@ -419,7 +423,13 @@ wkv6_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_const
                 tmem_ld32(tmem_addr(tmem, tlane, TM_S + 32 * hh), v);
                 tmem_wait_ld();
 #pragma unroll
-                for (int cc = 0; cc < 32; cc++) v[cc] = __float_as_uint(__uint_as_float(v[cc]) * ex.elam[32 * hh + cc]);
+                for (int c4 = 0; c4 < 8; c4++) {
+                    const float4 e = *reinterpret_cast<const float4 *>(&ex.elam[32 * hh + 4 * c4]);
+                    v[4 * c4 + 0] = __float_as_uint(__uint_as_float(v[4 * c4 + 0]) * e.x);
+                    v[4 * c4 + 1] = __float_as_uint(__uint_as_float(v[4 * c4 + 1]) * e.y);
+                    v[4 * c4 + 2] = __float_as_uint(__uint_as_float(v[4 * c4 + 2]) * e.z);
+                    v[4 * c4 + 3] = __float_as_uint(__uint_as_float(v[4 * c4 + 3]) * e.w);
+                }
                 tmem_st32(tmem_addr(tmem, tlane, TM_S + 32 * hh), v);
             }
             tmem_wait_st();
