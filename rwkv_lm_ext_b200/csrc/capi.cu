@@ -54,7 +54,8 @@ static int dispatch_forward(const Args &a) {
 }
 static int dispatch_backward(const Args &a) {
     const int impl = current_impl();
-    if (impl == WKV6_IMPL_TC) { set_error("tensor-core backward not available"); return WKV6_EUNSUPPORTED; }
+    if (impl != WKV6_IMPL_SIMT && tc_backward_supported(a)) return tc_backward(a);
+    if (impl == WKV6_IMPL_TC) { set_error("tensor-core backward does not support this call"); return WKV6_EUNSUPPORTED; }
     return simt_backward(a);
 }
 
@@ -110,7 +111,7 @@ int wkv6_forward_raww(int B, int T, int C, int H, const void *r, const void *k, 
 }
 size_t wkv6_backward_workspace_bytes(int B, int T, int C, int H) {
     (void)C;
-    return simt_backward_workspace_bytes(B, T, H);
+    return tc_backward_workspace_bytes(B, T, H);   // superset: SIMT scratch + state checkpoints + flag
 }
 int wkv6_backward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
                   const float *ew, const void *u, const void *gy, void *gr, void *gk, void *gv,

@@ -41,6 +41,10 @@ struct Args {
     void *gr = nullptr, *gk = nullptr, *gv = nullptr, *gw = nullptr, *gu = nullptr, *gs = nullptr;
     void *workspace = nullptr;
     size_t workspace_bytes = 0;
+    // SIMT kernels only: nullptr, or a device int; the kernels return immediately unless
+    // (*run_flag != 0) == run_if  (lets a fallback be enqueued without a host round trip)
+    const int *run_flag = nullptr;
+    int run_if = 1;
     cudaStream_t stream = nullptr;
 };
 
@@ -50,7 +54,11 @@ int simt_backward(const Args &a);
 size_t simt_backward_workspace_bytes(int B, int T, int H);
 
 int tc_forward(const Args &a);            // tcgen05 / TMA chunked forward
+int tc_forward_ex(const Args &a, void *ckpt, int *hz_flag);
 bool tc_forward_supported(const Args &a);
+int tc_backward(const Args &a);           // tcgen05 / TMA chunked backward (+ SIMT fallback on hazard)
+bool tc_backward_supported(const Args &a);
+size_t tc_backward_workspace_bytes(int B, int T, int H);
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);

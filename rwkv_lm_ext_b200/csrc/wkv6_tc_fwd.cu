@@ -73,7 +73,9 @@ struct Params {
     long long s0_bstride;
     void *sT;
     int sT_f32;
-    bf16 *y;
+    bf16 *y;          // nullptr: state-only pass (backward pre-pass)
+    bf16 *ckpt;       // nullptr or [B*H][NC][64 j][64 i]: bf16 state at the START of every chunk
+    int *hz_flag;     // nullptr or a device int set to 1 when any chunk took the hazard route
 };
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
@@ -229,7 +231,10 @@ wkv6_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_const
                 hs1 += l1[n];
             }
             ex.htot[hb][lane] = make_float2(hs0, hs1);
-            if (-hs0 > HAZARD2 || -hs1 > HAZARD2) atomicOr(&ex.hz[par], 1);
+            if (-hs0 > HAZARD2 || -hs1 > HAZARD2) {
+                atomicOr(&ex.hz[par], 1);
+                if (p.hz_flag) *p.hz_flag = 1;
+            }
             named_bar_sync<2, PREP_THREADS>();
 
             // ---- phase B: references, per-(block, channel) factors
@@ -372,8 +377,11 @@ wkv6_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_const
             tmem_st32(tmem_addr(tmem, tlane, TM_S + 32 * hh), v);
             if (act) {
 #pragma unroll
-                for (int ch = 0; ch < 4; ch++)
-                    *reinterpret_cast<uint4 *>(sm + OFF_SB + sw128(row, 64 * hh + 16 * ch)) = pack8(v + 8 * ch);
+                for (int ch = 0; ch < 4; ch++) {
+                    const uint4 o = pack8(v + 8 * ch);
+                    *reinterpret_cast<uint4 *>(sm + OFF_SB + sw128(row, 64 * hh + 16 * ch)) = o;
+                    if (p.ckpt) *reinterpret_cast<uint4 *>(p.ckpt + ((size_t)blockIdx.x * NC * 64 + row) * 64 + 32 * hh + 8 * ch) = o;
+                }
             }
         }
         tmem_wait_st();
@@ -447,7 +455,7 @@ wkv6_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_const
                 for (int hh = 0; hh < 2; hh++) {
                     tmem_ld32(tmem_addr(tmem, tlane, TM_Y + 32 * hh), v);
                     tmem_wait_ld();
-                    if (act && row < nv) {
+                    if (act && row < nv && p.y) {
 #pragma unroll
                         for (int ch = 0; ch < 4; ch++) *reinterpret_cast<uint4 *>(dst + 32 * hh + 8 * ch) = pack8(v + 8 * ch);
                     }
@@ -461,8 +469,12 @@ wkv6_tc_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_const
                 tmem_wait_ld();
                 if (act) {
 #pragma unroll
-                    for (int ch = 0; ch < 4; ch++)
-                        *reinterpret_cast<uint4 *>(sm + OFF_SB + sw128(row, 64 * hh + 16 * ch)) = pack8(v + 8 * ch);
+                    for (int ch = 0; ch < 4; ch++) {
+                        const uint4 o = pack8(v + 8 * ch);
+                        *reinterpret_cast<uint4 *>(sm + OFF_SB + sw128(row, 64 * hh + 16 * ch)) = o;
+                        if (p.ckpt && !last)
+                            *reinterpret_cast<uint4 *>(p.ckpt + (((size_t)blockIdx.x * NC + c + 1) * 64 + row) * 64 + 32 * hh + 8 * ch) = o;
+                    }
                     if (last && p.sT) {
                         const size_t idx = (((size_t)b * p.H + h) * 64 + row) * 64 + hh * 32;
 #pragma unroll
@@ -490,7 +502,12 @@ bool tc_forward_supported(const Args &a) {
            tc::get_encode_fn() != nullptr;
 }
 
-int tc_forward(const Args &a) {
+int tc_forward_ex(const Args &a, void *ckpt, int *hz_flag);
+int tc_forward(const Args &a) { return tc_forward_ex(a, nullptr, nullptr); }
+
+// ckpt: nullptr or bf16 [B*H][ceil(T/64)][64][64] receiving the state at the start of every chunk;
+// a.y may be nullptr (state-only pass).
+int tc_forward_ex(const Args &a, void *ckpt, int *hz_flag) {
     if (a.B * a.H == 0 || a.T == 0) return WKV6_OK;
     const int C = a.H * 64;
     CUtensorMap mr, mk, mv, mw;
@@ -506,6 +523,8 @@ int tc_forward(const Args &a) {
     p.s0 = a.s0; p.s0_f32 = a.s0_f32; p.s0_bstride = a.s0_bstride;
     p.sT = a.sT; p.sT_f32 = a.sT_f32;
     p.y = (bf16 *)a.y;
+    p.ckpt = (bf16 *)ckpt;
+    p.hz_flag = hz_flag;
     static bool attr_done = false;
     if (!attr_done) {
         WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
