@@ -81,6 +81,28 @@ WKV6_API int wkv6_backward_raww(int B, int T, int C, int H, const void *r, const
                        void *gw, void *gu, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Training pair behind the torch.autograd.Function wrappers (WKV_6 src/model.py:191-233, WKV_6STATE
+ * :137-182 and :83-128): the reference forward keeps r,k,v,w,u(,s) for backward with
+ * ctx.save_for_backward and its backward re-runs the whole state recurrence; here the forward also
+ * leaves, in `saved` (caller-owned, wkv6_saved_bytes), the bf16 state at the start of every
+ * 64-token chunk plus a flag header, and the backward consumes it instead of recomputing it.
+ *   s0: NULL (zero state) | [H,64,64] (s0_batched = 0, wkv6state) | [B,H,64,64] (s0_batched = 1,
+ *       wkv6infctx); bf16, or fp32 in the forward when s0_f32.  sT: NULL or [B,H,64,64] final state
+ *       out (may alias s0).  *saved_valid (host int) is set to 1 when `saved` was filled; pass
+ *       saved = NULL to wkv6_train_backward otherwise (it then recomputes, needing the larger
+ *       workspace of wkv6_backward_workspace_bytes).  gs: NULL iff s0 is NULL, else bf16 [B,H,64,64].
+ * ------------------------------------------------------------------------------------------ */
+WKV6_API size_t wkv6_saved_bytes(int B, int T, int C, int H);
+WKV6_API size_t wkv6_train_backward_workspace_bytes(int B, int T, int C, int H, int has_saved);
+WKV6_API int wkv6_train_forward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                       const void *w, const void *u, const void *s0, int s0_batched, int s0_f32,
+                       void *sT, int sT_f32, void *y, void *saved, int *saved_valid, void *stream);
+WKV6_API int wkv6_train_backward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                        const void *w, const void *u, const void *s0, int s0_batched, const void *gy,
+                        void *gr, void *gk, void *gv, void *gw, void *gu, void *gs, const void *saved,
+                        void *workspace, size_t workspace_bytes, void *stream);
+
+/* ------------------------------------------------------------------------------------------
  * (a3) wkv6state -- cuda/wkv6state_cuda.cu:298-311 bound by cuda/wkv6state_op.cpp:8-21.
  * w: raw bf16 logits.  s: bf16 [H,64,64], shared by the batch, read-only.
  * gs: bf16 [B,H,64,64] per-batch partials (wrapper sums over B, src/model.py:182).

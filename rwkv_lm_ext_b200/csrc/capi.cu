@@ -48,7 +48,11 @@ static int check_shape(int B, int T, int C, int H) {
 
 static int dispatch_forward(const Args &a) {
     const int impl = current_impl();
-    if (impl != WKV6_IMPL_SIMT && tc_forward_supported(a)) return tc_forward(a);
+    if (impl != WKV6_IMPL_SIMT && tc_forward_supported(a)) {
+        if (!a.saved) return tc_forward(a);
+        if (cudaMemsetAsync(a.saved, 0, SAVED_HEADER, a.stream) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return WKV6_ECUDA; }
+        return tc_forward_ex(a, (uint8_t *)a.saved + SAVED_HEADER, (int *)a.saved);
+    }
     if (impl == WKV6_IMPL_TC) { set_error("tensor-core forward does not support this call"); return WKV6_EUNSUPPORTED; }
     return simt_forward(a);
 }
@@ -124,6 +128,49 @@ int wkv6_backward_raww(int B, int T, int C, int H, const void *r, const void *k,
                        void *gw, void *gu, void *workspace, size_t workspace_bytes, void *stream) {
     return wkv6_bwd_common(B, T, C, H, r, k, v, w, W_RAW_BF16, u, nullptr, 0, gy, gr, gk, gv, gw, gu,
                            nullptr, nullptr, workspace, workspace_bytes, stream);
+}
+
+// ---------------------------------------------------------------------------- training pair
+size_t wkv6_saved_bytes(int B, int T, int C, int H) {
+    (void)C;
+    return tc_saved_bytes(B, T, H);
+}
+size_t wkv6_train_backward_workspace_bytes(int B, int T, int C, int H, int has_saved) {
+    (void)C;
+    return has_saved ? simt_backward_workspace_bytes(B, T, H) : tc_backward_workspace_bytes(B, T, H);
+}
+int wkv6_train_forward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                       const void *w, const void *u, const void *s0, int s0_batched, int s0_f32,
+                       void *sT, int sT_f32, void *y, void *saved, int *saved_valid, void *stream) {
+    if (saved_valid) *saved_valid = 0;
+    if (int rc = check_shape(B, T, C, H)) return rc;
+    if ((size_t)B * T == 0) return WKV6_OK;
+    REQUIRE_PTRS(r, k, v, w, u, y);
+    Args a;
+    a.B = B; a.T = T; a.H = H; a.r = r; a.k = k; a.v = v; a.w = w; a.w_kind = W_RAW_BF16; a.u = u;
+    a.s0 = s0; a.s0_f32 = s0_f32; a.s0_bstride = s0_batched ? (long long)H * N * N : 0;
+    a.sT = sT; a.sT_f32 = sT_f32; a.y = y; a.stream = (cudaStream_t)stream;
+    const bool save = saved && current_impl() != WKV6_IMPL_SIMT && tc_forward_supported(a);
+    if (save) a.saved = saved;
+    const int rc = dispatch_forward(a);
+    if (rc == WKV6_OK && save && saved_valid) *saved_valid = 1;
+    return rc;
+}
+int wkv6_train_backward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
+                        const void *w, const void *u, const void *s0, int s0_batched, const void *gy,
+                        void *gr, void *gk, void *gv, void *gw, void *gu, void *gs, const void *saved,
+                        void *workspace, size_t workspace_bytes, void *stream) {
+    if (int rc = check_shape(B, T, C, H)) return rc;
+    if ((size_t)B * T == 0) return WKV6_OK;
+    REQUIRE_PTRS(r, k, v, w, u, gy, gr, gk, gv, gw, gu);
+    if (s0) REQUIRE_PTRS(gs);
+    Args a;
+    a.B = B; a.T = T; a.H = H; a.r = r; a.k = k; a.v = v; a.w = w; a.w_kind = W_RAW_BF16; a.u = u;
+    a.s0 = s0; a.s0_bstride = s0_batched ? (long long)H * N * N : 0; a.gy = gy; a.gr = gr; a.gk = gk;
+    a.gv = gv; a.gw = gw; a.gu = gu; a.gs = gs; a.workspace = workspace; a.workspace_bytes = workspace_bytes;
+    a.saved = const_cast<void *>(saved);
+    a.stream = (cudaStream_t)stream;
+    return dispatch_backward(a);
 }
 
 // ------------------------------------------------------------------------------- wkv6state

@@ -45,6 +45,8 @@ struct Args {
     // (*run_flag != 0) == run_if  (lets a fallback be enqueued without a host round trip)
     const int *run_flag = nullptr;
     int run_if = 1;
+    // training pair: forward fills it (hazard flag header + bf16 chunk-start states), backward reads it
+    void *saved = nullptr;
     cudaStream_t stream = nullptr;
 };
 
@@ -59,6 +61,8 @@ bool tc_forward_supported(const Args &a);
 int tc_backward(const Args &a);           // tcgen05 / TMA chunked backward (+ SIMT fallback on hazard)
 bool tc_backward_supported(const Args &a);
 size_t tc_backward_workspace_bytes(int B, int T, int H);
+size_t tc_saved_bytes(int B, int T, int H);
+constexpr size_t SAVED_HEADER = 256;   // int[0] = hazard flag
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);

@@ -150,8 +150,67 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
           "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
         : "memory");
 }
+// 16 lanes x 32 columns of 32-bit in the mma-fragment layout: lane T of the warp gets, for column
+// group g = 0..3,  v[4g+0], v[4g+1] = (lane base + T/4,     columns c + 8g + 2(T%4) + {0,1})
+//                  v[4g+2], v[4g+3] = (lane base + T/4 + 8, same columns).
+// This reads an M = 64 accumulator (16 lanes per sub-partition) with all 32 threads busy, and the
+// registers (packed to bf16 pairs) are exactly ldmatrix / stmatrix 8x8 fragments.
+__device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.16x256b.x4.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_frag(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.16x256b.x4.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        :
+        : "r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+          "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// ------------------------------------------------------------------------------------------------
+// ldmatrix / stmatrix: four 8x8 b16 blocks per instruction; lane L supplies the shared address of
+// row (L % 8) of block (L / 8) (16 bytes each, any 16-byte-aligned address: swizzled tiles work).
+// Thread T holds of every block the pair (row T/4, columns 2(T%4), 2(T%4)+1); with .trans the block
+// is transposed on the way, i.e. the register pair is (column T/4 of memory, rows 2(T%4), +1).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void ldsm_x4(uint32_t saddr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(saddr) : "memory");
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t saddr, uint32_t &r0, uint32_t &r1, uint32_t &r2, uint32_t &r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3) : "r"(saddr) : "memory");
+}
+__device__ __forceinline__ void stsm_x4(uint32_t saddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};"
+                 :: "r"(saddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+__device__ __forceinline__ void stsm_x4_t(uint32_t saddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
+    asm volatile("stmatrix.sync.aligned.m8n8.x4.trans.shared.b16 [%0], {%1, %2, %3, %4};"
+                 :: "r"(saddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+
+// TMA tensor store (shared -> global), bulk-group completion
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap *map, const void *smem_src, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+                 :
+                 : "l"((uint64_t)map), "r"(smem_u32(smem_src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N_>
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N_) : "memory"); }
+template <int N_>
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N_) : "memory"); }
 
 // ------------------------------------------------------------------------------------------------
 // descriptors
@@ -207,6 +266,13 @@ inline bool make_btc_map(CUtensorMap *map, const void *ptr, int B, int T, int C,
                          int elem_bytes, int box_cols) {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) return false;
+    // the driver entry point needs a current context on THIS host thread; a thread that has only
+    // been handed work (e.g. PyTorch's autograd worker) may not have touched the runtime yet
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+        cudaFree(nullptr);
+        ctx_bound = true;
+    }
     cuuint64_t dims[3] = {(cuuint64_t)C, (cuuint64_t)T, (cuuint64_t)B};
     cuuint64_t strides[2] = {(cuuint64_t)C * elem_bytes, (cuuint64_t)T * C * elem_bytes};
     cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};

@@ -589,6 +589,11 @@ wkv6_tc_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_const
 
 }  // namespace
 
+size_t tc_saved_bytes(int B, int T, int H) {
+    const size_t NC = (size_t)(T + L - 1) / L;
+    return SAVED_HEADER + (size_t)B * H * NC * 8192;
+}
+
 size_t tc_backward_workspace_bytes(int B, int T, int H) {
     const size_t NC = (size_t)(T + L - 1) / L;
     return simt_backward_workspace_bytes(B, T, H) + (size_t)B * H * NC * 8192 + 256;
@@ -604,29 +609,41 @@ int tc_backward(const Args &a) {
     const int C = a.H * 64;
     const size_t NC = (size_t)(a.T + L - 1) / L;
     const size_t simt_ws = simt_backward_workspace_bytes(a.B, a.T, a.H);
-    if (!a.workspace || a.workspace_bytes < tc_backward_workspace_bytes(a.B, a.T, a.H)) {
-        set_error("workspace too small: need %zu bytes", tc_backward_workspace_bytes(a.B, a.T, a.H));
+    const size_t need = a.saved ? simt_ws : tc_backward_workspace_bytes(a.B, a.T, a.H);
+    if (!a.workspace || a.workspace_bytes < need) {
+        set_error("workspace too small: need %zu bytes", need);
         return WKV6_EWORKSPACE;
     }
     uint8_t *ws = (uint8_t *)a.workspace;
-    bf16 *ckpt = (bf16 *)(ws + simt_ws);
-    int *flag = (int *)(ws + simt_ws + (size_t)a.B * a.H * NC * 8192);
-    WKV6_CUDA_CHECK(cudaMemsetAsync(flag, 0, 256, a.stream));
-    // 1. forward pre-pass: state checkpoints at every chunk start + hazard flag (no y)
-    Args f = a;
-    f.y = nullptr;
-    f.sT = nullptr;
-    if (int rc = tc_forward_ex(f, ckpt, flag)) return rc;
+    bf16 *ckpt;
+    int *flag;
+    if (a.saved) {
+        // training pair: the forward already left the chunk-start states and the hazard flag
+        flag = (int *)a.saved;
+        ckpt = (bf16 *)((uint8_t *)a.saved + SAVED_HEADER);
+    } else {
+        ckpt = (bf16 *)(ws + simt_ws);
+        flag = (int *)(ws + simt_ws + (size_t)a.B * a.H * NC * 8192);
+        WKV6_CUDA_CHECK(cudaMemsetAsync(flag, 0, 256, a.stream));
+        // 1. forward pre-pass: state checkpoints at every chunk start + hazard flag (no y)
+        Args f = a;
+        f.y = nullptr;
+        f.sT = nullptr;
+        if (int rc = tc_forward_ex(f, ckpt, flag)) return rc;
+    }
     // 2. tensor-core reverse sweep (returns at once when the flag is raised)
     CUtensorMap mr, mk, mv, mw, mg, mc;
     const auto dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-    if (!tc::make_btc_map(&mr, a.r, a.B, a.T, C, L, dt, 2, 64) || !tc::make_btc_map(&mk, a.k, a.B, a.T, C, L, dt, 2, 64) ||
-        !tc::make_btc_map(&mv, a.v, a.B, a.T, C, L, dt, 2, 64) || !tc::make_btc_map(&mw, a.w, a.B, a.T, C, L, dt, 2, 64) ||
-        !tc::make_btc_map(&mg, a.gy, a.B, a.T, C, L, dt, 2, 64) ||
-        !tc::make_btc_map(&mc, ckpt, 1, (int)((size_t)a.B * a.H * NC * 64), 64, 64, dt, 2, 64)) {
-        set_error("cuTensorMapEncodeTiled failed (pointers must be 16-byte aligned)");
-        return WKV6_ECUDA;
-    }
+    const bool okm[6] = {tc::make_btc_map(&mr, a.r, a.B, a.T, C, L, dt, 2, 64), tc::make_btc_map(&mk, a.k, a.B, a.T, C, L, dt, 2, 64),
+                         tc::make_btc_map(&mv, a.v, a.B, a.T, C, L, dt, 2, 64), tc::make_btc_map(&mw, a.w, a.B, a.T, C, L, dt, 2, 64),
+                         tc::make_btc_map(&mg, a.gy, a.B, a.T, C, L, dt, 2, 64),
+                         tc::make_btc_map(&mc, ckpt, 1, (int)((size_t)a.B * a.H * NC * 64), 64, 64, dt, 2, 64)};
+    for (int i = 0; i < 6; i++)
+        if (!okm[i]) {
+            const void *ptrs[6] = {a.r, a.k, a.v, a.w, a.gy, ckpt};
+            set_error("cuTensorMapEncodeTiled failed for map %d (r,k,v,w,gy,ckpt), pointer %p (must be 16-byte aligned)", i, ptrs[i]);
+            return WKV6_ECUDA;
+        }
     Params p;
     p.B = a.B; p.T = a.T; p.H = a.H;
     p.u = (const bf16 *)a.u;

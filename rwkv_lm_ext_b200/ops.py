@@ -8,6 +8,7 @@ so that ``src.model.RUN_CUDA_RWKV6 = rwkv_lm_ext_b200.RUN_CUDA_RWKV6`` (see ``in
 Tmix layer of the unmodified reference models.  Host code is PyTorch (allocation, autograd
 plumbing, streams); all arithmetic happens in the C-ABI library.  No CPU fallback.
 """
+import ctypes
 import os
 
 import torch
@@ -34,6 +35,32 @@ def _workspace(lib, B, T, C, H, device):
     return torch.empty(max(n, 1), dtype=torch.uint8, device=device), n
 
 
+def _train_forward(ctx, lib, B, T, C, H, r, k, v, w, u, s0, s0_batched, sT, y):
+    """Forward of the training pair (include/wkv6_b200.h): when a gradient will be asked for, the
+    kernel also leaves the bf16 chunk-start states in ``ctx.saved_state`` -- kept next to
+    save_for_backward's r,k,v,w,u like the reference keeps its inputs (src/model.py:203) -- so that
+    backward does not re-run the recurrence."""
+    saved = None
+    if any(ctx.needs_input_grad):
+        saved = torch.empty(lib.wkv6_saved_bytes(B, T, C, H), dtype=torch.uint8, device=r.device)
+    valid = ctypes.c_int(0)
+    s0_f32 = int(s0 is not None and s0.dtype == torch.float32)
+    sT_f32 = int(sT is not None and sT.dtype == torch.float32)
+    check(lib.wkv6_train_forward(B, T, C, H, ptr(r), ptr(k), ptr(v), ptr(w), ptr(u), ptr(s0), int(s0_batched),
+                                 s0_f32, ptr(sT), sT_f32, ptr(y), ptr(saved), ctypes.byref(valid), stream_of(r)),
+          "wkv6_train_forward")
+    ctx.saved_state = saved if valid.value else None
+
+
+def _train_backward(ctx, lib, B, T, C, H, r, k, v, w, u, s0, s0_batched, gy, gr, gk, gv, gw, gu, gs):
+    saved = ctx.saved_state
+    n = lib.wkv6_train_backward_workspace_bytes(B, T, C, H, int(saved is not None))
+    ws = torch.empty(max(n, 1), dtype=torch.uint8, device=gy.device)
+    check(lib.wkv6_train_backward(B, T, C, H, ptr(r), ptr(k), ptr(v), ptr(w), ptr(u), ptr(s0), int(s0_batched),
+                                  ptr(gy), ptr(gr), ptr(gk), ptr(gv), ptr(gw), ptr(gu), ptr(gs), ptr(saved),
+                                  ptr(ws), n, stream_of(gy)), "wkv6_train_backward")
+
+
 # --------------------------------------------------------------------------------------------
 # WKV_6  (src/model.py:191-235)
 # --------------------------------------------------------------------------------------------
@@ -51,8 +78,7 @@ class WKV_6(torch.autograd.Function):
             ctx.save_for_backward(r, k, v, w, u)
             y = torch.empty((B, T, C), device=r.device, dtype=torch.bfloat16, memory_format=torch.contiguous_format)
             lib = _lib.load()
-            check(lib.wkv6_forward_raww(B, T, C, H, ptr(r), ptr(k), ptr(v), ptr(w), ptr(u), ptr(y), stream_of(r)),
-                  "wkv6_forward_raww")
+            _train_forward(ctx, lib, B, T, C, H, r, k, v, w, u, None, False, None, y)
             return y
 
     @staticmethod
@@ -65,10 +91,7 @@ class WKV_6(torch.autograd.Function):
             gr, gk, gv, gw = (torch.empty((B, T, C), device=gy.device, dtype=torch.bfloat16) for _ in range(4))
             gu = torch.empty((B, C), device=gy.device, dtype=torch.bfloat16)
             lib = _lib.load()
-            ws, n = _workspace(lib, B, T, C, H, gy.device)
-            check(lib.wkv6_backward_raww(B, T, C, H, ptr(r), ptr(k), ptr(v), ptr(w), ptr(u), ptr(gy), ptr(gr),
-                                         ptr(gk), ptr(gv), ptr(gw), ptr(gu), ptr(ws), n, stream_of(gy)),
-                  "wkv6_backward_raww")
+            _train_backward(ctx, lib, B, T, C, H, r, k, v, w, u, None, False, gy, gr, gk, gv, gw, gu, None)
             gu = torch.sum(gu, 0).view(H, C // H)          # src/model.py:232
             return (None, None, None, None, gr, gk, gv, gw, gu)
 
@@ -93,8 +116,7 @@ class WKV_6STATE(torch.autograd.Function):
             ctx.save_for_backward(r, k, v, w, u, s)
             y = torch.empty((B, T, C), device=r.device, dtype=torch.bfloat16, memory_format=torch.contiguous_format)
             lib = _lib.load()
-            check(lib.wkv6state_forward(B, T, C, H, ptr(r), ptr(k), ptr(v), ptr(w), ptr(u), ptr(s), ptr(y),
-                                        stream_of(r)), "wkv6state_forward")
+            _train_forward(ctx, lib, B, T, C, H, r, k, v, w, u, s, False, None, y)
             return y
 
     @staticmethod
@@ -108,10 +130,7 @@ class WKV_6STATE(torch.autograd.Function):
             gu = torch.empty((B, C), device=gy.device, dtype=torch.bfloat16)
             gs = torch.empty((B, H, C // H, C // H), device=gy.device, dtype=torch.bfloat16)
             lib = _lib.load()
-            ws, n = _workspace(lib, B, T, C, H, gy.device)
-            check(lib.wkv6state_backward(B, T, C, H, ptr(r), ptr(k), ptr(v), ptr(w), ptr(u), ptr(s), ptr(gy),
-                                         ptr(gr), ptr(gk), ptr(gv), ptr(gw), ptr(gu), ptr(gs), ptr(ws), n,
-                                         stream_of(gy)), "wkv6state_backward")
+            _train_backward(ctx, lib, B, T, C, H, r, k, v, w, u, s, False, gy, gr, gk, gv, gw, gu, gs)
             gu = torch.sum(gu, 0).view(H, C // H)                  # src/model.py:181
             gs = torch.sum(gs, 0).view(H, C // H, C // H)          # src/model.py:182
             return (None, None, None, None, gr, gk, gv, gw, gu, gs)
@@ -137,9 +156,7 @@ class WKV_6STATE_INFCTX(torch.autograd.Function):
             ctx.save_for_backward(r, k, v, w, u, s_init)
             y = torch.empty((B, T, C), device=r.device, dtype=torch.bfloat16, memory_format=torch.contiguous_format)
             lib = _lib.load()
-            fn = lib.wkv6infctx_forward if s.dtype == torch.bfloat16 else lib.wkv6infctx_forward_f32state
-            check(fn(B, T, C, H, ptr(r), ptr(k), ptr(v), ptr(w), ptr(u), ptr(s), ptr(y), stream_of(r)),
-                  "wkv6infctx_forward")
+            _train_forward(ctx, lib, B, T, C, H, r, k, v, w, u, s, True, s, y)
             ctx.mark_dirty(s)
             ctx.s_dtype = s.dtype
             return y, s
@@ -155,10 +172,7 @@ class WKV_6STATE_INFCTX(torch.autograd.Function):
             gu = torch.empty((B, C), device=gy.device, dtype=torch.bfloat16)
             gs = torch.empty((B, H, C // H, C // H), device=gy.device, dtype=torch.bfloat16)
             lib = _lib.load()
-            ws, n = _workspace(lib, B, T, C, H, gy.device)
-            check(lib.wkv6infctx_backward(B, T, C, H, ptr(r), ptr(k), ptr(v), ptr(w), ptr(u), ptr(s), ptr(gy),
-                                          ptr(gr), ptr(gk), ptr(gv), ptr(gw), ptr(gu), ptr(gs), ptr(ws), n,
-                                          stream_of(gy)), "wkv6infctx_backward")
+            _train_backward(ctx, lib, B, T, C, H, r, k, v, w, u, s, True, gy, gr, gk, gv, gw, gu, gs)
             gu = torch.sum(gu, 0).view(H, C // H)
             # per-sample state: its gradient is per sample too.  (The reference sums gs over the
             # batch into [H,64,64] even here, src/model.py:128 -- a shape that cannot flow back

@@ -34,3 +34,28 @@ def test_mma_layouts(a_mn, b_mn, manual, N, boff):
     got = D[:, :N]
     err = (got - want).abs().max().item()
     assert err < 1e-3 * max(1.0, want.abs().max().item()), f"flags={flags} N={N}: max err {err}\n{got[:4,:4]}\n{want[:4,:4]}"
+
+
+@pytest.mark.parametrize("co", [0, 1, 2, 3])
+def test_fragment_building_blocks(co):
+    """ldmatrix/stmatrix (+trans) on swizzled tiles, tcgen05.ld.16x256b fragment layout, TMA store,
+    and an MN-major N=16 B operand at a column offset inside the swizzle row."""
+    from rwkv_lm_ext_b200 import _lib
+    lib = _lib.load()
+    fn = lib.wkv6b200_tc_selftest2
+    fn.restype = ctypes.c_int
+    fn.argtypes = [ctypes.c_int] + [ctypes.c_void_p] * 6
+    g = torch.Generator().manual_seed(100 + co)
+    A = torch.randn(64, 64, generator=g).bfloat16().cuda()
+    B = torch.randn(64, 64, generator=g).bfloat16().cuda()
+    O = torch.zeros(64, 64, dtype=torch.bfloat16, device="cuda")
+    F = torch.full((64, 64), float("nan"), device="cuda")
+    D = torch.full((64, 16), float("nan"), device="cuda")
+    _lib.check(fn(co, A.data_ptr(), B.data_ptr(), O.data_ptr(), F.data_ptr(), D.data_ptr(),
+                  torch.cuda.current_stream().cuda_stream), "selftest2")
+    torch.cuda.synchronize()
+    assert torch.equal(F, A.float().t()), "ldmatrix.trans fragment layout"
+    assert torch.equal(O, A.t()), "stmatrix + TMA store"
+    want = A.float() @ B.float()[:, 16 * co:16 * co + 16]
+    err = (D - want).abs().max().item()
+    assert err < 1e-3 * max(1.0, want.abs().max().item()), f"co={co}: max err {err}\n{D[:4,:4]}\n{want[:4,:4]}"
