@@ -46,8 +46,56 @@ static int check_shape(int B, int T, int C, int H) {
             if (!_p[_i]) { set_error("%s: null pointer argument #%zu", __func__, _i); return WKV6_EINVAL; } \
     } while (0)
 
+// WKV6_B200_TC2=1 selects the previous generation of tensor-core kernels (warp-specialised, one
+// flag per call); the default is the role-uniform generation with per-stream hazard flags.
+static bool use_tc2() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("WKV6_B200_TC2"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+// per-stream hazard flags of a forward call that has no `saved` buffer: slices of a small per-device
+// ring (4 MB, allocated on first use, never freed), so that calls in flight on different CUDA
+// streams do not share flags
+static int *flag_slice(size_t n) {
+    constexpr size_t RING = 1u << 20;
+    static int *ring[64] = {};
+    static std::atomic<size_t> head[64];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64 || n > RING) return nullptr;
+    if (!ring[dev]) {
+        static std::atomic_flag lock = ATOMIC_FLAG_INIT;
+        while (lock.test_and_set()) {}
+        if (!ring[dev]) {
+            int *p = nullptr;
+            if (cudaMalloc((void **)&p, RING * sizeof(int)) == cudaSuccess) ring[dev] = p;
+        }
+        lock.clear();
+        if (!ring[dev]) return nullptr;
+    }
+    size_t off = head[dev].fetch_add(n) % RING;
+    if (off + n > RING) off = 0;      // wrap: only collides with a call issued ~1M stream-flags ago
+    return ring[dev] + off;
+}
+static int forward3(const Args &a) {
+    int *flags;
+    void *ckpt = nullptr;
+    const size_t nb = (size_t)a.B * a.H * sizeof(int);
+    if (a.saved) {
+        flags = (int *)a.saved;
+        ckpt = (uint8_t *)a.saved + tc3_saved_header(a.B, a.H);
+    } else {
+        flags = flag_slice((size_t)a.B * a.H);
+        if (!flags) { set_error("cannot get %zu bytes of flag scratch", nb); return WKV6_ECUDA; }
+    }
+    WKV6_CUDA_CHECK(cudaMemsetAsync(flags, 0, nb, a.stream));
+    if (int rc = tc3_forward(a, ckpt, flags)) return rc;
+    Args s = a;                       // exact route, only for the streams the kernel flagged
+    s.stream_flags = flags;
+    return simt_forward(s);
+}
 static int dispatch_forward(const Args &a) {
     const int impl = current_impl();
+    if (impl != WKV6_IMPL_SIMT && !use_tc2() && tc3_forward_supported(a)) return forward3(a);
     if (impl != WKV6_IMPL_SIMT && tc_forward_supported(a)) {
         if (!a.saved) return tc_forward(a);
         if (cudaMemsetAsync(a.saved, 0, SAVED_HEADER, a.stream) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return WKV6_ECUDA; }
@@ -58,6 +106,7 @@ static int dispatch_forward(const Args &a) {
 }
 static int dispatch_backward(const Args &a) {
     const int impl = current_impl();
+    if (impl != WKV6_IMPL_SIMT && !use_tc2() && tc3_backward_supported(a)) return tc3_backward(a);
     if (impl != WKV6_IMPL_SIMT && tc_backward_supported(a)) return tc_backward(a);
     if (impl == WKV6_IMPL_TC) { set_error("tensor-core backward does not support this call"); return WKV6_EUNSUPPORTED; }
     return simt_backward(a);
@@ -115,7 +164,8 @@ int wkv6_forward_raww(int B, int T, int C, int H, const void *r, const void *k, 
 }
 size_t wkv6_backward_workspace_bytes(int B, int T, int C, int H) {
     (void)C;
-    return tc_backward_workspace_bytes(B, T, H);   // superset: SIMT scratch + state checkpoints + flag
+    const size_t a = tc_backward_workspace_bytes(B, T, H), b = tc3_backward_workspace_bytes(B, T, H, false);
+    return a > b ? a : b;   // superset: SIMT scratch + chunk-start states + flags
 }
 int wkv6_backward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
                   const float *ew, const void *u, const void *gy, void *gr, void *gk, void *gv,
@@ -133,11 +183,12 @@ int wkv6_backward_raww(int B, int T, int C, int H, const void *r, const void *k,
 // ---------------------------------------------------------------------------- training pair
 size_t wkv6_saved_bytes(int B, int T, int C, int H) {
     (void)C;
-    return tc_saved_bytes(B, T, H);
+    const size_t a = tc_saved_bytes(B, T, H), b = tc3_saved_bytes(B, T, H);
+    return a > b ? a : b;
 }
 size_t wkv6_train_backward_workspace_bytes(int B, int T, int C, int H, int has_saved) {
     (void)C;
-    return has_saved ? simt_backward_workspace_bytes(B, T, H) : tc_backward_workspace_bytes(B, T, H);
+    return has_saved ? simt_backward_workspace_bytes(B, T, H) : wkv6_backward_workspace_bytes(B, T, C, H);
 }
 int wkv6_train_forward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
                        const void *w, const void *u, const void *s0, int s0_batched, int s0_f32,

@@ -1,0 +1,96 @@
+// Shared pieces of the role-uniform tcgen05 kernels (wkv6_tc3_fwd.cu / wkv6_tc3_bwd.cu).
+//
+// Thread <-> data mapping ("fragment mapping"), used by EVERY stage of both kernels.  A CTA has 8
+// compute warps; warp w = (sp = w % 4, ch = w / 4), lane T = (ri = T / 4, q = T % 4).  Of a 64 x 64
+// tile the thread owns rows  R_h = 16 sp + 8 h + ri  (h = 0,1)  and columns  c(g,e) = 32 ch + 8 g +
+// 2 q + e  (g = 0..3, e = 0,1): 16 elements, register index [4g + 2h + e] as tcgen05.ld.16x256b.x4
+// delivers an M = 64 accumulator (sub-partition sp, lanes 0-15).  For the operand preparation the
+// same thread owns CHANNELS i = R_h and TOKENS t = c(g,e): ldmatrix.trans / stmatrix.trans move
+// its bf16 pairs between that mapping and the [token][channel] shared-memory tiles, so the
+// per-channel quantities (decay prefix sums, references, state rows) never change threads between
+// the preparation, the TMEM epilogues and the output stage.
+#pragma once
+#include <cuda_bf16.h>
+
+#include "tc_common.cuh"
+
+namespace wkv6 {
+namespace tc3 {
+
+using namespace tc;
+typedef __nv_bfloat16 bf16;
+
+constexpr int L = 64;
+constexpr int CWARPS = 8, CTHREADS = 256, NTHREADS = CTHREADS + 32;
+constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+constexpr float HAZARD2 = 60.0f * LOG2E;   // log2 units per aligned 16-token span
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&t);
+}
+__device__ __forceinline__ float bf_lo(uint32_t x) { return __uint_as_float(x << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t x) { return __uint_as_float(x & 0xffff0000u); }
+__device__ __forceinline__ float fast_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// 2^n for an integer-valued n, exact; 0 below the normal range, clamped at 2^0 above
+__device__ __forceinline__ float pow2i_le0(float n) {
+    const int e = min(max((int)n, -127), 0);
+    return __int_as_float((e + 127) << 23);
+}
+// packed bf16 pair (x, x) of an exact power of two given as fp32
+__device__ __forceinline__ uint32_t bfpair(float x) {
+    const uint32_t hi = __float_as_uint(x) & 0xffff0000u;   // a power of two has no low mantissa bits
+    return hi | (hi >> 16);
+}
+// exact scaling of a packed bf16 pair by a packed pair of powers of two
+__device__ __forceinline__ uint32_t hmul2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mul.rn.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+
+struct Frag {
+    int warp, lane, sp, ch, ri, q;
+    uint32_t ti_off;     // byte offset (within a [token][channel] tile) this lane supplies to ldmatrix/stmatrix .x4:
+                         // row 32ch + 8(lane/8) + lane%8, 16-byte chunk of channels 16sp (+ 16 bytes for h = 1)
+    uint32_t rc_off;     // byte offset for a plain stmatrix .x4 of an accumulator fragment into a [row][col] tile:
+                         // row 16sp + lane%8 (+ 8 rows for h = 1), 16-byte chunk of columns 32ch + 8(lane/8)
+    __device__ __forceinline__ void init() {
+        warp = threadIdx.x >> 5;
+        lane = threadIdx.x & 31;
+        sp = warp & 3;
+        ch = (warp >> 2) & 1;
+        ri = lane >> 2;
+        q = lane & 3;
+        ti_off = sw128(32 * ch + 8 * (lane >> 3) + (lane & 7), 32 * sp);
+        rc_off = sw128(16 * sp + (lane & 7), 64 * ch + 16 * (lane >> 3));
+    }
+    // h = 1 moves the 16-byte chunk (ti) / the row by 8 (rc); both keep row % 8, so the swizzle XOR is unchanged
+    __device__ __forceinline__ uint32_t ti(int h) const { return ti_off ^ (h ? 16u : 0u); }
+    __device__ __forceinline__ uint32_t rc(int h) const { return rc_off + (h ? 1024u : 0u); }
+    __device__ __forceinline__ int row(int h) const { return 16 * sp + 8 * h + ri; }
+    __device__ __forceinline__ int col(int g, int e) const { return 32 * ch + 8 * g + 2 * q + e; }
+};
+
+// Hand-offs between the issuer warp and the compute warps go through hardware named barriers
+// (producer: bar.arrive, consumer: bar.sync, 288 threads): nobody spins.  Only lane 0 of the issuer
+// warp ever polls an mbarrier (TMA / tcgen05.commit completion); a compute warp spinning on
+// try_wait would take issue slots from the co-resident CTA that is doing useful work.
+enum : int { B_SCAN = 1, B_RAW, B_PREP, B_M1, B_T1, B_M2, B_T2, B_M3, B_T3 };
+template <int ID>
+__device__ __forceinline__ void bar_arrive_all() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(NTHREADS) : "memory"); }
+template <int ID>
+__device__ __forceinline__ void bar_sync_all() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(NTHREADS) : "memory"); }
+
+// 2^d as a packed bf16 pair for an integer d <= 0 (0 when below the normal range)
+__device__ __forceinline__ uint32_t bfpow2pair(int d) {
+    const uint32_t x = (uint32_t)(max(d, -127) + 127) << 7;
+    return x | (x << 16);
+}
+
+}  // namespace tc3
+}  // namespace wkv6

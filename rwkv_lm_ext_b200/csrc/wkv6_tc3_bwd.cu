@@ -1,0 +1,693 @@
+// WKV6 backward, chunked, on tcgen05 tensor cores fed by TMA -- role-uniform version (reverse sweep
+// over 64-token chunks; 2 CTAs per SM; thread <-> data mapping of tc3_common.cuh).
+//
+// Notation as in wkv6_tc3_fwd.cu, with TWO 32-token blocks per chunk (block p = tokens 32p..32p+31,
+// reference rho_p = exc at the block middle on the integer log2 grid; a warp's column half `ch` IS
+// its block).  Inputs per chunk: r,k,v,w,gy tiles, S_in = bf16 state at the chunk start ([i][j],
+// saved by the forward), G = dL/dS at the chunk end, fp32 in TMEM as [key i][value j].
+//
+//   M1  Bm[t,s]  = gy_t . v_s                               -> dA = strict-lower(Bm), bd[t] = Bm[t,t]
+//       A^T[s,t] = sum_i Kt_q[s,i] Rt[t,i]                  -> P^T = strict-upper + diag(sum_i r u k)
+//       Drs[i,t] = sum_j S_in[i,j] gy_t[j]
+//   T1  dA, P^T tiles (bf16);  q0_i = <S_in, G>_i;  G *= 2^Lam_i
+//   M2  gv[s,j]  = sum_t P^T[s,t] gy_t[j] + sum_i Kh[s,i] G[i,j]
+//       Dr[i,t]  = sum_{s<t} Kt_q[s,i] dA[t,s]              (q = block of t)
+//       G[i,j]  += sum_t Rh[t,i] gy_t[j]
+//   T2  gv tile;  gr_t[i] = E (Dr + 2^rho_q Drs) + u_i k_t[i] bd[t];   XA = Rt_own Dr + r E 2^rho_q Drs
+//   M3  Dk[i,s]  = sum_{t>s} Rp_p[t,i] dA[t,s]  (p = block of s);   Dks[i,s] = sum_j G_old[i,j] v_s[j]
+//   T3  gk_s[i] = F (Dk + 2^(Lam-rho_p) Dks) + u_i r_s[i] bd[s];   bf16 copy of the new G;
+//       gl_t[i] = 2^Lam_i q0_i + sum_{s<t} Be_s + sum_{t'>t} (Ae + Ai - Bi)_t' - Bi_t,   gw = l * gl
+//          Ae = r E 2^rho (S_in gy),  Be = k F 2^(Lam-rho) (G v)   (terms through the states)
+//          Ai = Rt_own * Dr,  Bi = Kt_own * Dk                     (intra-chunk pair terms)
+//       This is d_t <S_t, G_t>_i expanded so that no two large quantities are
+//       subtracted: with integer references all Kt_q / Rp_p versions are exact power-of-two multiples of
+//       one another, so Ai and Bi are sums of bit-identical pair products r k dA and their difference
+//       telescopes exactly, like the reference's fp32 suffix trick (cuda/wkv6_cuda.cu:161-227).
+//   E = 2^(exc - rho_q), F = 2^(rho_p - cum);  gr, gk, gw, gv leave through swizzled tiles + TMA stores.
+//
+// Streams whose forward raised the hazard flag are skipped here; the exact SIMT backward, enqueued
+// behind this kernel and predicated per stream on the same flag, handles them.
+#include "common.cuh"
+#include "tc3_common.cuh"
+
+namespace wkv6 {
+namespace {
+
+using namespace tc3;
+
+constexpr uint32_t OFF_R = 0, OFF_K = 8192, OFF_V = 16384, OFF_GY = 24576, OFF_W = 32768, OFF_PT = OFF_W;
+constexpr uint32_t OFF_SIN = 40960, OFF_GB = 49152;
+constexpr uint32_t OFF_KT = 57344;     // version 1 (rows 0..63) at +0, version 0 (rows 0..31) at +8192
+constexpr uint32_t OFF_RP = 69632;     // version 0 (rows 0..63) at +0, version 1 (rows 32..63, stored from row 0) at +8192
+constexpr uint32_t OFF_RH = 81920, OFF_KH = 90112, OFF_DA = 98304, OFF_TILES_END = 106496;
+// output tiles reuse operand tiles that are dead by the time they are written
+constexpr uint32_t OFF_GVT = OFF_RH, OFF_GRT = OFF_KT, OFF_GKT = OFF_DA, OFF_GWT = OFF_GY;
+__host__ __device__ constexpr uint32_t kt_ver(int q) { return q ? 0u : 8192u; }
+__host__ __device__ constexpr uint32_t rp_ver(int p) { return p ? 8192u : 0u; }
+
+struct Extra {
+    float gtot[8][64];        // decay total of every 8-token group, per channel (log2 units)
+    float pdu[4][64];         // per channel-quarter partial sums of r u k, per token
+    float bd[64];             // Bm[t,t]
+    float q0p[2][64];         // <S_in, G>_i, partial over each half of j
+    float htY[2][64], htX[2][64];   // per token-half totals of Be and of X = Ae + Ai - Bi, per channel
+    float gu_s[64];
+    uint64_t bar_rk, bar_w, bar_vg, bar_sin, bar_m1, bar_m2, bar_m3;
+    uint32_t tmem_base;
+};
+constexpr uint32_t SMEM_BYTES = OFF_TILES_END + sizeof(Extra);
+constexpr uint32_t TM_G = 0, TM_X0 = 64, TM_X1 = 128, TM_X2 = 192, TM_COLS = 256;
+
+struct Params {
+    int B, T, H;
+    const bf16 *u;
+    int has_s0;
+    bf16 *gu, *gs;
+    const int *hz_flags;
+};
+
+__device__ __forceinline__ uint32_t pack_frag(const uint32_t *v, int g, int hh) {
+    return pack2(__uint_as_float(v[4 * g + 2 * hh]), __uint_as_float(v[4 * g + 2 * hh + 1]));
+}
+
+__global__ void __launch_bounds__(NTHREADS, 2)
+wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_k,
+                    const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_w,
+                    const __grid_constant__ CUtensorMap map_gy, const __grid_constant__ CUtensorMap map_ck,
+                    const __grid_constant__ CUtensorMap map_gr, const __grid_constant__ CUtensorMap map_gk,
+                    const __grid_constant__ CUtensorMap map_gv, const __grid_constant__ CUtensorMap map_gw, Params p) {
+    if (p.hz_flags[blockIdx.x] != 0) return;        // the exact (SIMT) route handles this stream
+    extern __shared__ __align__(1024) uint8_t sm[];
+    Extra &ex = *reinterpret_cast<Extra *>(sm + OFF_TILES_END);
+    if ((smem_u32(sm) & 1023u) != 0) __trap();
+    const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
+    const int T = p.T, C = p.H * 64;
+    const int NC = (T + L - 1) / L;
+    Frag F;
+    F.init();
+    const int warp = F.warp, lane = F.lane;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&ex.bar_rk, 1);
+        mbar_init(&ex.bar_w, 1);
+        mbar_init(&ex.bar_vg, 1);
+        mbar_init(&ex.bar_sin, 1);
+        mbar_init(&ex.bar_m1, 1);
+        mbar_init(&ex.bar_m2, 1);
+        mbar_init(&ex.bar_m3, 1);
+        fence_barrier_init();
+    }
+    if (threadIdx.x < 64) ex.gu_s[threadIdx.x] = 0.f;
+    if (warp == 0) {
+        tmem_alloc(&ex.tmem_base, TM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = ex.tmem_base;
+    const uint32_t sbase = smem_u32(sm);
+
+    if (warp == CWARPS) {
+        // =====================================================================================
+        // issuer
+        // =====================================================================================
+        auto issue_rk = [&](int c) {
+            mbar_arrive_expect_tx(&ex.bar_rk, 2 * 8192);
+            tma_load_3d(sm + OFF_R, &map_r, &ex.bar_rk, h * 64, c * L, b);
+            tma_load_3d(sm + OFF_K, &map_k, &ex.bar_rk, h * 64, c * L, b);
+        };
+        auto issue_w = [&](int c) {
+            mbar_arrive_expect_tx(&ex.bar_w, 8192);
+            tma_load_3d(sm + OFF_W, &map_w, &ex.bar_w, h * 64, c * L, b);
+        };
+        auto issue_vg = [&](int c) {
+            mbar_arrive_expect_tx(&ex.bar_vg, 2 * 8192);
+            tma_load_3d(sm + OFF_V, &map_v, &ex.bar_vg, h * 64, c * L, b);
+            tma_load_3d(sm + OFF_GY, &map_gy, &ex.bar_vg, h * 64, c * L, b);
+        };
+        auto issue_sin = [&](int c) {
+            mbar_arrive_expect_tx(&ex.bar_sin, 8192);
+            tma_load_3d(sm + OFF_SIN, &map_ck, &ex.bar_sin, 0, (blockIdx.x * NC + c) * 64, 0);
+        };
+        if (lane == 0) {
+            tma_prefetch_desc(&map_r); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
+            tma_prefetch_desc(&map_w); tma_prefetch_desc(&map_gy); tma_prefetch_desc(&map_ck);
+            issue_rk(NC - 1);
+            issue_w(NC - 1);
+            issue_vg(NC - 1);
+            issue_sin(NC - 1);
+        }
+        const uint32_t kt = sbase + OFF_KT, rp = sbase + OFF_RP, rh = sbase + OFF_RH, kh = sbase + OFF_KH;
+        const uint32_t da = sbase + OFF_DA, pt = sbase + OFF_PT, gb = sbase + OFF_GB, sin = sbase + OFF_SIN;
+        const uint32_t vv = sbase + OFF_V, gy = sbase + OFF_GY;
+        constexpr uint32_t ID_KK = idesc_bf16(64, 64, 0, 0), ID_KM = idesc_bf16(64, 64, 0, 1), ID_MM = idesc_bf16(64, 64, 1, 1);
+        constexpr uint32_t ID32_KK = idesc_bf16(64, 32, 0, 0), ID32_MK = idesc_bf16(64, 32, 1, 0), ID32_MM = idesc_bf16(64, 32, 1, 1);
+        bar_sync_all<B_T3>();                                    // G = 0 written (TMEM + bf16 copy)
+        for (int it = 0; it < NC; it++) {
+            const int c = NC - 1 - it;
+            const uint32_t par = it & 1;
+            if (lane == 0) {
+                mbar_wait(&ex.bar_rk, par);
+                mbar_wait(&ex.bar_w, par);
+                tma_store_wait_read<1>();                        // gv / gr tiles of the previous chunk (RH, KT space)
+            }
+            __syncwarp();
+            bar_arrive_all<B_RAW>();
+            if (lane == 0 && it > 0) {
+                tma_store_wait_read<0>();                        // gk / gw tiles (DA, GY space)
+                issue_vg(c);
+            }
+            bar_sync_all<B_PREP>();                              // operands written, raw r,k,w consumed
+            if (lane == 0 && c > 0) issue_rk(c - 1);
+            if (lane == 0) {
+                mbar_wait(&ex.bar_vg, par);
+                mbar_wait(&ex.bar_sin, par);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; k++)   // Bm[t,s] = GY V^T
+                    mma_bf16_ss(tmem + TM_X0, smem_desc_sw128(gy + 32 * k, 8192, 1024), smem_desc_sw128(vv + 32 * k, 8192, 1024), ID_KK, k > 0);
+#pragma unroll
+                for (int q = 0; q < 2; q++)   // A^T[s, t in q] = Kt_q Rt_own^T
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        mma_bf16_ss(tmem + TM_X1 + 32 * q, smem_desc_sw128(kt + kt_ver(q) + 32 * k, 8192, 1024),
+                                    smem_desc_sw128(rp + rp_ver(q) + 32 * k, 8192, 1024), ID32_KK, k > 0);
+#pragma unroll
+                for (int k = 0; k < 4; k++)   // Drs[i,t] = S_in GY^T
+                    mma_bf16_ss(tmem + TM_X2, smem_desc_sw128(sin + 32 * k, 8192, 1024), smem_desc_sw128(gy + 32 * k, 8192, 1024), ID_KK, k > 0);
+                mma_commit(&ex.bar_m1);
+                mbar_wait(&ex.bar_m1, par);
+            }
+            __syncwarp();
+            bar_arrive_all<B_M1>();
+            bar_sync_all<B_T1>();                                // dA, P^T written; <S_in,G> taken; G decayed
+            if (lane == 0) {
+                if (c > 0) issue_sin(c - 1);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; k++)   // gv[s,j] = P^T GY ...
+                    mma_bf16_ss(tmem + TM_X0, smem_desc_sw128(pt + 32 * k, 8192, 1024), smem_desc_sw128(gy + 2048 * k, 8192, 1024), ID_KM, k > 0);
+#pragma unroll
+                for (int k = 0; k < 4; k++)   // ... + Kh G
+                    mma_bf16_ss(tmem + TM_X0, smem_desc_sw128(kh + 32 * k, 8192, 1024), smem_desc_sw128(gb + 2048 * k, 8192, 1024), ID_KM, 1);
+#pragma unroll
+                for (int q = 0; q < 2; q++)   // Dr[i, t in q] = sum_{s in blocks <= q} Kt_q[s,i] dA[t,s]
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++)
+                        if (ks < 2 * q + 2)
+                            mma_bf16_ss(tmem + TM_X1 + 32 * q, smem_desc_sw128(kt + kt_ver(q) + 2048 * ks, 8192, 1024),
+                                        smem_desc_sw128(da + 4096 * q + 32 * ks, 8192, 1024), ID32_MK, ks > 0);
+#pragma unroll
+                for (int k = 0; k < 4; k++)   // G[i,j] += Rh^T GY
+                    mma_bf16_ss(tmem + TM_G, smem_desc_sw128(rh + 2048 * k, 8192, 1024), smem_desc_sw128(gy + 2048 * k, 8192, 1024), ID_MM, 1);
+                mma_commit(&ex.bar_m2);
+                mbar_wait(&ex.bar_m2, par);
+                if (c > 0) issue_w(c - 1);                       // the P^T tile (= W space) is dead
+            }
+            __syncwarp();
+            bar_arrive_all<B_M2>();
+            bar_sync_all<B_T2>();                                // gv, gr tiles written; Dr, Drs consumed
+            if (lane == 0) {
+                tma_store_3d(&map_gv, sm + OFF_GVT, h * 64, c * L, b);
+                tma_store_3d(&map_gr, sm + OFF_GRT, h * 64, c * L, b);
+                tma_store_commit();
+                tc_fence_after();
+#pragma unroll
+                for (int pb = 0; pb < 2; pb++)   // Dk[i, s in p] = sum_{t >= 32p} Rp_p[t,i] dA[t,s]   (dA read MN-major)
+#pragma unroll
+                    for (int kk = 0; kk < 4; kk++)
+                        if (kk < 4 - 2 * pb)
+                            mma_bf16_ss(tmem + TM_X0 + 32 * pb, smem_desc_sw128(rp + rp_ver(pb) + 2048 * kk, 8192, 1024),
+                                        smem_desc_sw128(da + 4096 * pb + 2048 * kk + 64 * pb, 8192, 1024), ID32_MM, kk > 0);
+#pragma unroll
+                for (int k = 0; k < 4; k++)   // Dks[i,s] = G_old V^T
+                    mma_bf16_ss(tmem + TM_X1, smem_desc_sw128(gb + 32 * k, 8192, 1024), smem_desc_sw128(vv + 32 * k, 8192, 1024), ID_KK, k > 0);
+                mma_commit(&ex.bar_m3);
+                mbar_wait(&ex.bar_m3, par);
+            }
+            __syncwarp();
+            bar_arrive_all<B_M3>();
+            bar_sync_all<B_T3>();                                // gk, gw tiles written; new bf16 G
+            if (lane == 0) {
+                tma_store_3d(&map_gk, sm + OFF_GKT, h * 64, c * L, b);
+                tma_store_3d(&map_gw, sm + OFF_GWT, h * 64, c * L, b);
+                tma_store_commit();
+            }
+            __syncwarp();
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    } else {
+        // =====================================================================================
+        // compute warps
+        // =====================================================================================
+        const int sp = F.sp, ch = F.ch, q = F.q, ri = F.ri;
+        const float u_h[2] = {__bfloat162float(p.u[h * 64 + F.row(0)]), __bfloat162float(p.u[h * 64 + F.row(1)])};
+        const uint32_t tG = tmem_addr(tmem, 32 * sp, TM_G + 32 * ch);
+        float gu_acc[2] = {0.f, 0.f};
+        uint32_t v[16];
+
+        // G = 0 (TMEM) and its bf16 copy
+#pragma unroll
+        for (int x = 0; x < 16; x++) v[x] = 0u;
+        tmem_st_frag(tG, v);
+        stsm_x4(sbase + OFF_GB + F.rc(0), 0u, 0u, 0u, 0u);
+        stsm_x4(sbase + OFF_GB + F.rc(1), 0u, 0u, 0u, 0u);
+        tmem_wait_st();
+        fence_proxy_async();
+        tc_fence_before();
+        bar_arrive_all<B_T3>();
+
+        for (int it = 0; it < NC; it++) {
+            const int c = NC - 1 - it;
+            const int nv = min(L, T - c * L);
+            // ================================================================== P: operand preparation
+            bar_sync_all<B_RAW>();
+            float l[2][4][2], exq[2][4];
+            {
+                uint32_t wp[2][4];
+                ldsm_x4_t(sbase + OFF_W + F.ti(0), wp[0][0], wp[0][1], wp[0][2], wp[0][3]);
+                ldsm_x4_t(sbase + OFF_W + F.ti(1), wp[1][0], wp[1][1], wp[1][2], wp[1][3]);
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++)
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        float l0 = -fast_ex2(bf_lo(wp[hh][g]) * LOG2E) * LOG2E;
+                        float l1 = -fast_ex2(bf_hi(wp[hh][g]) * LOG2E) * LOG2E;
+                        if (nv < L) {                                   // ragged last chunk: no decay on the padded rows
+                            const int t0 = F.col(g, 0);
+                            if (t0 >= nv) l0 = 0.f;
+                            if (t0 + 1 >= nv) l1 = 0.f;
+                        }
+                        l[hh][g][0] = l0;
+                        l[hh][g][1] = l1;
+                        const float ps = l0 + l1;
+                        float x = ps, y;
+                        y = __shfl_up_sync(0xffffffffu, x, 1, 4);
+                        if (q >= 1) x += y;
+                        y = __shfl_up_sync(0xffffffffu, x, 2, 4);
+                        if (q >= 2) x += y;
+                        exq[hh][g] = x - ps;
+                        if (q == 3) ex.gtot[4 * ch + g][F.row(hh)] = x;
+                    }
+            }
+            named_bar_sync<B_SCAN, CTHREADS>();
+
+            uint32_t rr[2][4], kk[2][4];
+            ldsm_x4_t(sbase + OFF_R + F.ti(0), rr[0][0], rr[0][1], rr[0][2], rr[0][3]);
+            ldsm_x4_t(sbase + OFF_R + F.ti(1), rr[1][0], rr[1][1], rr[1][2], rr[1][3]);
+            ldsm_x4_t(sbase + OFF_K + F.ti(0), kk[0][0], kk[0][1], kk[0][2], kk[0][3]);
+            ldsm_x4_t(sbase + OFF_K + F.ti(1), kk[1][0], kk[1][1], kk[1][2], kk[1][3]);
+            float exc0[2][4];                       // exclusive decay prefix of the first token of each pair
+            float rqf[2], elam[2], elr[2], erho[2];
+            float du[4][2];
+#pragma unroll
+            for (int g = 0; g < 4; g++) du[g][0] = du[g][1] = 0.f;
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                float run = 0.f, gb[4], rho0 = 0.f, rho1 = 0.f;
+#pragma unroll
+                for (int x8 = 0; x8 < 8; x8++) {
+                    if (x8 == 2) rho0 = rintf(run);                       // middle of block 0, integer log2 grid
+                    if (x8 == 6) rho1 = rintf(run);                       // middle of block 1
+                    if ((x8 >> 2) == ch) gb[x8 & 3] = run;
+                    run += ex.gtot[x8][F.row(hh)];
+                }
+                const float lam = run, rq = ch ? rho1 : rho0;
+                const int ir0 = (int)rho0, ir1 = (int)rho1;
+                // 2^(rho1 - rho0) spans 32 tokens and may leave the bf16 range although the scaled values do
+                // not: apply it as two exact factors
+                const int d10 = ir1 - ir0;
+                const uint32_t f10a = bfpow2pair(d10 >> 1), f10b = bfpow2pair(d10 - (d10 >> 1)), erq = bfpow2pair(ch ? ir1 : ir0);
+                const float el = fast_ex2(lam - rq);
+                rqf[hh] = rq;
+                elam[hh] = fast_ex2(lam);
+                elr[hh] = el;
+                erho[hh] = fast_ex2(rq);
+                uint32_t rto[4], kto[4], rhp[4], khp[4];
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const float e0 = gb[g] + exq[hh][g], c0 = e0 + l[hh][g][0], c1 = c0 + l[hh][g][1];
+                    exc0[hh][g] = e0;
+                    const float r0 = bf_lo(rr[hh][g]), r1 = bf_hi(rr[hh][g]), k0 = bf_lo(kk[hh][g]), k1 = bf_hi(kk[hh][g]);
+                    const float rt0 = r0 * fast_ex2(e0 - rq), rt1 = r1 * fast_ex2(c0 - rq);
+                    const float kf0 = k0 * fast_ex2(rq - c0), kf1 = k1 * fast_ex2(rq - c1);
+                    rto[g] = pack2(rt0, rt1);
+                    kto[g] = pack2(kf0, kf1);
+                    rhp[g] = hmul2(rto[g], erq);                          // Rh = Rt * 2^rho (exact)
+                    khp[g] = pack2(kf0 * el, kf1 * el);                   // Kh = k * 2^(Lam - cum)
+                    du[g][0] = fmaf(r0 * u_h[hh], k0, du[g][0]);
+                    du[g][1] = fmaf(r1 * u_h[hh], k1, du[g][1]);
+                }
+                const uint32_t ti = F.ti(hh);
+                stsm_x4_t(sbase + OFF_RH + ti, rhp[0], rhp[1], rhp[2], rhp[3]);
+                stsm_x4_t(sbase + OFF_KH + ti, khp[0], khp[1], khp[2], khp[3]);
+                if (ch == 0) {      // block 0: own in Kt_0 / Rp_0, scaled to the later reference in Kt_1
+                    stsm_x4_t(sbase + OFF_KT + kt_ver(0) + ti, kto[0], kto[1], kto[2], kto[3]);
+                    stsm_x4_t(sbase + OFF_KT + kt_ver(1) + ti, hmul2(hmul2(kto[0], f10a), f10b), hmul2(hmul2(kto[1], f10a), f10b),
+                              hmul2(hmul2(kto[2], f10a), f10b), hmul2(hmul2(kto[3], f10a), f10b));
+                    stsm_x4_t(sbase + OFF_RP + rp_ver(0) + ti, rto[0], rto[1], rto[2], rto[3]);
+                } else {            // block 1: own in Kt_1 / Rp_1 (stored from row 0), scaled to the earlier reference in Rp_0
+                    stsm_x4_t(sbase + OFF_KT + kt_ver(1) + ti, kto[0], kto[1], kto[2], kto[3]);
+                    stsm_x4_t(sbase + OFF_RP + rp_ver(0) + ti, hmul2(hmul2(rto[0], f10a), f10b), hmul2(hmul2(rto[1], f10a), f10b),
+                              hmul2(hmul2(rto[2], f10a), f10b), hmul2(hmul2(rto[3], f10a), f10b));
+                    stsm_x4_t(sbase + OFF_RP + rp_ver(1) + ti - 4096u, rto[0], rto[1], rto[2], rto[3]);
+                }
+            }
+            {   // diag(u) term: reduce-scatter over the 8 lanes ri, then one partial per channel quarter
+                const bool b2 = lane & 16, b1 = lane & 8, b0 = lane & 4;
+                float a4[2][2], a2[2], a1;
+#pragma unroll
+                for (int gg = 0; gg < 2; gg++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const float keep = b2 ? du[2 + gg][e] : du[gg][e], send = b2 ? du[gg][e] : du[2 + gg][e];
+                        a4[gg][e] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                    }
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    const float keep = b1 ? a4[1][e] : a4[0][e], send = b1 ? a4[0][e] : a4[1][e];
+                    a2[e] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                }
+                {
+                    const float keep = b0 ? a2[1] : a2[0], send = b0 ? a2[0] : a2[1];
+                    a1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                }
+                ex.pdu[sp][32 * ch + 8 * ((b2 ? 2 : 0) + (b1 ? 1 : 0)) + 2 * q + (b0 ? 1 : 0)] = a1;
+            }
+            fence_proxy_async();
+            bar_arrive_all<B_PREP>();
+
+            // ================================================================== T1
+            bar_sync_all<B_M1>();
+            tc_fence_after();
+            // ---- Bm[t rows][s cols] -> dA[t][s] = Bm for s < t; bd[t] = Bm[t,t]
+            tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch), v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                const int rb8 = 2 * sp + hh;
+                uint32_t pk[4];
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const int cb8 = 4 * ch + g;
+                    const float a0 = __uint_as_float(v[4 * g + 2 * hh]), a1 = __uint_as_float(v[4 * g + 2 * hh + 1]);
+                    if (cb8 < rb8) pk[g] = pack2(a0, a1);
+                    else if (cb8 > rb8) pk[g] = 0u;
+                    else {
+                        const int d = 2 * q - ri;                         // (s - t) for e = 0
+                        pk[g] = pack2(d < 0 ? a0 : 0.f, d + 1 < 0 ? a1 : 0.f);
+                        if (d == 0) ex.bd[F.row(hh)] = a0;
+                        if (d + 1 == 0) ex.bd[F.row(hh)] = a1;
+                    }
+                }
+                stsm_x4(sbase + OFF_DA + F.rc(hh), pk[0], pk[1], pk[2], pk[3]);
+            }
+            // ---- A^T[s rows][t cols] -> P^T[s][t] = A^T for t > s, diag = sum_i r u k
+            tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X1 + 32 * ch), v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                const int rb8 = 2 * sp + hh;
+                uint32_t pk[4];
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const int cb8 = 4 * ch + g;
+                    const float a0 = __uint_as_float(v[4 * g + 2 * hh]), a1 = __uint_as_float(v[4 * g + 2 * hh + 1]);
+                    if (cb8 > rb8) pk[g] = pack2(a0, a1);
+                    else if (cb8 < rb8) pk[g] = 0u;
+                    else {
+                        const int s = F.row(hh);
+                        const float dg = ex.pdu[0][s] + ex.pdu[1][s] + ex.pdu[2][s] + ex.pdu[3][s];
+                        const int d = 2 * q - ri;                         // (t - s) for e = 0
+                        pk[g] = pack2(d > 0 ? a0 : (d == 0 ? dg : 0.f), d + 1 > 0 ? a1 : (d + 1 == 0 ? dg : 0.f));
+                    }
+                }
+                stsm_x4(sbase + OFF_PT + F.rc(hh), pk[0], pk[1], pk[2], pk[3]);
+            }
+            // ---- G rows (key channel i): q0_i = <S_in, G>_i (partial over my half of j), then decay by 2^Lam_i
+            tmem_ld_frag(tG, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                uint32_t s4[4];
+                ldsm_x4(sbase + OFF_SIN + F.rc(hh), s4[0], s4[1], s4[2], s4[3]);
+                float qs = 0.f;
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    qs = fmaf(bf_lo(s4[g]), __uint_as_float(v[4 * g + 2 * hh]), qs);
+                    qs = fmaf(bf_hi(s4[g]), __uint_as_float(v[4 * g + 2 * hh + 1]), qs);
+                }
+                qs += __shfl_xor_sync(0xffffffffu, qs, 1);
+                qs += __shfl_xor_sync(0xffffffffu, qs, 2);
+                if (q == 0) ex.q0p[ch][F.row(hh)] = qs;
+#pragma unroll
+                for (int g = 0; g < 4; g++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++)
+                        v[4 * g + 2 * hh + e] = __float_as_uint(__uint_as_float(v[4 * g + 2 * hh + e]) * elam[hh]);
+            }
+            tmem_st_frag(tG, v);
+            tmem_wait_st();
+            fence_proxy_async();
+            tc_fence_before();
+            bar_arrive_all<B_T1>();
+
+            // ================================================================== T2: gv tile, gr tile, XA
+            bar_sync_all<B_M2>();
+            tc_fence_after();
+            tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch), v);
+            tmem_wait_ld();
+            stsm_x4(sbase + OFF_GVT + F.rc(0), pack_frag(v, 0, 0), pack_frag(v, 1, 0), pack_frag(v, 2, 0), pack_frag(v, 3, 0));
+            stsm_x4(sbase + OFF_GVT + F.rc(1), pack_frag(v, 0, 1), pack_frag(v, 1, 1), pack_frag(v, 2, 1), pack_frag(v, 3, 1));
+            float xa[2][4][2];
+            uint32_t grp[2][4];
+#pragma unroll
+            for (int gh = 0; gh < 2; gh++) {
+                uint32_t d8[8], s8[8];
+                tmem_ld_frag2(tmem_addr(tmem, 32 * sp, TM_X1 + 32 * ch + 16 * gh), d8);
+                tmem_ld_frag2(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 16 * gh), s8);
+                tmem_wait_ld();
+#pragma unroll
+                for (int g2 = 0; g2 < 2; g2++) {
+                    const int g = 2 * gh + g2;
+                    const float2 bd2 = *reinterpret_cast<const float2 *>(&ex.bd[F.col(g, 0)]);
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        const float e0 = exc0[hh][g], c0 = e0 + l[hh][g][0];
+                        const float E0 = fast_ex2(e0 - rqf[hh]), E1 = fast_ex2(c0 - rqf[hh]);
+                        const float r0 = bf_lo(rr[hh][g]), r1 = bf_hi(rr[hh][g]), k0 = bf_lo(kk[hh][g]), k1 = bf_hi(kk[hh][g]);
+                        const float dr0 = __uint_as_float(d8[4 * g2 + 2 * hh]), dr1 = __uint_as_float(d8[4 * g2 + 2 * hh + 1]);
+                        const float ds0 = erho[hh] * __uint_as_float(s8[4 * g2 + 2 * hh]), ds1 = erho[hh] * __uint_as_float(s8[4 * g2 + 2 * hh + 1]);
+                        const float re0 = r0 * E0, re1 = r1 * E1;
+                        const uint32_t rtp = pack2(re0, re1);                 // Rt_own exactly as the MMAs saw it
+                        xa[hh][g][0] = fmaf(re0, ds0, bf_lo(rtp) * dr0);
+                        xa[hh][g][1] = fmaf(re1, ds1, bf_hi(rtp) * dr1);
+                        grp[hh][g] = pack2(fmaf(E0, dr0 + ds0, u_h[hh] * k0 * bd2.x), fmaf(E1, dr1 + ds1, u_h[hh] * k1 * bd2.y));
+                    }
+                }
+            }
+            stsm_x4_t(sbase + OFF_GRT + F.ti(0), grp[0][0], grp[0][1], grp[0][2], grp[0][3]);
+            stsm_x4_t(sbase + OFF_GRT + F.ti(1), grp[1][0], grp[1][1], grp[1][2], grp[1][3]);
+            fence_proxy_async();
+            tc_fence_before();
+            bar_arrive_all<B_T2>();
+
+            // ================================================================== T3: gk tile, gw tile, new bf16 G
+            bar_sync_all<B_M3>();
+            tc_fence_after();
+            float tt[2][4][2];                 // everything of gl that does not need the other token half
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                float be[4][2], xx[4][2], bi[4][2];
+                uint32_t gkp[4];
+#pragma unroll
+                for (int gh = 0; gh < 2; gh++) {
+                    uint32_t d8[8], s8[8];
+                    tmem_ld_frag2(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch + 16 * gh), d8);
+                    tmem_ld_frag2(tmem_addr(tmem, 32 * sp, TM_X1 + 32 * ch + 16 * gh), s8);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int g2 = 0; g2 < 2; g2++) {
+                        const int g = 2 * gh + g2;
+                        const float2 bd2 = *reinterpret_cast<const float2 *>(&ex.bd[F.col(g, 0)]);
+                        const float c0 = exc0[hh][g] + l[hh][g][0], c1 = c0 + l[hh][g][1];
+                        const float F0 = fast_ex2(rqf[hh] - c0), F1 = fast_ex2(rqf[hh] - c1);
+                        const float r0 = bf_lo(rr[hh][g]), r1 = bf_hi(rr[hh][g]), k0 = bf_lo(kk[hh][g]), k1 = bf_hi(kk[hh][g]);
+                        const float dk0 = __uint_as_float(d8[4 * g2 + 2 * hh]), dk1 = __uint_as_float(d8[4 * g2 + 2 * hh + 1]);
+                        const float ds0 = elr[hh] * __uint_as_float(s8[4 * g2 + 2 * hh]), ds1 = elr[hh] * __uint_as_float(s8[4 * g2 + 2 * hh + 1]);
+                        const float kf0 = k0 * F0, kf1 = k1 * F1;
+                        const uint32_t ktp = pack2(kf0, kf1);                 // Kt_own exactly as the MMAs saw it
+                        bi[g][0] = bf_lo(ktp) * dk0;
+                        bi[g][1] = bf_hi(ktp) * dk1;
+                        be[g][0] = kf0 * ds0;
+                        be[g][1] = kf1 * ds1;
+                        xx[g][0] = xa[hh][g][0] - bi[g][0];
+                        xx[g][1] = xa[hh][g][1] - bi[g][1];
+                        gkp[g] = pack2(fmaf(F0, dk0 + ds0, u_h[hh] * r0 * bd2.x), fmaf(F1, dk1 + ds1, u_h[hh] * r1 * bd2.y));
+                        gu_acc[hh] = fmaf(r0 * k0, bd2.x, fmaf(r1 * k1, bd2.y, gu_acc[hh]));
+                    }
+                }
+                stsm_x4_t(sbase + OFF_GKT + F.ti(hh), gkp[0], gkp[1], gkp[2], gkp[3]);
+                // scans along t inside my token half: prefix of Be, suffix of X
+                float incY[4], totY[4], incX[4], totX[4];
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    float x = be[g][0] + be[g][1], z = xx[g][0] + xx[g][1], y;
+                    y = __shfl_up_sync(0xffffffffu, x, 1, 4);
+                    if (q >= 1) x += y;
+                    y = __shfl_up_sync(0xffffffffu, z, 1, 4);
+                    if (q >= 1) z += y;
+                    y = __shfl_up_sync(0xffffffffu, x, 2, 4);
+                    if (q >= 2) x += y;
+                    y = __shfl_up_sync(0xffffffffu, z, 2, 4);
+                    if (q >= 2) z += y;
+                    incY[g] = x;
+                    incX[g] = z;
+                    totY[g] = __shfl_sync(0xffffffffu, x, 3, 4);
+                    totX[g] = __shfl_sync(0xffffffffu, z, 3, 4);
+                }
+                float preY = 0.f, sufX = 0.f;
+#pragma unroll
+                for (int g = 0; g < 4; g++) {        // preY: groups before g
+                    const float py = be[g][0] + be[g][1];
+                    tt[hh][g][0] = preY + (incY[g] - py) - bi[g][0];
+                    tt[hh][g][1] = preY + (incY[g] - py) + be[g][0] - bi[g][1];
+                    preY += totY[g];
+                }
+#pragma unroll
+                for (int g = 3; g >= 0; g--) {       // sufX: groups after g
+                    tt[hh][g][0] += sufX + (totX[g] - incX[g]) + xx[g][1];
+                    tt[hh][g][1] += sufX + (totX[g] - incX[g]);
+                    sufX += totX[g];
+                }
+                if (q == 0) {
+                    ex.htY[ch][F.row(hh)] = preY;
+                    ex.htX[ch][F.row(hh)] = sufX;
+                }
+            }
+            // ---- new G -> bf16 operand copy [i][j]; after chunk 0 it is dL/dS_0
+            tmem_ld_frag(tG, v);
+            tmem_wait_ld();
+            stsm_x4(sbase + OFF_GB + F.rc(0), pack_frag(v, 0, 0), pack_frag(v, 1, 0), pack_frag(v, 2, 0), pack_frag(v, 3, 0));
+            stsm_x4(sbase + OFF_GB + F.rc(1), pack_frag(v, 0, 1), pack_frag(v, 1, 1), pack_frag(v, 2, 1), pack_frag(v, 3, 1));
+            if (c == 0 && p.gs) {
+#pragma unroll
+                for (int g = 0; g < 4; g++)
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++)
+#pragma unroll
+                        for (int e = 0; e < 2; e++)   // gs[b,h,j,i] = dL/dS_0[i][j]
+                            p.gs[(((size_t)b * p.H + h) * 64 + F.col(g, e)) * 64 + F.row(hh)] =
+                                __float2bfloat16_rn(__uint_as_float(v[4 * g + 2 * hh + e]));
+            }
+            named_bar_sync<B_SCAN, CTHREADS>();          // token-half totals of both scans are in shared memory
+            {
+                uint32_t gwp[2][4];
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    const int i = F.row(hh);
+                    const float base = (ex.q0p[0][i] + ex.q0p[1][i]) * elam[hh] + (ch ? ex.htY[0][i] : ex.htX[1][i]);
+#pragma unroll
+                    for (int g = 0; g < 4; g++) {
+                        float gw0 = l[hh][g][0] * LN2 * (base + tt[hh][g][0]);
+                        const float gw1 = l[hh][g][1] * LN2 * (base + tt[hh][g][1]);
+                        if (c == 0 && !p.has_s0 && ch == 0 && g == 0 && q == 0) gw0 = 0.f;   // t = 0 with S_0 = 0
+                        gwp[hh][g] = pack2(gw0, gw1);
+                    }
+                }
+                stsm_x4_t(sbase + OFF_GWT + F.ti(0), gwp[0][0], gwp[0][1], gwp[0][2], gwp[0][3]);
+                stsm_x4_t(sbase + OFF_GWT + F.ti(1), gwp[1][0], gwp[1][1], gwp[1][2], gwp[1][3]);
+            }
+            fence_proxy_async();
+            tc_fence_before();
+            bar_arrive_all<B_T3>();
+        }
+        // gu[b, i] = sum_t r k bd: reduce over the 4 lanes q and the two token halves
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+            float x = gu_acc[hh];
+            x += __shfl_xor_sync(0xffffffffu, x, 1);
+            x += __shfl_xor_sync(0xffffffffu, x, 2);
+            if (q == 0) atomicAdd(&ex.gu_s[F.row(hh)], x);
+        }
+        named_bar_sync<B_SCAN, CTHREADS>();
+        if (threadIdx.x < 64) p.gu[(size_t)b * C + h * 64 + threadIdx.x] = __float2bfloat16_rn(ex.gu_s[threadIdx.x]);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, TM_COLS);
+}
+
+}  // namespace
+
+size_t tc3_saved_header(int B, int H) { return (((size_t)B * H * sizeof(int)) + 1023) / 1024 * 1024; }
+size_t tc3_saved_bytes(int B, int T, int H) {
+    const size_t NC = (size_t)(T + L - 1) / L;
+    return tc3_saved_header(B, H) + (size_t)B * H * NC * 8192;
+}
+size_t tc3_backward_workspace_bytes(int B, int T, int H, bool has_saved) {
+    return simt_backward_workspace_bytes(B, T, H) + (has_saved ? 0 : tc3_saved_bytes(B, T, H));
+}
+bool tc3_backward_supported(const Args &a) {
+    return a.io_dtype == WKV6_BF16 && a.w_kind == W_RAW_BF16 && a.mask == nullptr && a.T >= 1 && !a.s0_f32 &&
+           tc::get_encode_fn() != nullptr;
+}
+
+int tc3_backward(const Args &a) {
+    if (a.B * a.H == 0 || a.T == 0) return WKV6_OK;
+    const int C = a.H * 64;
+    const size_t NC = (size_t)(a.T + L - 1) / L;
+    const size_t simt_ws = simt_backward_workspace_bytes(a.B, a.T, a.H);
+    const size_t need = tc3_backward_workspace_bytes(a.B, a.T, a.H, a.saved != nullptr);
+    if (!a.workspace || a.workspace_bytes < need) {
+        set_error("workspace too small: need %zu bytes", need);
+        return WKV6_EWORKSPACE;
+    }
+    uint8_t *sv = a.saved ? (uint8_t *)a.saved : (uint8_t *)a.workspace + simt_ws;
+    int *flags = (int *)sv;
+    bf16 *ckpt = (bf16 *)(sv + tc3_saved_header(a.B, a.H));
+    if (!a.saved) {
+        // no training pair: recompute the chunk-start states (and the per-stream hazard flags) first
+        WKV6_CUDA_CHECK(cudaMemsetAsync(flags, 0, (size_t)a.B * a.H * sizeof(int), a.stream));
+        Args f = a;
+        f.y = nullptr;
+        f.sT = nullptr;
+        if (int rc = tc3_forward(f, ckpt, flags)) return rc;
+    }
+    CUtensorMap mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw;
+    const auto dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    const void *ptrs[10] = {a.r, a.k, a.v, a.w, a.gy, ckpt, a.gr, a.gk, a.gv, a.gw};
+    CUtensorMap *maps[10] = {&mr, &mk, &mv, &mw, &mg, &mc, &ogr, &ogk, &ogv, &ogw};
+    for (int i = 0; i < 10; i++) {
+        const bool ok = (i == 5) ? tc::make_btc_map(maps[i], ptrs[i], 1, (int)((size_t)a.B * a.H * NC * 64), 64, 64, dt, 2, 64)
+                                 : tc::make_btc_map(maps[i], ptrs[i], a.B, a.T, C, L, dt, 2, 64);
+        if (!ok) {
+            set_error("cuTensorMapEncodeTiled failed for tensor %d (r,k,v,w,gy,ckpt,gr,gk,gv,gw), pointer %p (16-byte alignment required)", i, ptrs[i]);
+            return WKV6_ECUDA;
+        }
+    }
+    Params p;
+    p.B = a.B; p.T = a.T; p.H = a.H;
+    p.u = (const bf16 *)a.u;
+    p.has_s0 = a.s0 != nullptr;
+    p.gu = (bf16 *)a.gu; p.gs = (bf16 *)a.gs;
+    p.hz_flags = flags;
+    static bool attr_done = false;
+    if (!attr_done) {
+        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             cudaSharedmemCarveoutMaxShared));
+        attr_done = true;
+    }
+    wkv6_tc3_bwd_kernel<<<a.B * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
+    count_launch();
+    WKV6_CUDA_CHECK(cudaGetLastError());
+    // exact route for the flagged streams only
+    Args s = a;
+    s.stream_flags = flags;
+    s.workspace_bytes = simt_ws;
+    return simt_backward(s);
+}
+
+}  // namespace wkv6
