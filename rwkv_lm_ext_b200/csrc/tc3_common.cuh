@@ -57,6 +57,7 @@ struct Frag {
     int warp, lane, sp, ch, ri, q;
     uint32_t ti_off;     // byte offset (within a [token][channel] tile) this lane supplies to ldmatrix/stmatrix .x4:
                          // row 32ch + 8(lane/8) + lane%8, 16-byte chunk of channels 16sp (+ 16 bytes for h = 1)
+    uint32_t ti1_off;    // same for .x1 (one 8-token group): row 32ch + lane%8; add 1024 per group, ^16 for h = 1
     uint32_t rc_off;     // byte offset for a plain stmatrix .x4 of an accumulator fragment into a [row][col] tile:
                          // row 16sp + lane%8 (+ 8 rows for h = 1), 16-byte chunk of columns 32ch + 8(lane/8)
     __device__ __forceinline__ void init() {
@@ -67,10 +68,12 @@ struct Frag {
         ri = lane >> 2;
         q = lane & 3;
         ti_off = sw128(32 * ch + 8 * (lane >> 3) + (lane & 7), 32 * sp);
+        ti1_off = sw128(32 * ch + (lane & 7), 32 * sp);
         rc_off = sw128(16 * sp + (lane & 7), 64 * ch + 16 * (lane >> 3));
     }
     // h = 1 moves the 16-byte chunk (ti) / the row by 8 (rc); both keep row % 8, so the swizzle XOR is unchanged
     __device__ __forceinline__ uint32_t ti(int h) const { return ti_off ^ (h ? 16u : 0u); }
+    __device__ __forceinline__ uint32_t ti1(int g, int h) const { return (ti1_off + 1024u * g) ^ (h ? 16u : 0u); }
     __device__ __forceinline__ uint32_t rc(int h) const { return rc_off + (h ? 1024u : 0u); }
     __device__ __forceinline__ int row(int h) const { return 16 * sp + 8 * h + ri; }
     __device__ __forceinline__ int col(int g, int e) const { return 32 * ch + 8 * g + 2 * q + e; }

@@ -164,6 +164,17 @@ __device__ __forceinline__ void tmem_ld_frag(uint32_t taddr, uint32_t (&v)[16]) 
         : "r"(taddr)
         : "memory");
 }
+// same layout, 8 columns: v[2h + e]
+__device__ __forceinline__ void tmem_ld_frag1(uint32_t taddr, uint32_t (&v)[4]) {
+    asm volatile("tcgen05.ld.sync.aligned.16x256b.x1.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_frag1(uint32_t taddr, const uint32_t (&v)[4]) {
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x1.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3])
+                 : "memory");
+}
 // same layout, 16 columns: v[4g + 2h + e], g = 0,1
 __device__ __forceinline__ void tmem_ld_frag2(uint32_t taddr, uint32_t (&v)[8]) {
     asm volatile("tcgen05.ld.sync.aligned.16x256b.x2.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -200,6 +211,9 @@ __device__ __forceinline__ void ldsm_x4_t(uint32_t saddr, uint32_t &r0, uint32_t
 __device__ __forceinline__ void stsm_x4(uint32_t saddr, uint32_t r0, uint32_t r1, uint32_t r2, uint32_t r3) {
     asm volatile("stmatrix.sync.aligned.m8n8.x4.shared.b16 [%0], {%1, %2, %3, %4};"
                  :: "r"(saddr), "r"(r0), "r"(r1), "r"(r2), "r"(r3) : "memory");
+}
+__device__ __forceinline__ void stsm_x1_t(uint32_t saddr, uint32_t r0) {   // lanes 0-7 supply addresses
+    asm volatile("stmatrix.sync.aligned.m8n8.x1.trans.shared.b16 [%0], {%1};" ::"r"(saddr), "r"(r0) : "memory");
 }
 __device__ __forceinline__ void stsm_x2_t(uint32_t saddr, uint32_t r0, uint32_t r1) {   // lanes 0-15 supply addresses
     asm volatile("stmatrix.sync.aligned.m8n8.x2.trans.shared.b16 [%0], {%1, %2};" ::"r"(saddr), "r"(r0), "r"(r1) : "memory");

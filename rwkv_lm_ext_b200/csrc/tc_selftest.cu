@@ -150,6 +150,16 @@ __global__ void __launch_bounds__(256) selftest2_kernel(const __grid_constant__ 
         const uint32_t ao = smem_u32(tO) + sw128(16 * sp + 8 * h + (lane & 7), 64 * ch + 16 * (lane >> 3));
         stsm_x4(ao, x[h][0], x[h][1], x[h][2], x[h][3]);
     }
+    // shadow lanes: an M = 64 accumulator only occupies lanes 0-15 of each 32-lane sub-partition; park a
+    // pattern in lanes 16-31 of the accumulator columns and check below that the MMA leaves it alone
+    {
+        uint32_t pat[16];
+#pragma unroll
+        for (int x = 0; x < 16; x++) pat[x] = __float_as_uint(1000.f + 64.f * threadIdx.x + x);
+        tmem_st_frag(tmem_addr(tmem, 32 * sp + 16, 32 * ch), pat);
+        tmem_wait_st();
+        tc_fence_before();
+    }
     fence_proxy_async();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -177,6 +187,15 @@ __global__ void __launch_bounds__(256) selftest2_kernel(const __grid_constant__ 
                 const int row = 16 * sp + 8 * hh + ri, col = 32 * ch + 8 * g + 2 * q + e;
                 if (col < 16) D[row * 16 + col] = __uint_as_float(v[4 * g + 2 * hh + e]);
             }
+    {
+        uint32_t pat[16];
+        tmem_ld_frag(tmem_addr(tmem, 32 * sp + 16, 32 * ch), pat);
+        tmem_wait_ld();
+        int bad = 0;
+#pragma unroll
+        for (int x = 0; x < 16; x++) bad |= (__uint_as_float(pat[x]) != 1000.f + 64.f * threadIdx.x + x);
+        if (bad) D[64 * 16] = 1.f;        // one extra float after the D matrix: shadow lanes were disturbed
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, 64);

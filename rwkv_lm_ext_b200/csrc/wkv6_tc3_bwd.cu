@@ -57,6 +57,10 @@ struct Extra {
 };
 constexpr uint32_t SMEM_BYTES = OFF_TILES_END + sizeof(Extra);
 constexpr uint32_t TM_G = 0, TM_X0 = 64, TM_X1 = 128, TM_X2 = 192, TM_COLS = 256;
+// An M = 64 accumulator only occupies lanes 0-15 of each 32-lane TMEM sub-partition; lanes 16-31 of the
+// same columns are used as per-thread scratch ("parking") for what the operand preparation hands to the
+// output stages, so that it does not sit in registers across the three MMA round trips.
+constexpr uint32_t PARK_L = 0, PARK_RK = 64, PARK_E = 128;
 
 struct Params {
     int B, T, H;
@@ -244,6 +248,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         const int sp = F.sp, ch = F.ch, q = F.q, ri = F.ri;
         const float u_h[2] = {__bfloat162float(p.u[h * 64 + F.row(0)]), __bfloat162float(p.u[h * 64 + F.row(1)])};
         const uint32_t tG = tmem_addr(tmem, 32 * sp, TM_G + 32 * ch);
+        const uint32_t tPark = tmem_addr(tmem, 32 * sp + 16, 32 * ch);
         float gu_acc[2] = {0.f, 0.f};
         uint32_t v[16];
 
@@ -263,6 +268,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             const int nv = min(L, T - c * L);
             // ================================================================== P: operand preparation
             bar_sync_all<B_RAW>();
+            float rqf[2], elam[2], elr[2], erho[2];
+            {   // ---- everything per element lives only inside this block
             float l[2][4][2], exq[2][4];
             {
                 uint32_t wp[2][4];
@@ -299,7 +306,6 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             ldsm_x4_t(sbase + OFF_K + F.ti(0), kk[0][0], kk[0][1], kk[0][2], kk[0][3]);
             ldsm_x4_t(sbase + OFF_K + F.ti(1), kk[1][0], kk[1][1], kk[1][2], kk[1][3]);
             float exc0[2][4];                       // exclusive decay prefix of the first token of each pair
-            float rqf[2], elam[2], elr[2], erho[2];
             float du[4][2];
 #pragma unroll
             for (int g = 0; g < 4; g++) du[g][0] = du[g][1] = 0.f;
@@ -374,6 +380,35 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     a1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
                 }
                 ex.pdu[sp][32 * ch + 8 * ((b2 ? 2 : 0) + (b1 ? 1 : 0)) + 2 * q + (b0 ? 1 : 0)] = a1;
+            }
+            {   // park l, (r,k), exc in the shadow lanes (fragment order [4g + 2h + e])
+                uint32_t pk[16];
+#pragma unroll
+                for (int g = 0; g < 4; g++)
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        pk[4 * g + 2 * hh] = __float_as_uint(l[hh][g][0]);
+                        pk[4 * g + 2 * hh + 1] = __float_as_uint(l[hh][g][1]);
+                    }
+                tmem_st_frag(tPark + PARK_L, pk);
+#pragma unroll
+                for (int g = 0; g < 4; g++)
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        pk[4 * g + 2 * hh] = rr[hh][g];
+                        pk[4 * g + 2 * hh + 1] = kk[hh][g];
+                    }
+                tmem_st_frag(tPark + PARK_RK, pk);
+#pragma unroll
+                for (int g = 0; g < 4; g++)
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        pk[4 * g + 2 * hh] = __float_as_uint(exc0[hh][g]);
+                        pk[4 * g + 2 * hh + 1] = 0u;
+                    }
+                tmem_st_frag(tPark + PARK_E, pk);
+                tmem_wait_st();
+            }
             }
             fence_proxy_async();
             bar_arrive_all<B_PREP>();
@@ -460,35 +495,35 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             tmem_wait_ld();
             stsm_x4(sbase + OFF_GVT + F.rc(0), pack_frag(v, 0, 0), pack_frag(v, 1, 0), pack_frag(v, 2, 0), pack_frag(v, 3, 0));
             stsm_x4(sbase + OFF_GVT + F.rc(1), pack_frag(v, 0, 1), pack_frag(v, 1, 1), pack_frag(v, 2, 1), pack_frag(v, 3, 1));
-            float xa[2][4][2];
-            uint32_t grp[2][4];
+            // per 8-token group: Dr, Drs -> gr (tile) and XA, which is parked in the Drs columns (TMEM) until T3
 #pragma unroll
-            for (int gh = 0; gh < 2; gh++) {
-                uint32_t d8[8], s8[8];
-                tmem_ld_frag2(tmem_addr(tmem, 32 * sp, TM_X1 + 32 * ch + 16 * gh), d8);
-                tmem_ld_frag2(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 16 * gh), s8);
+            for (int g = 0; g < 4; g++) {
+                uint32_t d4[4], s4[4], x4[4];
+                uint32_t pl[4], prk[4], pe[4];
+                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X1 + 32 * ch + 8 * g), d4);
+                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 8 * g), s4);
+                tmem_ld_frag1(tPark + PARK_L + 8 * g, pl);
+                tmem_ld_frag1(tPark + PARK_RK + 8 * g, prk);
+                tmem_ld_frag1(tPark + PARK_E + 8 * g, pe);
                 tmem_wait_ld();
+                const float2 bd2 = *reinterpret_cast<const float2 *>(&ex.bd[F.col(g, 0)]);
 #pragma unroll
-                for (int g2 = 0; g2 < 2; g2++) {
-                    const int g = 2 * gh + g2;
-                    const float2 bd2 = *reinterpret_cast<const float2 *>(&ex.bd[F.col(g, 0)]);
-#pragma unroll
-                    for (int hh = 0; hh < 2; hh++) {
-                        const float e0 = exc0[hh][g], c0 = e0 + l[hh][g][0];
-                        const float E0 = fast_ex2(e0 - rqf[hh]), E1 = fast_ex2(c0 - rqf[hh]);
-                        const float r0 = bf_lo(rr[hh][g]), r1 = bf_hi(rr[hh][g]), k0 = bf_lo(kk[hh][g]), k1 = bf_hi(kk[hh][g]);
-                        const float dr0 = __uint_as_float(d8[4 * g2 + 2 * hh]), dr1 = __uint_as_float(d8[4 * g2 + 2 * hh + 1]);
-                        const float ds0 = erho[hh] * __uint_as_float(s8[4 * g2 + 2 * hh]), ds1 = erho[hh] * __uint_as_float(s8[4 * g2 + 2 * hh + 1]);
-                        const float re0 = r0 * E0, re1 = r1 * E1;
-                        const uint32_t rtp = pack2(re0, re1);                 // Rt_own exactly as the MMAs saw it
-                        xa[hh][g][0] = fmaf(re0, ds0, bf_lo(rtp) * dr0);
-                        xa[hh][g][1] = fmaf(re1, ds1, bf_hi(rtp) * dr1);
-                        grp[hh][g] = pack2(fmaf(E0, dr0 + ds0, u_h[hh] * k0 * bd2.x), fmaf(E1, dr1 + ds1, u_h[hh] * k1 * bd2.y));
-                    }
+                for (int hh = 0; hh < 2; hh++) {
+                    const float e0 = __uint_as_float(pe[2 * hh]), c0 = e0 + __uint_as_float(pl[2 * hh]);
+                    const float E0 = fast_ex2(e0 - rqf[hh]), E1 = fast_ex2(c0 - rqf[hh]);
+                    const float r0 = bf_lo(prk[2 * hh]), r1 = bf_hi(prk[2 * hh]), k0 = bf_lo(prk[2 * hh + 1]), k1 = bf_hi(prk[2 * hh + 1]);
+                    const float dr0 = __uint_as_float(d4[2 * hh]), dr1 = __uint_as_float(d4[2 * hh + 1]);
+                    const float ds0 = erho[hh] * __uint_as_float(s4[2 * hh]), ds1 = erho[hh] * __uint_as_float(s4[2 * hh + 1]);
+                    const float re0 = r0 * E0, re1 = r1 * E1;
+                    const uint32_t rtp = pack2(re0, re1);                 // Rt_own exactly as the MMAs saw it
+                    x4[2 * hh] = __float_as_uint(fmaf(re0, ds0, bf_lo(rtp) * dr0));
+                    x4[2 * hh + 1] = __float_as_uint(fmaf(re1, ds1, bf_hi(rtp) * dr1));
+                    const float ub = u_h[hh] * bd2.x, ub1 = u_h[hh] * bd2.y;
+                    stsm_x1_t(sbase + OFF_GRT + F.ti1(g, hh), pack2(fmaf(E0, dr0 + ds0, ub * k0), fmaf(E1, dr1 + ds1, ub1 * k1)));
                 }
+                tmem_st_frag1(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 8 * g), x4);
             }
-            stsm_x4_t(sbase + OFF_GRT + F.ti(0), grp[0][0], grp[0][1], grp[0][2], grp[0][3]);
-            stsm_x4_t(sbase + OFF_GRT + F.ti(1), grp[1][0], grp[1][1], grp[1][2], grp[1][3]);
+            tmem_wait_st();
             fence_proxy_async();
             tc_fence_before();
             bar_arrive_all<B_T2>();
@@ -496,74 +531,61 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             // ================================================================== T3: gk tile, gw tile, new bf16 G
             bar_sync_all<B_M3>();
             tc_fence_after();
-            float tt[2][4][2];                 // everything of gl that does not need the other token half
+            // per 8-token group: Dk, Dks, XA -> gk (tile), running scans; the part of gl that does not need the
+            // other token half replaces XA in TMEM
+            float runY[2] = {0.f, 0.f}, runX[2] = {0.f, 0.f};
 #pragma unroll
-            for (int hh = 0; hh < 2; hh++) {
-                float be[4][2], xx[4][2], bi[4][2];
-                uint32_t gkp[4];
+            for (int g = 0; g < 4; g++) {
+                uint32_t d4[4], s4[4], x4[4];
+                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch + 8 * g), d4);
+                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X1 + 32 * ch + 8 * g), s4);
+                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 8 * g), x4);
+                uint32_t pl[4], prk[4], pe[4];
+                tmem_ld_frag1(tPark + PARK_L + 8 * g, pl);
+                tmem_ld_frag1(tPark + PARK_RK + 8 * g, prk);
+                tmem_ld_frag1(tPark + PARK_E + 8 * g, pe);
+                tmem_wait_ld();
+                const float2 bd2 = *reinterpret_cast<const float2 *>(&ex.bd[F.col(g, 0)]);
 #pragma unroll
-                for (int gh = 0; gh < 2; gh++) {
-                    uint32_t d8[8], s8[8];
-                    tmem_ld_frag2(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch + 16 * gh), d8);
-                    tmem_ld_frag2(tmem_addr(tmem, 32 * sp, TM_X1 + 32 * ch + 16 * gh), s8);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int g2 = 0; g2 < 2; g2++) {
-                        const int g = 2 * gh + g2;
-                        const float2 bd2 = *reinterpret_cast<const float2 *>(&ex.bd[F.col(g, 0)]);
-                        const float c0 = exc0[hh][g] + l[hh][g][0], c1 = c0 + l[hh][g][1];
-                        const float F0 = fast_ex2(rqf[hh] - c0), F1 = fast_ex2(rqf[hh] - c1);
-                        const float r0 = bf_lo(rr[hh][g]), r1 = bf_hi(rr[hh][g]), k0 = bf_lo(kk[hh][g]), k1 = bf_hi(kk[hh][g]);
-                        const float dk0 = __uint_as_float(d8[4 * g2 + 2 * hh]), dk1 = __uint_as_float(d8[4 * g2 + 2 * hh + 1]);
-                        const float ds0 = elr[hh] * __uint_as_float(s8[4 * g2 + 2 * hh]), ds1 = elr[hh] * __uint_as_float(s8[4 * g2 + 2 * hh + 1]);
-                        const float kf0 = k0 * F0, kf1 = k1 * F1;
-                        const uint32_t ktp = pack2(kf0, kf1);                 // Kt_own exactly as the MMAs saw it
-                        bi[g][0] = bf_lo(ktp) * dk0;
-                        bi[g][1] = bf_hi(ktp) * dk1;
-                        be[g][0] = kf0 * ds0;
-                        be[g][1] = kf1 * ds1;
-                        xx[g][0] = xa[hh][g][0] - bi[g][0];
-                        xx[g][1] = xa[hh][g][1] - bi[g][1];
-                        gkp[g] = pack2(fmaf(F0, dk0 + ds0, u_h[hh] * r0 * bd2.x), fmaf(F1, dk1 + ds1, u_h[hh] * r1 * bd2.y));
-                        gu_acc[hh] = fmaf(r0 * k0, bd2.x, fmaf(r1 * k1, bd2.y, gu_acc[hh]));
-                    }
+                for (int hh = 0; hh < 2; hh++) {
+                    const float c0 = __uint_as_float(pe[2 * hh]) + __uint_as_float(pl[2 * hh]), c1 = c0 + __uint_as_float(pl[2 * hh + 1]);
+                    const float F0 = fast_ex2(rqf[hh] - c0), F1 = fast_ex2(rqf[hh] - c1);
+                    const float r0 = bf_lo(prk[2 * hh]), r1 = bf_hi(prk[2 * hh]), k0 = bf_lo(prk[2 * hh + 1]), k1 = bf_hi(prk[2 * hh + 1]);
+                    const float dk0 = __uint_as_float(d4[2 * hh]), dk1 = __uint_as_float(d4[2 * hh + 1]);
+                    const float ds0 = elr[hh] * __uint_as_float(s4[2 * hh]), ds1 = elr[hh] * __uint_as_float(s4[2 * hh + 1]);
+                    const float kf0 = k0 * F0, kf1 = k1 * F1;
+                    const uint32_t ktp = pack2(kf0, kf1);                 // Kt_own exactly as the MMAs saw it
+                    const float bi0 = bf_lo(ktp) * dk0, bi1 = bf_hi(ktp) * dk1;
+                    const float be0 = kf0 * ds0, be1 = kf1 * ds1;
+                    const float x0 = __uint_as_float(x4[2 * hh]) - bi0, x1 = __uint_as_float(x4[2 * hh + 1]) - bi1;
+                    const float ub = u_h[hh] * bd2.x, ub1 = u_h[hh] * bd2.y;
+                    stsm_x1_t(sbase + OFF_GKT + F.ti1(g, hh), pack2(fmaf(F0, dk0 + ds0, ub * r0), fmaf(F1, dk1 + ds1, ub1 * r1)));
+                    gu_acc[hh] = fmaf(r0 * k0, bd2.x, fmaf(r1 * k1, bd2.y, gu_acc[hh]));
+                    // inclusive scans over the 4 lanes of the group: y = Be, z = X
+                    const float py = be0 + be1, px = x0 + x1;
+                    float y = py, z = px, tmp;
+                    tmp = __shfl_up_sync(0xffffffffu, y, 1, 4);
+                    if (q >= 1) y += tmp;
+                    tmp = __shfl_up_sync(0xffffffffu, z, 1, 4);
+                    if (q >= 1) z += tmp;
+                    tmp = __shfl_up_sync(0xffffffffu, y, 2, 4);
+                    if (q >= 2) y += tmp;
+                    tmp = __shfl_up_sync(0xffffffffu, z, 2, 4);
+                    if (q >= 2) z += tmp;
+                    // exclusive prefix of Be minus inclusive prefix of X minus Bi_t (the suffix of X is total - inclusive)
+                    const float pe = runY[hh] + (y - py), xi = runX[hh] + (z - px) + x0;
+                    x4[2 * hh] = __float_as_uint(pe - bi0 - xi);
+                    x4[2 * hh + 1] = __float_as_uint(pe + be0 - bi1 - (xi + x1));
+                    runY[hh] += __shfl_sync(0xffffffffu, y, 3, 4);
+                    runX[hh] += __shfl_sync(0xffffffffu, z, 3, 4);
                 }
-                stsm_x4_t(sbase + OFF_GKT + F.ti(hh), gkp[0], gkp[1], gkp[2], gkp[3]);
-                // scans along t inside my token half: prefix of Be, suffix of X
-                float incY[4], totY[4], incX[4], totX[4];
+                tmem_st_frag1(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 8 * g), x4);
+            }
+            if (q == 0) {
 #pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    float x = be[g][0] + be[g][1], z = xx[g][0] + xx[g][1], y;
-                    y = __shfl_up_sync(0xffffffffu, x, 1, 4);
-                    if (q >= 1) x += y;
-                    y = __shfl_up_sync(0xffffffffu, z, 1, 4);
-                    if (q >= 1) z += y;
-                    y = __shfl_up_sync(0xffffffffu, x, 2, 4);
-                    if (q >= 2) x += y;
-                    y = __shfl_up_sync(0xffffffffu, z, 2, 4);
-                    if (q >= 2) z += y;
-                    incY[g] = x;
-                    incX[g] = z;
-                    totY[g] = __shfl_sync(0xffffffffu, x, 3, 4);
-                    totX[g] = __shfl_sync(0xffffffffu, z, 3, 4);
-                }
-                float preY = 0.f, sufX = 0.f;
-#pragma unroll
-                for (int g = 0; g < 4; g++) {        // preY: groups before g
-                    const float py = be[g][0] + be[g][1];
-                    tt[hh][g][0] = preY + (incY[g] - py) - bi[g][0];
-                    tt[hh][g][1] = preY + (incY[g] - py) + be[g][0] - bi[g][1];
-                    preY += totY[g];
-                }
-#pragma unroll
-                for (int g = 3; g >= 0; g--) {       // sufX: groups after g
-                    tt[hh][g][0] += sufX + (totX[g] - incX[g]) + xx[g][1];
-                    tt[hh][g][1] += sufX + (totX[g] - incX[g]);
-                    sufX += totX[g];
-                }
-                if (q == 0) {
-                    ex.htY[ch][F.row(hh)] = preY;
-                    ex.htX[ch][F.row(hh)] = sufX;
+                for (int hh = 0; hh < 2; hh++) {
+                    ex.htY[ch][F.row(hh)] = runY[hh];
+                    ex.htX[ch][F.row(hh)] = runX[hh];
                 }
             }
             // ---- new G -> bf16 operand copy [i][j]; after chunk 0 it is dL/dS_0
@@ -581,23 +603,26 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                             p.gs[(((size_t)b * p.H + h) * 64 + F.col(g, e)) * 64 + F.row(hh)] =
                                 __float2bfloat16_rn(__uint_as_float(v[4 * g + 2 * hh + e]));
             }
+            tmem_wait_st();
             named_bar_sync<B_SCAN, CTHREADS>();          // token-half totals of both scans are in shared memory
-            {
-                uint32_t gwp[2][4];
+            uint32_t lp[16];
+            tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch), v);
+            tmem_ld_frag(tPark + PARK_L, lp);
+            tmem_wait_ld();
 #pragma unroll
-                for (int hh = 0; hh < 2; hh++) {
-                    const int i = F.row(hh);
-                    const float base = (ex.q0p[0][i] + ex.q0p[1][i]) * elam[hh] + (ch ? ex.htY[0][i] : ex.htX[1][i]);
+            for (int hh = 0; hh < 2; hh++) {
+                const int i = F.row(hh);
+                // 2^Lam <S_in,G> + X over my half (suffix = total - inclusive) + what the other half contributes
+                const float base = (ex.q0p[0][i] + ex.q0p[1][i]) * elam[hh] + runX[hh] + (ch ? ex.htY[0][i] : ex.htX[1][i]);
+                uint32_t gwp[4];
 #pragma unroll
-                    for (int g = 0; g < 4; g++) {
-                        float gw0 = l[hh][g][0] * LN2 * (base + tt[hh][g][0]);
-                        const float gw1 = l[hh][g][1] * LN2 * (base + tt[hh][g][1]);
-                        if (c == 0 && !p.has_s0 && ch == 0 && g == 0 && q == 0) gw0 = 0.f;   // t = 0 with S_0 = 0
-                        gwp[hh][g] = pack2(gw0, gw1);
-                    }
+                for (int g = 0; g < 4; g++) {
+                    float gw0 = __uint_as_float(lp[4 * g + 2 * hh]) * LN2 * (base + __uint_as_float(v[4 * g + 2 * hh]));
+                    const float gw1 = __uint_as_float(lp[4 * g + 2 * hh + 1]) * LN2 * (base + __uint_as_float(v[4 * g + 2 * hh + 1]));
+                    if (c == 0 && !p.has_s0 && ch == 0 && g == 0 && q == 0) gw0 = 0.f;   // t = 0 with S_0 = 0
+                    gwp[g] = pack2(gw0, gw1);
                 }
-                stsm_x4_t(sbase + OFF_GWT + F.ti(0), gwp[0][0], gwp[0][1], gwp[0][2], gwp[0][3]);
-                stsm_x4_t(sbase + OFF_GWT + F.ti(1), gwp[1][0], gwp[1][1], gwp[1][2], gwp[1][3]);
+                stsm_x4_t(sbase + OFF_GWT + F.ti(hh), gwp[0], gwp[1], gwp[2], gwp[3]);
             }
             fence_proxy_async();
             tc_fence_before();

@@ -50,12 +50,15 @@ def test_fragment_building_blocks(co):
     B = torch.randn(64, 64, generator=g).bfloat16().cuda()
     O = torch.zeros(64, 64, dtype=torch.bfloat16, device="cuda")
     F = torch.full((64, 64), float("nan"), device="cuda")
-    D = torch.full((64, 16), float("nan"), device="cuda")
+    D = torch.full((64 * 16 + 1,), float("nan"), device="cuda")
+    D[-1] = 0.0
     _lib.check(fn(co, A.data_ptr(), B.data_ptr(), O.data_ptr(), F.data_ptr(), D.data_ptr(),
                   torch.cuda.current_stream().cuda_stream), "selftest2")
     torch.cuda.synchronize()
     assert torch.equal(F, A.float().t()), "ldmatrix.trans fragment layout"
     assert torch.equal(O, A.t()), "stmatrix + TMA store"
+    assert D[-1].item() == 0.0, "an M=64 MMA disturbed TMEM lanes 16-31 (used as per-thread scratch)"
+    D = D[:-1].view(64, 16)
     want = A.float() @ B.float()[:, 16 * co:16 * co + 16]
     err = (D - want).abs().max().item()
     assert err < 1e-3 * max(1.0, want.abs().max().item()), f"co={co}: max err {err}\n{D[:4,:4]}\n{want[:4,:4]}"
