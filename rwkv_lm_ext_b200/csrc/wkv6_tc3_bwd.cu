@@ -68,6 +68,7 @@ struct Params {
     int has_s0;
     bf16 *gu, *gs;
     const int *hz_flags;
+    long long *dbg;           // nullptr, or [gridDim][NC][8] clock64 stamps of warp 0 at the stage boundaries (profiling aid)
 };
 
 __device__ __forceinline__ uint32_t pack_frag(const uint32_t *v, int g, int hh) {
@@ -263,11 +264,14 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         tc_fence_before();
         bar_arrive_all<B_T3>();
 
+#define STAMP(k) do { if (p.dbg && threadIdx.x == 0) p.dbg[((size_t)blockIdx.x * NC + it) * 8 + (k)] = clock64(); } while (0)
         for (int it = 0; it < NC; it++) {
             const int c = NC - 1 - it;
             const int nv = min(L, T - c * L);
             // ================================================================== P: operand preparation
             bar_sync_all<B_RAW>();
+            asm volatile("fence.acq_rel.cta;" ::: "memory");
+            STAMP(0);
             float rqf[2], elam[2], elr[2], erho[2];
             {   // ---- everything per element lives only inside this block
             float l[2][4][2], exq[2][4];
@@ -411,11 +415,13 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             }
             }
             fence_proxy_async();
+            STAMP(1);
             bar_arrive_all<B_PREP>();
 
             // ================================================================== T1
             bar_sync_all<B_M1>();
             tc_fence_after();
+            STAMP(2);
             // ---- Bm[t rows][s cols] -> dA[t][s] = Bm for s < t; bd[t] = Bm[t,t]
             tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch), v);
             tmem_wait_ld();
@@ -486,11 +492,13 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             tmem_wait_st();
             fence_proxy_async();
             tc_fence_before();
+            STAMP(3);
             bar_arrive_all<B_T1>();
 
             // ================================================================== T2: gv tile, gr tile, XA
             bar_sync_all<B_M2>();
             tc_fence_after();
+            STAMP(4);
             tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch), v);
             tmem_wait_ld();
             stsm_x4(sbase + OFF_GVT + F.rc(0), pack_frag(v, 0, 0), pack_frag(v, 1, 0), pack_frag(v, 2, 0), pack_frag(v, 3, 0));
@@ -526,11 +534,13 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             tmem_wait_st();
             fence_proxy_async();
             tc_fence_before();
+            STAMP(5);
             bar_arrive_all<B_T2>();
 
             // ================================================================== T3: gk tile, gw tile, new bf16 G
             bar_sync_all<B_M3>();
             tc_fence_after();
+            STAMP(6);
             // per 8-token group: Dk, Dks, XA -> gk (tile), running scans; the part of gl that does not need the
             // other token half replaces XA in TMEM
             float runY[2] = {0.f, 0.f}, runX[2] = {0.f, 0.f};
@@ -618,14 +628,19 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
                     float gw0 = __uint_as_float(lp[4 * g + 2 * hh]) * LN2 * (base + __uint_as_float(v[4 * g + 2 * hh]));
-                    const float gw1 = __uint_as_float(lp[4 * g + 2 * hh + 1]) * LN2 * (base + __uint_as_float(v[4 * g + 2 * hh + 1]));
+                    float gw1 = __uint_as_float(lp[4 * g + 2 * hh + 1]) * LN2 * (base + __uint_as_float(v[4 * g + 2 * hh + 1]));
                     if (c == 0 && !p.has_s0 && ch == 0 && g == 0 && q == 0) gw0 = 0.f;   // t = 0 with S_0 = 0
+                    if (c == NC - 1) {      // the last decay feeds no output: exactly 0 like cuda/wkv6_cuda.cu:226
+                        if (F.col(g, 0) == nv - 1) gw0 = 0.f;
+                        if (F.col(g, 1) == nv - 1) gw1 = 0.f;
+                    }
                     gwp[g] = pack2(gw0, gw1);
                 }
                 stsm_x4_t(sbase + OFF_GWT + F.ti(hh), gwp[0], gwp[1], gwp[2], gwp[3]);
             }
             fence_proxy_async();
             tc_fence_before();
+            STAMP(7);
             bar_arrive_all<B_T3>();
         }
         // gu[b, i] = sum_t r k bd: reduce over the 4 lanes q and the two token halves
@@ -645,6 +660,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
 }
 
 }  // namespace
+
+void *g_tc3_bwd_stamps = nullptr;   // profiling aid, set through wkv6b200_debug_stamps()
 
 size_t tc3_saved_header(int B, int H) { return (((size_t)B * H * sizeof(int)) + 1023) / 1024 * 1024; }
 size_t tc3_saved_bytes(int B, int T, int H) {
@@ -698,6 +715,7 @@ int tc3_backward(const Args &a) {
     p.has_s0 = a.s0 != nullptr;
     p.gu = (bf16 *)a.gu; p.gs = (bf16 *)a.gs;
     p.hz_flags = flags;
+    p.dbg = (long long *)g_tc3_bwd_stamps;
     static bool attr_done = false;
     if (!attr_done) {
         WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));

@@ -1,25 +1,29 @@
-// WKV6 forward, chunked, on tcgen05 tensor cores fed by TMA -- role-uniform version.
+// WKV6 forward, chunked, on tcgen05 tensor cores fed by TMA -- role-uniform, software-pipelined.
 //
 // One CTA owns one (batch, head) stream and walks its T tokens in chunks of L = 64; 2 CTAs per SM.
 // Per chunk (i = key channel, j = value channel, l_t = -exp(w_t), cum =
-// inclusive prefix sum of l inside the chunk, exc = cum - l, Lam = cum at the chunk end):
+// inclusive prefix sum of l inside the chunk, exc = cum - l, Lam = cum at the chunk end), with two
+// 32-token blocks q (reference rho_q = exc at the block middle rounded to the INTEGER log2 grid, so
+// every scaled operand stays within 16 decay steps of 1 and the two versions of Kt are exact
+// power-of-two multiples of one another -- bf16 mul.rn, no second exp):
 //
-//   M1  A^T[s,t] = sum_i Kt_q[s,i] * Rt[t,i]        4 x (64 x 16 x 64), one per 16-token target block q
-//        Rt[t] = r_t * 2^(exc_t - rho_q),  Kt_q[s] = k_s * 2^(rho_q - cum_s),  rho_q = exc at the middle
-//        of block q rounded to the INTEGER log2 grid: every factor stays within 8 decay steps of 1,
-//        and the versions Kt_q are exact power-of-two multiples of one another (bf16 mul.rn, no exp)
-//       Y[t,j]   = sum_i Rh[t,i] * S[i,j]           Rh = r * 2^exc          (state from earlier chunks)
-//   T1  P = strict-lower(A) + diag(sum_i r u k)  (bf16),   S[i,j] *= 2^Lam_i  (in TMEM)
-//   M2  Y[t,j]  += sum_s P[t,s] * V[s,j];    S[i,j] += sum_s Kh[s,i] * V[s,j]    Kh = k * 2^(Lam - cum),
-//        split into bf16 hi + lo so that the fp32 master state keeps ~16 mantissa bits per update
-//   T2  y tile -> TMA store;  bf16 copy of S for the next chunk's M1 (and, for training, TMA-stored
-//        as the chunk-start checkpoint the backward kernel reads)
+//   A    A^T[s,t] = sum_i Kt_q[s,i] * Rt[t,i]        2 x (64 x 32 x 64), one per target block q
+//         Rt[t] = r_t * 2^(exc_t - rho_q),   Kt_q[s] = k_s * 2^(rho_q - cum_s)
+//   T1   P = strict-lower(A) + diag(sum_i r u k)  (bf16),   S[i,j] *= 2^Lam_i  (fp32, in TMEM)
+//   M2   Y[t,j]  = sum_i Rh[t,i] * S_in[i,j] + sum_s P[t,s] * V[s,j]          Rh = r * 2^exc
+//        S[i,j] += sum_s Kh[s,i] * V[s,j]     Kh = k * 2^(Lam - cum), split into bf16 hi + lo so that the
+//         fp32 master state keeps ~16 mantissa bits per update
+//   T2   y tile -> TMA store;  bf16 copy of S for the next chunk (and, for training, TMA-stored as the
+//         chunk-start checkpoint the backward kernel reads)
 //
 // 8 compute warps do EVERY stage in the fragment mapping of tc3_common.cuh (a thread keeps its two
 // channels from the decay scan to the state rows it rescales); warp 8 issues TMA and tcgen05.mma.
-// While one CTA waits for its MMAs the co-resident CTA computes.  Chunks whose decay is too strong
-// for the block references (more than e^-60 inside an aligned 16-token span) raise the stream's hazard flag: the
-// exact SIMT kernel, enqueued behind this one and predicated per stream on that flag, redoes them.
+// The operand preparation of chunk c+1 runs while the tensor cores work on M2 of chunk c (only the
+// tiles M2 still reads -- Rh, Kh -- are written after it), and A of chunk c+1 is queued behind M2, so
+// the compute warps never wait for a full MMA round trip; the co-resident CTA fills what is left.
+// Streams whose decay is too strong for the block references (more than e^-60 inside an aligned
+// 16-token span) raise their hazard flag: the exact SIMT kernel, enqueued behind this one and
+// predicated per stream on that flag, redoes them.
 #include "common.cuh"
 #include "tc3_common.cuh"
 
@@ -29,20 +33,22 @@ namespace {
 using namespace tc3;
 
 constexpr uint32_t OFF_R = 0, OFF_K = 8192, OFF_W = 16384, OFF_V = 24576;
-constexpr uint32_t OFF_KT = 32768;                       // 160 rows: versions q = 3,2,1,0
-__host__ __device__ constexpr uint32_t kt_off(int q) { return q == 0 ? 18432u : q == 1 ? 14336u : q == 2 ? 8192u : 0u; }
-constexpr uint32_t OFF_RT = 53248, OFF_P = OFF_RT;       // P is written after the MMAs reading Rt are done
-constexpr uint32_t OFF_RH = 61440, OFF_KH = 69632, OFF_KL = 77824, OFF_SB = 86016, OFF_YT = 94208;
+constexpr uint32_t OFF_KT = 32768;                       // version 1 (rows 0..63) at +0, version 0 (rows 0..31) at +8192
+__host__ __device__ constexpr uint32_t kt_ver(int q) { return q ? 0u : 8192u; }
+constexpr uint32_t OFF_RT = 45056, OFF_P = 53248, OFF_RH = 61440, OFF_KH = 69632, OFF_KL = 77824, OFF_SB = 86016, OFF_YT = 94208;
 constexpr uint32_t OFF_TILES_END = 102400;
 struct Extra {
     float gtot[8][64];        // decay total of every 8-token group, per channel (log2 units)
     float pdu[4][64];         // per channel-quarter partial sums of r u k, per token
-    uint64_t bar_rkw, bar_v, bar_m1, bar_m2;
+    uint64_t bar_rkw, bar_v, bar_a, bar_m2;
     uint32_t tmem_base;
     int hz;
 };
 constexpr uint32_t SMEM_BYTES = OFF_TILES_END + sizeof(Extra);
 constexpr uint32_t TM_A = 0, TM_Y = 64, TM_S = 128, TM_COLS = 256;
+// named barriers (288 threads): B_RAW raw r,k,w landed; B_PA Kt / Rt written; B_PB Rh / Kh written;
+// B_A A^T done; B_T1 P written, S decayed; B_M2 Y and S done; B_T2 y tile and bf16 S written
+enum : int { B_PA = B_PREP, B_PB = B_M3, B_A = B_M1 };
 
 struct Params {
     int B, T, H;
@@ -74,7 +80,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
     if (threadIdx.x == 0) {
         mbar_init(&ex.bar_rkw, 1);
         mbar_init(&ex.bar_v, 1);
-        mbar_init(&ex.bar_m1, 1);
+        mbar_init(&ex.bar_a, 1);
         mbar_init(&ex.bar_m2, 1);
         ex.hz = 0;
         fence_barrier_init();
@@ -91,7 +97,8 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
 
     if (warp == CWARPS) {
         // =====================================================================================
-        // issuer: TMA loads / stores and every tcgen05.mma, one thread
+        // issuer: TMA loads / stores and every tcgen05.mma (lane 0); all 32 lanes take part in the
+        // named barriers
         // =====================================================================================
         auto issue_rkw = [&](int c) {
             mbar_arrive_expect_tx(&ex.bar_rkw, 3 * 8192);
@@ -103,6 +110,20 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             mbar_arrive_expect_tx(&ex.bar_v, 8192);
             tma_load_3d(sm + OFF_V, &map_v, &ex.bar_v, h * 64, c * L, b);
         };
+        const uint32_t kt = sbase + OFF_KT, rt = sbase + OFF_RT, rh = sbase + OFF_RH, kh = sbase + OFF_KH;
+        const uint32_t kl = sbase + OFF_KL, pp = sbase + OFF_P, sb = sbase + OFF_SB, vv = sbase + OFF_V;
+        constexpr uint32_t ID32_KK = idesc_bf16(64, 32, 0, 0);
+        constexpr uint32_t ID_KM = idesc_bf16(64, 64, 0, 1);
+        constexpr uint32_t ID_MM = idesc_bf16(64, 64, 1, 1);
+        auto issue_A = [&]() {                               // A^T[s, t in q] = Kt_q Rt_own^T
+#pragma unroll
+            for (int qq = 0; qq < 2; qq++)
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    mma_bf16_ss(tmem + TM_A + 32 * qq, smem_desc_sw128(kt + kt_ver(qq) + 32 * k, 8192, 1024),
+                                smem_desc_sw128(rt + 4096 * qq + 32 * k, 8192, 1024), ID32_KK, k > 0);
+            mma_commit(&ex.bar_a);
+        };
         if (lane == 0) {
             tma_prefetch_desc(&map_r);
             tma_prefetch_desc(&map_k);
@@ -110,45 +131,43 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             tma_prefetch_desc(&map_w);
             issue_rkw(0);
             issue_v(0);
+            mbar_wait(&ex.bar_rkw, 0);
         }
-        const uint32_t kt = sbase + OFF_KT, rt = sbase + OFF_RT, rh = sbase + OFF_RH, kh = sbase + OFF_KH;
-        const uint32_t kl = sbase + OFF_KL, pp = sbase + OFF_P, sb = sbase + OFF_SB, vv = sbase + OFF_V;
-        constexpr uint32_t ID_A = idesc_bf16(64, 16, 0, 0);
-        constexpr uint32_t ID_KM = idesc_bf16(64, 64, 0, 1);
-        constexpr uint32_t ID_MM = idesc_bf16(64, 64, 1, 1);
+        __syncwarp();
+        bar_arrive_all<B_RAW>();
+        bar_sync_all<B_PA>();
+        if (lane == 0) {
+            tc_fence_after();
+            issue_A();
+            if (NC > 1) issue_rkw(1);
+        }
+        __syncwarp();
+        bar_sync_all<B_PB>();
+        bar_sync_all<B_T2>();                                    // initial state in TMEM / shared
+        if (lane == 0) {
+            if (p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (blockIdx.x * NC) * 64, 0);
+            tma_store_commit();
+        }
         for (int c = 0; c < NC; c++) {
             const uint32_t par = c & 1;
-            if (lane == 0) mbar_wait(&ex.bar_rkw, par);
+            const bool more = c + 1 < NC;
+            if (lane == 0) mbar_wait(&ex.bar_a, par);
             __syncwarp();
-            bar_arrive_all<B_RAW>();                             // raw r,k,w landed
-            bar_sync_all<B_PREP>();                              // operands written, raw r,k,w consumed
-            if (lane == 0 && c + 1 < NC) issue_rkw(c + 1);
-            bar_sync_all<B_T2>();                                // completion #c: bf16 S ready, TMEM A / Y free
-            if (lane == 0) {
-                if (p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (blockIdx.x * NC + c) * 64, 0);
-                if (c > 0 && p.has_y) tma_store_3d(&map_y, sm + OFF_YT, h * 64, (c - 1) * L, b);
-                tma_store_commit();
-                tc_fence_after();
-#pragma unroll
-                for (int qq = 0; qq < 4; qq++)                   // A^T blocks
-#pragma unroll
-                    for (int k = 0; k < 4; k++)
-                        mma_bf16_ss(tmem + TM_A + 16 * qq, smem_desc_sw128(kt + kt_off(qq) + 32 * k, 8192, 1024),
-                                    smem_desc_sw128(rt + 2048 * qq + 32 * k, 8192, 1024), ID_A, k > 0);
-#pragma unroll
-                for (int k = 0; k < 4; k++)                      // Y = Rh * S_in      (S tile is [i][j]: MN-major B)
-                    mma_bf16_ss(tmem + TM_Y, smem_desc_sw128(rh + 32 * k, 8192, 1024),
-                                smem_desc_sw128(sb + 2048 * k, 8192, 1024), ID_KM, k > 0);
-                mma_commit(&ex.bar_m1);
-                mbar_wait(&ex.bar_m1, par);
+            bar_arrive_all<B_A>();
+            if (more) {
+                if (lane == 0) mbar_wait(&ex.bar_rkw, par ^ 1);
+                __syncwarp();
+                bar_arrive_all<B_RAW>();
             }
-            __syncwarp();
-            bar_arrive_all<B_M1>();
             bar_sync_all<B_T1>();                                // P written, S decayed
             if (lane == 0) {
                 mbar_wait(&ex.bar_v, par);
                 tma_store_wait_read<0>();                        // SB / YT may be rewritten once M2 is done
                 tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; k++)                      // Y = Rh * S_in      (S tile is [i][j]: MN-major B)
+                    mma_bf16_ss(tmem + TM_Y, smem_desc_sw128(rh + 32 * k, 8192, 1024),
+                                smem_desc_sw128(sb + 2048 * k, 8192, 1024), ID_KM, k > 0);
 #pragma unroll
                 for (int k = 0; k < 4; k++)                      // Y += P * V
                     mma_bf16_ss(tmem + TM_Y, smem_desc_sw128(pp + 32 * k, 8192, 1024),
@@ -162,18 +181,32 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     mma_bf16_ss(tmem + TM_S, smem_desc_sw128(kl + 2048 * k, 8192, 1024),
                                 smem_desc_sw128(vv + 2048 * k, 8192, 1024), ID_MM, 1);
                 mma_commit(&ex.bar_m2);
+            }
+            __syncwarp();
+            if (more) {
+                bar_sync_all<B_PA>();                            // Kt / Rt of chunk c+1 written, its raw tiles consumed
+                if (lane == 0) {
+                    tc_fence_after();
+                    issue_A();                                   // queued behind M2 on the tensor pipe
+                    if (c + 2 < NC) issue_rkw(c + 2);
+                }
+                __syncwarp();
+            }
+            if (lane == 0) {
                 mbar_wait(&ex.bar_m2, par);                      // V is free again
-                if (c + 1 < NC) issue_v(c + 1);
+                if (more) issue_v(c + 1);
             }
             __syncwarp();
             bar_arrive_all<B_M2>();
+            if (more) bar_sync_all<B_PB>();
+            bar_sync_all<B_T2>();                                // y tile and the new bf16 S written
+            if (lane == 0) {
+                if (p.has_y) tma_store_3d(&map_y, sm + OFF_YT, h * 64, c * L, b);
+                if (more && p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (blockIdx.x * NC + c + 1) * 64, 0);
+                tma_store_commit();
+            }
         }
-        bar_sync_all<B_T2>();                                    // completion #NC
-        if (lane == 0) {
-            if (p.has_y) tma_store_3d(&map_y, sm + OFF_YT, h * 64, (NC - 1) * L, b);
-            tma_store_commit();
-            tma_store_wait_all<0>();
-        }
+        if (lane == 0) tma_store_wait_all<0>();
     } else {
         // =====================================================================================
         // compute warps
@@ -209,10 +242,12 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         tc_fence_before();
         bar_arrive_all<B_T2>();
 
-        for (int c = 0; c < NC; c++) {
+        // Operand preparation of chunk c: Kt (both versions) and Rt go to shared memory at once; Rh, Kh (hi,
+        // lo) and 2^Lam stay in registers until the MMAs of the previous chunk no longer read those tiles.
+        uint32_t rhp[2][4], khp[2][4], klp[2][4];
+        float elam_nx[2];
+        auto prepare = [&](int c) {
             const int nv = min(L, T - c * L);
-            // ================================================================== P: operand preparation
-            bar_sync_all<B_RAW>();
             float l[2][4][2], exq[2][4];
             {
                 uint32_t wp[2][4];
@@ -254,61 +289,51 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             ldsm_x4_t(sbase + OFF_R + F.ti(1), rr[1][0], rr[1][1], rr[1][2], rr[1][3]);
             ldsm_x4_t(sbase + OFF_K + F.ti(0), kk[0][0], kk[0][1], kk[0][2], kk[0][3]);
             ldsm_x4_t(sbase + OFF_K + F.ti(1), kk[1][0], kk[1][1], kk[1][2], kk[1][3]);
-            float elam[2];
             float du[4][2];
 #pragma unroll
             for (int g = 0; g < 4; g++) du[g][0] = du[g][1] = 0.f;
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
                 // prefix over the 8 groups of this channel: start of my groups, block references, total
-                float run = 0.f, gb[4], rho[4];
+                float run = 0.f, gb[4], rho0 = 0.f, rho1 = 0.f;
 #pragma unroll
                 for (int x8 = 0; x8 < 8; x8++) {
-                    if (x8 & 1) rho[x8 >> 1] = rintf(run);                 // block middle, integer log2 grid
+                    if (x8 == 2) rho0 = rintf(run);                       // middle of block 0, integer log2 grid
+                    if (x8 == 6) rho1 = rintf(run);                       // middle of block 1
                     if ((x8 >> 2) == ch) gb[x8 & 3] = run;
                     run += ex.gtot[x8][F.row(hh)];
                 }
-                const float lam = run;
-                elam[hh] = fast_ex2(lam);
-                const float rqa = ch ? rho[2] : rho[0], rqb = ch ? rho[3] : rho[1];      // my two blocks
-                const int ir0 = (int)rho[0], ir1 = (int)rho[1], ir2 = (int)rho[2], ir3 = (int)rho[3];
-                const uint32_t erqa = bfpow2pair(ch ? ir2 : ir0), erqb = bfpow2pair(ch ? ir3 : ir1);
-                uint32_t rto[4], kto[4], rhp[4], khp[4], klp[4];
+                const float lam = run, rq = ch ? rho1 : rho0;
+                const int ir0 = (int)rho0, ir1 = (int)rho1, d10 = ir1 - ir0;
+                const uint32_t erq = bfpow2pair(ch ? ir1 : ir0);
+                const float el = fast_ex2(lam - rq);
+                elam_nx[hh] = fast_ex2(lam);
+                uint32_t rto[4], kto[4];
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
-                    const float rq = (g < 2) ? rqa : rqb;
-                    const float exc0 = gb[g] + exq[hh][g], cum0 = exc0 + l[hh][g][0], cum1 = cum0 + l[hh][g][1];
+                    const float e0 = gb[g] + exq[hh][g], c0 = e0 + l[hh][g][0], c1 = c0 + l[hh][g][1];
                     const float r0 = bf_lo(rr[hh][g]), r1 = bf_hi(rr[hh][g]), k0 = bf_lo(kk[hh][g]), k1 = bf_hi(kk[hh][g]);
-                    const float rt0 = r0 * fast_ex2(exc0 - rq), rt1 = r1 * fast_ex2(cum0 - rq);
-                    const float kf0 = k0 * fast_ex2(rq - cum0), kf1 = k1 * fast_ex2(rq - cum1);
+                    const float rt0 = r0 * fast_ex2(e0 - rq), rt1 = r1 * fast_ex2(c0 - rq);
+                    const float kf0 = k0 * fast_ex2(rq - c0), kf1 = k1 * fast_ex2(rq - c1);
                     rto[g] = pack2(rt0, rt1);
                     kto[g] = pack2(kf0, kf1);
-                    rhp[g] = hmul2(rto[g], (g < 2) ? erqa : erqb);                      // Rh = Rt * 2^rho (exact)
-                    const float el = fast_ex2(lam - rq);
-                    const float kh0 = kf0 * el, kh1 = kf1 * el;
-                    khp[g] = pack2(kh0, kh1);
-                    klp[g] = pack2(kh0 - bf_lo(khp[g]), kh1 - bf_hi(khp[g]));
+                    rhp[hh][g] = hmul2(rto[g], erq);                      // Rh = Rt * 2^rho (exact)
+                    const float kh0 = kf0 * el, kh1 = kf1 * el;           // Kh = k * 2^(Lam - cum)
+                    khp[hh][g] = pack2(kh0, kh1);
+                    klp[hh][g] = pack2(kh0 - bf_lo(khp[hh][g]), kh1 - bf_hi(khp[hh][g]));
                     du[g][0] = fmaf(r0 * u_h[hh], k0, du[g][0]);
                     du[g][1] = fmaf(r1 * u_h[hh], k1, du[g][1]);
                 }
                 const uint32_t ti = F.ti(hh);
                 stsm_x4_t(sbase + OFF_RT + ti, rto[0], rto[1], rto[2], rto[3]);
-                stsm_x4_t(sbase + OFF_RH + ti, rhp[0], rhp[1], rhp[2], rhp[3]);
-                stsm_x4_t(sbase + OFF_KH + ti, khp[0], khp[1], khp[2], khp[3]);
-                stsm_x4_t(sbase + OFF_KL + ti, klp[0], klp[1], klp[2], klp[3]);
-                // Kt versions: version qq holds rows s <= 16qq+15 scaled to the reference of block qq
-                if (ch == 0) {
-                    const uint32_t f10 = bfpow2pair(ir1 - ir0);
-                    const uint32_t f20 = bfpow2pair(ir2 - ir0), f21 = bfpow2pair(ir2 - ir1);
-                    const uint32_t f30 = bfpow2pair(ir3 - ir0), f31 = bfpow2pair(ir3 - ir1);
-                    stsm_x2_t(sbase + OFF_KT + kt_off(0) + ti, kto[0], kto[1]);
-                    stsm_x4_t(sbase + OFF_KT + kt_off(1) + ti, hmul2(kto[0], f10), hmul2(kto[1], f10), kto[2], kto[3]);
-                    stsm_x4_t(sbase + OFF_KT + kt_off(2) + ti, hmul2(kto[0], f20), hmul2(kto[1], f20), hmul2(kto[2], f21), hmul2(kto[3], f21));
-                    stsm_x4_t(sbase + OFF_KT + kt_off(3) + ti, hmul2(kto[0], f30), hmul2(kto[1], f30), hmul2(kto[2], f31), hmul2(kto[3], f31));
+                if (ch == 0) {      // block 0: own in Kt_0, scaled to the later reference in Kt_1 (2^(rho1-rho0) spans 32
+                                    // tokens and may leave the bf16 range although the products do not: two exact factors)
+                    const uint32_t fa = bfpow2pair(d10 >> 1), fb = bfpow2pair(d10 - (d10 >> 1));
+                    stsm_x4_t(sbase + OFF_KT + kt_ver(0) + ti, kto[0], kto[1], kto[2], kto[3]);
+                    stsm_x4_t(sbase + OFF_KT + kt_ver(1) + ti, hmul2(hmul2(kto[0], fa), fb), hmul2(hmul2(kto[1], fa), fb),
+                              hmul2(hmul2(kto[2], fa), fb), hmul2(hmul2(kto[3], fa), fb));
                 } else {
-                    const uint32_t f32_ = bfpow2pair(ir3 - ir2);
-                    stsm_x2_t(sbase + OFF_KT + kt_off(2) + ti, kto[0], kto[1]);
-                    stsm_x4_t(sbase + OFF_KT + kt_off(3) + ti, hmul2(kto[0], f32_), hmul2(kto[1], f32_), kto[2], kto[3]);
+                    stsm_x4_t(sbase + OFF_KT + kt_ver(1) + ti, kto[0], kto[1], kto[2], kto[3]);
                 }
             }
             // ---- diag(u) term: sum over channels of r u k per token; reduce-scatter over the 8 lanes ri
@@ -334,10 +359,29 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 ex.pdu[sp][32 * ch + 8 * ((b2 ? 2 : 0) + (b1 ? 1 : 0)) + 2 * q + (b0 ? 1 : 0)] = a1;
             }
             fence_proxy_async();
-            bar_arrive_all<B_PREP>();
+            bar_arrive_all<B_PA>();
+        };
+        auto store_deferred = [&]() {
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                const uint32_t ti = F.ti(hh);
+                stsm_x4_t(sbase + OFF_RH + ti, rhp[hh][0], rhp[hh][1], rhp[hh][2], rhp[hh][3]);
+                stsm_x4_t(sbase + OFF_KH + ti, khp[hh][0], khp[hh][1], khp[hh][2], khp[hh][3]);
+                stsm_x4_t(sbase + OFF_KL + ti, klp[hh][0], klp[hh][1], klp[hh][2], klp[hh][3]);
+            }
+            fence_proxy_async();
+            bar_arrive_all<B_PB>();
+        };
 
+        bar_sync_all<B_RAW>();
+        prepare(0);
+        store_deferred();
+        float elam[2] = {elam_nx[0], elam_nx[1]};
+
+        for (int c = 0; c < NC; c++) {
+            const bool more = c + 1 < NC;
             // ================================================================== T1: A^T -> P, decay S
-            bar_sync_all<B_M1>();
+            bar_sync_all<B_A>();
             tc_fence_after();
             tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_A + 32 * ch), v);
             tmem_wait_ld();
@@ -376,9 +420,19 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             tc_fence_before();
             bar_arrive_all<B_T1>();
 
-            // ================================================================== T2: y tile, new bf16 S
+            // ================================================================== P of the next chunk, under M2
+            if (more) {
+                bar_sync_all<B_RAW>();
+                prepare(c + 1);
+            }
             bar_sync_all<B_M2>();
             tc_fence_after();
+            if (more) {
+                store_deferred();
+                elam[0] = elam_nx[0];
+                elam[1] = elam_nx[1];
+            }
+            // ================================================================== T2: y tile, new bf16 S
             if (p.has_y) {
                 tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_Y + 32 * ch), v);
                 tmem_wait_ld();
