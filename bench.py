@@ -116,8 +116,8 @@ def run_cpu(steps, warmup, budget_s=20.0):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--kernel-impl", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -161,7 +161,7 @@ def main():
     torch.cuda.synchronize()
 
     def step(r, k, v, w, u, gy, ev=None):
-        leaves = [t.requires_grad_(True) for t in (r, k, v, w, u)]
+        leaves = [t.detach().requires_grad_(True) for t in (r, k, v, w, u)]
         if ev:
             ev[0].record()
         y = M.RUN_CUDA_RWKV6(B, T, C, H, *leaves)
@@ -204,29 +204,53 @@ def main():
         ms = float(tms.item())
     value = world * B * T / (ms * 1e-3)
 
-    # ---- end to end: host buffers in, results out, inside the timed region
+    # ---- end to end: host buffers in, results out, inside the timed region.  Three CUDA streams form
+    # the pipeline a data-parallel worker would run: copy-in of step i+1 and copy-out of step i-1
+    # overlap the kernels of step i (PCIe is full duplex); every step still moves all of its inputs
+    # from pinned host memory and all of its results back.
     e2e = None
     if not args.no_e2e:
-        outs_host = [torch.empty(B, T, C, dtype=torch.bfloat16).pin_memory() for _ in range(5)]
-        gu_host = torch.empty(H, N, dtype=torch.bfloat16).pin_memory()
+        NBUF = 2
+        outs_host = [[torch.empty(B, T, C, dtype=torch.bfloat16).pin_memory() for _ in range(5)] for _ in range(NBUF)]
+        gu_host = [torch.empty(H, N, dtype=torch.bfloat16).pin_memory() for _ in range(NBUF)]
+        dev_in = [[torch.empty_like(t, device=dev) for t in host] for _ in range(NBUF)]
         h2d = sum(t.numel() * t.element_size() for t in host)
-        d2h = sum(t.numel() * t.element_size() for t in outs_host) + gu_host.numel() * 2
+        d2h = sum(t.numel() * t.element_size() for t in outs_host[0]) + gu_host[0].numel() * 2
+        s_in, s_cmp, s_out = torch.cuda.Stream(), torch.cuda.Stream(), torch.cuda.Stream()
+        ev_in = [torch.cuda.Event() for _ in range(NBUF)]
+        ev_cmp = [torch.cuda.Event() for _ in range(NBUF)]
+        ev_out = [torch.cuda.Event() for _ in range(NBUF)]
+        keep = [None] * NBUF
 
-        def e2e_step():
-            dv = [t.to(dev, non_blocking=True) for t in host]
-            y, grads = step(*dv)
-            for dst, src in zip(outs_host, [y] + grads[:4]):
-                dst.copy_(src, non_blocking=True)
-            gu_host.copy_(grads[4], non_blocking=True)
+        def e2e_steps(n):
+            for i in range(n):
+                j = i % NBUF
+                with torch.cuda.stream(s_in):
+                    s_in.wait_event(ev_cmp[j])                  # the kernels that read this input buffer are done
+                    for d, src in zip(dev_in[j], host):
+                        d.copy_(src, non_blocking=True)
+                    ev_in[j].record(s_in)
+                with torch.cuda.stream(s_cmp):
+                    s_cmp.wait_event(ev_in[j])
+                    s_cmp.wait_event(ev_out[j])                 # results of step i-NBUF have left the device
+                    y, grads = step(*dev_in[j])
+                    keep[j] = (y, grads)
+                    ev_cmp[j].record(s_cmp)
+                with torch.cuda.stream(s_out):
+                    s_out.wait_event(ev_cmp[j])
+                    for dst, src in zip(outs_host[j], [y] + grads[:4]):
+                        dst.copy_(src, non_blocking=True)
+                    gu_host[j].copy_(grads[4], non_blocking=True)
+                    ev_out[j].record(s_out)
+            for st in (s_in, s_cmp, s_out):
+                torch.cuda.current_stream().wait_stream(st)
 
-        for _ in range(2):
-            e2e_step()
+        e2e_steps(3)
         barrier()
-        ksteps = max(3, min(args.steps, 10))
+        ksteps = max(4, min(args.steps, 12))
         a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        for _ in range(ksteps):
-            e2e_step()
+        e2e_steps(ksteps)
         b_.record()
         barrier()
         ems = a.elapsed_time(b_) / ksteps
@@ -236,7 +260,8 @@ def main():
             ems = float(tms.item())
         e2e = {"value": world * B * T / (ems * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "ms_per_step": ems, "steps": ksteps,
-               "api": "rwkv_lm_ext_b200.RUN_CUDA_RWKV6 + .backward, pinned host tensors"}
+               "api": "rwkv_lm_ext_b200.RUN_CUDA_RWKV6 + .backward; pinned host tensors in, all results out, "
+                      "copy-in / kernels / copy-out of consecutive steps pipelined on 3 CUDA streams"}
 
     if rank != 0:
         if world > 1:
@@ -250,8 +275,14 @@ def main():
     dom_bytes = elems * (BYTES_BWD if dom_is_bwd else BYTES_FWD)
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     impl_name = {0: "auto", 1: "simt", 2: "tc"}[M.load().wkv6b200_get_impl()]
+    traffic = None
+    try:      # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json")))
+        traffic = tj["wkv6_tc3_bwd_kernel" if dom_is_bwd else "wkv6_tc3_fwd_kernel"]["dram_bytes_per_launch"]
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "peak_source": peak_src,
                 "kernel": ("wkv6 backward" if dom_is_bwd else "wkv6 forward") + f" ({impl_name})",
                 "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
                 "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,

@@ -47,13 +47,6 @@ static int check_shape(int B, int T, int C, int H) {
             if (!_p[_i]) { set_error("%s: null pointer argument #%zu", __func__, _i); return WKV6_EINVAL; } \
     } while (0)
 
-// WKV6_B200_TC2=1 selects the previous generation of tensor-core kernels (warp-specialised, one
-// flag per call); the default is the role-uniform generation with per-stream hazard flags.
-static bool use_tc2() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("WKV6_B200_TC2"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1;
-}
 // per-stream hazard flags of a forward call that has no `saved` buffer: slices of a small per-device
 // ring (4 MB, allocated on first use, never freed), so that calls in flight on different CUDA
 // streams do not share flags
@@ -96,19 +89,13 @@ static int forward3(const Args &a) {
 }
 static int dispatch_forward(const Args &a) {
     const int impl = current_impl();
-    if (impl != WKV6_IMPL_SIMT && !use_tc2() && tc3_forward_supported(a)) return forward3(a);
-    if (impl != WKV6_IMPL_SIMT && tc_forward_supported(a)) {
-        if (!a.saved) return tc_forward(a);
-        if (cudaMemsetAsync(a.saved, 0, SAVED_HEADER, a.stream) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return WKV6_ECUDA; }
-        return tc_forward_ex(a, (uint8_t *)a.saved + SAVED_HEADER, (int *)a.saved);
-    }
+    if (impl != WKV6_IMPL_SIMT && tc3_forward_supported(a)) return forward3(a);
     if (impl == WKV6_IMPL_TC) { set_error("tensor-core forward does not support this call"); return WKV6_EUNSUPPORTED; }
     return simt_forward(a);
 }
 static int dispatch_backward(const Args &a) {
     const int impl = current_impl();
-    if (impl != WKV6_IMPL_SIMT && !use_tc2() && tc3_backward_supported(a)) return tc3_backward(a);
-    if (impl != WKV6_IMPL_SIMT && tc_backward_supported(a)) return tc_backward(a);
+    if (impl != WKV6_IMPL_SIMT && tc3_backward_supported(a)) return tc3_backward(a);
     if (impl == WKV6_IMPL_TC) { set_error("tensor-core backward does not support this call"); return WKV6_EUNSUPPORTED; }
     return simt_backward(a);
 }
@@ -168,8 +155,7 @@ int wkv6_forward_raww(int B, int T, int C, int H, const void *r, const void *k, 
 }
 size_t wkv6_backward_workspace_bytes(int B, int T, int C, int H) {
     (void)C;
-    const size_t a = tc_backward_workspace_bytes(B, T, H), b = tc3_backward_workspace_bytes(B, T, H, false);
-    return a > b ? a : b;   // superset: SIMT scratch + chunk-start states + flags
+    return tc3_backward_workspace_bytes(B, T, H, false);   // superset: SIMT scratch + chunk-start states + flags
 }
 int wkv6_backward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
                   const float *ew, const void *u, const void *gy, void *gr, void *gk, void *gv,
@@ -187,8 +173,7 @@ int wkv6_backward_raww(int B, int T, int C, int H, const void *r, const void *k,
 // ---------------------------------------------------------------------------- training pair
 size_t wkv6_saved_bytes(int B, int T, int C, int H) {
     (void)C;
-    const size_t a = tc_saved_bytes(B, T, H), b = tc3_saved_bytes(B, T, H);
-    return a > b ? a : b;
+    return tc3_saved_bytes(B, T, H);
 }
 size_t wkv6_train_backward_workspace_bytes(int B, int T, int C, int H, int has_saved) {
     (void)C;
@@ -205,7 +190,7 @@ int wkv6_train_forward(int B, int T, int C, int H, const void *r, const void *k,
     a.B = B; a.T = T; a.H = H; a.r = r; a.k = k; a.v = v; a.w = w; a.w_kind = W_RAW_BF16; a.u = u;
     a.s0 = s0; a.s0_f32 = s0_f32; a.s0_bstride = s0_batched ? (long long)H * N * N : 0;
     a.sT = sT; a.sT_f32 = sT_f32; a.y = y; a.stream = (cudaStream_t)stream;
-    const bool save = saved && current_impl() != WKV6_IMPL_SIMT && tc_forward_supported(a);
+    const bool save = saved && current_impl() != WKV6_IMPL_SIMT && tc3_forward_supported(a);
     if (save) a.saved = saved;
     const int rc = dispatch_forward(a);
     if (rc == WKV6_OK && save && saved_valid) *saved_valid = 1;

@@ -41,13 +41,10 @@ struct Args {
     void *gr = nullptr, *gk = nullptr, *gv = nullptr, *gw = nullptr, *gu = nullptr, *gs = nullptr;
     void *workspace = nullptr;
     size_t workspace_bytes = 0;
-    // SIMT kernels only: nullptr, or a device int; the kernels return immediately unless
-    // (*run_flag != 0) == run_if  (lets a fallback be enqueued without a host round trip)
-    const int *run_flag = nullptr;
-    int run_if = 1;
-    // same, one int per (b,h) stream: block `s` runs only when stream_flags[s] != 0
+    // SIMT kernels only: nullptr, or one device int per (b,h) stream: block `s` runs only when
+    // stream_flags[s] != 0 (lets the exact fallback be enqueued without a host round trip)
     const int *stream_flags = nullptr;
-    // training pair: forward fills it (hazard flag header + bf16 chunk-start states), backward reads it
+    // training pair: forward fills it (per-stream hazard flags + bf16 chunk-start states), backward reads it
     void *saved = nullptr;
     cudaStream_t stream = nullptr;
 };
@@ -57,13 +54,6 @@ int simt_forward(const Args &a);
 int simt_backward(const Args &a);
 size_t simt_backward_workspace_bytes(int B, int T, int H);
 
-int tc_forward(const Args &a);            // tcgen05 / TMA chunked forward
-int tc_forward_ex(const Args &a, void *ckpt, int *hz_flag);
-bool tc_forward_supported(const Args &a);
-int tc_backward(const Args &a);           // tcgen05 / TMA chunked backward (+ SIMT fallback on hazard)
-bool tc_backward_supported(const Args &a);
-size_t tc_backward_workspace_bytes(int B, int T, int H);
-size_t tc_saved_bytes(int B, int T, int H);
 int tc3_forward(const Args &a, void *ckpt, int *hz_flags);   // role-uniform tcgen05 forward (per-stream hazard flags)
 bool tc3_forward_supported(const Args &a);
 int tc3_backward(const Args &a);                             // role-uniform tcgen05 backward (+ per-stream SIMT fallback)
@@ -71,7 +61,6 @@ bool tc3_backward_supported(const Args &a);
 size_t tc3_saved_header(int B, int H);
 size_t tc3_saved_bytes(int B, int T, int H);
 size_t tc3_backward_workspace_bytes(int B, int T, int H, bool has_saved);
-constexpr size_t SAVED_HEADER = 256;   // int[0] = hazard flag
 
 void set_error(const char *fmt, ...);
 void count_launch(int n = 1);

@@ -146,7 +146,6 @@ __global__ void __launch_bounds__(NT) fwd_kernel(Args a, int mode) {
 // ---------------------------------------------------------------------------------------------
 template <typename IO, int WK>
 __global__ void __launch_bounds__(NT) bwd_f_kernel(Args a, int mode, float *Abuf) {
-    if (a.run_flag && ((*a.run_flag != 0) != (a.run_if != 0))) return;
     if (a.stream_flags && a.stream_flags[blockIdx.x] == 0) return;
     const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
     const int x = threadIdx.x & (N - 1), g = threadIdx.x >> 6;
@@ -254,7 +253,6 @@ __global__ void __launch_bounds__(NT) bwd_f_kernel(Args a, int mode, float *Abuf
 // ---------------------------------------------------------------------------------------------
 template <typename IO, int WK>
 __global__ void __launch_bounds__(NT) bwd_r_kernel(Args a, int mode, const float *Abuf) {
-    if (a.run_flag && ((*a.run_flag != 0) != (a.run_if != 0))) return;
     if (a.stream_flags && a.stream_flags[blockIdx.x] == 0) return;
     const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
     const int x = threadIdx.x & (N - 1), g = threadIdx.x >> 6;

@@ -99,6 +99,47 @@ def test_wkv6_vs_oracle(M, O, B, T, H, decay, impl):
     assert grads[3][:, -1].abs().max().item() == 0.0
 
 
+def test_mixed_hazard_streams(M, O):
+    """One (b,h) stream decays by far more than e^-60 inside 16 tokens, the others are model-like:
+    the tensor-core kernels flag that stream only and the exact SIMT kernels redo it (forward and
+    backward, through the training pair), all in one call."""
+    B, T, H = 2, 200, 2
+    r, k, v, w, u, gy = make_inputs(B, T, H, seed=11, decay="model")
+    w[1, 40:120, 64:128] = 3.0            # stream (b=1, h=1): exp(3) = 20 nats per token
+    ref = O.wkv6_backward(r, k, v, w, u, gy)
+    y, grads = _run_fwd_bwd(M, r, k, v, w, u, gy)
+    assert_bf16_close(y, ref["y"], "y")
+    for g, key in zip(grads, ("gr", "gk", "gv", "gw", "gu")):
+        assert_bf16_close(g, ref[key], key)
+    # and the in-place state variant: the flagged stream's final state must come from the exact kernel
+    s0 = (torch.randn(B, H, 64, 64, generator=torch.Generator().manual_seed(3)) * 0.5).bfloat16()
+    y_ref, s_ref = O.wkv6infctx_forward(r, k, v, w, u, s0)
+    s = s0.clone().to(DEV)
+    with torch.no_grad():
+        y2, _ = M.RUN_CUDA_RWKV6_STATE(B, T, H * 64, H, *(t.to(DEV) for t in (r, k, v, w, u)), s)
+    assert_bf16_close(y2, y_ref, "infctx y")
+    assert_bf16_close(s, s_ref, "infctx final state")
+
+
+def test_native_raww_backward_without_saved_state(M):
+    """wkv6_backward_raww (no training pair): the library recomputes the chunk-start states itself."""
+    import ctypes
+    from rwkv_lm_ext_b200 import _lib
+    B, T, H = 2, 130, 2
+    C = H * 64
+    r, k, v, w, u, gy = make_inputs(B, T, H, seed=8, decay="model", device=DEV)
+    lib = _lib.load()
+    gr, gk, gv, gw = (torch.empty_like(r) for _ in range(4))
+    gu = torch.empty(B, C, device=DEV, dtype=torch.bfloat16)
+    n = lib.wkv6_backward_workspace_bytes(B, T, C, H)
+    ws = torch.empty(n, dtype=torch.uint8, device=DEV)
+    _lib.check(lib.wkv6_backward_raww(B, T, C, H, *(t.data_ptr() for t in (r, k, v, w, u, gy, gr, gk, gv, gw, gu)),
+                                      ws.data_ptr(), n, torch.cuda.current_stream().cuda_stream), "wkv6_backward_raww")
+    _, grads = _run_fwd_bwd(M, r, k, v, w, u, gy)
+    for a, b_ in zip((gr, gk, gv, gw, gu.sum(0).view(H, 64)), grads):
+        assert relrms(a, b_) < 1e-6
+
+
 def test_native_surface_matches_python_surface(M):
     """cuda/wkv6_op.cpp signatures (fp32 ew = -exp(w), caller-allocated outputs)."""
     B, T, H = 2, 70, 2
