@@ -99,7 +99,7 @@ def run_cpu(steps, warmup, budget_s=20.0):
     from rwkv_lm_ext_b200.synthetic import make_inputs
     s = CPU_SAMPLE
     r, k, v, w, u, gy = (t.float() for t in make_inputs(s["B"], s["T"], s["H"], seed=0, decay="model"))
-    cores = c_oracle.num_threads()
+    cores = c_oracle.use_all_cores()
     for _ in range(warmup):
         c_oracle.forward(r[:, :256], k[:, :256], v[:, :256], w[:, :256], u)
         c_oracle.backward(r[:, :256], k[:, :256], v[:, :256], w[:, :256], u, gy[:, :256])

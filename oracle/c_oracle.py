@@ -39,6 +39,13 @@ def num_threads() -> int:
     return int(lib().wkv6_oracle_num_threads())
 
 
+def use_all_cores() -> int:
+    """Use every host core the process may run on (torchrun exports OMP_NUM_THREADS=1)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    lib().wkv6_oracle_set_threads(int(n))
+    return num_threads()
+
+
 def forward(r, k, v, w, u, s0=None, w_kind=0, want_state=False):
     """r,k,v,w [B,T,C]; u [H,64]; s0 None | [H,64,64] | [B,H,64,64] in [value,key] layout.
     Returns y fp32 [B,T,C] (and the final state [B,H,64,64] when want_state)."""

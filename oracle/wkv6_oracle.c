@@ -36,6 +36,15 @@ static inline float log_decay(float w, int w_kind) {
     return logf(w > 1e-38f ? w : 1e-38f);
 }
 
+/* n > 0: use n threads from now on (launchers such as torchrun export OMP_NUM_THREADS=1) */
+void wkv6_oracle_set_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int wkv6_oracle_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
