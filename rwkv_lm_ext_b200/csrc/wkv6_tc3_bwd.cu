@@ -149,46 +149,50 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         constexpr uint32_t ID_KK = idesc_bf16(64, 64, 0, 0), ID_KM = idesc_bf16(64, 64, 0, 1), ID_MM = idesc_bf16(64, 64, 1, 1);
         constexpr uint32_t ID32_KK = idesc_bf16(64, 32, 0, 0), ID32_MK = idesc_bf16(64, 32, 1, 0), ID32_MM = idesc_bf16(64, 32, 1, 1);
         bar_sync_all<B_T3>();                                    // G = 0 written (TMEM + bf16 copy)
+#define ISTAMP(k) do { if (p.dbg && lane == 0) p.dbg[(size_t)gridDim.x * NC * 8 + ((size_t)blockIdx.x * NC + it) * 8 + (k)] = clock64(); } while (0)
+        if (lane == 0) {
+            mbar_wait(&ex.bar_rk, 0);
+            mbar_wait(&ex.bar_w, 0);
+        }
+        __syncwarp();
+        bar_arrive_all<B_RAW>();
         for (int it = 0; it < NC; it++) {
             const int c = NC - 1 - it;
             const uint32_t par = it & 1;
-            if (lane == 0) {
-                mbar_wait(&ex.bar_rk, par);
-                mbar_wait(&ex.bar_w, par);
-                tma_store_wait_read<1>();                        // gv / gr tiles of the previous chunk (RH, KT space)
-            }
-            __syncwarp();
-            bar_arrive_all<B_RAW>();
             if (lane == 0 && it > 0) {
                 tma_store_wait_read<0>();                        // gk / gw tiles (DA, GY space)
                 issue_vg(c);
             }
             bar_sync_all<B_PREP>();                              // operands written, raw r,k,w consumed
-            if (lane == 0 && c > 0) issue_rk(c - 1);
-            if (lane == 0) {
-                mbar_wait(&ex.bar_vg, par);
-                mbar_wait(&ex.bar_sin, par);
+            asm volatile("fence.acq_rel.cta;" ::: "memory");
+            ISTAMP(0);
+            if (elect_one()) {
                 tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < 4; k++)   // Bm[t,s] = GY V^T
-                    mma_bf16_ss(tmem + TM_X0, smem_desc_sw128(gy + 32 * k, 8192, 1024), smem_desc_sw128(vv + 32 * k, 8192, 1024), ID_KK, k > 0);
-#pragma unroll
-                for (int q = 0; q < 2; q++)   // A^T[s, t in q] = Kt_q Rt_own^T
+                for (int q = 0; q < 2; q++)   // A^T[s, t in q] = Kt_q Rt_own^T     (needs only what the compute warps wrote)
 #pragma unroll
                     for (int k = 0; k < 4; k++)
                         mma_bf16_ss(tmem + TM_X1 + 32 * q, smem_desc_sw128(kt + kt_ver(q) + 32 * k, 8192, 1024),
                                     smem_desc_sw128(rp + rp_ver(q) + 32 * k, 8192, 1024), ID32_KK, k > 0);
+                mbar_wait(&ex.bar_vg, par);
+                ISTAMP(1);
+#pragma unroll
+                for (int k = 0; k < 4; k++)   // Bm[t,s] = GY V^T
+                    mma_bf16_ss(tmem + TM_X0, smem_desc_sw128(gy + 32 * k, 8192, 1024), smem_desc_sw128(vv + 32 * k, 8192, 1024), ID_KK, k > 0);
+                mbar_wait(&ex.bar_sin, par);
 #pragma unroll
                 for (int k = 0; k < 4; k++)   // Drs[i,t] = S_in GY^T
                     mma_bf16_ss(tmem + TM_X2, smem_desc_sw128(sin + 32 * k, 8192, 1024), smem_desc_sw128(gy + 32 * k, 8192, 1024), ID_KK, k > 0);
                 mma_commit(&ex.bar_m1);
+                ISTAMP(2);
                 mbar_wait(&ex.bar_m1, par);
+                ISTAMP(3);
             }
             __syncwarp();
             bar_arrive_all<B_M1>();
+            if (lane == 0 && c > 0) issue_rk(c - 1);             // raw r,k of this chunk were consumed by the preparation
             bar_sync_all<B_T1>();                                // dA, P^T written; <S_in,G> taken; G decayed
-            if (lane == 0) {
-                if (c > 0) issue_sin(c - 1);
+            if (elect_one()) {
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 4; k++)   // gv[s,j] = P^T GY ...
@@ -208,15 +212,17 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     mma_bf16_ss(tmem + TM_G, smem_desc_sw128(rh + 2048 * k, 8192, 1024), smem_desc_sw128(gy + 2048 * k, 8192, 1024), ID_MM, 1);
                 mma_commit(&ex.bar_m2);
                 mbar_wait(&ex.bar_m2, par);
-                if (c > 0) issue_w(c - 1);                       // the P^T tile (= W space) is dead
             }
             __syncwarp();
             bar_arrive_all<B_M2>();
+            if (lane == 0 && c > 0) {
+                issue_sin(c - 1);                                // S_in of this chunk: read by M1 and T1 only
+                issue_w(c - 1);                                  // the P^T tile (= W space) is dead
+            }
             bar_sync_all<B_T2>();                                // gv, gr tiles written; Dr, Drs consumed
-            if (lane == 0) {
-                tma_store_3d(&map_gv, sm + OFF_GVT, h * 64, c * L, b);
-                tma_store_3d(&map_gr, sm + OFF_GRT, h * 64, c * L, b);
-                tma_store_commit();
+            asm volatile("fence.acq_rel.cta;" ::: "memory");
+            ISTAMP(4);
+            if (elect_one()) {
                 tc_fence_after();
 #pragma unroll
                 for (int pb = 0; pb < 2; pb++)   // Dk[i, s in p] = sum_{t >= 32p} Rp_p[t,i] dA[t,s]   (dA read MN-major)
@@ -229,10 +235,21 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 for (int k = 0; k < 4; k++)   // Dks[i,s] = G_old V^T
                     mma_bf16_ss(tmem + TM_X1, smem_desc_sw128(gb + 32 * k, 8192, 1024), smem_desc_sw128(vv + 32 * k, 8192, 1024), ID_KK, k > 0);
                 mma_commit(&ex.bar_m3);
+                tma_store_3d(&map_gv, sm + OFF_GVT, h * 64, c * L, b);
+                tma_store_3d(&map_gr, sm + OFF_GRT, h * 64, c * L, b);
+                tma_store_commit();
+                ISTAMP(5);
                 mbar_wait(&ex.bar_m3, par);
+                ISTAMP(6);
             }
             __syncwarp();
             bar_arrive_all<B_M3>();
+            if (lane == 0 && c > 0) {                            // everything the next operand preparation needs, while T3 runs
+                mbar_wait(&ex.bar_rk, par ^ 1);
+                mbar_wait(&ex.bar_w, par ^ 1);
+                tma_store_wait_read<0>();                        // gv / gr tiles of this chunk (RH, KT space) have left
+            }
+            __syncwarp();
             bar_sync_all<B_T3>();                                // gk, gw tiles written; new bf16 G
             if (lane == 0) {
                 tma_store_3d(&map_gk, sm + OFF_GKT, h * 64, c * L, b);
@@ -240,6 +257,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 tma_store_commit();
             }
             __syncwarp();
+            if (c > 0) bar_arrive_all<B_RAW>();
         }
         if (lane == 0) tma_store_wait_all<0>();
     } else {

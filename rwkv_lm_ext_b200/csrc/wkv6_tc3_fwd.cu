@@ -136,7 +136,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         __syncwarp();
         bar_arrive_all<B_RAW>();
         bar_sync_all<B_PA>();
-        if (lane == 0) {
+        if (elect_one()) {
             tc_fence_after();
             issue_A();
             if (NC > 1) issue_rkw(1);
@@ -160,7 +160,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 bar_arrive_all<B_RAW>();
             }
             bar_sync_all<B_T1>();                                // P written, S decayed
-            if (lane == 0) {
+            if (elect_one()) {
                 mbar_wait(&ex.bar_v, par);
                 tma_store_wait_read<0>();                        // SB / YT may be rewritten once M2 is done
                 tc_fence_after();
@@ -185,7 +185,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             __syncwarp();
             if (more) {
                 bar_sync_all<B_PA>();                            // Kt / Rt of chunk c+1 written, its raw tiles consumed
-                if (lane == 0) {
+                if (elect_one()) {
                     tc_fence_after();
                     issue_A();                                   // queued behind M2 on the tensor pipe
                     if (c + 2 < NC) issue_rkw(c + 2);
