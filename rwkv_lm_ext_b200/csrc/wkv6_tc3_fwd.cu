@@ -148,12 +148,12 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             if (p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (blockIdx.x * NC) * 64, 0);
             tma_store_commit();
         }
+        if (lane == 0) mbar_wait(&ex.bar_a, 0);
+        __syncwarp();
+        bar_arrive_all<B_A>();
         for (int c = 0; c < NC; c++) {
             const uint32_t par = c & 1;
             const bool more = c + 1 < NC;
-            if (lane == 0) mbar_wait(&ex.bar_a, par);
-            __syncwarp();
-            bar_arrive_all<B_A>();
             if (more) {
                 if (lane == 0) mbar_wait(&ex.bar_rkw, par ^ 1);
                 __syncwarp();
@@ -161,13 +161,12 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             }
             bar_sync_all<B_T1>();                                // P written, S decayed
             if (elect_one()) {
-                mbar_wait(&ex.bar_v, par);
-                tma_store_wait_read<0>();                        // SB / YT may be rewritten once M2 is done
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 4; k++)                      // Y = Rh * S_in      (S tile is [i][j]: MN-major B)
                     mma_bf16_ss(tmem + TM_Y, smem_desc_sw128(rh + 32 * k, 8192, 1024),
                                 smem_desc_sw128(sb + 2048 * k, 8192, 1024), ID_KM, k > 0);
+                mbar_wait(&ex.bar_v, par);
 #pragma unroll
                 for (int k = 0; k < 4; k++)                      // Y += P * V
                     mma_bf16_ss(tmem + TM_Y, smem_desc_sw128(pp + 32 * k, 8192, 1024),
@@ -193,12 +192,18 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 __syncwarp();
             }
             if (lane == 0) {
-                mbar_wait(&ex.bar_m2, par);                      // V is free again
-                if (more) issue_v(c + 1);
+                mbar_wait(&ex.bar_m2, par);
+                tma_store_wait_read<0>();                        // SB / YT of the previous stores may be rewritten now
             }
             __syncwarp();
             bar_arrive_all<B_M2>();
-            if (more) bar_sync_all<B_PB>();
+            if (lane == 0 && more) issue_v(c + 1);               // V is free again
+            if (more) {
+                bar_sync_all<B_PB>();
+                if (lane == 0) mbar_wait(&ex.bar_a, par ^ 1);    // A^T of chunk c+1 ran right behind M2
+                __syncwarp();
+                bar_arrive_all<B_A>();
+            }
             bar_sync_all<B_T2>();                                // y tile and the new bf16 S written
             if (lane == 0) {
                 if (p.has_y) tma_store_3d(&map_y, sm + OFF_YT, h * 64, c * L, b);
