@@ -6,9 +6,10 @@
  *   - returns 0 on success, a negative WKV6_E* code otherwise (wkv6b200_last_error() has text);
  *   - is asynchronous: work is enqueued on `stream` (a cudaStream_t; NULL = legacy default
  *     stream, which is what the reference's bare <<<>>> launches use, cuda/wkv6_cuda.cu:233);
- *   - never allocates device memory: the caller owns every buffer, including the workspace
- *     (size from the matching *_workspace_bytes) -- the reference wrappers likewise pre-allocate all
- *     outputs with torch.empty (src/model.py:211,225-230).
+ *   - the caller owns every buffer, including the workspace (size from the matching
+ *     *_workspace_bytes) -- the reference wrappers likewise pre-allocate all outputs with
+ *     torch.empty (src/model.py:211,225-230).  The library itself only keeps one 4 MB per-device
+ *     ring of per-stream flags, plus the scratch noted at wkv6_forward.
  *
  * Layout contract (identical to the reference): r,k,v,w,y,gy,g* are [B,T,C] contiguous,
  * C = H*64 (head size is fixed at 64 like -D_N_=64, src/model.py:189); u is [H,64];
@@ -63,6 +64,11 @@ WKV6_API uint64_t    wkv6b200_launch_count(void);
  * r,k,v,u,y,gy,gr,gk,gv,gw,gu: bf16.  ew: fp32 [B,T,C] = -exp(w) (src/model.py:210).
  * gu: [B,C] per-batch partials (the wrapper sums over B, src/model.py:232).
  * gw[:,0] and gw[:,T-1] are exact zeros (cuda/wkv6_cuda.cu:201,226).
+ * Implementation note: the tensor-core kernels read raw bf16 logits, so these two entries first
+ * recover them (bf16(log(-ew)), exact when ew was built from bf16 logits as src/model.py:210 does);
+ * streams where that round trip is not exact are computed by the fp32 SIMT kernels from ew itself.
+ * wkv6_forward has no workspace argument in the reference, so it takes B*T*C*2 bytes of
+ * stream-ordered scratch (cudaMallocAsync, kept cached); wkv6_backward uses its workspace.
  * ------------------------------------------------------------------------------------------ */
 WKV6_API int wkv6_forward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
                  const float *ew, const void *u, void *y, void *stream);

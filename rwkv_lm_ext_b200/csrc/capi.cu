@@ -87,15 +87,68 @@ static int forward3(const Args &a) {
     s.stream_flags = flags;
     return simt_forward(s);
 }
+// the same call with the fp32 log-decay converted to raw bf16 logits (tensor-core kernels), exact SIMT
+// kernels on the original values for the streams where that conversion is not lossless
+static Args with_raw_w(const Args &a, void *w_raw) {
+    Args t = a;
+    t.w = w_raw;
+    t.w_kind = W_RAW_BF16;
+    return t;
+}
+static bool ew_convertible(const Args &a) {
+    return a.w_kind == W_LOG_F32 && tc3_forward_supported(with_raw_w(a, const_cast<void *>(a.w)));
+}
+static int forward3_ew(const Args &a) {
+    // the reference's entry has no workspace argument: stream-ordered scratch, kept cached in the pool
+    static bool pool_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !pool_set[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool_set[dev] = true;
+    }
+    const size_t nb = (size_t)a.B * a.H * sizeof(int);
+    int *flags = flag_slice((size_t)a.B * a.H);
+    if (!flags) { set_error("cannot get %zu bytes of flag scratch", nb); return WKV6_ECUDA; }
+    void *w_raw = nullptr;
+    WKV6_CUDA_CHECK(cudaMallocAsync(&w_raw, (size_t)a.B * a.T * a.H * 64 * 2, a.stream));
+    int rc = cudaMemsetAsync(flags, 0, nb, a.stream) == cudaSuccess ? WKV6_OK : WKV6_ECUDA;
+    if (rc == WKV6_OK) rc = ew_to_raw_bf16(a.B, a.T, a.H, (const float *)a.w, w_raw, flags, a.stream);
+    if (rc == WKV6_OK) rc = tc3_forward(with_raw_w(a, w_raw), nullptr, flags);
+    if (rc == WKV6_OK) {
+        Args s = a;
+        s.stream_flags = flags;
+        rc = simt_forward(s);
+    }
+    cudaFreeAsync(w_raw, a.stream);
+    return rc;
+}
 static int dispatch_forward(const Args &a) {
     const int impl = current_impl();
     if (impl != WKV6_IMPL_SIMT && tc3_forward_supported(a)) return forward3(a);
+    if (impl != WKV6_IMPL_SIMT && ew_convertible(a) && !a.saved) return forward3_ew(a);
     if (impl == WKV6_IMPL_TC) { set_error("tensor-core forward does not support this call"); return WKV6_EUNSUPPORTED; }
     return simt_forward(a);
 }
 static int dispatch_backward(const Args &a) {
     const int impl = current_impl();
     if (impl != WKV6_IMPL_SIMT && tc3_backward_supported(a)) return tc3_backward(a);
+    if (impl != WKV6_IMPL_SIMT && a.w_kind == W_LOG_F32 && !a.saved && tc3_backward_supported(with_raw_w(a, const_cast<void *>(a.w)))) {
+        // workspace: [tensor-core backward workspace][raw bf16 logits]
+        const size_t base = tc3_backward_workspace_bytes(a.B, a.T, a.H, false), need = base + (size_t)a.B * a.T * a.H * 64 * 2;
+        if (!a.workspace || a.workspace_bytes < need) { set_error("workspace too small: need %zu bytes", need); return WKV6_EWORKSPACE; }
+        void *w_raw = (uint8_t *)a.workspace + base;
+        int *flags = (int *)((uint8_t *)a.workspace + simt_backward_workspace_bytes(a.B, a.T, a.H));
+        if (cudaMemsetAsync(flags, 0, (size_t)a.B * a.H * sizeof(int), a.stream) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return WKV6_ECUDA; }
+        if (int rc = ew_to_raw_bf16(a.B, a.T, a.H, (const float *)a.w, w_raw, flags, a.stream)) return rc;
+        Args t = with_raw_w(a, w_raw);
+        t.workspace_bytes = base;
+        return tc3_backward(t, &a, true);
+    }
     if (impl == WKV6_IMPL_TC) { set_error("tensor-core backward does not support this call"); return WKV6_EUNSUPPORTED; }
     return simt_backward(a);
 }
@@ -155,7 +208,8 @@ int wkv6_forward_raww(int B, int T, int C, int H, const void *r, const void *k, 
 }
 size_t wkv6_backward_workspace_bytes(int B, int T, int C, int H) {
     (void)C;
-    return tc3_backward_workspace_bytes(B, T, H, false);   // superset: SIMT scratch + chunk-start states + flags
+    // superset: SIMT scratch + per-stream flags + chunk-start states (+ raw bf16 logits for the fp32-ew entries)
+    return tc3_backward_workspace_bytes(B, T, H, false) + (size_t)B * T * H * N * 2;
 }
 int wkv6_backward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
                   const float *ew, const void *u, const void *gy, void *gr, void *gk, void *gv,

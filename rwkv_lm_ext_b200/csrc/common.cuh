@@ -56,7 +56,11 @@ size_t simt_backward_workspace_bytes(int B, int T, int H);
 
 int tc3_forward(const Args &a, void *ckpt, int *hz_flags);   // role-uniform tcgen05 forward (per-stream hazard flags)
 bool tc3_forward_supported(const Args &a);
-int tc3_backward(const Args &a);                             // role-uniform tcgen05 backward (+ per-stream SIMT fallback)
+// role-uniform tcgen05 backward (+ per-stream SIMT fallback, which runs on `exact` when given: the
+// call as the caller made it, e.g. with the fp32 log-decay instead of the converted bf16 logits)
+int tc3_backward(const Args &a, const Args *exact = nullptr, bool flags_preset = false);
+// fp32 ew = -exp(w) -> raw bf16 logits; raises flags[b*H+h] where the round trip is not exact
+int ew_to_raw_bf16(int B, int T, int H, const float *ew, void *w_raw, int *flags, cudaStream_t stream);
 bool tc3_backward_supported(const Args &a);
 size_t tc3_saved_header(int B, int H);
 size_t tc3_saved_bytes(int B, int T, int H);

@@ -230,6 +230,36 @@ __global__ void __launch_bounds__(256) gn_gate_kernel(size_t ngroups, int C, flo
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// fp32 log-decay ew = -exp(w) (what the reference's wkv6 / wkv6_bi pybind entries receive,
+// src/model.py:210) -> the raw bf16 logits w the tensor-core kernels read.  The reference builds ew
+// from a bf16 w, so bf16(log(-ew)) recovers that w exactly; a stream in which some element does not
+// survive the round trip (ew was not made from bf16 logits) gets its flag raised and is computed by
+// the exact SIMT kernels from the original fp32 values.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ew_to_raw_kernel(size_t n8, int T, int H, const float *__restrict__ ew,
+                                                        bf16 *__restrict__ w, int *__restrict__ flags) {
+    const size_t C = (size_t)H * 64;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 a = reinterpret_cast<const float4 *>(ew)[2 * i], b = reinterpret_cast<const float4 *>(ew)[2 * i + 1];
+        const float x[8] = {-a.x, -a.y, -a.z, -a.w, -b.x, -b.y, -b.z, -b.w};
+        float f[8];
+        bool bad = false;
+#pragma unroll
+        for (int e = 0; e < 8; e++) {
+            const float lw = logf(x[e]);                    // x = 0 -> -inf (no decay), x < 0 -> NaN (flagged)
+            f[e] = lw;
+            const float back = expf(rb(lw));
+            bad |= !(fabsf(back - x[e]) <= 1e-5f * x[e]);
+        }
+        st8(w + 8 * i, pack8(f));
+        if (bad) {
+            const size_t e0 = 8 * i, bt = e0 / C, c = e0 % C;
+            flags[(bt / T) * H + c / 64] = 1;
+        }
+    }
+}
+
 int grid_for(size_t items, int block) {
     size_t g = (items + block - 1) / block;
     const size_t cap = 148 * 16;
@@ -237,6 +267,18 @@ int grid_for(size_t items, int block) {
 }
 
 }  // namespace
+}  // namespace wkv6
+
+// internal (not part of the C ABI)
+namespace wkv6 {
+int ew_to_raw_bf16(int B, int T, int H, const float *ew, void *w_raw, int *flags, cudaStream_t stream) {
+    const size_t n8 = (size_t)B * T * H * 64 / 8;
+    if (n8 == 0) return WKV6_OK;
+    ew_to_raw_kernel<<<grid_for(n8, 256), 256, 0, stream>>>(n8, T, H, ew, (bf16 *)w_raw, flags);
+    count_launch();
+    WKV6_CUDA_CHECK(cudaGetLastError());
+    return WKV6_OK;
+}
 }  // namespace wkv6
 
 using namespace wkv6;

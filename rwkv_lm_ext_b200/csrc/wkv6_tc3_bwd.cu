@@ -694,7 +694,7 @@ bool tc3_backward_supported(const Args &a) {
            tc::get_encode_fn() != nullptr;
 }
 
-int tc3_backward(const Args &a) {
+int tc3_backward(const Args &a, const Args *exact, bool flags_preset) {
     if (a.B * a.H == 0 || a.T == 0) return WKV6_OK;
     const int C = a.H * 64;
     const size_t NC = (size_t)(a.T + L - 1) / L;
@@ -709,7 +709,7 @@ int tc3_backward(const Args &a) {
     bf16 *ckpt = (bf16 *)(sv + tc3_saved_header(a.B, a.H));
     if (!a.saved) {
         // no training pair: recompute the chunk-start states (and the per-stream hazard flags) first
-        WKV6_CUDA_CHECK(cudaMemsetAsync(flags, 0, (size_t)a.B * a.H * sizeof(int), a.stream));
+        if (!flags_preset) WKV6_CUDA_CHECK(cudaMemsetAsync(flags, 0, (size_t)a.B * a.H * sizeof(int), a.stream));
         Args f = a;
         f.y = nullptr;
         f.sT = nullptr;
@@ -745,7 +745,8 @@ int tc3_backward(const Args &a) {
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
     // exact route for the flagged streams only
-    Args s = a;
+    Args s = exact ? *exact : a;
+    s.workspace = a.workspace;
     s.stream_flags = flags;
     s.workspace_bytes = simt_ws;
     return simt_backward(s);

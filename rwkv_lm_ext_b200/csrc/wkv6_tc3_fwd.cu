@@ -67,6 +67,7 @@ __global__ void __launch_bounds__(NTHREADS, 2)
 wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_ck, Params p) {
+    if (p.hz_flags[blockIdx.x] != 0) return;        // flagged before launch (inexact logit conversion): exact route
     extern __shared__ __align__(1024) uint8_t sm[];
     Extra &ex = *reinterpret_cast<Extra *>(sm + OFF_TILES_END);
     if ((smem_u32(sm) & 1023u) != 0) __trap();

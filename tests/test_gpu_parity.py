@@ -140,6 +140,42 @@ def test_native_raww_backward_without_saved_state(M):
         assert relrms(a, b_) < 1e-6
 
 
+def test_native_fp32_logdecay_entries(M, O):
+    """cuda/wkv6_op.cpp surface: w is fp32 -exp(w).  When it was made from bf16 logits (what the reference
+    does, src/model.py:210) the tensor-core kernels run on the recovered logits; a stream whose values do
+    not survive the bf16 round trip is computed exactly by the SIMT kernels -- both in one call."""
+    B, T, H = 2, 150, 2
+    C = H * 64
+    r, k, v, w, u, gy = make_inputs(B, T, H, seed=13, decay="model")
+    ew = -torch.exp(w.float())
+    ew[1, :, 64:] = -torch.exp(w.float()[1, :, 64:] + 0.001)       # stream (1,1): not representable as bf16 logits
+    dv = lambda t: t.to(DEV).contiguous()
+    rd, kd, vd, ud, gyd, ewd = map(dv, (r, k, v, u, gy, ew))
+    y = torch.empty_like(rd)
+    M.wkv6_cuda.forward(B, T, C, H, rd, kd, vd, ewd, ud, y)
+    gr, gk, gv, gw = (torch.empty_like(rd) for _ in range(4))
+    gu = torch.empty(B, C, device=DEV, dtype=torch.bfloat16)
+    M.wkv6_cuda.backward(B, T, C, H, rd, kd, vd, ewd, ud, gyd, gr, gk, gv, gw, gu)
+    # reference values: fp64 recurrence on the same fp32 log-decay
+    y_ref, _ = O.wkv6_recurrence(r, k, v, ew, u, w_is_log_decay=True)
+    assert_bf16_close(y, y_ref, "y (fp32 log-decay entry)")
+    M.set_impl("simt")
+    try:
+        y_s = torch.empty_like(rd)
+        M.wkv6_cuda.forward(B, T, C, H, rd, kd, vd, ewd, ud, y_s)
+        g_s = [torch.empty_like(rd) for _ in range(4)]
+        gu_s = torch.empty(B, C, device=DEV, dtype=torch.bfloat16)
+        M.wkv6_cuda.backward(B, T, C, H, rd, kd, vd, ewd, ud, gyd, *g_s, gu_s)
+    finally:
+        M.set_impl("auto")
+    # the inexact stream must be bit-identical to the SIMT result, the others within tensor-core rounding
+    assert torch.equal(y[1, :, 64:], y_s[1, :, 64:])
+    for a, b_ in zip((gr, gk, gv, gw), g_s):
+        assert torch.equal(a[1, :, 64:], b_[1, :, 64:])
+        assert relrms(a, b_) < 6e-3
+    assert relrms(gu, gu_s) < 6e-3
+
+
 def test_native_surface_matches_python_surface(M):
     """cuda/wkv6_op.cpp signatures (fp32 ew = -exp(w), caller-allocated outputs)."""
     B, T, H = 2, 70, 2
