@@ -1,0 +1,61 @@
+"""Achieved HBM bandwidth of the memory-bound kernels at the 1B6 shape (B=8, T=4096, C=2048), against the
+measured copy peak (MEASURED_PEAKS.json).  CUDA events on the launching stream, inputs larger than L2.
+usage: python profiles/bench_elementwise.py  ->  one JSON line per kernel"""
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import rwkv_lm_ext_b200 as M
+from rwkv_lm_ext_b200 import heads
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+try:
+    PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
+except Exception:
+    PEAK = 6650.0
+M.load()
+dev = "cuda"
+B, T, C, H = 8, 4096, 2048, 32
+g = torch.Generator(device=dev).manual_seed(0)
+x = torch.randn(B, T, C, device=dev, generator=g).bfloat16()
+y = torch.randn(B, T, C, device=dev, generator=g).bfloat16()
+gate = torch.randn(B, T, C, device=dev, generator=g).bfloat16()
+m = torch.randn(5, B, T, C, device=dev, generator=g).bfloat16()
+maa = torch.randn(5, C, device=dev, generator=g).bfloat16()
+maa_x = torch.randn(C, device=dev, generator=g).bfloat16()
+ln_w = torch.randn(C, device=dev, generator=g).bfloat16()
+ln_b = torch.randn(C, device=dev, generator=g).bfloat16()
+idx = torch.randint(2, 65536, (B * 64, 512), device=dev, generator=g)
+idx[:, -1] = 1
+xe = torch.randn(B * 64, 512, 1024, device=dev, generator=g).bfloat16()       # 512 passages x 512 tokens x 1024: 537 MB
+lens = torch.full((B * 64,), 511, device=dev, dtype=torch.int64)
+mask, rev = heads.create_mask_and_rev_idx(idx, 1, 0)
+E = B * T * C
+
+
+def timeit(fn, n=20):
+    for _ in range(3):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+cases = [
+    ("tmix_ddlerp_mix", lambda: heads.tmix_ddlerp_mix(x, maa, m), E * 22),          # x 2 + m 10 + out 10 B/elem
+    ("tmix_shift_lerp", lambda: heads.tmix_shift_lerp(x, maa_x), E * 4),
+    ("groupnorm_gate", lambda: heads.groupnorm_gate(y, gate, ln_w, ln_b, H, 64e-5), E * 6),
+    ("pooling weightedmean", lambda: heads.pooling(xe, lens, "weightedmean", "infer"), xe.numel() * 2),
+    ("reverse_x (gather_tokens)", lambda: heads.reverse_x(xe, rev), xe.numel() * 4),
+    ("create_mask_rev_idx", lambda: heads.create_mask_and_rev_idx(idx, 1, 0), idx.numel() * 20),   # idx 8 + mask 4 + rev 8
+    ("eos_index", lambda: heads.eos_index(idx, 1), idx.numel() * 8),
+]
+for name, fn, nbytes in cases:
+    ms = timeit(fn)
+    gbs = nbytes / (ms * 1e-3) / 1e9
+    print(json.dumps({"kernel": name, "ms": round(ms, 4), "algorithmic_bytes": nbytes, "achieved_gbs": round(gbs, 1),
+                      "peak_gbs": PEAK, "frac": round(gbs / PEAK, 3)}), flush=True)
