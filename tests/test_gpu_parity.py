@@ -355,6 +355,59 @@ def test_full_shape_properties(M):
     assert relrms(y, ys) < 6e-3
 
 
+def test_bidirectional_encoder_composition(M, O):
+    """BASELINE config 3 in miniature: padded passages -> mask / reverse index (our kernel) -> the
+    reverse-gather + WKV6 + un-reverse composition of the bidirectional models (src/model_bi.py:345-348,
+    src/model_ext.py:398-437) built from this library's pieces, against the oracle."""
+    B, T, H = 3, 200, 2
+    C = H * 64
+    g = torch.Generator().manual_seed(5)
+    idx = torch.randint(2, 1000, (B, T), generator=g)
+    lens = [200, 131, 64]
+    for b_, n in enumerate(lens):
+        idx[b_, n - 1] = 1            # embedding / eos id
+        idx[b_, n:] = 0               # padding
+    r, k, v, w, u, _ = make_inputs(B, T, H, seed=17, decay="model")
+    mask_ref = O.create_mask(idx, 1, 0)
+    rev_ref = O.reverse_x_idx(mask_ref, T)
+    y_ref = O.wkv6_bi_sum_forward(r, k, v, w, u, rev_ref)
+    mask, rev = M.create_mask_and_rev_idx(idx.to(DEV), 1, 0)
+    assert torch.equal(mask.cpu(), mask_ref.to(torch.int32)) and torch.equal(rev.cpu(), rev_ref)
+    dv = lambda t: t.to(DEV)
+    with torch.no_grad():
+        y1 = M.RUN_CUDA_RWKV6(B, T, C, H, dv(r), dv(k), dv(v), dv(w), dv(u))
+        y2 = M.RUN_CUDA_RWKV6(B, T, C, H, dv(r), M.reverse_x(dv(k), rev), M.reverse_x(dv(v), rev), dv(w), dv(u))
+        y = y1.float() + M.reverse_x(y2, rev).float()
+    assert_bf16_close(y, y_ref, "bidirectional sum")
+    pos = M.eos_index(idx.to(DEV), 1)
+    assert pos.cpu().tolist() == [n - 1 for n in lens]
+
+
+def test_infctx_long_context_chain_3b_shape(M):
+    """BASELINE config 5 in miniature: 3B shape (H = 40), a 16k-token context as 4 chunks of 4096 tokens
+    with the state carried in fp32 (extension) and in bf16 (the reference's container,
+    src/infctx_module.py:36-38), against one uninterrupted SIMT pass."""
+    B, T, H, NCH = 1, 4096, 40, 4
+    C = H * 64
+    r, k, v, w, u, _ = make_inputs(B, T * NCH, H, seed=21, decay="model", device=DEV)
+    with torch.no_grad():
+        M.set_impl("simt")
+        try:
+            s_ref = torch.zeros(B, H, 64, 64, device=DEV)
+            y_ref, s_ref = M.RUN_CUDA_RWKV6_STATE(B, T * NCH, C, H, r, k, v, w, u, s_ref)
+        finally:
+            M.set_impl("auto")
+        for dt, tol in ((torch.float32, STATE_RELRMS), (torch.bfloat16, 1e-2)):
+            s = torch.zeros(B, H, 64, 64, device=DEV, dtype=dt)
+            ys = []
+            for c in range(NCH):
+                sl = slice(c * T, (c + 1) * T)
+                yc, s = M.RUN_CUDA_RWKV6_STATE(B, T, C, H, *(t[:, sl].contiguous() for t in (r, k, v, w)), u, s)
+                ys.append(yc)
+            assert relrms(torch.cat(ys, 1), y_ref) < 6e-3, dt
+            assert relrms(s, s_ref) < tol, (dt, relrms(s, s_ref))
+
+
 def test_empty_inputs(M):
     z = torch.empty(0, 8, 64, device=DEV, dtype=torch.bfloat16)
     u = torch.zeros(1, 64, device=DEV, dtype=torch.bfloat16)
