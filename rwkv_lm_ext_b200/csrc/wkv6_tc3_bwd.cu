@@ -60,7 +60,7 @@ constexpr uint32_t TM_G = 0, TM_X0 = 64, TM_X1 = 128, TM_X2 = 192, TM_COLS = 256
 // An M = 64 accumulator only occupies lanes 0-15 of each 32-lane TMEM sub-partition; lanes 16-31 of the
 // same columns are used as per-thread scratch ("parking") for what the operand preparation hands to the
 // output stages, so that it does not sit in registers across the three MMA round trips.
-constexpr uint32_t PARK_L = 0, PARK_RK = 64, PARK_E = 128;
+constexpr uint32_t PARK_L = 0, PARK_RK = 64, PARK_E = 128, PARK_X = 192;
 
 struct Params {
     int B, T, H;
@@ -179,11 +179,11 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
 #pragma unroll
                 for (int k = 0; k < 4; k++)   // Bm[t,s] = GY V^T
                     mma_bf16_ss(tmem + TM_X0, smem_desc_sw128(gy + 32 * k, 8192, 1024), smem_desc_sw128(vv + 32 * k, 8192, 1024), ID_KK, k > 0);
+                mma_commit(&ex.bar_m1);          // T1 needs A^T and Bm only
                 mbar_wait(&ex.bar_sin, par);
 #pragma unroll
-                for (int k = 0; k < 4; k++)   // Drs[i,t] = S_in GY^T
+                for (int k = 0; k < 4; k++)   // Drs[i,t] = S_in GY^T                (first read in T2: covered by the M2 commit)
                     mma_bf16_ss(tmem + TM_X2, smem_desc_sw128(sin + 32 * k, 8192, 1024), smem_desc_sw128(gy + 32 * k, 8192, 1024), ID_KK, k > 0);
-                mma_commit(&ex.bar_m1);
                 ISTAMP(2);
                 mbar_wait(&ex.bar_m1, par);
                 ISTAMP(3);
@@ -191,26 +191,31 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             __syncwarp();
             bar_arrive_all<B_M1>();
             if (lane == 0 && c > 0) issue_rk(c - 1);             // raw r,k of this chunk were consumed by the preparation
-            bar_sync_all<B_T1>();                                // dA, P^T written; <S_in,G> taken; G decayed
+            bar_sync_all<B_T1A>();                               // dA written
+            if (elect_one()) {
+                tc_fence_after();
+#pragma unroll
+                for (int q = 0; q < 2; q++)   // Dr[i, t in q] = sum_{s in blocks <= q} Kt_q[s,i] dA[t,s]     (runs under the rest of T1)
+#pragma unroll
+                    for (int ks = 0; ks < 4; ks++)
+                        if (ks < 2 * q + 2)
+                            mma_bf16_ss(tmem + TM_X0 + 32 * q, smem_desc_sw128(kt + kt_ver(q) + 2048 * ks, 8192, 1024),
+                                        smem_desc_sw128(da + 4096 * q + 32 * ks, 8192, 1024), ID32_MK, ks > 0);
+            }
+            __syncwarp();
+            bar_sync_all<B_T1>();                                // P^T written; <S_in,G> taken; G decayed
             if (elect_one()) {
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 4; k++)   // gv[s,j] = P^T GY ...
-                    mma_bf16_ss(tmem + TM_X0, smem_desc_sw128(pt + 32 * k, 8192, 1024), smem_desc_sw128(gy + 2048 * k, 8192, 1024), ID_KM, k > 0);
+                    mma_bf16_ss(tmem + TM_X1, smem_desc_sw128(pt + 32 * k, 8192, 1024), smem_desc_sw128(gy + 2048 * k, 8192, 1024), ID_KM, k > 0);
 #pragma unroll
                 for (int k = 0; k < 4; k++)   // ... + Kh G
-                    mma_bf16_ss(tmem + TM_X0, smem_desc_sw128(kh + 32 * k, 8192, 1024), smem_desc_sw128(gb + 2048 * k, 8192, 1024), ID_KM, 1);
+                    mma_bf16_ss(tmem + TM_X1, smem_desc_sw128(kh + 32 * k, 8192, 1024), smem_desc_sw128(gb + 2048 * k, 8192, 1024), ID_KM, 1);
+                mma_commit(&ex.bar_m2);          // T2 needs gv, Dr, Drs
 #pragma unroll
-                for (int q = 0; q < 2; q++)   // Dr[i, t in q] = sum_{s in blocks <= q} Kt_q[s,i] dA[t,s]
-#pragma unroll
-                    for (int ks = 0; ks < 4; ks++)
-                        if (ks < 2 * q + 2)
-                            mma_bf16_ss(tmem + TM_X1 + 32 * q, smem_desc_sw128(kt + kt_ver(q) + 2048 * ks, 8192, 1024),
-                                        smem_desc_sw128(da + 4096 * q + 32 * ks, 8192, 1024), ID32_MK, ks > 0);
-#pragma unroll
-                for (int k = 0; k < 4; k++)   // G[i,j] += Rh^T GY
+                for (int k = 0; k < 4; k++)   // G[i,j] += Rh^T GY                    (first read in T3: covered by the M3 commit)
                     mma_bf16_ss(tmem + TM_G, smem_desc_sw128(rh + 2048 * k, 8192, 1024), smem_desc_sw128(gy + 2048 * k, 8192, 1024), ID_MM, 1);
-                mma_commit(&ex.bar_m2);
                 mbar_wait(&ex.bar_m2, par);
             }
             __syncwarp();
@@ -219,7 +224,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 issue_sin(c - 1);                                // S_in of this chunk: read by M1 and T1 only
                 issue_w(c - 1);                                  // the P^T tile (= W space) is dead
             }
-            bar_sync_all<B_T2>();                                // gv, gr tiles written; Dr, Drs consumed
+            bar_sync_all<B_T2A>();                               // Dr, Drs consumed (gr tile written, XA parked)
             asm volatile("fence.acq_rel.cta;" ::: "memory");
             ISTAMP(4);
             if (elect_one()) {
@@ -233,21 +238,24 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                                         smem_desc_sw128(da + 4096 * pb + 2048 * kk + 64 * pb, 8192, 1024), ID32_MM, kk > 0);
 #pragma unroll
                 for (int k = 0; k < 4; k++)   // Dks[i,s] = G_old V^T
-                    mma_bf16_ss(tmem + TM_X1, smem_desc_sw128(gb + 32 * k, 8192, 1024), smem_desc_sw128(vv + 32 * k, 8192, 1024), ID_KK, k > 0);
+                    mma_bf16_ss(tmem + TM_X2, smem_desc_sw128(gb + 32 * k, 8192, 1024), smem_desc_sw128(vv + 32 * k, 8192, 1024), ID_KK, k > 0);
                 mma_commit(&ex.bar_m3);
-                tma_store_3d(&map_gv, sm + OFF_GVT, h * 64, c * L, b);
-                tma_store_3d(&map_gr, sm + OFF_GRT, h * 64, c * L, b);
-                tma_store_commit();
                 ISTAMP(5);
                 mbar_wait(&ex.bar_m3, par);
                 ISTAMP(6);
             }
             __syncwarp();
             bar_arrive_all<B_M3>();
-            if (lane == 0 && c > 0) {                            // everything the next operand preparation needs, while T3 runs
-                mbar_wait(&ex.bar_rk, par ^ 1);
-                mbar_wait(&ex.bar_w, par ^ 1);
-                tma_store_wait_read<0>();                        // gv / gr tiles of this chunk (RH, KT space) have left
+            bar_sync_all<B_T2>();                                // gv tile written (under M3)
+            if (lane == 0) {
+                tma_store_3d(&map_gv, sm + OFF_GVT, h * 64, c * L, b);
+                tma_store_3d(&map_gr, sm + OFF_GRT, h * 64, c * L, b);
+                tma_store_commit();
+                if (c > 0) {                                     // everything the next operand preparation needs, while T3 runs
+                    mbar_wait(&ex.bar_rk, par ^ 1);
+                    mbar_wait(&ex.bar_w, par ^ 1);
+                    tma_store_wait_read<0>();                    // gv / gr tiles of this chunk (RH, KT space) have left
+                }
             }
             __syncwarp();
             bar_sync_all<B_T3>();                                // gk, gw tiles written; new bf16 G
@@ -462,6 +470,9 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 }
                 stsm_x4(sbase + OFF_DA + F.rc(hh), pk[0], pk[1], pk[2], pk[3]);
             }
+            fence_proxy_async();
+            tc_fence_before();
+            bar_arrive_all<B_T1A>();                     // Dr (into the Bm columns) can start while P^T and G are handled
             // ---- A^T[s rows][t cols] -> P^T[s][t] = A^T for t > s, diag = sum_i r u k
             tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X1 + 32 * ch), v);
             tmem_wait_ld();
@@ -517,16 +528,12 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             bar_sync_all<B_M2>();
             tc_fence_after();
             STAMP(4);
-            tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch), v);
-            tmem_wait_ld();
-            stsm_x4(sbase + OFF_GVT + F.rc(0), pack_frag(v, 0, 0), pack_frag(v, 1, 0), pack_frag(v, 2, 0), pack_frag(v, 3, 0));
-            stsm_x4(sbase + OFF_GVT + F.rc(1), pack_frag(v, 0, 1), pack_frag(v, 1, 1), pack_frag(v, 2, 1), pack_frag(v, 3, 1));
-            // per 8-token group: Dr, Drs -> gr (tile) and XA, which is parked in the Drs columns (TMEM) until T3
+            // per 8-token group: Dr, Drs -> gr (tile) and XA, which is parked in the shadow lanes until T3
 #pragma unroll
             for (int g = 0; g < 4; g++) {
                 uint32_t d4[4], s4[4], x4[4];
                 uint32_t pl[4], prk[4], pe[4];
-                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X1 + 32 * ch + 8 * g), d4);
+                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch + 8 * g), d4);
                 tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 8 * g), s4);
                 tmem_ld_frag1(tPark + PARK_L + 8 * g, pl);
                 tmem_ld_frag1(tPark + PARK_RK + 8 * g, prk);
@@ -547,12 +554,20 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     const float ub = u_h[hh] * bd2.x, ub1 = u_h[hh] * bd2.y;
                     stsm_x1_t(sbase + OFF_GRT + F.ti1(g, hh), pack2(fmaf(E0, dr0 + ds0, ub * k0), fmaf(E1, dr1 + ds1, ub1 * k1)));
                 }
-                tmem_st_frag1(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 8 * g), x4);
+                tmem_st_frag1(tPark + PARK_X + 8 * g, x4);
             }
             tmem_wait_st();
             fence_proxy_async();
             tc_fence_before();
             STAMP(5);
+            bar_arrive_all<B_T2A>();                     // Dk / Dks may overwrite the Dr / Drs columns
+            // ---- gv rows -> tile (runs while the tensor cores work on M3)
+            tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X1 + 32 * ch), v);
+            tmem_wait_ld();
+            stsm_x4(sbase + OFF_GVT + F.rc(0), pack_frag(v, 0, 0), pack_frag(v, 1, 0), pack_frag(v, 2, 0), pack_frag(v, 3, 0));
+            stsm_x4(sbase + OFF_GVT + F.rc(1), pack_frag(v, 0, 1), pack_frag(v, 1, 1), pack_frag(v, 2, 1), pack_frag(v, 3, 1));
+            fence_proxy_async();
+            tc_fence_before();
             bar_arrive_all<B_T2>();
 
             // ================================================================== T3: gk tile, gw tile, new bf16 G
@@ -566,8 +581,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             for (int g = 0; g < 4; g++) {
                 uint32_t d4[4], s4[4], x4[4];
                 tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch + 8 * g), d4);
-                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X1 + 32 * ch + 8 * g), s4);
-                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 8 * g), x4);
+                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 8 * g), s4);
+                tmem_ld_frag1(tPark + PARK_X + 8 * g, x4);
                 uint32_t pl[4], prk[4], pe[4];
                 tmem_ld_frag1(tPark + PARK_L + 8 * g, pl);
                 tmem_ld_frag1(tPark + PARK_RK + 8 * g, prk);
@@ -607,7 +622,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     runY[hh] += __shfl_sync(0xffffffffu, y, 3, 4);
                     runX[hh] += __shfl_sync(0xffffffffu, z, 3, 4);
                 }
-                tmem_st_frag1(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 8 * g), x4);
+                tmem_st_frag1(tPark + PARK_X + 8 * g, x4);
             }
             if (q == 0) {
 #pragma unroll
@@ -634,7 +649,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             tmem_wait_st();
             named_bar_sync<B_SCAN, CTHREADS>();          // token-half totals of both scans are in shared memory
             uint32_t lp[16];
-            tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch), v);
+            tmem_ld_frag(tPark + PARK_X, v);
             tmem_ld_frag(tPark + PARK_L, lp);
             tmem_wait_ld();
 #pragma unroll
