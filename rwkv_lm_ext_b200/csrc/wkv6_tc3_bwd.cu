@@ -50,7 +50,7 @@ struct Extra {
     float pdu[4][64];         // per channel-quarter partial sums of r u k, per token
     float bd[64];             // Bm[t,t]
     float q0p[2][64];         // <S_in, G>_i, partial over each half of j
-    float htY[2][64], htX[2][64];   // per token-half totals of Be and of X = Ae + Ai - Bi, per channel
+    float htY[2][64], htX[2][64];   // per token-half totals of D = Be - X and of X = Ae + Ai - Bi, per channel
     float gu_s[64];
     uint64_t bar_rk, bar_w, bar_vg, bar_sin, bar_m1, bar_m2, bar_m3;
     uint32_t tmem_base;
@@ -576,7 +576,9 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             STAMP(6);
             // per 8-token group: Dk, Dks, XA -> gk (tile), running scans; the part of gl that does not need the
             // other token half replaces XA in TMEM
-            float runY[2] = {0.f, 0.f}, runX[2] = {0.f, 0.f};
+            // With D = Be - X:  gl_t = 2^Lam q0 + sum_all X + sum_{s<t} D_s - XA_t   (X_t + Bi_t = XA_t), so one
+            // exclusive prefix scan of D plus the totals of X are enough.
+            float runD[2] = {0.f, 0.f}, runX[2] = {0.f, 0.f};
 #pragma unroll
             for (int g = 0; g < 4; g++) {
                 uint32_t d4[4], s4[4], x4[4];
@@ -598,36 +600,33 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     const float ds0 = elr[hh] * __uint_as_float(s4[2 * hh]), ds1 = elr[hh] * __uint_as_float(s4[2 * hh + 1]);
                     const float kf0 = k0 * F0, kf1 = k1 * F1;
                     const uint32_t ktp = pack2(kf0, kf1);                 // Kt_own exactly as the MMAs saw it
-                    const float bi0 = bf_lo(ktp) * dk0, bi1 = bf_hi(ktp) * dk1;
-                    const float be0 = kf0 * ds0, be1 = kf1 * ds1;
-                    const float x0 = __uint_as_float(x4[2 * hh]) - bi0, x1 = __uint_as_float(x4[2 * hh + 1]) - bi1;
-                    const float ub = u_h[hh] * bd2.x, ub1 = u_h[hh] * bd2.y;
-                    stsm_x1_t(sbase + OFF_GKT + F.ti1(g, hh), pack2(fmaf(F0, dk0 + ds0, ub * r0), fmaf(F1, dk1 + ds1, ub1 * r1)));
-                    gu_acc[hh] = fmaf(r0 * k0, bd2.x, fmaf(r1 * k1, bd2.y, gu_acc[hh]));
-                    // inclusive scans over the 4 lanes of the group: y = Be, z = X
-                    const float py = be0 + be1, px = x0 + x1;
-                    float y = py, z = px, tmp;
+                    const float xa0 = __uint_as_float(x4[2 * hh]), xa1 = __uint_as_float(x4[2 * hh + 1]);
+                    const float x0 = fmaf(-bf_lo(ktp), dk0, xa0), x1 = fmaf(-bf_hi(ktp), dk1, xa1);      // X = XA - Bi
+                    const float d0 = fmaf(kf0, ds0, -x0), d1 = fmaf(kf1, ds1, -x1);                      // D = Be - X
+                    const float br0 = bd2.x * r0, br1 = bd2.y * r1;
+                    stsm_x1_t(sbase + OFF_GKT + F.ti1(g, hh), pack2(fmaf(F0, dk0 + ds0, u_h[hh] * br0), fmaf(F1, dk1 + ds1, u_h[hh] * br1)));
+                    gu_acc[hh] = fmaf(br0, k0, fmaf(br1, k1, gu_acc[hh]));
+                    // exclusive prefix of D over the 4 lanes of the group; total of X
+                    const float pd = d0 + d1;
+                    float y = pd, z = x0 + x1, tmp;
                     tmp = __shfl_up_sync(0xffffffffu, y, 1, 4);
                     if (q >= 1) y += tmp;
-                    tmp = __shfl_up_sync(0xffffffffu, z, 1, 4);
-                    if (q >= 1) z += tmp;
+                    z += __shfl_xor_sync(0xffffffffu, z, 1);
                     tmp = __shfl_up_sync(0xffffffffu, y, 2, 4);
                     if (q >= 2) y += tmp;
-                    tmp = __shfl_up_sync(0xffffffffu, z, 2, 4);
-                    if (q >= 2) z += tmp;
-                    // exclusive prefix of Be minus inclusive prefix of X minus Bi_t (the suffix of X is total - inclusive)
-                    const float pe = runY[hh] + (y - py), xi = runX[hh] + (z - px) + x0;
-                    x4[2 * hh] = __float_as_uint(pe - bi0 - xi);
-                    x4[2 * hh + 1] = __float_as_uint(pe + be0 - bi1 - (xi + x1));
-                    runY[hh] += __shfl_sync(0xffffffffu, y, 3, 4);
-                    runX[hh] += __shfl_sync(0xffffffffu, z, 3, 4);
+                    z += __shfl_xor_sync(0xffffffffu, z, 2);
+                    const float ex0 = runD[hh] + (y - pd);
+                    x4[2 * hh] = __float_as_uint(ex0 - xa0);
+                    x4[2 * hh + 1] = __float_as_uint(ex0 + d0 - xa1);
+                    runD[hh] += __shfl_sync(0xffffffffu, y, 3, 4);
+                    runX[hh] += z;
                 }
                 tmem_st_frag1(tPark + PARK_X + 8 * g, x4);
             }
             if (q == 0) {
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++) {
-                    ex.htY[ch][F.row(hh)] = runY[hh];
+                    ex.htY[ch][F.row(hh)] = runD[hh];
                     ex.htX[ch][F.row(hh)] = runX[hh];
                 }
             }
@@ -655,8 +654,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
                 const int i = F.row(hh);
-                // 2^Lam <S_in,G> + X over my half (suffix = total - inclusive) + what the other half contributes
-                const float base = (ex.q0p[0][i] + ex.q0p[1][i]) * elam[hh] + runX[hh] + (ch ? ex.htY[0][i] : ex.htX[1][i]);
+                // 2^Lam <S_in,G> + total X of both halves + D of the earlier half
+                const float base = (ex.q0p[0][i] + ex.q0p[1][i]) * elam[hh] + runX[hh] + (ch ? ex.htY[0][i] + ex.htX[0][i] : ex.htX[1][i]);
                 uint32_t gwp[4];
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
