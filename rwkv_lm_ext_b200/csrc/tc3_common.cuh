@@ -23,6 +23,7 @@ typedef __nv_bfloat16 bf16;
 constexpr int L = 64;
 constexpr int CWARPS = 8, CTHREADS = 256, NTHREADS = CTHREADS + 32;
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
+constexpr float LOG2_LOG2E = 0.5287663729448977f;   // log2(log2(e)): exp(w) * log2(e) = 2^(w log2(e) + log2(log2(e)))
 constexpr float HAZARD2 = 60.0f * LOG2E;   // log2 units per aligned 16-token span
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {

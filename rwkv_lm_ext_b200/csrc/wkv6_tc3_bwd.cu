@@ -309,8 +309,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 for (int hh = 0; hh < 2; hh++)
 #pragma unroll
                     for (int g = 0; g < 4; g++) {
-                        float l0 = -fast_ex2(bf_lo(wp[hh][g]) * LOG2E) * LOG2E;
-                        float l1 = -fast_ex2(bf_hi(wp[hh][g]) * LOG2E) * LOG2E;
+                        float l0 = -fast_ex2(fmaf(bf_lo(wp[hh][g]), LOG2E, LOG2_LOG2E));   // -exp(w) * log2(e)
+                        float l1 = -fast_ex2(fmaf(bf_hi(wp[hh][g]), LOG2E, LOG2_LOG2E));
                         if (nv < L) {                                   // ragged last chunk: no decay on the padded rows
                             const int t0 = F.col(g, 0);
                             if (t0 >= nv) l0 = 0.f;
