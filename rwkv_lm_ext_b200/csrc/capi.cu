@@ -98,8 +98,9 @@ static Args with_raw_w(const Args &a, void *w_raw) {
 static bool ew_convertible(const Args &a) {
     return a.w_kind == W_LOG_F32 && tc3_forward_supported(with_raw_w(a, const_cast<void *>(a.w)));
 }
-static int forward3_ew(const Args &a) {
-    // the reference's entry has no workspace argument: stream-ordered scratch, kept cached in the pool
+// stream-ordered scratch (cudaMallocAsync) stays cached in the device's default pool instead of going
+// back to the OS at every synchronisation
+static void ensure_pool_keeps_memory() {
     static bool pool_set[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -111,6 +112,10 @@ static int forward3_ew(const Args &a) {
         }
         pool_set[dev] = true;
     }
+}
+static int forward3_ew(const Args &a) {
+    // the reference's entry has no workspace argument: stream-ordered scratch, kept cached in the pool
+    ensure_pool_keeps_memory();
     const size_t nb = (size_t)a.B * a.H * sizeof(int);
     int *flags = flag_slice((size_t)a.B * a.H);
     if (!flags) { set_error("cannot get %zu bytes of flag scratch", nb); return WKV6_ECUDA; }
@@ -131,6 +136,14 @@ static int dispatch_forward(const Args &a) {
     const int impl = current_impl();
     if (impl != WKV6_IMPL_SIMT && tc3_forward_supported(a)) return forward3(a);
     if (impl != WKV6_IMPL_SIMT && ew_convertible(a) && !a.saved) return forward3_ew(a);
+    if (impl != WKV6_IMPL_SIMT && bi_forward_tc_supported(a) && !a.saved) {
+        ensure_pool_keeps_memory();
+        const size_t nb = (size_t)a.B * a.H * sizeof(int);
+        int *flags = flag_slice((size_t)a.B * a.H);
+        if (!flags) { set_error("cannot get %zu bytes of flag scratch", nb); return WKV6_ECUDA; }
+        WKV6_CUDA_CHECK(cudaMemsetAsync(flags, 0, nb, a.stream));
+        return bi_forward_tc(a, flags);
+    }
     if (impl == WKV6_IMPL_TC) { set_error("tensor-core forward does not support this call"); return WKV6_EUNSUPPORTED; }
     return simt_forward(a);
 }

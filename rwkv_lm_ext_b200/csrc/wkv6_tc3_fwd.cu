@@ -116,7 +116,8 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         constexpr uint32_t ID32_KK = idesc_bf16(64, 32, 0, 0);
         constexpr uint32_t ID_KM = idesc_bf16(64, 64, 0, 1);
         constexpr uint32_t ID_MM = idesc_bf16(64, 64, 1, 1);
-        auto issue_A = [&]() {                               // A^T[s, t in q] = Kt_q Rt_own^T
+        auto issue_A = [&]() {                               // A^T[s, t in q] = Kt_q Rt_own^T   (not in a state-only pass)
+            if (p.has_y)
 #pragma unroll
             for (int qq = 0; qq < 2; qq++)
 #pragma unroll
@@ -163,11 +164,13 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             bar_sync_all<B_T1>();                                // P written, S decayed
             if (elect_one()) {
                 tc_fence_after();
+                if (p.has_y)
 #pragma unroll
                 for (int k = 0; k < 4; k++)                      // Y = Rh * S_in      (S tile is [i][j]: MN-major B)
                     mma_bf16_ss(tmem + TM_Y, smem_desc_sw128(rh + 32 * k, 8192, 1024),
                                 smem_desc_sw128(sb + 2048 * k, 8192, 1024), ID_KM, k > 0);
                 mbar_wait(&ex.bar_v, par);
+                if (p.has_y)
 #pragma unroll
                 for (int k = 0; k < 4; k++)                      // Y += P * V
                     mma_bf16_ss(tmem + TM_Y, smem_desc_sw128(pp + 32 * k, 8192, 1024),
@@ -389,6 +392,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             // ================================================================== T1: A^T -> P, decay S
             bar_sync_all<B_A>();
             tc_fence_after();
+            if (p.has_y) {
             tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_A + 32 * ch), v);
             tmem_wait_ld();
 #pragma unroll
@@ -410,6 +414,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     }
                 }
                 stsm_x4_t(sbase + OFF_P + F.ti(hh), pk[0], pk[1], pk[2], pk[3]);       // P[t][s]
+            }
             }
             tmem_ld_frag(tS, v);
             tmem_wait_ld();

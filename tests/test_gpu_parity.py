@@ -276,10 +276,12 @@ def test_rwkv6_inference_op(M, O, dtype):
 # ---------------------------------------------------------------------------------------------
 # bidirectional op
 # ---------------------------------------------------------------------------------------------
-def test_wkv6_bi_vs_oracle(M, O):
-    B, T, H = 4, 64, 2
+@pytest.mark.parametrize("decay,T", [("randn", 64), ("model", 64), ("model", 200)])
+def test_wkv6_bi_vs_oracle(M, O, decay, T):
+    """randn decays take the exact SIMT route per stream, model-like ones the two tensor-core passes."""
+    B, H = 4, 2
     C = H * 64
-    r, k, v, w, u, gy = make_inputs(B, T, H, seed=21, decay="randn")
+    r, k, v, w, u, gy = make_inputs(B, T, H, seed=21, decay=decay)
     mask = torch.ones(B, T, dtype=torch.int32)
     mask[0, 60:] = 0          # cuda/wkv6_bi.py:66-67 smoke masks
     mask[1, 40:] = 0
@@ -290,6 +292,11 @@ def test_wkv6_bi_vs_oracle(M, O):
     y.backward(gy.to(DEV))
     assert_bf16_close(y, ref["y"], "bi y")
     assert y[0, 61:].abs().max().item() == 0.0 and y[1, 41:].abs().max().item() == 0.0
+    # native entry (fp32 log-decay, cuda/wkv6_bi_op.cpp:8-14) gives the same forward
+    y_n = torch.empty_like(y)
+    M.wkv6_bi_cuda.forward(B, T, C, H, mask.to(DEV), *(t.detach() for t in leaves[:3]),
+                           (-torch.exp(leaves[3].detach().float())).contiguous(), leaves[4].detach(), y_n)
+    assert relrms(y_n, y.detach()) < 1e-6
     for t, key in zip(leaves, ("gr", "gk", "gv", "gw", "gu")):
         assert_bf16_close(t.grad, ref[key], f"bi {key}")
 
