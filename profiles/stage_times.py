@@ -14,7 +14,7 @@ fn = lib.wkv6b200_debug_stamps
 fn.argtypes = [ctypes.c_void_p]
 r, k, v, w, u, gy = make_inputs(B, T, H, seed=0, decay="model", device="cuda")
 NC = T // 64
-buf = torch.zeros(2, B * H, NC, 8, dtype=torch.int64, device="cuda")
+buf = torch.zeros(B * H, NC, 8, dtype=torch.int64, device="cuda")
 for it in range(3):
     leaves = [t.detach().requires_grad_(True) for t in (r, k, v, w, u)]
     y = M.RUN_CUDA_RWKV6(B, T, H * 64, H, *leaves)
@@ -23,9 +23,8 @@ for it in range(3):
     y.backward(gy)
     torch.cuda.synchronize()
 fn(None)
-s = buf[0].cpu().double()
-si = buf[1].cpu().double()
-names = ["P", "wait M1", "T1", "wait M2", "T2", "wait M3", "T3", "to next P"]
+s = buf.cpu().double()
+names = ["P", "wait Bm", "T1 (a+b)", "wait Dr", "T2a", "T2b + wait M3", "T3", "to next P"]
 d = torch.stack([s[:, :, 1] - s[:, :, 0], s[:, :, 2] - s[:, :, 1], s[:, :, 3] - s[:, :, 2], s[:, :, 4] - s[:, :, 3],
                  s[:, :, 5] - s[:, :, 4], s[:, :, 6] - s[:, :, 5], s[:, :, 7] - s[:, :, 6]], -1)[:, 2:-2]
 nxt = (s[:, 1:, 0] - s[:, :-1, 7])[:, 2:-2]
@@ -36,11 +35,3 @@ print(f"  {names[-1]:10s} {nxt.mean():8.0f}   (min {nxt.min():6.0f}  max {nxt.ma
 per_chunk = (s[:, 1:, 0] - s[:, :-1, 0])[:, 2:-2]
 print(f"  chunk period {per_chunk.mean():8.0f}")
 
-# issuer warp: M1 = [PREP wake, operands landed, MMAs issued + commit, commit observed]; M3 = [T2 wake, issued, observed]
-di = torch.stack([si[:, :, 1] - si[:, :, 0], si[:, :, 2] - si[:, :, 1], si[:, :, 3] - si[:, :, 2],
-                  si[:, :, 5] - si[:, :, 4], si[:, :, 6] - si[:, :, 5]], -1)[:, 2:-2]
-for i, n in enumerate(["M1: wait TMA (v,gy,S_in)", "M1: issue 16 MMAs", "M1: commit -> observed", "M3: stores + issue 10 MMAs", "M3: commit -> observed"]):
-    print(f"  issuer {n:28s} {di[..., i].mean():8.0f}   (min {di[..., i].min():6.0f}  max {di[..., i].max():7.0f})")
-# compute side: PREP arrive (stamp 1) -> issuer wake (istamp 0); issuer observed (istamp 3) -> compute resumes (stamp 2)
-print(f"  hop compute->issuer (B_PREP) {(si[:, :, 0] - s[:, :, 1])[:, 2:-2].mean():8.0f}")
-print(f"  hop issuer->compute (B_M1)   {(s[:, :, 2] - si[:, :, 3])[:, 2:-2].mean():8.0f}")

@@ -84,7 +84,7 @@ struct Frag {
 // (producer: bar.arrive, consumer: bar.sync, 288 threads): nobody spins.  Only lane 0 of the issuer
 // warp ever polls an mbarrier (TMA / tcgen05.commit completion); a compute warp spinning on
 // try_wait would take issue slots from the co-resident CTA that is doing useful work.
-enum : int { B_SCAN = 1, B_RAW, B_PREP, B_M1, B_T1, B_M2, B_T2, B_M3, B_T3, B_T1A, B_T2A };
+enum : int { B_SCAN = 1, B_RAW, B_PREP, B_M1, B_T1, B_M2, B_T2, B_M3, B_T3, B_T1A, B_T2A, B_BM, B_DR, B_FREE };
 template <int ID>
 __device__ __forceinline__ void bar_arrive_all() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(NTHREADS) : "memory"); }
 template <int ID>

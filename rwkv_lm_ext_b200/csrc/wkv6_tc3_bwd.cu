@@ -41,7 +41,7 @@ constexpr uint32_t OFF_KT = 57344;     // version 1 (rows 0..63) at +0, version 
 constexpr uint32_t OFF_RP = 69632;     // version 0 (rows 0..63) at +0, version 1 (rows 32..63, stored from row 0) at +8192
 constexpr uint32_t OFF_RH = 81920, OFF_KH = 90112, OFF_DA = 98304, OFF_TILES_END = 106496;
 // output tiles reuse operand tiles that are dead by the time they are written
-constexpr uint32_t OFF_GVT = OFF_RH, OFF_GRT = OFF_KT, OFF_GKT = OFF_DA, OFF_GWT = OFF_GY;
+constexpr uint32_t OFF_GVT = OFF_RH, OFF_GRT = OFF_KT, OFF_GKT = OFF_DA, OFF_GWT = OFF_RP;
 __host__ __device__ constexpr uint32_t kt_ver(int q) { return q ? 0u : 8192u; }
 __host__ __device__ constexpr uint32_t rp_ver(int p) { return p ? 8192u : 0u; }
 
@@ -52,7 +52,7 @@ struct Extra {
     float q0p[2][64];         // <S_in, G>_i, partial over each half of j
     float htY[2][64], htX[2][64];   // per token-half totals of D = Be - X and of X = Ae + Ai - Bi, per channel
     float gu_s[64];
-    uint64_t bar_rk, bar_w, bar_vg, bar_sin, bar_m1, bar_m2, bar_m3;
+    uint64_t bar_rk, bar_w, bar_vg, bar_sin, bar_bm, bar_m1, bar_dr, bar_m2, bar_m3;
     uint32_t tmem_base;
 };
 constexpr uint32_t SMEM_BYTES = OFF_TILES_END + sizeof(Extra);
@@ -97,7 +97,9 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         mbar_init(&ex.bar_w, 1);
         mbar_init(&ex.bar_vg, 1);
         mbar_init(&ex.bar_sin, 1);
+        mbar_init(&ex.bar_bm, 1);
         mbar_init(&ex.bar_m1, 1);
+        mbar_init(&ex.bar_dr, 1);
         mbar_init(&ex.bar_m2, 1);
         mbar_init(&ex.bar_m3, 1);
         fence_barrier_init();
@@ -149,7 +151,6 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         constexpr uint32_t ID_KK = idesc_bf16(64, 64, 0, 0), ID_KM = idesc_bf16(64, 64, 0, 1), ID_MM = idesc_bf16(64, 64, 1, 1);
         constexpr uint32_t ID32_KK = idesc_bf16(64, 32, 0, 0), ID32_MK = idesc_bf16(64, 32, 1, 0), ID32_MM = idesc_bf16(64, 32, 1, 1);
         bar_sync_all<B_T3>();                                    // G = 0 written (TMEM + bf16 copy)
-#define ISTAMP(k) do { if (p.dbg && lane == 0) p.dbg[(size_t)gridDim.x * NC * 8 + ((size_t)blockIdx.x * NC + it) * 8 + (k)] = clock64(); } while (0)
         if (lane == 0) {
             mbar_wait(&ex.bar_rk, 0);
             mbar_wait(&ex.bar_w, 0);
@@ -159,60 +160,65 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         for (int it = 0; it < NC; it++) {
             const int c = NC - 1 - it;
             const uint32_t par = it & 1;
-            if (lane == 0 && it > 0) {
-                tma_store_wait_read<0>();                        // gk / gw tiles (DA, GY space)
-                issue_vg(c);
+            if (lane == 0 && it > 0) tma_store_wait_read<0>();   // every output tile of the previous chunk has left shared memory
+            __syncwarp();
+            bar_arrive_all<B_FREE>();                            // ... so the preparation may overwrite RH, KT, RP (and T1 DA)
+            // ---- products that need nothing from the operand preparation run under it
+            if (elect_one()) {
+                mbar_wait(&ex.bar_vg, par);
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 4; k++)   // Bm[t,s] = GY V^T
+                    mma_bf16_ss(tmem + TM_X0, smem_desc_sw128(gy + 32 * k, 8192, 1024), smem_desc_sw128(vv + 32 * k, 8192, 1024), ID_KK, k > 0);
+                mbar_wait(&ex.bar_sin, par);
+#pragma unroll
+                for (int k = 0; k < 4; k++)   // Drs[i,t] = S_in GY^T
+                    mma_bf16_ss(tmem + TM_X2, smem_desc_sw128(sin + 32 * k, 8192, 1024), smem_desc_sw128(gy + 32 * k, 8192, 1024), ID_KK, k > 0);
+                mma_commit(&ex.bar_bm);
+                mbar_wait(&ex.bar_bm, par);
             }
+            __syncwarp();
+            bar_arrive_all<B_BM>();
             bar_sync_all<B_PREP>();                              // operands written, raw r,k,w consumed
-            asm volatile("fence.acq_rel.cta;" ::: "memory");
-            ISTAMP(0);
             if (elect_one()) {
                 tc_fence_after();
 #pragma unroll
-                for (int q = 0; q < 2; q++)   // A^T[s, t in q] = Kt_q Rt_own^T     (needs only what the compute warps wrote)
+                for (int q = 0; q < 2; q++)   // A^T[s, t in q] = Kt_q Rt_own^T            (runs under T1a)
 #pragma unroll
                     for (int k = 0; k < 4; k++)
                         mma_bf16_ss(tmem + TM_X1 + 32 * q, smem_desc_sw128(kt + kt_ver(q) + 32 * k, 8192, 1024),
                                     smem_desc_sw128(rp + rp_ver(q) + 32 * k, 8192, 1024), ID32_KK, k > 0);
-                mbar_wait(&ex.bar_vg, par);
-                ISTAMP(1);
-#pragma unroll
-                for (int k = 0; k < 4; k++)   // Bm[t,s] = GY V^T
-                    mma_bf16_ss(tmem + TM_X0, smem_desc_sw128(gy + 32 * k, 8192, 1024), smem_desc_sw128(vv + 32 * k, 8192, 1024), ID_KK, k > 0);
-                mma_commit(&ex.bar_m1);          // T1 needs A^T and Bm only
-                mbar_wait(&ex.bar_sin, par);
-#pragma unroll
-                for (int k = 0; k < 4; k++)   // Drs[i,t] = S_in GY^T                (first read in T2: covered by the M2 commit)
-                    mma_bf16_ss(tmem + TM_X2, smem_desc_sw128(sin + 32 * k, 8192, 1024), smem_desc_sw128(gy + 32 * k, 8192, 1024), ID_KK, k > 0);
-                ISTAMP(2);
+                mma_commit(&ex.bar_m1);
                 mbar_wait(&ex.bar_m1, par);
-                ISTAMP(3);
             }
             __syncwarp();
             bar_arrive_all<B_M1>();
             if (lane == 0 && c > 0) issue_rk(c - 1);             // raw r,k of this chunk were consumed by the preparation
-            bar_sync_all<B_T1A>();                               // dA written
+            bar_sync_all<B_T1A>();                               // dA written, Bm consumed
             if (elect_one()) {
                 tc_fence_after();
 #pragma unroll
-                for (int q = 0; q < 2; q++)   // Dr[i, t in q] = sum_{s in blocks <= q} Kt_q[s,i] dA[t,s]     (runs under the rest of T1)
+                for (int q = 0; q < 2; q++)   // Dr[i, t in q] = sum_{s in blocks <= q} Kt_q[s,i] dA[t,s]     (runs under T1b)
 #pragma unroll
                     for (int ks = 0; ks < 4; ks++)
                         if (ks < 2 * q + 2)
                             mma_bf16_ss(tmem + TM_X0 + 32 * q, smem_desc_sw128(kt + kt_ver(q) + 2048 * ks, 8192, 1024),
                                         smem_desc_sw128(da + 4096 * q + 32 * ks, 8192, 1024), ID32_MK, ks > 0);
+                mma_commit(&ex.bar_dr);
+                mbar_wait(&ex.bar_dr, par);
             }
             __syncwarp();
+            bar_arrive_all<B_DR>();
             bar_sync_all<B_T1>();                                // P^T written; <S_in,G> taken; G decayed
             if (elect_one()) {
                 tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < 4; k++)   // gv[s,j] = P^T GY ...
+                for (int k = 0; k < 4; k++)   // gv[s,j] = P^T GY ...                               (runs under T2a)
                     mma_bf16_ss(tmem + TM_X1, smem_desc_sw128(pt + 32 * k, 8192, 1024), smem_desc_sw128(gy + 2048 * k, 8192, 1024), ID_KM, k > 0);
 #pragma unroll
                 for (int k = 0; k < 4; k++)   // ... + Kh G
                     mma_bf16_ss(tmem + TM_X1, smem_desc_sw128(kh + 32 * k, 8192, 1024), smem_desc_sw128(gb + 2048 * k, 8192, 1024), ID_KM, 1);
-                mma_commit(&ex.bar_m2);          // T2 needs gv, Dr, Drs
+                mma_commit(&ex.bar_m2);
 #pragma unroll
                 for (int k = 0; k < 4; k++)   // G[i,j] += Rh^T GY                    (first read in T3: covered by the M3 commit)
                     mma_bf16_ss(tmem + TM_G, smem_desc_sw128(rh + 2048 * k, 8192, 1024), smem_desc_sw128(gy + 2048 * k, 8192, 1024), ID_MM, 1);
@@ -221,16 +227,14 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             __syncwarp();
             bar_arrive_all<B_M2>();
             if (lane == 0 && c > 0) {
-                issue_sin(c - 1);                                // S_in of this chunk: read by M1 and T1 only
+                issue_sin(c - 1);                                // S_in of this chunk: read by Drs and T1 only
                 issue_w(c - 1);                                  // the P^T tile (= W space) is dead
             }
             bar_sync_all<B_T2A>();                               // Dr, Drs consumed (gr tile written, XA parked)
-            asm volatile("fence.acq_rel.cta;" ::: "memory");
-            ISTAMP(4);
             if (elect_one()) {
                 tc_fence_after();
 #pragma unroll
-                for (int pb = 0; pb < 2; pb++)   // Dk[i, s in p] = sum_{t >= 32p} Rp_p[t,i] dA[t,s]   (dA read MN-major)
+                for (int pb = 0; pb < 2; pb++)   // Dk[i, s in p] = sum_{t >= 32p} Rp_p[t,i] dA[t,s]   (dA read MN-major; under T2b)
 #pragma unroll
                     for (int kk = 0; kk < 4; kk++)
                         if (kk < 4 - 2 * pb)
@@ -240,9 +244,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 for (int k = 0; k < 4; k++)   // Dks[i,s] = G_old V^T
                     mma_bf16_ss(tmem + TM_X2, smem_desc_sw128(gb + 32 * k, 8192, 1024), smem_desc_sw128(vv + 32 * k, 8192, 1024), ID_KK, k > 0);
                 mma_commit(&ex.bar_m3);
-                ISTAMP(5);
                 mbar_wait(&ex.bar_m3, par);
-                ISTAMP(6);
+                if (c > 0) issue_vg(c - 1);                      // V, GY are dead: the loads have T3 and a whole preparation to land
             }
             __syncwarp();
             bar_arrive_all<B_M3>();
@@ -251,10 +254,9 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 tma_store_3d(&map_gv, sm + OFF_GVT, h * 64, c * L, b);
                 tma_store_3d(&map_gr, sm + OFF_GRT, h * 64, c * L, b);
                 tma_store_commit();
-                if (c > 0) {                                     // everything the next operand preparation needs, while T3 runs
+                if (c > 0) {                                     // the raw tiles of the next chunk, while T3 runs
                     mbar_wait(&ex.bar_rk, par ^ 1);
                     mbar_wait(&ex.bar_w, par ^ 1);
-                    tma_store_wait_read<0>();                    // gv / gr tiles of this chunk (RH, KT space) have left
                 }
             }
             __syncwarp();
@@ -329,6 +331,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     }
             }
             named_bar_sync<B_SCAN, CTHREADS>();
+            bar_sync_all<B_FREE>();              // the output tiles of the previous chunk (RH, KT, RP, DA space) have been stored
 
             uint32_t rr[2][4], kk[2][4];
             ldsm_x4_t(sbase + OFF_R + F.ti(0), rr[0][0], rr[0][1], rr[0][2], rr[0][3]);
@@ -445,7 +448,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             bar_arrive_all<B_PREP>();
 
             // ================================================================== T1
-            bar_sync_all<B_M1>();
+            bar_sync_all<B_BM>();                        // Bm and Drs were issued before the preparation started
             tc_fence_after();
             STAMP(2);
             // ---- Bm[t rows][s cols] -> dA[t][s] = Bm for s < t; bd[t] = Bm[t,t]
@@ -473,6 +476,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             fence_proxy_async();
             tc_fence_before();
             bar_arrive_all<B_T1A>();                     // Dr (into the Bm columns) can start while P^T and G are handled
+            bar_sync_all<B_M1>();                        // A^T ran under the conversion above
+            tc_fence_after();
             // ---- A^T[s rows][t cols] -> P^T[s][t] = A^T for t > s, diag = sum_i r u k
             tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X1 + 32 * ch), v);
             tmem_wait_ld();
@@ -525,7 +530,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             bar_arrive_all<B_T1>();
 
             // ================================================================== T2: gv tile, gr tile, XA
-            bar_sync_all<B_M2>();
+            bar_sync_all<B_DR>();                        // Dr ran under T1b; gv is not needed yet
             tc_fence_after();
             STAMP(4);
             // per 8-token group: Dr, Drs -> gr (tile) and XA, which is parked in the shadow lanes until T3
@@ -562,6 +567,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             STAMP(5);
             bar_arrive_all<B_T2A>();                     // Dk / Dks may overwrite the Dr / Drs columns
             // ---- gv rows -> tile (runs while the tensor cores work on M3)
+            bar_sync_all<B_M2>();
+            tc_fence_after();
             tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X1 + 32 * ch), v);
             tmem_wait_ld();
             stsm_x4(sbase + OFF_GVT + F.rc(0), pack_frag(v, 0, 0), pack_frag(v, 1, 0), pack_frag(v, 2, 0), pack_frag(v, 3, 0));
