@@ -96,7 +96,7 @@ static Args with_raw_w(const Args &a, void *w_raw) {
     return t;
 }
 static bool ew_convertible(const Args &a) {
-    return a.w_kind == W_LOG_F32 && tc3_forward_supported(with_raw_w(a, const_cast<void *>(a.w)));
+    return (a.w_kind == W_LOG_F32 || a.w_kind == W_DECAY_F32) && tc3_forward_supported(with_raw_w(a, const_cast<void *>(a.w)));
 }
 // stream-ordered scratch (cudaMallocAsync) stays cached in the device's default pool instead of going
 // back to the OS at every synchronisation
@@ -122,7 +122,7 @@ static int forward3_ew(const Args &a) {
     void *w_raw = nullptr;
     WKV6_CUDA_CHECK(cudaMallocAsync(&w_raw, (size_t)a.B * a.T * a.H * 64 * 2, a.stream));
     int rc = cudaMemsetAsync(flags, 0, nb, a.stream) == cudaSuccess ? WKV6_OK : WKV6_ECUDA;
-    if (rc == WKV6_OK) rc = ew_to_raw_bf16(a.B, a.T, a.H, (const float *)a.w, w_raw, flags, a.stream);
+    if (rc == WKV6_OK) rc = ew_to_raw_bf16(a.B, a.T, a.H, (const float *)a.w, w_raw, flags, a.stream, a.w_kind == W_DECAY_F32);
     if (rc == WKV6_OK) rc = tc3_forward(with_raw_w(a, w_raw), nullptr, flags);
     if (rc == WKV6_OK) {
         Args s = a;

@@ -62,8 +62,8 @@ int tc3_backward(const Args &a, const Args *exact = nullptr, bool flags_preset =
 // wkv6_bi forward as two launches of the chunked forward kernel around a reverse-gather / combine pair
 int bi_forward_tc(const Args &a, int *flags);
 bool bi_forward_tc_supported(const Args &a);
-// fp32 ew = -exp(w) -> raw bf16 logits; raises flags[b*H+h] where the round trip is not exact
-int ew_to_raw_bf16(int B, int T, int H, const float *ew, void *w_raw, int *flags, cudaStream_t stream);
+// fp32 ew = -exp(w) (or decay = exp(-exp(w)) with from_decay) -> raw bf16 logits; raises flags[b*H+h] where the round trip is not exact
+int ew_to_raw_bf16(int B, int T, int H, const float *ew, void *w_raw, int *flags, cudaStream_t stream, int from_decay = 0);
 bool tc3_backward_supported(const Args &a);
 size_t tc3_saved_header(int B, int H);
 size_t tc3_saved_bytes(int B, int T, int H);

@@ -237,20 +237,23 @@ __global__ void __launch_bounds__(256) gn_gate_kernel(size_t ngroups, int C, flo
 // survive the round trip (ew was not made from bf16 logits) gets its flag raised and is computed by
 // the exact SIMT kernels from the original fp32 values.
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) ew_to_raw_kernel(size_t n8, int T, int H, const float *__restrict__ ew,
+// mode 0: in = ew = -exp(w);  mode 1: in = decay = exp(-exp(w)) (the rwkv6 inference entry, src/model_run.py:64)
+__global__ void __launch_bounds__(256) ew_to_raw_kernel(size_t n8, int T, int H, int mode, const float *__restrict__ in,
                                                         bf16 *__restrict__ w, int *__restrict__ flags) {
     const size_t C = (size_t)H * 64;
+    const float tol = mode ? 2e-4f : 1e-5f;               // log(decay) of a slow channel carries fewer exact bits
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
-        const float4 a = reinterpret_cast<const float4 *>(ew)[2 * i], b = reinterpret_cast<const float4 *>(ew)[2 * i + 1];
-        const float x[8] = {-a.x, -a.y, -a.z, -a.w, -b.x, -b.y, -b.z, -b.w};
+        const float4 a = reinterpret_cast<const float4 *>(in)[2 * i], b = reinterpret_cast<const float4 *>(in)[2 * i + 1];
+        float x[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
         float f[8];
         bool bad = false;
 #pragma unroll
         for (int e = 0; e < 8; e++) {
+            x[e] = mode ? -logf(x[e]) : -x[e];              // exp(w)
             const float lw = logf(x[e]);                    // x = 0 -> -inf (no decay), x < 0 -> NaN (flagged)
             f[e] = lw;
             const float back = expf(rb(lw));
-            bad |= !(fabsf(back - x[e]) <= 1e-5f * x[e]);
+            bad |= !(fabsf(back - x[e]) <= tol * x[e]);
         }
         st8(w + 8 * i, pack8(f));
         if (bad) {
@@ -271,10 +274,10 @@ int grid_for(size_t items, int block) {
 
 // internal (not part of the C ABI)
 namespace wkv6 {
-int ew_to_raw_bf16(int B, int T, int H, const float *ew, void *w_raw, int *flags, cudaStream_t stream) {
+int ew_to_raw_bf16(int B, int T, int H, const float *ew, void *w_raw, int *flags, cudaStream_t stream, int from_decay) {
     const size_t n8 = (size_t)B * T * H * 64 / 8;
     if (n8 == 0) return WKV6_OK;
-    ew_to_raw_kernel<<<grid_for(n8, 256), 256, 0, stream>>>(n8, T, H, ew, (bf16 *)w_raw, flags);
+    ew_to_raw_kernel<<<grid_for(n8, 256), 256, 0, stream>>>(n8, T, H, from_decay, ew, (bf16 *)w_raw, flags);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
     return WKV6_OK;

@@ -254,8 +254,9 @@ def test_wkv6infctx_in_place_state_and_chain(M, O):
 
 
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16, torch.float32])
-def test_rwkv6_inference_op(M, O, dtype):
-    T, H = 50, 3
+@pytest.mark.parametrize("T", [50, 700])
+def test_rwkv6_inference_op(M, O, dtype, T):
+    H = 3
     C = H * 64
     r, k, v, w, u, _ = make_inputs(1, T, H, seed=9, decay="model")
     cast = lambda t: t.float().to(dtype)
