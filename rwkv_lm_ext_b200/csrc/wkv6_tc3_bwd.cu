@@ -755,12 +755,14 @@ int tc3_backward(const Args &a, const Args *exact, bool flags_preset) {
     p.gu = (bf16 *)a.gu; p.gs = (bf16 *)a.gs;
     p.hz_flags = flags;
     p.dbg = (long long *)g_tc3_bwd_stamps;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {};          // function attributes are per device
+    int dev = 0;
+    WKV6_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                              cudaSharedmemCarveoutMaxShared));
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     wkv6_tc3_bwd_kernel<<<a.B * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
     count_launch();

@@ -517,12 +517,14 @@ int tc3_forward(const Args &a, void *ckpt, int *hz_flags) {
     p.has_y = a.y != nullptr;
     p.has_ckpt = ckpt != nullptr;
     p.hz_flags = hz_flags;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static bool attr_done[64] = {};          // function attributes are per device
+    int dev = 0;
+    WKV6_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
         WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                              cudaSharedmemCarveoutMaxShared));
-        attr_done = true;
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
     wkv6_tc3_fwd_kernel<<<a.B * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
     count_launch();

@@ -416,6 +416,22 @@ def test_infctx_long_context_chain_3b_shape(M):
             assert relrms(s, s_ref) < tol, (dt, relrms(s, s_ref))
 
 
+def test_very_long_single_call_and_many_streams(M):
+    """T = 65536 in one call (1024 chunks per stream) and a grid of 4096 streams: tensor-core path == SIMT."""
+    for (B, T, H) in ((1, 65536, 2), (64, 128, 64)):
+        C = H * 64
+        r, k, v, w, u, gy = make_inputs(B, T, H, seed=31, decay="model", device=DEV)
+        y, grads = _run_fwd_bwd(M, r, k, v, w, u, gy)
+        M.set_impl("simt")
+        try:
+            ys, gs = _run_fwd_bwd(M, r, k, v, w, u, gy)
+        finally:
+            M.set_impl("auto")
+        assert relrms(y, ys) < 6e-3
+        for a, b_ in zip(grads, gs):
+            assert relrms(a, b_) < 8e-3
+
+
 def test_empty_inputs(M):
     z = torch.empty(0, 8, 64, device=DEV, dtype=torch.bfloat16)
     u = torch.zeros(1, 64, device=DEV, dtype=torch.bfloat16)
