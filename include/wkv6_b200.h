@@ -143,6 +143,9 @@ WKV6_API int wkv6infctx_backward(int B, int T, int C, int H, const void *r, cons
  * (a5) wkv6_bi -- cuda/wkv6_bi_cuda.cu:363-376 bound by cuda/wkv6_bi_op.cpp:8-21.
  * mask: int32 [B,T].  p[b] = first t with mask==0, or T-1.  y[t>p] = 0 (reference: unwritten).
  * ew: fp32 -exp(w).  Backward = gradient of this forward.
+ * Implementation: two runs of the chunked tensor-core kernels (tokens as they are / each row's first
+ * p+1 tokens reversed with u = 0) around a reverse-gather and a combine pass; they take B*T*C*2 x 5
+ * (forward) or x 10 (backward) bytes of stream-ordered scratch (cudaMallocAsync).
  * ------------------------------------------------------------------------------------------ */
 WKV6_API int wkv6_bi_forward(int B, int T, int C, int H, const int *mask, const void *r, const void *k,
                     const void *v, const float *ew, const void *u, void *y, void *stream);

@@ -150,6 +150,10 @@ static int dispatch_forward(const Args &a) {
 static int dispatch_backward(const Args &a) {
     const int impl = current_impl();
     if (impl != WKV6_IMPL_SIMT && tc3_backward_supported(a)) return tc3_backward(a);
+    if (impl != WKV6_IMPL_SIMT && a.mask && !a.saved && !a.s0 && bi_forward_tc_supported(a)) {
+        ensure_pool_keeps_memory();
+        return bi_backward_tc(a);
+    }
     if (impl != WKV6_IMPL_SIMT && a.w_kind == W_LOG_F32 && !a.saved && tc3_backward_supported(with_raw_w(a, const_cast<void *>(a.w)))) {
         // workspace: [tensor-core backward workspace][raw bf16 logits]
         const size_t base = tc3_backward_workspace_bytes(a.B, a.T, a.H, false), need = base + (size_t)a.B * a.T * a.H * 64 * 2;

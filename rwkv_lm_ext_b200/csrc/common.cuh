@@ -58,10 +58,11 @@ int tc3_forward(const Args &a, void *ckpt, int *hz_flags);   // role-uniform tcg
 bool tc3_forward_supported(const Args &a);
 // role-uniform tcgen05 backward (+ per-stream SIMT fallback, which runs on `exact` when given: the
 // call as the caller made it, e.g. with the fp32 log-decay instead of the converted bf16 logits)
-int tc3_backward(const Args &a, const Args *exact = nullptr, bool flags_preset = false);
+int tc3_backward(const Args &a, const Args *exact = nullptr, bool flags_preset = false, bool run_fallback = true);
 // wkv6_bi forward as two launches of the chunked forward kernel around a reverse-gather / combine pair
 int bi_forward_tc(const Args &a, int *flags);
 bool bi_forward_tc_supported(const Args &a);
+int bi_backward_tc(const Args &a);
 // fp32 ew = -exp(w) (or decay = exp(-exp(w)) with from_decay) -> raw bf16 logits; raises flags[b*H+h] where the round trip is not exact
 int ew_to_raw_bf16(int B, int T, int H, const float *ew, void *w_raw, int *flags, cudaStream_t stream, int from_decay = 0);
 bool tc3_backward_supported(const Args &a);

@@ -72,6 +72,46 @@ __global__ void __launch_bounds__(256) bi_combine_kernel(int T, int C, const int
     }
 }
 
+// masked / reversed output gradient: gm[b,t] = t <= p ? gy[b,t] : 0;  gr[b,t] = t <= p ? gy[b,p-t] : 0
+__global__ void __launch_bounds__(256) bi_gy_kernel(int T, int C, const int *__restrict__ p, const bf16 *__restrict__ gy,
+                                                    bf16 *__restrict__ gm, bf16 *__restrict__ grev) {
+    const int b = blockIdx.x / T, t = blockIdx.x % T;
+    const int pb = p[b];
+    const size_t doff = (size_t)blockIdx.x * C, so = ((size_t)b * T + (t <= pb ? pb - t : t)) * C;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    for (int c = threadIdx.x * 8; c < C; c += blockDim.x * 8) {
+        *reinterpret_cast<uint4 *>(gm + doff + c) = t <= pb ? *reinterpret_cast<const uint4 *>(gy + doff + c) : z;
+        *reinterpret_cast<uint4 *>(grev + doff + c) = t <= pb ? *reinterpret_cast<const uint4 *>(gy + so + c) : z;
+    }
+}
+
+// g[b,t,:] += g2[b,p-t,:] for t <= p, for the four gradients at once (bf16 accumulation like the forward)
+__global__ void __launch_bounds__(256) bi_combine4_kernel(int T, int C, const int *__restrict__ p, bf16 *__restrict__ g0,
+                                                          bf16 *__restrict__ g1, bf16 *__restrict__ g2, bf16 *__restrict__ g3,
+                                                          const bf16 *__restrict__ h0, const bf16 *__restrict__ h1,
+                                                          const bf16 *__restrict__ h2, const bf16 *__restrict__ h3) {
+    const int b = blockIdx.x / T, t = blockIdx.x % T;
+    const int pb = p[b];
+    if (t > pb) return;
+    const size_t doff = (size_t)blockIdx.x * C, so = ((size_t)b * T + (pb - t)) * C;
+    bf16 *g[4] = {g0, g1, g2, g3};
+    const bf16 *h[4] = {h0, h1, h2, h3};
+    for (int c = threadIdx.x * 8; c < C; c += blockDim.x * 8)
+#pragma unroll
+        for (int x = 0; x < 4; x++) {
+            uint4 a = *reinterpret_cast<const uint4 *>(g[x] + doff + c);
+            const uint4 bb = *reinterpret_cast<const uint4 *>(h[x] + so + c);
+            __nv_bfloat162 *pa = reinterpret_cast<__nv_bfloat162 *>(&a);
+            const __nv_bfloat162 *pc = reinterpret_cast<const __nv_bfloat162 *>(&bb);
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                const float2 u = __bfloat1622float2(pa[e]), z = __bfloat1622float2(pc[e]);
+                pa[e] = __floats2bfloat162_rn(u.x + z.x, u.y + z.y);
+            }
+            *reinterpret_cast<uint4 *>(g[x] + doff + c) = a;
+        }
+}
+
 }  // namespace
 
 bool bi_forward_tc_supported(const Args &a) {
@@ -128,6 +168,74 @@ int bi_forward_tc(const Args &a, int *flags) {
         Args s = a;
         s.stream_flags = flags;
         rc = simt_forward(s);
+    }
+    cudaFreeAsync(sc, a.stream);
+    return rc;
+}
+
+// wkv6_bi backward: the gradient of the two-pass forward above is two runs of the chunked backward kernel
+// (pass 1 on the tokens as they are with gy masked beyond p; pass 2 on the reversed tokens with the reversed
+// gy and u = 0), the second un-reversed and added.  a.workspace must hold wkv6_backward_workspace_bytes.
+int bi_backward_tc(const Args &a) {
+    if (a.B * a.H == 0 || a.T == 0) return WKV6_OK;
+    const int C = a.H * N;
+    const size_t n = (size_t)a.B * a.T * C * sizeof(bf16);
+    const bool convert = a.w_kind == W_LOG_F32;
+    const size_t base = tc3_backward_workspace_bytes(a.B, a.T, a.H, false);
+    if (!a.workspace || a.workspace_bytes < base) { set_error("workspace too small: need %zu bytes", base); return WKV6_EWORKSPACE; }
+    const size_t nflag = (size_t)a.B * a.H * sizeof(int);
+    const size_t small = ((size_t)a.H * N * sizeof(bf16) + (size_t)a.B * C * sizeof(bf16) + (size_t)a.B * sizeof(int) + nflag + 1023) / 256 * 256;
+    const size_t total = (10 + (convert ? 1 : 0)) * n + small;
+    uint8_t *sc = nullptr;
+    WKV6_CUDA_CHECK(cudaMallocAsync((void **)&sc, total, a.stream));
+    bf16 *t[10];
+    for (int i = 0; i < 10; i++) t[i] = (bf16 *)(sc + i * n);       // r',k',v',w', gy_m, gy_r, gr2,gk2,gv2,gw2
+    uint8_t *q = sc + 10 * n;
+    const void *w_raw = a.w;
+    if (convert) { w_raw = q; q += n; }
+    bf16 *u0 = (bf16 *)q;
+    bf16 *gu2 = (bf16 *)(q + (size_t)a.H * N * sizeof(bf16));
+    int *p = (int *)((uint8_t *)gu2 + (size_t)a.B * C * sizeof(bf16));
+    int *allflags = p + ((a.B + 63) / 64) * 64;
+    int *wsflags = (int *)((uint8_t *)a.workspace + simt_backward_workspace_bytes(a.B, a.T, a.H));   // where tc3_backward keeps them
+    int rc = WKV6_OK;
+    auto ck = [&](cudaError_t e) { if (e != cudaSuccess && rc == WKV6_OK) { set_error("wkv6_bi backward: %s", cudaGetErrorString(e)); rc = WKV6_ECUDA; } };
+    ck(cudaMemsetAsync(u0, 0, (size_t)a.H * N * sizeof(bf16), a.stream));
+    ck(cudaMemsetAsync(allflags, 0, nflag, a.stream));
+    ck(cudaMemsetAsync(wsflags, 0, nflag, a.stream));
+    if (rc == WKV6_OK && convert) rc = ew_to_raw_bf16(a.B, a.T, a.H, (const float *)a.w, const_cast<void *>(w_raw), wsflags, a.stream);
+    if (rc == WKV6_OK) {
+        bi_last_kernel<<<a.B, 256, 0, a.stream>>>(a.T, a.mask, p);
+        bi_reverse4_kernel<<<a.B * a.T, 256, 0, a.stream>>>(a.T, C, p, (const bf16 *)a.r, (const bf16 *)a.k, (const bf16 *)a.v,
+                                                            (const bf16 *)w_raw, t[0], t[1], t[2], t[3]);
+        bi_gy_kernel<<<a.B * a.T, 256, 0, a.stream>>>(a.T, C, p, (const bf16 *)a.gy, t[4], t[5]);
+        count_launch(3);
+        ck(cudaGetLastError());
+    }
+    // streams flagged in pass 1 are skipped by pass 2 (same flag words) and redone below by the exact kernels
+    if (rc == WKV6_OK) {
+        Args b1 = a;
+        b1.mask = nullptr; b1.w = w_raw; b1.w_kind = W_RAW_BF16; b1.gy = t[4]; b1.workspace_bytes = base; b1.stream_flags = nullptr;
+        rc = tc3_backward(b1, nullptr, true, /*run_fallback=*/false);
+    }
+    if (rc == WKV6_OK) {
+        Args b2 = a;
+        b2.mask = nullptr; b2.w_kind = W_RAW_BF16; b2.r = t[0]; b2.k = t[1]; b2.v = t[2]; b2.w = t[3]; b2.u = u0; b2.gy = t[5];
+        b2.gr = t[6]; b2.gk = t[7]; b2.gv = t[8]; b2.gw = t[9]; b2.gu = gu2; b2.workspace_bytes = base;
+        rc = tc3_backward(b2, nullptr, true, /*run_fallback=*/false);
+    }
+    if (rc == WKV6_OK) {
+        bi_combine4_kernel<<<a.B * a.T, 256, 0, a.stream>>>(a.T, C, p, (bf16 *)a.gr, (bf16 *)a.gk, (bf16 *)a.gv, (bf16 *)a.gw,
+                                                            t[6], t[7], t[8], t[9]);
+        count_launch();
+        ck(cudaGetLastError());
+        ck(cudaMemcpyAsync(allflags, wsflags, nflag, cudaMemcpyDeviceToDevice, a.stream));
+    }
+    if (rc == WKV6_OK) {          // exact bidirectional backward for the flagged streams, from the caller's own tensors
+        Args s = a;
+        s.stream_flags = allflags;
+        s.workspace_bytes = simt_backward_workspace_bytes(a.B, a.T, a.H);
+        rc = simt_backward(s);
     }
     cudaFreeAsync(sc, a.stream);
     return rc;

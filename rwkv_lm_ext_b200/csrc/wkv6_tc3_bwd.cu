@@ -715,7 +715,7 @@ bool tc3_backward_supported(const Args &a) {
            tc::get_encode_fn() != nullptr;
 }
 
-int tc3_backward(const Args &a, const Args *exact, bool flags_preset) {
+int tc3_backward(const Args &a, const Args *exact, bool flags_preset, bool run_fallback) {
     if (a.B * a.H == 0 || a.T == 0) return WKV6_OK;
     const int C = a.H * 64;
     const size_t NC = (size_t)(a.T + L - 1) / L;
@@ -767,6 +767,7 @@ int tc3_backward(const Args &a, const Args *exact, bool flags_preset) {
     wkv6_tc3_bwd_kernel<<<a.B * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
+    if (!run_fallback) return WKV6_OK;      // the caller runs its own exact route on the flags in the workspace
     // exact route for the flagged streams only
     Args s = exact ? *exact : a;
     s.workspace = a.workspace;
