@@ -208,6 +208,37 @@ WKV6_API int tmix_shift_lerp_bf16(int B, int T, int C, const void *x, const void
 WKV6_API int groupnorm_gate_bf16(int BT, int C, int H, float eps, const void *y, const void *g,
                         const void *ln_w, const void *ln_b, void *out, void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Gradients of the memory-bound neighbours, so the fused forwards above can replace the eager
+ * chains of src/model.py:434-468 / src/model_ext.py:1708-1738 inside a training graph.  Data
+ * gradients are bf16 like their tensors; parameter gradients (sums over all B*T rows) are fp32
+ * (deterministic two-stage reduction).  ws: caller-owned scratch of
+ * elementwise_backward_workspace_bytes(B*T, C, nparam) bytes (nparam = 5 ddlerp, 1 shift-lerp,
+ * 2 GroupNorm).  gshift (bf16 [B,C]) is written only when shift_state is given; may be NULL.
+ * ------------------------------------------------------------------------------------------ */
+WKV6_API size_t elementwise_backward_workspace_bytes(int BT, int C, int nparam);
+/* gx [B,T,C], gm [5,B,T,C], gmaa fp32 [5,C] from gout [5,B,T,C] (the grads of xw,xk,xv,xr,xg). */
+WKV6_API int tmix_ddlerp_mix_backward_bf16(int B, int T, int C, const void *x, const void *shift_state,
+                                  const void *maa, const void *m, const void *gout, void *gx, void *gm,
+                                  float *gmaa, void *gshift, void *ws, size_t ws_bytes, void *stream);
+WKV6_API int tmix_shift_lerp_backward_bf16(int B, int T, int C, const void *x, const void *shift_state,
+                                  const void *maa_x, const void *gout, void *gx, float *gmaa_x,
+                                  void *gshift, void *ws, size_t ws_bytes, void *stream);
+/* gy, gg bf16 [B*T,C]; gln_w, gln_b fp32 [C]. */
+WKV6_API int groupnorm_gate_backward_bf16(int BT, int C, int H, float eps, const void *y, const void *g,
+                                 const void *ln_w, const void *ln_b, const void *gout, void *gy, void *gg,
+                                 float *gln_w, float *gln_b, void *ws, size_t ws_bytes, void *stream);
+/* gx[b,t,:] = gout[b,:] * weight(t) / L inside the pooled range, 0 outside (kind 0 or 2). */
+WKV6_API int pooling_backward_bf16(int kind, int variant, int B, int T, int D, const int64_t *actual_len,
+                          const float *gout_f32, void *gx, void *stream);
+/* gradient of gather_rows_bf16: gx[b,t,:] = (t == pos[b]) ? gout[b,:] : 0.  Writes all of gx. */
+WKV6_API int scatter_rows_bf16(int B, int T, int D, const void *gout, const int64_t *pos, void *gx,
+                      void *stream);
+/* gradient of gather_tokens_bf16 for a per-row permutation (what reverse_x_idx builds):
+ * gx[b,rev_idx[b,t],:] = gout[b,t,:]. */
+WKV6_API int scatter_tokens_bf16(int B, int T, int D, const void *gout, const int64_t *rev_idx, void *gx,
+                        void *stream);
+
 #ifdef __cplusplus
 }
 #endif

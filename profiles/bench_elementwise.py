@@ -45,7 +45,45 @@ def timeit(fn, n=20):
     return a.elapsed_time(b) / n
 
 
+# backward kernels: called through the C ABI with preallocated outputs
+from rwkv_lm_ext_b200 import _lib
+from rwkv_lm_ext_b200._lib import ptr
+lib = _lib.load()
+st = torch.cuda.current_stream().cuda_stream
+go5 = torch.randn(5, B, T, C, device=dev, generator=g).bfloat16()
+gx, gm = torch.empty_like(x), torch.empty_like(m)
+gy, gg = torch.empty_like(y), torch.empty_like(y)
+gmaa = torch.empty(5, C, device=dev)
+glw, glb = torch.empty(C, device=dev), torch.empty(C, device=dev)
+ws = torch.empty(lib.elementwise_backward_workspace_bytes(B * T, C, 5), dtype=torch.uint8, device=dev)
+gxe = torch.empty_like(xe)
+goe = torch.randn(B * 64, 1024, device=dev, generator=g)
+
+
+def ddlerp_bwd():
+    assert lib.tmix_ddlerp_mix_backward_bf16(B, T, C, ptr(x), None, ptr(maa), ptr(m), ptr(go5), ptr(gx), ptr(gm),
+                                             ptr(gmaa), None, ptr(ws), ws.numel(), st) == 0
+
+
+def shift_bwd():
+    assert lib.tmix_shift_lerp_backward_bf16(B, T, C, ptr(x), None, ptr(maa_x), ptr(go5), ptr(gx), ptr(gmaa), None,
+                                             ptr(ws), ws.numel(), st) == 0
+
+
+def gn_bwd():
+    assert lib.groupnorm_gate_backward_bf16(B * T, C, H, 64e-5, ptr(y), ptr(gate), ptr(ln_w), ptr(ln_b), ptr(go5), ptr(gy),
+                                            ptr(gg), ptr(glw), ptr(glb), ptr(ws), ws.numel(), st) == 0
+
+
+def pool_bwd():
+    assert lib.pooling_backward_bf16(0, 1, B * 64, 512, 1024, ptr(lens), ptr(goe), ptr(gxe), st) == 0
+
+
 cases = [
+    ("tmix_ddlerp_mix backward", ddlerp_bwd, E * 34),          # x 2 + gout 10 + m 10 -> gx 2 + gm 10 B/elem
+    ("tmix_shift_lerp backward", shift_bwd, E * 6),            # x, gout -> gx
+    ("groupnorm_gate backward", gn_bwd, E * 10),               # y, g, gout -> gy, gg
+    ("pooling weightedmean backward", pool_bwd, xe.numel() * 2),
     ("tmix_ddlerp_mix", lambda: heads.tmix_ddlerp_mix(x, maa, m), E * 22),          # x 2 + m 10 + out 10 B/elem
     ("tmix_shift_lerp", lambda: heads.tmix_shift_lerp(x, maa_x), E * 4),
     ("groupnorm_gate", lambda: heads.groupnorm_gate(y, gate, ln_w, ln_b, H, 64e-5), E * 6),

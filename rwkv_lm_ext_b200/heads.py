@@ -25,15 +25,46 @@ def eos_index(idx: torch.Tensor, token_id: int) -> torch.Tensor:
     return pos
 
 
-def gather_rows(x: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
-    """== x[torch.arange(B), pos]  for x bf16 [B,T,D]."""
-    _cuda(x)
-    assert x.dtype == torch.bfloat16 and x.dim() == 3 and pos.dtype == torch.int64
-    x = x.contiguous()
+def _ws(lib, BT, C, nparam, device):
+    return torch.empty(max(1, lib.elementwise_backward_workspace_bytes(BT, C, nparam)), dtype=torch.uint8, device=device)
+
+
+def _needs_grad(*ts):
+    return torch.is_grad_enabled() and any(t is not None and t.requires_grad for t in ts)
+
+
+def _gather_rows_fwd(x, pos):
     B, T, D = x.shape
     out = torch.empty(B, D, dtype=torch.bfloat16, device=x.device)
-    check(_lib.load().gather_rows_bf16(B, T, D, ptr(x), ptr(pos.contiguous()), ptr(out), stream_of(x)), "gather_rows_bf16")
+    check(_lib.load().gather_rows_bf16(B, T, D, ptr(x), ptr(pos), ptr(out), stream_of(x)), "gather_rows_bf16")
     return out
+
+
+class _GatherRows(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pos):
+        ctx.save_for_backward(pos)
+        ctx.shape = x.shape
+        return _gather_rows_fwd(x, pos)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (pos,) = ctx.saved_tensors
+        B, T, D = ctx.shape
+        gout = gout.contiguous()
+        gx = torch.empty(B, T, D, dtype=torch.bfloat16, device=gout.device)
+        check(_lib.load().scatter_rows_bf16(B, T, D, ptr(gout), ptr(pos), ptr(gx), stream_of(gout)), "scatter_rows_bf16")
+        return gx, None
+
+
+def gather_rows(x: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
+    """== x[torch.arange(B), pos]  for x bf16 [B,T,D]  (differentiable w.r.t. x)."""
+    _cuda(x)
+    assert x.dtype == torch.bfloat16 and x.dim() == 3 and pos.dtype == torch.int64
+    x, pos = x.contiguous(), pos.contiguous()
+    if _needs_grad(x):
+        return _GatherRows.apply(x, pos)
+    return _gather_rows_fwd(x, pos)
 
 
 def eos_gather(x: torch.Tensor, idx: torch.Tensor, token_id: int):
@@ -45,9 +76,35 @@ def eos_gather(x: torch.Tensor, idx: torch.Tensor, token_id: int):
 _KIND = {"weightedmean": 0, "lasttoken": 1, "avg": 2}
 
 
+def _pooling_fwd(x, alen, kind, variant):
+    B, T, D = x.shape
+    out = torch.empty(B, D, dtype=torch.float32, device=x.device)
+    check(_lib.load().pooling_bf16(kind, variant, B, T, D, ptr(x), ptr(alen), ptr(out), stream_of(x)), "pooling_bf16")
+    return out
+
+
+class _Pooling(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, alen, kind, variant):
+        ctx.save_for_backward(alen)
+        ctx.meta = (x.shape, kind, variant)
+        return _pooling_fwd(x, alen, kind, variant)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (alen,) = ctx.saved_tensors
+        (B, T, D), kind, variant = ctx.meta
+        gout = gout.float().contiguous()
+        gx = torch.empty(B, T, D, dtype=torch.bfloat16, device=gout.device)
+        check(_lib.load().pooling_backward_bf16(kind, variant, B, T, D, ptr(alen), ptr(gout), ptr(gx), stream_of(gout)),
+              "pooling_backward_bf16")
+        return gx, None, None, None
+
+
 def pooling(x: torch.Tensor, actual_len: torch.Tensor, pooling_type: str, variant: str = "train") -> torch.Tensor:
     """variant="train": src/model_ext.py:1708-1738 (bf16 result for weightedmean / avg);
-    variant="infer": src/model_run.py:777-797 (L = actual_len + 1, fp32 result)."""
+    variant="infer": src/model_run.py:777-797 (L = actual_len + 1, fp32 result).
+    Differentiable w.r.t. x."""
     _cuda(x)
     assert x.dtype == torch.bfloat16 and x.dim() == 3
     if pooling_type == "lasttoken":
@@ -55,10 +112,9 @@ def pooling(x: torch.Tensor, actual_len: torch.Tensor, pooling_type: str, varian
     if pooling_type not in _KIND or (variant == "infer" and pooling_type == "avg"):
         raise ValueError(pooling_type)
     x = x.contiguous()
-    B, T, D = x.shape
-    out = torch.empty(B, D, dtype=torch.float32, device=x.device)
-    check(_lib.load().pooling_bf16(_KIND[pooling_type], 1 if variant == "infer" else 0, B, T, D, ptr(x),
-                                   ptr(actual_len.to(torch.int64).contiguous()), ptr(out), stream_of(x)), "pooling_bf16")
+    alen = actual_len.to(torch.int64).contiguous()
+    kind, var = _KIND[pooling_type], 1 if variant == "infer" else 0
+    out = _Pooling.apply(x, alen, kind, var) if _needs_grad(x) else _pooling_fwd(x, alen, kind, var)
     return out.bfloat16() if variant == "train" else out
 
 
@@ -76,50 +132,163 @@ def create_mask_and_rev_idx(idx: torch.Tensor, emb_id: int = 1, pad_id: int = 0)
     return mask, rev
 
 
-def reverse_x(x: torch.Tensor, rev_idx: torch.Tensor) -> torch.Tensor:
-    """== torch.gather(x, 1, rev_idx[..., None].expand(-1, -1, D))  (src/model_ext.py:418-419)."""
-    _cuda(x)
-    assert x.dtype == torch.bfloat16 and x.dim() == 3 and rev_idx.dtype == torch.int64
-    x = x.contiguous()
+def _reverse_fwd(x, rev_idx):
     B, T, D = x.shape
     out = torch.empty_like(x)
-    check(_lib.load().gather_tokens_bf16(B, T, D, ptr(x), ptr(rev_idx.contiguous()), ptr(out), stream_of(x)),
-          "gather_tokens_bf16")
+    check(_lib.load().gather_tokens_bf16(B, T, D, ptr(x), ptr(rev_idx), ptr(out), stream_of(x)), "gather_tokens_bf16")
     return out
+
+
+class _ReverseX(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, rev_idx):
+        ctx.save_for_backward(rev_idx)
+        return _reverse_fwd(x, rev_idx)
+
+    @staticmethod
+    def backward(ctx, gout):
+        (rev_idx,) = ctx.saved_tensors
+        gout = gout.contiguous()
+        B, T, D = gout.shape
+        gx = torch.empty_like(gout)
+        check(_lib.load().scatter_tokens_bf16(B, T, D, ptr(gout), ptr(rev_idx), ptr(gx), stream_of(gout)), "scatter_tokens_bf16")
+        return gx, None
+
+
+def reverse_x(x: torch.Tensor, rev_idx: torch.Tensor) -> torch.Tensor:
+    """== torch.gather(x, 1, rev_idx[..., None].expand(-1, -1, D))  (src/model_ext.py:418-419).
+    Differentiable w.r.t. x when rev_idx is a per-row permutation (what reverse_x_idx builds)."""
+    _cuda(x)
+    assert x.dtype == torch.bfloat16 and x.dim() == 3 and rev_idx.dtype == torch.int64
+    x, rev_idx = x.contiguous(), rev_idx.contiguous()
+    if _needs_grad(x):
+        return _ReverseX.apply(x, rev_idx)
+    return _reverse_fwd(x, rev_idx)
+
+
+def _shift_lerp_fwd(x, shift_state, maa_x):
+    B, T, C = x.shape
+    out = torch.empty_like(x)
+    check(_lib.load().tmix_shift_lerp_bf16(B, T, C, ptr(x), ptr(shift_state), ptr(maa_x), ptr(out), stream_of(x)),
+          "tmix_shift_lerp_bf16")
+    return out
+
+
+class _ShiftLerp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, shift_state, maa_x):
+        ctx.save_for_backward(x, shift_state, maa_x)
+        return _shift_lerp_fwd(x, shift_state, maa_x)
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, shift_state, maa_x = ctx.saved_tensors
+        lib = _lib.load()
+        B, T, C = x.shape
+        gout = gout.contiguous()
+        gx = torch.empty_like(x)
+        gmaa = torch.empty(C, dtype=torch.float32, device=x.device)
+        gshift = torch.empty_like(shift_state) if shift_state is not None else None
+        ws = _ws(lib, B * T, C, 1, x.device)
+        check(lib.tmix_shift_lerp_backward_bf16(B, T, C, ptr(x), ptr(shift_state), ptr(maa_x), ptr(gout), ptr(gx), ptr(gmaa),
+                                                ptr(gshift), ptr(ws), ws.numel(), stream_of(x)), "tmix_shift_lerp_backward_bf16")
+        return gx, gshift, gmaa.to(maa_x.dtype)
 
 
 def tmix_shift_lerp(x, maa_x, shift_state=None):
-    """xxx = x + (time_shift(x) - x) * time_maa_x  (src/model.py:437-439)."""
+    """xxx = x + (time_shift(x) - x) * time_maa_x  (src/model.py:437-439).  Differentiable w.r.t.
+    x, time_maa_x and the shift state."""
     _cuda(x)
     assert x.dtype == torch.bfloat16
     x = x.contiguous()
+    shift_state = shift_state.contiguous() if shift_state is not None else None
+    flat = maa_x.contiguous().view(-1)
+    if _needs_grad(x, maa_x, shift_state):
+        return _ShiftLerp.apply(x, shift_state, flat)
+    return _shift_lerp_fwd(x, shift_state, flat)
+
+
+def _ddlerp_fwd(x, shift_state, maa, m):
     B, T, C = x.shape
-    out = torch.empty_like(x)
-    check(_lib.load().tmix_shift_lerp_bf16(B, T, C, ptr(x), ptr(shift_state), ptr(maa_x.contiguous().view(-1)), ptr(out),
-                                           stream_of(x)), "tmix_shift_lerp_bf16")
+    out = torch.empty(5, B, T, C, dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().tmix_ddlerp_mix_bf16(B, T, C, ptr(x), ptr(shift_state), ptr(maa), ptr(m), ptr(out), stream_of(x)),
+          "tmix_ddlerp_mix_bf16")
     return out
+
+
+class _DdlerpMix(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, shift_state, maa, m):
+        ctx.save_for_backward(x, shift_state, maa, m)
+        return _ddlerp_fwd(x, shift_state, maa, m)
+
+    @staticmethod
+    def backward(ctx, gout):
+        x, shift_state, maa, m = ctx.saved_tensors
+        lib = _lib.load()
+        B, T, C = x.shape
+        gout = gout.contiguous()
+        gx, gm = torch.empty_like(x), torch.empty_like(m)
+        gmaa = torch.empty(5, C, dtype=torch.float32, device=x.device)
+        gshift = torch.empty_like(shift_state) if shift_state is not None else None
+        ws = _ws(lib, B * T, C, 5, x.device)
+        check(lib.tmix_ddlerp_mix_backward_bf16(B, T, C, ptr(x), ptr(shift_state), ptr(maa), ptr(m), ptr(gout), ptr(gx),
+                                                ptr(gm), ptr(gmaa), ptr(gshift), ptr(ws), ws.numel(), stream_of(x)),
+              "tmix_ddlerp_mix_backward_bf16")
+        return gx, gshift, gmaa.to(maa.dtype), gm
 
 
 def tmix_ddlerp_mix(x, maa_wkvrg, m, shift_state=None):
     """xw,xk,xv,xr,xg = x + xx * (time_maa_n + m_n)  (src/model.py:444-448).
-    maa_wkvrg bf16 [5,C]; m bf16 [5,B,T,C] (the LoRA bmm output).  Returns a [5,B,T,C] tensor."""
+    maa_wkvrg bf16 [5,C]; m bf16 [5,B,T,C] (the LoRA bmm output).  Returns a [5,B,T,C] tensor.
+    Differentiable w.r.t. x, maa_wkvrg, m and the shift state."""
     _cuda(x)
     assert x.dtype == torch.bfloat16 and m.dtype == torch.bfloat16
-    x = x.contiguous()
-    B, T, C = x.shape
-    out = torch.empty(5, B, T, C, dtype=torch.bfloat16, device=x.device)
-    check(_lib.load().tmix_ddlerp_mix_bf16(B, T, C, ptr(x), ptr(shift_state), ptr(maa_wkvrg.contiguous()),
-                                           ptr(m.contiguous()), ptr(out), stream_of(x)), "tmix_ddlerp_mix_bf16")
+    x, m, maa = x.contiguous(), m.contiguous(), maa_wkvrg.contiguous()
+    shift_state = shift_state.contiguous() if shift_state is not None else None
+    if _needs_grad(x, maa, m, shift_state):
+        return _DdlerpMix.apply(x, shift_state, maa, m)
+    return _ddlerp_fwd(x, shift_state, maa, m)
+
+
+def _gn_fwd(y, g, ln_w, ln_b, H, eps):
+    B, T, C = y.shape
+    out = torch.empty_like(y)
+    check(_lib.load().groupnorm_gate_bf16(B * T, C, H, float(eps), ptr(y), ptr(g), ptr(ln_w), ptr(ln_b), ptr(out),
+                                          stream_of(y)), "groupnorm_gate_bf16")
     return out
+
+
+class _GroupNormGate(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, g, ln_w, ln_b, H, eps):
+        ctx.save_for_backward(y, g, ln_w, ln_b)
+        ctx.meta = (H, eps)
+        return _gn_fwd(y, g, ln_w, ln_b, H, eps)
+
+    @staticmethod
+    def backward(ctx, gout):
+        y, g, ln_w, ln_b = ctx.saved_tensors
+        H, eps = ctx.meta
+        lib = _lib.load()
+        B, T, C = y.shape
+        gout = gout.contiguous()
+        gy, gg = torch.empty_like(y), torch.empty_like(g)
+        gw = torch.empty(C, dtype=torch.float32, device=y.device)
+        gb = torch.empty(C, dtype=torch.float32, device=y.device)
+        ws = _ws(lib, B * T, C, 2, y.device)
+        check(lib.groupnorm_gate_backward_bf16(B * T, C, H, float(eps), ptr(y), ptr(g), ptr(ln_w), ptr(ln_b), ptr(gout),
+                                               ptr(gy), ptr(gg), ptr(gw), ptr(gb), ptr(ws), ws.numel(), stream_of(y)),
+              "groupnorm_gate_backward_bf16")
+        return gy, gg, gw.to(ln_w.dtype), gb.to(ln_b.dtype), None, None
 
 
 def groupnorm_gate(y, g, ln_w, ln_b, H, eps):
-    """ln_x(y.view(B*T, C)).view(B,T,C) * g  (src/model.py:461-467, without the output Linear)."""
+    """ln_x(y.view(B*T, C)).view(B,T,C) * g  (src/model.py:461-467, without the output Linear).
+    Differentiable w.r.t. y, g and the GroupNorm affine parameters."""
     _cuda(y)
     assert y.dtype == torch.bfloat16 and g.dtype == torch.bfloat16
-    y = y.contiguous()
-    B, T, C = y.shape
-    out = torch.empty_like(y)
-    check(_lib.load().groupnorm_gate_bf16(B * T, C, H, float(eps), ptr(y), ptr(g.contiguous()), ptr(ln_w.contiguous()),
-                                          ptr(ln_b.contiguous()), ptr(out), stream_of(y)), "groupnorm_gate_bf16")
-    return out
+    y, g, ln_w, ln_b = y.contiguous(), g.contiguous(), ln_w.contiguous(), ln_b.contiguous()
+    if _needs_grad(y, g, ln_w, ln_b):
+        return _GroupNormGate.apply(y, g, ln_w, ln_b, H, eps)
+    return _gn_fwd(y, g, ln_w, ln_b, H, eps)

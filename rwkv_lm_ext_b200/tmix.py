@@ -1,0 +1,101 @@
+"""The whole RWKV-6 time-mix layer on the fused kernels.
+
+`tmix_x060_forward(layer, x)` computes what `RWKV_Tmix_x060.forward` does (src/model.py:434-477):
+token-shift + ddlerp, the five Linears (left to cuBLAS), the decay LoRA, WKV6, GroupNorm * gate and
+the output Linear, on any module that carries the reference's parameter names
+
+    time_maa_x/w/k/v/r/g [1,1,C]   time_maa_w1 [C,5R]   time_maa_w2 [5,R,C]
+    time_decay [1,1,C]             time_decay_w1 [C,D]  time_decay_w2 [D,C]      time_faaaa [H,64]
+    receptance, key, value, gate, output (bias-free Linears, plain or LoRA-wrapped)   ln_x (GroupNorm)
+
+so it can be bound onto the reference's own layers without touching their state_dict:
+
+    import types, rwkv_lm_ext_b200 as wkv
+    for blk in model.blocks:
+        blk.att.forward = types.MethodType(wkv.tmix_x060_forward, blk.att)
+
+The eager chain's ~25 elementwise passes over [B,T,C] become 3 kernels (shift-lerp, ddlerp mix,
+GroupNorm*gate) plus the `silu`; every piece is differentiable (heads.py, ops.py), so the same call
+serves SFT.  Variants: `time_state` attribute present -> state tuning (src/model.py:560-584);
+`last_state` given -> infctx (src/model.py:738-781), returning `(out, (last_token, wkv_state))`.
+"""
+import torch
+import torch.nn.functional as F
+
+from . import heads, ops
+
+
+def _maa5(layer):
+    C = layer.time_maa_w.shape[-1]
+    return torch.cat([layer.time_maa_w.view(1, C), layer.time_maa_k.view(1, C), layer.time_maa_v.view(1, C),
+                      layer.time_maa_r.view(1, C), layer.time_maa_g.view(1, C)], 0)
+
+
+def tmix_x060_project(layer, x, shift_state=None):
+    """jit_func (src/model.py:434-459 / :738-762): x [B,T,C] bf16 -> r, k, v, g, w (each [B,T,C])."""
+    B, T, C = x.shape
+    xxx = heads.tmix_shift_lerp(x, layer.time_maa_x, shift_state)
+    R = layer.time_maa_w2.shape[1]
+    lora = torch.tanh(xxx.view(B * T, C) @ layer.time_maa_w1).view(B * T, 5, R).transpose(0, 1)
+    m = torch.bmm(lora, layer.time_maa_w2).view(5, B, T, C)
+    xw, xk, xv, xr, xg = heads.tmix_ddlerp_mix(x, _maa5(layer), m, shift_state).unbind(0)
+    r = layer.receptance(xr)
+    k = layer.key(xk)
+    v = layer.value(xv)
+    g = F.silu(layer.gate(xg))
+    # time_decay + tanh(xw @ W1) @ W2 with the bias add as the GEMM epilogue
+    w = torch.addmm(layer.time_decay.view(-1), torch.tanh(xw.view(B * T, C) @ layer.time_decay_w1),
+                    layer.time_decay_w2).view(B, T, -1)
+    return r, k, v, g, w
+
+
+def tmix_x060_finish(layer, y, g):
+    """jit_func_2 (src/model.py:461-468): GroupNorm over heads, * g, output Linear."""
+    H = layer.time_faaaa.shape[0]
+    return layer.output(heads.groupnorm_gate(y, g, layer.ln_x.weight, layer.ln_x.bias, H, layer.ln_x.eps))
+
+
+def tmix_x060_forward(layer, x, last_state=None):
+    """Drop-in for RWKV_Tmix_x060.forward (plain, state-tuning and infctx flavours)."""
+    B, T, C = x.shape
+    H = layer.time_faaaa.shape[0]
+    if last_state is not None:                                  # infctx: (shift_state [B,C], wkv_state [B,H,64,64])
+        shift_state, wkv_state = (last_state.shift_state, last_state.wkv_state) if hasattr(last_state, "shift_state") else last_state
+        r, k, v, g, w = tmix_x060_project(layer, x, shift_state)
+        y, new_state = ops.WKV_6STATE_INFCTX.apply(B, T, C, H, r, k, v, w, layer.time_faaaa, wkv_state.clone().contiguous())
+        return tmix_x060_finish(layer, y, g), (x[:, -1], new_state)
+    r, k, v, g, w = tmix_x060_project(layer, x)
+    if getattr(layer, "time_state", None) is not None:          # state tuning
+        y = ops.WKV_6STATE.apply(B, T, C, H, r, k, v, w, layer.time_faaaa, layer.time_state)
+    else:
+        y = ops.RUN_CUDA_RWKV6(B, T, C, H, r, k, v, w, layer.time_faaaa)
+    return tmix_x060_finish(layer, y, g)
+
+
+class Tmix_x060(torch.nn.Module):
+    """A self-contained layer with the reference's parameter names and initialisation shapes
+    (src/model.py:375-432), for tests and benchmarks; real models keep their own layers and bind
+    `tmix_x060_forward` onto them."""
+
+    def __init__(self, n_embd, n_head, lora_r=32, decay_r=64, head_size_divisor=8, state_tuning=False):
+        super().__init__()
+        C = n_embd
+        assert C == n_head * 64
+        self.n_head = n_head
+        z = lambda *s: torch.nn.Parameter(torch.zeros(*s))
+        self.time_maa_x, self.time_maa_w, self.time_maa_k = z(1, 1, C), z(1, 1, C), z(1, 1, C)
+        self.time_maa_v, self.time_maa_r, self.time_maa_g = z(1, 1, C), z(1, 1, C), z(1, 1, C)
+        self.time_maa_w1, self.time_maa_w2 = z(C, 5 * lora_r), z(5, lora_r, C)
+        self.time_decay, self.time_decay_w1, self.time_decay_w2 = z(1, 1, C), z(C, decay_r), z(decay_r, C)
+        self.time_faaaa = z(n_head, 64)
+        if state_tuning:
+            self.time_state = z(n_head, 64, 64)
+        self.receptance = torch.nn.Linear(C, C, bias=False)
+        self.key = torch.nn.Linear(C, C, bias=False)
+        self.value = torch.nn.Linear(C, C, bias=False)
+        self.output = torch.nn.Linear(C, C, bias=False)
+        self.gate = torch.nn.Linear(C, C, bias=False)
+        self.ln_x = torch.nn.GroupNorm(n_head, C, eps=1e-5 * head_size_divisor ** 2)
+
+    def forward(self, x, last_state=None):
+        return tmix_x060_forward(self, x, last_state)

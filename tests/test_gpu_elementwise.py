@@ -139,3 +139,115 @@ def test_groupnorm_gate(M, O):
     ln.bias.data.copy_(lb)
     eager = ln(y.to(DEV).view(B * T, C)).view(B, T, C) * gate.to(DEV)
     assert relrms(got, eager) < 4e-3
+
+
+# --------------------------------------------------------------------------------------------------
+# gradients of the memory-bound pieces: fp64 autograd of the oracle expressions is the reference
+# --------------------------------------------------------------------------------------------------
+def _leaf64(t):
+    return t.detach().cpu().double().requires_grad_(True)
+
+
+@pytest.mark.parametrize("B,T,C,with_state", [(2, 37, 256, False), (3, 130, 768, True), (1, 1, 64, True), (5, 64, 320, False)])
+def test_ddlerp_backward(M, B, T, C, with_state):
+    g = torch.Generator().manual_seed(11)
+    x = torch.randn(B, T, C, generator=g).bfloat16().to(DEV).requires_grad_(True)
+    maa_x = torch.rand(1, 1, C, generator=g).bfloat16().to(DEV).requires_grad_(True)
+    maa = torch.rand(5, C, generator=g).bfloat16().to(DEV).requires_grad_(True)
+    m = (torch.randn(5, B, T, C, generator=g) * 0.3).bfloat16().to(DEV).requires_grad_(True)
+    st = torch.randn(B, C, generator=g).bfloat16().to(DEV).requires_grad_(True) if with_state else None
+    go1 = torch.randn(B, T, C, generator=g).bfloat16().to(DEV)
+    go5 = torch.randn(5, B, T, C, generator=g).bfloat16().to(DEV)
+
+    def ref(x, maa_x, maa, m, st):
+        prev = torch.zeros(B, 1, C, dtype=x.dtype) if st is None else st.unsqueeze(1)
+        xx = torch.cat([prev, x[:, :-1]], 1) - x
+        return x + xx * maa_x, torch.stack([x + xx * (maa[n] + m[n]) for n in range(5)])
+
+    leaves = [_leaf64(t) if t is not None else None for t in (x, maa_x, maa, m, st)]
+    r1, r5 = ref(*leaves)
+    (r1 * go1.cpu().double()).sum().backward()
+    want1 = [l.grad.clone() if l is not None and l.grad is not None else None for l in leaves]
+    for l in leaves:
+        if l is not None:
+            l.grad = None
+    (r5 * go5.cpu().double()).sum().backward()
+    want5 = [l.grad if l is not None else None for l in leaves]
+
+    out1 = M.tmix_shift_lerp(x, maa_x, st)
+    out1.backward(go1)
+    assert_bf16_close(x.grad, want1[0], "shift_lerp gx")
+    assert_bf16_close(maa_x.grad, want1[1], "shift_lerp gmaa_x")
+    if with_state:
+        assert_bf16_close(st.grad, want1[4], "shift_lerp gshift")
+        st.grad = None
+    x.grad = None
+    out5 = M.tmix_ddlerp_mix(x, maa, m, st)
+    out5.backward(go5)
+    assert_bf16_close(x.grad, want5[0], "ddlerp gx")
+    assert_bf16_close(maa.grad, want5[2], "ddlerp gmaa")
+    assert_bf16_close(m.grad, want5[3], "ddlerp gm")
+    if with_state:
+        assert_bf16_close(st.grad, want5[4], "ddlerp gshift")
+
+
+@pytest.mark.parametrize("B,T,H", [(3, 21, 4), (2, 300, 12), (1, 1, 1)])
+def test_groupnorm_gate_backward(M, O, B, T, H):
+    g = torch.Generator().manual_seed(13)
+    C = H * 64
+    eps = 1e-5 * 8 ** 2
+    y = (torch.randn(B, T, C, generator=g) * 3).bfloat16().to(DEV).requires_grad_(True)
+    gate = torch.randn(B, T, C, generator=g).bfloat16().to(DEV).requires_grad_(True)
+    lw = (torch.rand(C, generator=g) + 0.5).bfloat16().to(DEV).requires_grad_(True)
+    lb = (torch.randn(C, generator=g) * 0.1).bfloat16().to(DEV).requires_grad_(True)
+    go = torch.randn(B, T, C, generator=g).bfloat16().to(DEV)
+    leaves = [_leaf64(t) for t in (y, gate, lw, lb)]
+    (O.groupnorm_gate(*leaves, H, eps) * go.cpu().double()).sum().backward()
+    M.groupnorm_gate(y, gate, lw, lb, H, eps).backward(go)
+    for name, t, l in zip(("gy", "gg", "gln_w", "gln_b"), (y, gate, lw, lb), leaves):
+        assert_bf16_close(t.grad, l.grad, "gn*gate " + name)
+
+
+def test_heads_backward(M, O):
+    """pooling / eos gather / reverse gather inside autograd (training heads, src/model_ext.py:1708-1769)."""
+    g = torch.Generator().manual_seed(17)
+    B, T, D = 5, 40, 136
+    xb = torch.randn(B, T, D, generator=g).bfloat16()
+    L = torch.tensor([1, 7, 39, 20, 12])
+    go = torch.randn(B, D, generator=g).bfloat16()
+    for kind, variant in (("weightedmean", "train"), ("avg", "train"), ("lasttoken", "train"), ("weightedmean", "infer")):
+        x = xb.to(DEV).requires_grad_(True)
+        out = M.pooling(x, L.to(DEV), kind, variant)
+        out.backward(go.to(DEV).to(out.dtype))
+        x64 = xb.double().requires_grad_(True)
+        if kind == "lasttoken":
+            ref = x64[torch.arange(B), L]
+        else:                                # the fp64 form of oracle.pooling (which rounds its result to bf16)
+            Lp = (L + 1 if variant == "infer" else L).unsqueeze(1)
+            if kind == "weightedmean":
+                wts = (torch.arange(1, T + 1).double() / Lp) * (torch.arange(T) <= Lp)
+            else:
+                wts = (torch.arange(T).unsqueeze(0) < Lp).double()
+            ref = (x64 * wts.unsqueeze(-1)).sum(1) / Lp
+            assert relrms(out, O.pooling(xb, L, kind, variant)) < 1e-2
+        (ref * go.double()).sum().backward()
+        assert_bf16_close(x.grad, x64.grad, f"pooling {kind}/{variant} gx")
+    # eos gather: gradient lands on the gathered row only, bit-exact
+    idx = torch.randint(2, 100, (B, T), generator=g)
+    idx[0, 5] = 1
+    idx[2, 0] = 1
+    idx[3, T - 1] = 1
+    x = xb.to(DEV).requires_grad_(True)
+    rows, pos = M.eos_gather(x, idx.to(DEV), 1)
+    rows.backward(go.to(DEV))
+    want = torch.zeros(B, T, D, dtype=torch.bfloat16)
+    want[torch.arange(B), pos.cpu()] = go
+    assert torch.equal(x.grad.cpu(), want)
+    # reverse gather
+    mask, rev = M.create_mask_and_rev_idx(idx.to(DEV), 1, 0)
+    x = xb.to(DEV).requires_grad_(True)
+    gor = torch.randn(B, T, D, generator=g).bfloat16().to(DEV)
+    M.reverse_x(x, rev).backward(gor)
+    x2 = xb.to(DEV).requires_grad_(True)
+    torch.gather(x2, 1, rev.unsqueeze(-1).expand(-1, -1, D)).backward(gor)
+    assert torch.equal(x.grad, x2.grad)
