@@ -203,9 +203,10 @@ WKV6_API int tmix_ddlerp_mix_bf16(int B, int T, int C, const void *x, const void
 /* xxx = x + (shift(x)-x)*maa_x  (src/model.py:439-441), the LoRA input.  bf16. */
 WKV6_API int tmix_shift_lerp_bf16(int B, int T, int C, const void *x, const void *shift_state,
                          const void *maa_x, void *out, void *stream);
-/* (a8) GroupNorm(H groups, eps) * g  of jit_func_2 (src/model.py:461-467), fwd only.
- * y,g,out bf16 [B*T,C]; ln_w, ln_b bf16 [C]. */
-WKV6_API int groupnorm_gate_bf16(int BT, int C, int H, float eps, const void *y, const void *g,
+/* (a8) GroupNorm(H groups, eps) * g  of jit_func_2 (src/model.py:461-467).
+ * y,g,out bf16 [B*T,C]; ln_w, ln_b bf16 [C].  gate_act: 0 = g is the gate itself; 1 = g is the
+ * gate Linear's output and silu (src/model.py:454) is applied here, saving a pass over [B,T,C]. */
+WKV6_API int groupnorm_gate_bf16(int BT, int C, int H, float eps, int gate_act, const void *y, const void *g,
                         const void *ln_w, const void *ln_b, void *out, void *stream);
 
 /* ------------------------------------------------------------------------------------------
@@ -213,20 +214,22 @@ WKV6_API int groupnorm_gate_bf16(int BT, int C, int H, float eps, const void *y,
  * chains of src/model.py:434-468 / src/model_ext.py:1708-1738 inside a training graph.  Data
  * gradients are bf16 like their tensors; parameter gradients (sums over all B*T rows) are fp32
  * (deterministic two-stage reduction).  ws: caller-owned scratch of
- * elementwise_backward_workspace_bytes(B*T, C, nparam) bytes (nparam = 5 ddlerp, 1 shift-lerp,
+ * elementwise_backward_workspace_bytes(B, T, C, nparam) bytes (nparam = 5 ddlerp, 1 shift-lerp,
  * 2 GroupNorm).  gshift (bf16 [B,C]) is written only when shift_state is given; may be NULL.
  * ------------------------------------------------------------------------------------------ */
-WKV6_API size_t elementwise_backward_workspace_bytes(int BT, int C, int nparam);
-/* gx [B,T,C], gm [5,B,T,C], gmaa fp32 [5,C] from gout [5,B,T,C] (the grads of xw,xk,xv,xr,xg). */
+WKV6_API size_t elementwise_backward_workspace_bytes(int B, int T, int C, int nparam);
+/* gx [B,T,C], gm [5,B,T,C], gmaa fp32 [5,C] from the gradients of xw,xk,xv,xr,xg (five separate
+ * [B,T,C] tensors: they come out of five different Linear backward passes). */
 WKV6_API int tmix_ddlerp_mix_backward_bf16(int B, int T, int C, const void *x, const void *shift_state,
-                                  const void *maa, const void *m, const void *gout, void *gx, void *gm,
+                                  const void *maa, const void *m, const void *gxw, const void *gxk,
+                                  const void *gxv, const void *gxr, const void *gxg, void *gx, void *gm,
                                   float *gmaa, void *gshift, void *ws, size_t ws_bytes, void *stream);
 WKV6_API int tmix_shift_lerp_backward_bf16(int B, int T, int C, const void *x, const void *shift_state,
                                   const void *maa_x, const void *gout, void *gx, float *gmaa_x,
                                   void *gshift, void *ws, size_t ws_bytes, void *stream);
 /* gy, gg bf16 [B*T,C]; gln_w, gln_b fp32 [C]. */
-WKV6_API int groupnorm_gate_backward_bf16(int BT, int C, int H, float eps, const void *y, const void *g,
-                                 const void *ln_w, const void *ln_b, const void *gout, void *gy, void *gg,
+WKV6_API int groupnorm_gate_backward_bf16(int BT, int C, int H, float eps, int gate_act, const void *y,
+                                 const void *g, const void *ln_w, const void *ln_b, const void *gout, void *gy, void *gg,
                                  float *gln_w, float *gln_b, void *ws, size_t ws_bytes, void *stream);
 /* gx[b,t,:] = gout[b,:] * weight(t) / L inside the pooled range, 0 outside (kind 0 or 2). */
 WKV6_API int pooling_backward_bf16(int kind, int variant, int B, int T, int D, const int64_t *actual_len,

@@ -55,14 +55,14 @@ gx, gm = torch.empty_like(x), torch.empty_like(m)
 gy, gg = torch.empty_like(y), torch.empty_like(y)
 gmaa = torch.empty(5, C, device=dev)
 glw, glb = torch.empty(C, device=dev), torch.empty(C, device=dev)
-ws = torch.empty(lib.elementwise_backward_workspace_bytes(B * T, C, 5), dtype=torch.uint8, device=dev)
+ws = torch.empty(lib.elementwise_backward_workspace_bytes(B, T, C, 5), dtype=torch.uint8, device=dev)
 gxe = torch.empty_like(xe)
 goe = torch.randn(B * 64, 1024, device=dev, generator=g)
 
 
 def ddlerp_bwd():
-    assert lib.tmix_ddlerp_mix_backward_bf16(B, T, C, ptr(x), None, ptr(maa), ptr(m), ptr(go5), ptr(gx), ptr(gm),
-                                             ptr(gmaa), None, ptr(ws), ws.numel(), st) == 0
+    assert lib.tmix_ddlerp_mix_backward_bf16(B, T, C, ptr(x), None, ptr(maa), ptr(m), *[ptr(go5[i]) for i in range(5)], ptr(gx),
+                                             ptr(gm), ptr(gmaa), None, ptr(ws), ws.numel(), st) == 0
 
 
 def shift_bwd():
@@ -71,7 +71,7 @@ def shift_bwd():
 
 
 def gn_bwd():
-    assert lib.groupnorm_gate_backward_bf16(B * T, C, H, 64e-5, ptr(y), ptr(gate), ptr(ln_w), ptr(ln_b), ptr(go5), ptr(gy),
+    assert lib.groupnorm_gate_backward_bf16(B * T, C, H, 64e-5, 1, ptr(y), ptr(gate), ptr(ln_w), ptr(ln_b), ptr(go5), ptr(gy),
                                             ptr(gg), ptr(glw), ptr(glb), ptr(ws), ws.numel(), st) == 0
 
 

@@ -45,11 +45,11 @@ SIGNATURES = {
     "gather_tokens_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "tmix_ddlerp_mix_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     "tmix_shift_lerp_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
-    "groupnorm_gate_bf16": (c_i, [c_i, c_i, c_i, c_f, c_p, c_p, c_p, c_p, c_p, c_p]),
-    "elementwise_backward_workspace_bytes": (c_sz, [c_i, c_i, c_i]),
-    "tmix_ddlerp_mix_backward_bf16": (c_i, [c_i, c_i, c_i] + [c_p] * 10 + [c_sz, c_p]),
+    "groupnorm_gate_bf16": (c_i, [c_i, c_i, c_i, c_f, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "elementwise_backward_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i]),
+    "tmix_ddlerp_mix_backward_bf16": (c_i, [c_i, c_i, c_i] + [c_p] * 14 + [c_sz, c_p]),
     "tmix_shift_lerp_backward_bf16": (c_i, [c_i, c_i, c_i] + [c_p] * 8 + [c_sz, c_p]),
-    "groupnorm_gate_backward_bf16": (c_i, [c_i, c_i, c_i, c_f] + [c_p] * 10 + [c_sz, c_p]),
+    "groupnorm_gate_backward_bf16": (c_i, [c_i, c_i, c_i, c_f, c_i] + [c_p] * 10 + [c_sz, c_p]),
     "pooling_backward_bf16": (c_i, [c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "scatter_rows_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "scatter_tokens_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),

@@ -103,4 +103,10 @@ template <int WK> __device__ __forceinline__ float load_logdecay(const void *w, 
     return __logf(fmaxf(((const float *)w)[idx], 1e-38f));
 }
 
+// ddlerp_tma.cu: TMA-fed token-shift ddlerp backward (nout = 5 with m, or 1 without).  Returns 1 when
+// the pointers are not 16-byte aligned (caller falls back to the register-fed kernel).
+size_t ddlerp_tma_partial_slots(int nout, int B, int T, int C);
+int ddlerp_backward_tma(int nout, int B, int T, int C, const void *x, const void *shift, const void *maa, const void *m,
+                        const void *const *gouts, void *gx, void *gm, void *gshift, float *partial, int *slots,
+                        cudaStream_t stream);
 }  // namespace wkv6

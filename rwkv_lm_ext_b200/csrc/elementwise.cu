@@ -194,6 +194,7 @@ __global__ void __launch_bounds__(256) shift_lerp_kernel(int B, int T, int C, co
 }
 
 // GroupNorm over 64-channel groups, then * g.  8 lanes (8 channels each) per group.
+template <bool SILU>
 __global__ void __launch_bounds__(256) gn_gate_kernel(size_t ngroups, int C, float eps, const bf16 *__restrict__ y,
                                                       const bf16 *__restrict__ g, const bf16 *__restrict__ lw,
                                                       const bf16 *__restrict__ lb, bf16 *__restrict__ out) {
@@ -224,6 +225,10 @@ __global__ void __launch_bounds__(256) gn_gate_kernel(size_t ngroups, int C, flo
         unpack8(ld8(lw + c), wf);
         unpack8(ld8(lb + c), bfv);
         unpack8(ld8(g + i * 8), gf);
+        if (SILU) {                                        // g = F.silu(gate(xg)) of jit_func, as a bf16 tensor
+#pragma unroll
+            for (int e = 0; e < 8; e++) gf[e] = rb(gf[e] / (1.f + __expf(-gf[e])));
+        }
 #pragma unroll
         for (int e = 0; e < 8; e++) o[e] = rb((f[e] - mean) * rstd * wf[e] + bfv[e]) * gf[e];
         if (live) st8(out + i * 8, pack8(o));
@@ -369,14 +374,18 @@ int tmix_shift_lerp_bf16(int B, int T, int C, const void *x, const void *shift_s
     return WKV6_OK;
 }
 
-int groupnorm_gate_bf16(int BT, int C, int H, float eps, const void *y, const void *g, const void *ln_w,
-                        const void *ln_b, void *out, void *stream) {
+int groupnorm_gate_bf16(int BT, int C, int H, float eps, int gate_act, const void *y, const void *g,
+                        const void *ln_w, const void *ln_b, void *out, void *stream) {
     if (BT < 0 || H <= 0 || C != H * 64) { set_error("groupnorm_gate_bf16: need C == H*64"); return WKV6_EINVAL; }
     if (BT == 0) return WKV6_OK;
     if (!y || !g || !ln_w || !ln_b || !out) { set_error("groupnorm_gate_bf16: null pointer"); return WKV6_EINVAL; }
     const size_t ngroups = (size_t)BT * H;
-    gn_gate_kernel<<<grid_for(ngroups * 8, 256), 256, 0, (cudaStream_t)stream>>>(
-        ngroups, C, eps, (const bf16 *)y, (const bf16 *)g, (const bf16 *)ln_w, (const bf16 *)ln_b, (bf16 *)out);
+    if (gate_act)
+        gn_gate_kernel<true><<<grid_for(ngroups * 8, 256), 256, 0, (cudaStream_t)stream>>>(
+            ngroups, C, eps, (const bf16 *)y, (const bf16 *)g, (const bf16 *)ln_w, (const bf16 *)ln_b, (bf16 *)out);
+    else
+        gn_gate_kernel<false><<<grid_for(ngroups * 8, 256), 256, 0, (cudaStream_t)stream>>>(
+            ngroups, C, eps, (const bf16 *)y, (const bf16 *)g, (const bf16 *)ln_w, (const bf16 *)ln_b, (bf16 *)out);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
     return WKV6_OK;

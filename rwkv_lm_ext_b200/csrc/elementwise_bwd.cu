@@ -10,6 +10,7 @@
 // token lanes in shared memory and written as fp32 partials [S][n][C]; a second, tiny kernel sums
 // the S partials in a fixed order -> deterministic, no atomics.
 #include "common.cuh"
+#include <algorithm>
 
 namespace wkv6 {
 namespace {
@@ -42,6 +43,7 @@ constexpr int TL = 8;  // token lanes (warps) per block
 #endif
 
 struct Split { int rows_per_split, rows_per_lane; };
+struct Ptr5 { const bf16 *p[5]; };   // the five incoming gradients (xw,xk,xv,xr,xg) are separate tensors
 
 // ------------------------------------------------------------------------------------------------
 // out_n = x + xx * coef_n,  xx = bf16(prev - x),  coef_n = bf16(maa_n + m_n)   (HAS_M)  or  maa_n
@@ -75,7 +77,7 @@ template <> struct VecIO<4> {
 template <int NOUT, bool HAS_M, int V>
 __global__ void __launch_bounds__(256, DD_MINB) ddlerp_bwd_kernel(int B, int T, int C, Split sp, const bf16 *__restrict__ x,
                                                          const bf16 *__restrict__ shift, const bf16 *__restrict__ maa,
-                                                         const bf16 *__restrict__ m, const bf16 *__restrict__ gout,
+                                                         const bf16 *__restrict__ m, const Ptr5 gout,
                                                          bf16 *__restrict__ gx, bf16 *__restrict__ gm,
                                                          bf16 *__restrict__ gshift, float *__restrict__ partial) {
     typedef VecIO<V> IO;
@@ -115,7 +117,7 @@ __global__ void __launch_bounds__(256, DD_MINB) ddlerp_bwd_kernel(int B, int T, 
 #pragma unroll
             for (int n = 0; n < NOUT; n++) {
                 float gf[V], cf[V];
-                IO::ld(gout + n * plane + (size_t)row * C + c, gf);
+                IO::ld(gout.p[n] + (size_t)row * C + c, gf);
                 if (HAS_M) {
                     IO::ld(m + n * plane + (size_t)row * C + c, cf);
 #pragma unroll
@@ -221,6 +223,7 @@ __global__ void sum_partials_kernel(int S, int n, size_t stride, const float *__
 //   gn = gz * w ;  gy = rstd * (gn - mean(gn) - n * mean(gn * n))
 // 8 consecutive lanes = one group.
 // ------------------------------------------------------------------------------------------------
+template <bool SILU>
 __global__ void __launch_bounds__(256) gn_gate_bwd_kernel(long long BT, int C, float eps, Split sp,
                                                           const bf16 *__restrict__ y, const bf16 *__restrict__ g,
                                                           const bf16 *__restrict__ lw, const bf16 *__restrict__ lb,
@@ -267,8 +270,14 @@ __global__ void __launch_bounds__(256) gn_gate_bwd_kernel(long long BT, int C, f
         for (int e = 0; e < 8; e++) {
             f[e] *= rstd;                                  // n
             const float z = rb(fmaf(f[e], wf[e], bfv[e]));
-            ggv[e] = go[e] * z;
-            const float gz = go[e] * gf[e];
+            float gate = gf[e], dgate = 1.f;
+            if (SILU) {                                    // gate = silu(graw), as bf16 like the eager op
+                const float sg = 1.f / (1.f + __expf(-gf[e]));
+                gate = rb(gf[e] * sg);
+                dgate = sg * (1.f + gf[e] * (1.f - sg));
+            }
+            ggv[e] = go[e] * z * dgate;
+            const float gz = go[e] * gate;
             aw[e] = fmaf(gz, f[e], aw[e]);
             ab[e] += gz;
             gn[e] = gz * wf[e];
@@ -402,24 +411,47 @@ using namespace wkv6;
 
 extern "C" {
 
-size_t elementwise_backward_workspace_bytes(int BT, int C, int nparam) {
-    if (BT <= 0 || C <= 0 || nparam <= 0) return 0;
-    return (size_t)(nparam == 2 ? splits_for(BT, C) : splits_for(BT, C, DD_COLS, DD_LANES)) * nparam * C * sizeof(float);
+size_t elementwise_backward_workspace_bytes(int B, int T, int C, int nparam) {
+    if (B <= 0 || T <= 0 || C <= 0 || nparam <= 0) return 0;
+    const long long BT = (long long)B * T;
+    size_t slots = nparam == 2 ? splits_for(BT, C) : splits_for(BT, C, DD_COLS, DD_LANES);
+    if (nparam != 2) slots = std::max(slots, ddlerp_tma_partial_slots(nparam, B, T, C));
+    return slots * nparam * C * sizeof(float);
 }
 
 int tmix_ddlerp_mix_backward_bf16(int B, int T, int C, const void *x, const void *shift_state, const void *maa,
-                                  const void *m, const void *gout, void *gx, void *gm, float *gmaa,
+                                  const void *m, const void *gxw, const void *gxk, const void *gxv,
+                                  const void *gxr, const void *gxg, void *gx, void *gm, float *gmaa,
                                   void *gshift, void *ws, size_t ws_bytes, void *stream) {
     if (B < 0 || T < 0 || C <= 0 || (C & 7)) { set_error("tmix_ddlerp_mix_backward_bf16: need C %% 8 == 0"); return WKV6_EINVAL; }
     const long long BT = (long long)B * T;
     if (BT == 0) return WKV6_OK;
-    if (!x || !maa || !m || !gout || !gx || !gm || !gmaa || !ws) { set_error("tmix_ddlerp_mix_backward_bf16: null pointer"); return WKV6_EINVAL; }
+    if (!x || !maa || !m || !gxw || !gxk || !gxv || !gxr || !gxg || !gx || !gm || !gmaa || !ws) {
+        set_error("tmix_ddlerp_mix_backward_bf16: null pointer");
+        return WKV6_EINVAL;
+    }
+    Ptr5 gout;
+    gout.p[0] = (const bf16 *)gxw; gout.p[1] = (const bf16 *)gxk; gout.p[2] = (const bf16 *)gxv;
+    gout.p[3] = (const bf16 *)gxr; gout.p[4] = (const bf16 *)gxg;
+    if (ws_bytes < elementwise_backward_workspace_bytes(B, T, C, 5)) { set_error("tmix_ddlerp_mix_backward_bf16: workspace too small"); return WKV6_EINVAL; }
+    if (wkv6b200_get_impl() != WKV6_IMPL_SIMT) {
+        const void *gs[5] = {gxw, gxk, gxv, gxr, gxg};
+        int slots = 0;
+        const int rc = ddlerp_backward_tma(5, B, T, C, x, shift_state, maa, m, gs, gx, gm, shift_state ? gshift : nullptr,
+                                           (float *)ws, &slots, (cudaStream_t)stream);
+        if (rc <= 0) {
+            if (rc < 0) return rc;
+            sum_partials_kernel<<<(5 * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(slots, 5 * C, (size_t)5 * C, (const float *)ws, gmaa);
+            count_launch();
+            WKV6_CUDA_CHECK(cudaGetLastError());
+            return WKV6_OK;
+        }
+    }
     const int S = splits_for(BT, C, DD_COLS, DD_LANES);
-    if (ws_bytes < (size_t)S * 5 * C * sizeof(float)) { set_error("tmix_ddlerp_mix_backward_bf16: workspace too small"); return WKV6_EINVAL; }
     dim3 grid((C + DD_COLS - 1) / DD_COLS, S);
     ddlerp_bwd_kernel<5, true, DD_V><<<grid, 256, 0, (cudaStream_t)stream>>>(
         B, T, C, split_of(BT, S, DD_LANES), (const bf16 *)x, (const bf16 *)shift_state, (const bf16 *)maa, (const bf16 *)m,
-        (const bf16 *)gout, (bf16 *)gx, (bf16 *)gm, shift_state ? (bf16 *)gshift : nullptr, (float *)ws);
+        gout, (bf16 *)gx, (bf16 *)gm, shift_state ? (bf16 *)gshift : nullptr, (float *)ws);
     sum_partials_kernel<<<(5 * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(S, 5 * C, (size_t)5 * C, (const float *)ws, gmaa);
     count_launch(2);
     WKV6_CUDA_CHECK(cudaGetLastError());
@@ -433,21 +465,36 @@ int tmix_shift_lerp_backward_bf16(int B, int T, int C, const void *x, const void
     const long long BT = (long long)B * T;
     if (BT == 0) return WKV6_OK;
     if (!x || !maa_x || !gout || !gx || !gmaa_x || !ws) { set_error("tmix_shift_lerp_backward_bf16: null pointer"); return WKV6_EINVAL; }
+    Ptr5 g1;
+    for (int i = 0; i < 5; i++) g1.p[i] = (const bf16 *)gout;
+    if (ws_bytes < elementwise_backward_workspace_bytes(B, T, C, 1)) { set_error("tmix_shift_lerp_backward_bf16: workspace too small"); return WKV6_EINVAL; }
+    if (wkv6b200_get_impl() != WKV6_IMPL_SIMT) {
+        const void *gs[1] = {gout};
+        int slots = 0;
+        const int rc = ddlerp_backward_tma(1, B, T, C, x, shift_state, maa_x, nullptr, gs, gx, nullptr,
+                                           shift_state ? gshift : nullptr, (float *)ws, &slots, (cudaStream_t)stream);
+        if (rc <= 0) {
+            if (rc < 0) return rc;
+            sum_partials_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(slots, C, (size_t)C, (const float *)ws, gmaa_x);
+            count_launch();
+            WKV6_CUDA_CHECK(cudaGetLastError());
+            return WKV6_OK;
+        }
+    }
     const int S = splits_for(BT, C, DD_COLS, DD_LANES);
-    if (ws_bytes < (size_t)S * C * sizeof(float)) { set_error("tmix_shift_lerp_backward_bf16: workspace too small"); return WKV6_EINVAL; }
     dim3 grid((C + DD_COLS - 1) / DD_COLS, S);
     ddlerp_bwd_kernel<1, false, DD_V><<<grid, 256, 0, (cudaStream_t)stream>>>(
         B, T, C, split_of(BT, S, DD_LANES), (const bf16 *)x, (const bf16 *)shift_state, (const bf16 *)maa_x, nullptr,
-        (const bf16 *)gout, (bf16 *)gx, nullptr, shift_state ? (bf16 *)gshift : nullptr, (float *)ws);
+        g1, (bf16 *)gx, nullptr, shift_state ? (bf16 *)gshift : nullptr, (float *)ws);
     sum_partials_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(S, C, (size_t)C, (const float *)ws, gmaa_x);
     count_launch(2);
     WKV6_CUDA_CHECK(cudaGetLastError());
     return WKV6_OK;
 }
 
-int groupnorm_gate_backward_bf16(int BT, int C, int H, float eps, const void *y, const void *g, const void *ln_w,
-                                 const void *ln_b, const void *gout, void *gy, void *gg, float *gln_w,
-                                 float *gln_b, void *ws, size_t ws_bytes, void *stream) {
+int groupnorm_gate_backward_bf16(int BT, int C, int H, float eps, int gate_act, const void *y, const void *g,
+                                 const void *ln_w, const void *ln_b, const void *gout, void *gy, void *gg,
+                                 float *gln_w, float *gln_b, void *ws, size_t ws_bytes, void *stream) {
     if (BT < 0 || H <= 0 || C != H * 64) { set_error("groupnorm_gate_backward_bf16: need C == H*64"); return WKV6_EINVAL; }
     if (BT == 0) return WKV6_OK;
     if (!y || !g || !ln_w || !ln_b || !gout || !gy || !gg || !gln_w || !gln_b || !ws) {
@@ -461,9 +508,14 @@ int groupnorm_gate_backward_bf16(int BT, int C, int H, float eps, const void *y,
     }
     dim3 grid((C + 255) / 256, S);
     float *partial = (float *)ws;
-    gn_gate_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(BT, C, eps, split_of(BT, S), (const bf16 *)y,
-                                                               (const bf16 *)g, (const bf16 *)ln_w, (const bf16 *)ln_b,
-                                                               (const bf16 *)gout, (bf16 *)gy, (bf16 *)gg, partial);
+    if (gate_act)
+        gn_gate_bwd_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            BT, C, eps, split_of(BT, S), (const bf16 *)y, (const bf16 *)g, (const bf16 *)ln_w, (const bf16 *)ln_b,
+            (const bf16 *)gout, (bf16 *)gy, (bf16 *)gg, partial);
+    else
+        gn_gate_bwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(
+            BT, C, eps, split_of(BT, S), (const bf16 *)y, (const bf16 *)g, (const bf16 *)ln_w, (const bf16 *)ln_b,
+            (const bf16 *)gout, (bf16 *)gy, (bf16 *)gg, partial);
     sum_partials_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(S, C, (size_t)2 * C, partial, gln_w);
     sum_partials_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(S, C, (size_t)2 * C, partial + C, gln_b);
     count_launch(3);

@@ -295,7 +295,7 @@ inline PFN_encodeTiled get_encode_fn() {
 }
 
 inline bool make_btc_map(CUtensorMap *map, const void *ptr, int B, int T, int C, int box_rows, CUtensorMapDataType dt,
-                         int elem_bytes, int box_cols) {
+                         int elem_bytes, int box_cols, bool swizzle128 = true) {
     PFN_encodeTiled enc = get_encode_fn();
     if (!enc) return false;
     // the driver entry point needs a current context on THIS host thread; a thread that has only
@@ -309,8 +309,11 @@ inline bool make_btc_map(CUtensorMap *map, const void *ptr, int B, int T, int C,
     cuuint64_t strides[2] = {(cuuint64_t)C * elem_bytes, (cuuint64_t)T * C * elem_bytes};
     cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
+    // swizzle128 = false: rows land in shared memory back to back (streaming kernels that read the
+    // tile with plain 16-byte loads); the inner box extent may then be up to 256 elements
     return enc(map, dt, 3, const_cast<void *>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+               swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+               swizzle128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 

@@ -25,8 +25,8 @@ def eos_index(idx: torch.Tensor, token_id: int) -> torch.Tensor:
     return pos
 
 
-def _ws(lib, BT, C, nparam, device):
-    return torch.empty(max(1, lib.elementwise_backward_workspace_bytes(BT, C, nparam)), dtype=torch.uint8, device=device)
+def _ws(lib, B, T, C, nparam, device):
+    return torch.empty(max(1, lib.elementwise_backward_workspace_bytes(B, T, C, nparam)), dtype=torch.uint8, device=device)
 
 
 def _needs_grad(*ts):
@@ -189,7 +189,7 @@ class _ShiftLerp(torch.autograd.Function):
         gx = torch.empty_like(x)
         gmaa = torch.empty(C, dtype=torch.float32, device=x.device)
         gshift = torch.empty_like(shift_state) if shift_state is not None else None
-        ws = _ws(lib, B * T, C, 1, x.device)
+        ws = _ws(lib, B, T, C, 1, x.device)
         check(lib.tmix_shift_lerp_backward_bf16(B, T, C, ptr(x), ptr(shift_state), ptr(maa_x), ptr(gout), ptr(gx), ptr(gmaa),
                                                 ptr(gshift), ptr(ws), ws.numel(), stream_of(x)), "tmix_shift_lerp_backward_bf16")
         return gx, gshift, gmaa.to(maa_x.dtype)
@@ -217,31 +217,35 @@ def _ddlerp_fwd(x, shift_state, maa, m):
 
 
 class _DdlerpMix(torch.autograd.Function):
+    """Five outputs (views of one [5,B,T,C] buffer), five incoming gradients: the consumers are five
+    different Linears, so autograd never has to stack their gradients into one tensor."""
+
     @staticmethod
     def forward(ctx, x, shift_state, maa, m):
         ctx.save_for_backward(x, shift_state, maa, m)
-        return _ddlerp_fwd(x, shift_state, maa, m)
+        return tuple(_ddlerp_fwd(x, shift_state, maa, m).unbind(0))
 
     @staticmethod
-    def backward(ctx, gout):
+    def backward(ctx, *gouts):
         x, shift_state, maa, m = ctx.saved_tensors
         lib = _lib.load()
         B, T, C = x.shape
-        gout = gout.contiguous()
+        gouts = [torch.zeros_like(x) if g is None else g.contiguous() for g in gouts]
         gx, gm = torch.empty_like(x), torch.empty_like(m)
         gmaa = torch.empty(5, C, dtype=torch.float32, device=x.device)
         gshift = torch.empty_like(shift_state) if shift_state is not None else None
-        ws = _ws(lib, B * T, C, 5, x.device)
-        check(lib.tmix_ddlerp_mix_backward_bf16(B, T, C, ptr(x), ptr(shift_state), ptr(maa), ptr(m), ptr(gout), ptr(gx),
-                                                ptr(gm), ptr(gmaa), ptr(gshift), ptr(ws), ws.numel(), stream_of(x)),
+        ws = _ws(lib, B, T, C, 5, x.device)
+        check(lib.tmix_ddlerp_mix_backward_bf16(B, T, C, ptr(x), ptr(shift_state), ptr(maa), ptr(m), *[ptr(g) for g in gouts],
+                                                ptr(gx), ptr(gm), ptr(gmaa), ptr(gshift), ptr(ws), ws.numel(), stream_of(x)),
               "tmix_ddlerp_mix_backward_bf16")
         return gx, gshift, gmaa.to(maa.dtype), gm
 
 
 def tmix_ddlerp_mix(x, maa_wkvrg, m, shift_state=None):
     """xw,xk,xv,xr,xg = x + xx * (time_maa_n + m_n)  (src/model.py:444-448).
-    maa_wkvrg bf16 [5,C]; m bf16 [5,B,T,C] (the LoRA bmm output).  Returns a [5,B,T,C] tensor.
-    Differentiable w.r.t. x, maa_wkvrg, m and the shift state."""
+    maa_wkvrg bf16 [5,C]; m bf16 [5,B,T,C] (the LoRA bmm output).  Returns a [5,B,T,C] tensor
+    (inference) or the tuple of its five [B,T,C] slices (when a gradient is needed): unpack or index
+    it either way.  Differentiable w.r.t. x, maa_wkvrg, m and the shift state."""
     _cuda(x)
     assert x.dtype == torch.bfloat16 and m.dtype == torch.bfloat16
     x, m, maa = x.contiguous(), m.contiguous(), maa_wkvrg.contiguous()
@@ -251,44 +255,49 @@ def tmix_ddlerp_mix(x, maa_wkvrg, m, shift_state=None):
     return _ddlerp_fwd(x, shift_state, maa, m)
 
 
-def _gn_fwd(y, g, ln_w, ln_b, H, eps):
+_GATE_ACT = {None: 0, "none": 0, "silu": 1}
+
+
+def _gn_fwd(y, g, ln_w, ln_b, H, eps, act):
     B, T, C = y.shape
     out = torch.empty_like(y)
-    check(_lib.load().groupnorm_gate_bf16(B * T, C, H, float(eps), ptr(y), ptr(g), ptr(ln_w), ptr(ln_b), ptr(out),
+    check(_lib.load().groupnorm_gate_bf16(B * T, C, H, float(eps), act, ptr(y), ptr(g), ptr(ln_w), ptr(ln_b), ptr(out),
                                           stream_of(y)), "groupnorm_gate_bf16")
     return out
 
 
 class _GroupNormGate(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, y, g, ln_w, ln_b, H, eps):
+    def forward(ctx, y, g, ln_w, ln_b, H, eps, act):
         ctx.save_for_backward(y, g, ln_w, ln_b)
-        ctx.meta = (H, eps)
-        return _gn_fwd(y, g, ln_w, ln_b, H, eps)
+        ctx.meta = (H, eps, act)
+        return _gn_fwd(y, g, ln_w, ln_b, H, eps, act)
 
     @staticmethod
     def backward(ctx, gout):
         y, g, ln_w, ln_b = ctx.saved_tensors
-        H, eps = ctx.meta
+        H, eps, act = ctx.meta
         lib = _lib.load()
         B, T, C = y.shape
         gout = gout.contiguous()
         gy, gg = torch.empty_like(y), torch.empty_like(g)
         gw = torch.empty(C, dtype=torch.float32, device=y.device)
         gb = torch.empty(C, dtype=torch.float32, device=y.device)
-        ws = _ws(lib, B * T, C, 2, y.device)
-        check(lib.groupnorm_gate_backward_bf16(B * T, C, H, float(eps), ptr(y), ptr(g), ptr(ln_w), ptr(ln_b), ptr(gout),
+        ws = _ws(lib, B, T, C, 2, y.device)
+        check(lib.groupnorm_gate_backward_bf16(B * T, C, H, float(eps), act, ptr(y), ptr(g), ptr(ln_w), ptr(ln_b), ptr(gout),
                                                ptr(gy), ptr(gg), ptr(gw), ptr(gb), ptr(ws), ws.numel(), stream_of(y)),
               "groupnorm_gate_backward_bf16")
-        return gy, gg, gw.to(ln_w.dtype), gb.to(ln_b.dtype), None, None
+        return gy, gg, gw.to(ln_w.dtype), gb.to(ln_b.dtype), None, None, None
 
 
-def groupnorm_gate(y, g, ln_w, ln_b, H, eps):
+def groupnorm_gate(y, g, ln_w, ln_b, H, eps, gate_act=None):
     """ln_x(y.view(B*T, C)).view(B,T,C) * g  (src/model.py:461-467, without the output Linear).
-    Differentiable w.r.t. y, g and the GroupNorm affine parameters."""
+    gate_act="silu": g is the gate Linear's raw output and F.silu (src/model.py:454) is applied
+    inside the kernel.  Differentiable w.r.t. y, g and the GroupNorm affine parameters."""
     _cuda(y)
     assert y.dtype == torch.bfloat16 and g.dtype == torch.bfloat16
     y, g, ln_w, ln_b = y.contiguous(), g.contiguous(), ln_w.contiguous(), ln_b.contiguous()
+    act = _GATE_ACT[gate_act]
     if _needs_grad(y, g, ln_w, ln_b):
-        return _GroupNormGate.apply(y, g, ln_w, ln_b, H, eps)
-    return _gn_fwd(y, g, ln_w, ln_b, H, eps)
+        return _GroupNormGate.apply(y, g, ln_w, ln_b, H, eps, act)
+    return _gn_fwd(y, g, ln_w, ln_b, H, eps, act)

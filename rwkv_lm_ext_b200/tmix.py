@@ -20,7 +20,6 @@ serves SFT.  Variants: `time_state` attribute present -> state tuning (src/model
 `last_state` given -> infctx (src/model.py:738-781), returning `(out, (last_token, wkv_state))`.
 """
 import torch
-import torch.nn.functional as F
 
 from . import heads, ops
 
@@ -32,17 +31,18 @@ def _maa5(layer):
 
 
 def tmix_x060_project(layer, x, shift_state=None):
-    """jit_func (src/model.py:434-459 / :738-762): x [B,T,C] bf16 -> r, k, v, g, w (each [B,T,C])."""
+    """jit_func (src/model.py:434-459 / :738-762): x [B,T,C] bf16 -> r, k, v, g_raw, w (each [B,T,C]);
+    g_raw is the gate Linear's output BEFORE silu (tmix_x060_finish applies it in-kernel)."""
     B, T, C = x.shape
     xxx = heads.tmix_shift_lerp(x, layer.time_maa_x, shift_state)
     R = layer.time_maa_w2.shape[1]
     lora = torch.tanh(xxx.view(B * T, C) @ layer.time_maa_w1).view(B * T, 5, R).transpose(0, 1)
     m = torch.bmm(lora, layer.time_maa_w2).view(5, B, T, C)
-    xw, xk, xv, xr, xg = heads.tmix_ddlerp_mix(x, _maa5(layer), m, shift_state).unbind(0)
+    xw, xk, xv, xr, xg = heads.tmix_ddlerp_mix(x, _maa5(layer), m, shift_state)
     r = layer.receptance(xr)
     k = layer.key(xk)
     v = layer.value(xv)
-    g = F.silu(layer.gate(xg))
+    g = layer.gate(xg)                      # raw: silu is applied inside the GroupNorm*gate kernel
     # time_decay + tanh(xw @ W1) @ W2 with the bias add as the GEMM epilogue
     w = torch.addmm(layer.time_decay.view(-1), torch.tanh(xw.view(B * T, C) @ layer.time_decay_w1),
                     layer.time_decay_w2).view(B, T, -1)
@@ -50,9 +50,9 @@ def tmix_x060_project(layer, x, shift_state=None):
 
 
 def tmix_x060_finish(layer, y, g):
-    """jit_func_2 (src/model.py:461-468): GroupNorm over heads, * g, output Linear."""
+    """jit_func_2 (src/model.py:461-468): GroupNorm over heads, * silu(g_raw), output Linear."""
     H = layer.time_faaaa.shape[0]
-    return layer.output(heads.groupnorm_gate(y, g, layer.ln_x.weight, layer.ln_x.bias, H, layer.ln_x.eps))
+    return layer.output(heads.groupnorm_gate(y, g, layer.ln_x.weight, layer.ln_x.bias, H, layer.ln_x.eps, gate_act="silu"))
 
 
 def tmix_x060_forward(layer, x, last_state=None):

@@ -182,8 +182,9 @@ def test_ddlerp_backward(M, B, T, C, with_state):
         assert_bf16_close(st.grad, want1[4], "shift_lerp gshift")
         st.grad = None
     x.grad = None
-    out5 = M.tmix_ddlerp_mix(x, maa, m, st)
-    out5.backward(go5)
+    out5 = M.tmix_ddlerp_mix(x, maa, m, st)          # five [B,T,C] outputs when a gradient is needed
+    assert len(out5) == 5
+    torch.autograd.backward(list(out5), [go5[n] for n in range(5)])
     assert_bf16_close(x.grad, want5[0], "ddlerp gx")
     assert_bf16_close(maa.grad, want5[2], "ddlerp gmaa")
     assert_bf16_close(m.grad, want5[3], "ddlerp gm")
@@ -191,8 +192,9 @@ def test_ddlerp_backward(M, B, T, C, with_state):
         assert_bf16_close(st.grad, want5[4], "ddlerp gshift")
 
 
+@pytest.mark.parametrize("act", [None, "silu"])
 @pytest.mark.parametrize("B,T,H", [(3, 21, 4), (2, 300, 12), (1, 1, 1)])
-def test_groupnorm_gate_backward(M, O, B, T, H):
+def test_groupnorm_gate_backward(M, O, B, T, H, act):
     g = torch.Generator().manual_seed(13)
     C = H * 64
     eps = 1e-5 * 8 ** 2
@@ -202,8 +204,12 @@ def test_groupnorm_gate_backward(M, O, B, T, H):
     lb = (torch.randn(C, generator=g) * 0.1).bfloat16().to(DEV).requires_grad_(True)
     go = torch.randn(B, T, C, generator=g).bfloat16().to(DEV)
     leaves = [_leaf64(t) for t in (y, gate, lw, lb)]
-    (O.groupnorm_gate(*leaves, H, eps) * go.cpu().double()).sum().backward()
-    M.groupnorm_gate(y, gate, lw, lb, H, eps).backward(go)
+    gate64 = torch.nn.functional.silu(leaves[1]) if act == "silu" else leaves[1]
+    ref = O.groupnorm_gate(leaves[0], gate64, leaves[2], leaves[3], H, eps)
+    (ref * go.cpu().double()).sum().backward()
+    out = M.groupnorm_gate(y, gate, lw, lb, H, eps, gate_act=act)
+    assert_bf16_close(out, ref, "gn*gate fwd")
+    out.backward(go)
     for name, t, l in zip(("gy", "gg", "gln_w", "gln_b"), (y, gate, lw, lb), leaves):
         assert_bf16_close(t.grad, l.grad, "gn*gate " + name)
 
