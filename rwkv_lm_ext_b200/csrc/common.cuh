@@ -109,4 +109,10 @@ size_t ddlerp_tma_partial_slots(int nout, int B, int T, int C);
 int ddlerp_backward_tma(int nout, int B, int T, int C, const void *x, const void *shift, const void *maa, const void *m,
                         const void *const *gouts, void *gx, void *gm, void *gshift, float *partial, int *slots,
                         cudaStream_t stream);
+// seg_scan.cu: time-axis segmentation for calls with few streams (see the file header)
+int seg_count(int B, int T, int H);
+int seg_decay(int rows, int Tseg, int C, const void *w, float *lam, cudaStream_t stream);
+int seg_scan(int B, int nseg, int H, const float *lam, const float *s_loc, const void *s0, int s0_f32,
+             long long s0_bstride, float *s_start, void *sT, int sT_f32, int reverse, cudaStream_t stream);
+int seg_flags_merge(int B, int nseg, int H, int *seg_flags, int *stream_flags, cudaStream_t stream);
 }  // namespace wkv6

@@ -1,0 +1,138 @@
+// Time-axis segmentation for calls with few (b,h) streams.
+//
+// The chunked kernels map one stream to one CTA, so a call with B*H < 148 streams (infctx training
+// with B = 1, inference prefill, small SFT buckets) leaves most SMs idle.  The recurrence is linear in
+// the state, so a sequence can be cut into `nseg` segments that run as independent "batch rows":
+//     S_end(seg) = diag(exp(Lam_seg)) * S_start(seg) + S_loc(seg)
+// with S_loc the final state of the segment run from a ZERO state and Lam_seg the segment's total
+// log-decay.  Forward = state-only pass over all segments (S_loc) + the two small kernels below
+// (Lam, scan over segments) + the ordinary forward over all segments with S_start as initial states.
+// [B,T,C] viewed as [B*nseg, T/nseg, C] is the same memory, so the big kernels run unchanged.
+#include "common.cuh"
+#include <cstdlib>
+
+namespace wkv6 {
+namespace {
+
+typedef __nv_bfloat16 bf16;
+
+// lam[row, c] = sum_t -exp(w[row, t, c])      rows = B*nseg segments of Tseg tokens
+// grid (ceil(C/256), rows), block 256 = 32 column lanes (8 channels) x 8 token lanes
+__global__ void __launch_bounds__(256) seg_decay_kernel(int Tseg, int C, const bf16 *__restrict__ w, float *__restrict__ lam) {
+    const int lane = threadIdx.x & 31, tl = threadIdx.x >> 5;
+    const int c = (blockIdx.x * 32 + lane) * 8;
+    const size_t row = blockIdx.y;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (c < C) {
+        const bf16 *base = w + row * (size_t)Tseg * C + c;
+        for (int t = tl; t < Tseg; t += 8) {
+            const uint4 u = *reinterpret_cast<const uint4 *>(base + (size_t)t * C);
+            const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float2 f = __bfloat1622float2(h[i]);
+                acc[2 * i] -= __expf(f.x);
+                acc[2 * i + 1] -= __expf(f.y);
+            }
+        }
+    }
+    __shared__ float red[8][256 + 8];
+#pragma unroll
+    for (int e = 0; e < 8; e++) red[tl][lane * 8 + e] = acc[e];
+    __syncthreads();
+    const int cc = blockIdx.x * 256 + threadIdx.x;
+    if (cc < C) {
+        float s = 0.f;
+#pragma unroll
+        for (int l = 0; l < 8; l++) s += red[l][threadIdx.x];
+        lam[row * C + cc] = s;
+    }
+}
+
+// Scan over the segments of one (b,h) stream, element-wise on the 64x64 state (caller layout
+// [value j][key i], the decay acts on the key index = fastest dimension).
+//   S_start[b,0] = s0 (or 0);  S_start[b,seg+1] = exp(lam[b,seg,h,i]) * S_start[b,seg] + S_loc[b,seg]
+// reverse = 1 walks the segments from the last to the first (the backward's state-gradient chain).
+// grid B*H, block 256, 16 elements per thread.
+__global__ void __launch_bounds__(256) seg_scan_kernel(int nseg, int H, const float *__restrict__ lam,
+                                                       const float *__restrict__ s_loc, const void *__restrict__ s0,
+                                                       int s0_f32, long long s0_bstride, float *__restrict__ s_start,
+                                                       void *__restrict__ sT, int sT_f32, int reverse) {
+    const int b = blockIdx.x / H, h = blockIdx.x % H;
+    const size_t C = (size_t)H * 64;
+    for (int e = threadIdx.x; e < 4096; e += 256) {
+        const int i = e & 63;
+        float S = 0.f;
+        if (s0) {
+            const size_t idx = (size_t)b * s0_bstride + (size_t)h * 4096 + e;
+            S = s0_f32 ? ((const float *)s0)[idx] : __bfloat162float(((const bf16 *)s0)[idx]);
+        }
+        for (int q = 0; q < nseg; q++) {
+            const int seg = reverse ? nseg - 1 - q : q;
+            const size_t row = (size_t)b * nseg + seg;
+            s_start[(row * H + h) * 4096 + e] = S;
+            S = __expf(lam[row * C + h * 64 + i]) * S + s_loc[(row * H + h) * 4096 + e];
+        }
+        if (sT) {
+            const size_t idx = ((size_t)b * H + h) * 4096 + e;
+            if (sT_f32) ((float *)sT)[idx] = S;
+            else ((bf16 *)sT)[idx] = __float2bfloat16_rn(S);
+        }
+    }
+}
+
+// a stream is flagged when any of its segments is; then all its segments are (so later segmented
+// launches skip them and the exact route recomputes the whole stream)
+__global__ void seg_flags_kernel(int n, int nseg, int H, int *__restrict__ seg_flags, int *__restrict__ stream_flags) {
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;   // b*H + h
+    if (s >= n) return;
+    const int b = s / H, h = s % H;
+    int f = stream_flags[s];
+    for (int q = 0; q < nseg; q++) f |= seg_flags[((size_t)b * nseg + q) * H + h];
+    f = f != 0;
+    stream_flags[s] = f;
+    for (int q = 0; q < nseg; q++) seg_flags[((size_t)b * nseg + q) * H + h] = f;
+}
+
+}  // namespace
+
+// number of segments for a call with B*H streams of T tokens (1 = do not segment)
+int seg_count(int B, int T, int H) {
+    const long long streams = (long long)B * H;
+    static const bool off = getenv("WKV6B200_NO_SEG") != nullptr;     // A/B switch for profiles/bench_few_streams.py
+    // the extra launches (state-only pass, decay sums, scan, flag merges: ~40 us of launch latency)
+    // only pay off when a stream keeps its SM busy for a few hundred microseconds: T >= 8192
+    if (off || streams <= 0 || streams >= 148 || T < 8192) return 1;
+    int n = (int)(296 / streams);
+    if (n > T / 128) n = T / 128;                 // at least two chunks per segment
+    while (n > 1 && T % (n * 64) != 0) n--;       // segments are whole chunks of the same length
+    return n < 2 ? 1 : n;
+}
+
+int seg_decay(int rows, int Tseg, int C, const void *w, float *lam, cudaStream_t stream) {
+    dim3 grid((C + 255) / 256, rows);
+    seg_decay_kernel<<<grid, 256, 0, stream>>>(Tseg, C, (const bf16 *)w, lam);
+    count_launch();
+    WKV6_CUDA_CHECK(cudaGetLastError());
+    return WKV6_OK;
+}
+
+int seg_scan(int B, int nseg, int H, const float *lam, const float *s_loc, const void *s0, int s0_f32,
+             long long s0_bstride, float *s_start, void *sT, int sT_f32, int reverse, cudaStream_t stream) {
+    seg_scan_kernel<<<B * H, 256, 0, stream>>>(nseg, H, lam, s_loc, s0, s0_f32, s0_bstride, s_start, sT, sT_f32, reverse);
+    count_launch();
+    WKV6_CUDA_CHECK(cudaGetLastError());
+    return WKV6_OK;
+}
+
+int seg_flags_merge(int B, int nseg, int H, int *seg_flags, int *stream_flags, cudaStream_t stream) {
+    const int n = B * H;
+    if (n == 0) return WKV6_OK;
+    // n < 148 by construction: one small block
+    seg_flags_kernel<<<(n + 127) / 128, 128, 0, stream>>>(n, nseg, H, seg_flags, stream_flags);
+    count_launch();
+    WKV6_CUDA_CHECK(cudaGetLastError());
+    return WKV6_OK;
+}
+
+}  // namespace wkv6

@@ -432,6 +432,34 @@ def test_very_long_single_call_and_many_streams(M):
             assert relrms(a, b_) < 8e-3
 
 
+def test_segmented_forward_few_streams(M):
+    """Forward-only calls with few streams and T >= 8192 are cut into time segments that run as
+    independent batch rows (csrc/seg_scan.cu); y and the carried state must match the exact SIMT route."""
+    from rwkv_lm_ext_b200 import _lib
+    B, T, H = 1, 16384, 3
+    C = H * 64
+    r, k, v, w, u, _ = make_inputs(B, T, H, seed=41, decay="model", device=DEV)
+    g = torch.Generator().manual_seed(42)
+    s0 = (torch.randn(B, H, 64, 64, generator=g) * 0.3).to(DEV)
+    lib = _lib.load()
+    outs = []
+    for impl in ("auto", "simt"):
+        M.set_impl(impl)
+        try:
+            st = s0.clone()
+            y = torch.empty_like(r)
+            _lib.check(lib.wkv6infctx_forward_f32state(B, T, C, H, _lib.ptr(r), _lib.ptr(k), _lib.ptr(v), _lib.ptr(w),
+                                                       _lib.ptr(u), _lib.ptr(st), _lib.ptr(y), _lib.stream_of(r)), "infctx fwd")
+            with torch.no_grad():
+                y0 = M.RUN_CUDA_RWKV6(B, T, C, H, r, k, v, w, u)
+            outs.append((y, st, y0))
+        finally:
+            M.set_impl("auto")
+    (y, st, y0), (ys, sts, y0s) = outs
+    assert relrms(y, ys) < 6e-3 and relrms(y0, y0s) < 6e-3
+    assert relrms(st, sts) < 2e-3
+
+
 def test_empty_inputs(M):
     z = torch.empty(0, 8, 64, device=DEV, dtype=torch.bfloat16)
     u = torch.zeros(1, 64, device=DEV, dtype=torch.bfloat16)
