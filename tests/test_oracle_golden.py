@@ -129,3 +129,48 @@ def test_bi_semantics():
     yq = O.wkv6_bi_forward(mask, r, k, v, w, u, ref_quirks=True)
     _close(yq[0], yf[0], 1e-12)
     _close(yq[1], y[1], 0.0)
+
+
+def test_oracle_pieces_compose_to_the_reference_encoder(golden_dir):
+    """tests/golden/encoder_2x128.npz holds RwkvEncoder.encode_sentence (src/model_encoder_run.py) run on
+    its CPU path.  Rebuilding that forward from the oracle's pieces alone (mask / reverse index / reverse
+    gather, tmix_ddlerp, tmix_decay, the recurrence, groupnorm_gate, eos gather) pins those restatements
+    against the reference's own model code."""
+    z = np.load(os.path.join(golden_dir, "encoder_2x128.npz"))
+    P = {k[2:]: torch.from_numpy(z[k].astype(np.float64)) for k in z.files if k.startswith("w:")}
+    idx = torch.from_numpy(z["idx"])
+    L, D = int(z["n_layer"]), int(z["n_embd"])
+    H = D // 64
+    ln = lambda x, p: torch.nn.functional.layer_norm(x, (D,), P[p + ".weight"], P[p + ".bias"])
+    mask = O.create_mask(idx, int(z["emb_id"]), int(z["pad_id"]))
+    rev = O.reverse_x_idx(mask, idx.shape[1])
+    x = P["emb.weight"][idx]
+    for i in range(L):
+        pre = f"blocks.{i}."
+        if i == 0:
+            x = ln(x, pre + "ln0")
+        a = pre + "att."
+        maa5 = torch.cat([P[a + "time_maa_" + n].view(1, D) for n in "wkvrg"])
+
+        def project(xin):
+            xw, xk, xv, xr, xg = O.tmix_ddlerp(xin, P[a + "time_maa_x"].view(D), maa5, P[a + "time_maa_w1"], P[a + "time_maa_w2"])
+            r, k, v = xr @ P[a + "receptance.weight"].T, xk @ P[a + "key.weight"].T, xv @ P[a + "value.weight"].T
+            g = torch.nn.functional.silu(xg @ P[a + "gate.weight"].T)
+            return r, k, v, g, O.tmix_decay(xw, P[a + "time_decay"], P[a + "time_decay_w1"], P[a + "time_decay_w2"])
+        h = ln(x, pre + "ln1")
+        r, k, v, g, w = project(h)
+        rr, rk, rv, _, rw = project(O.reverse_x(h, rev))
+        y = O.wkv6_forward(r, k, v, w, P[a + "time_faaaa"])
+        ry = O.reverse_x(O.wkv6_forward(rr, rk, rv, rw, P[a + "time_faaaa"]), rev)
+        att = O.groupnorm_gate((y + ry) / 2, g, P[a + "ln_x.weight"], P[a + "ln_x.bias"], H, 1e-5 * 64) @ P[a + "output.weight"].T
+        x = x + att
+        f = pre + "ffn."
+        h = ln(x, pre + "ln2")
+        xx = torch.nn.functional.pad(h, (0, 0, 1, -1)) - h
+        kk = torch.relu((h + xx * P[f + "time_maa_k"]) @ P[f + "key.weight"].T) ** 2
+        x = x + torch.sigmoid((h + xx * P[f + "time_maa_r"]) @ P[f + "receptance.weight"].T) * (kk @ P[f + "value.weight"].T)
+    hidden = ln(x, "ln_out")
+    _close(hidden, torch.from_numpy(z["hidden"]), 2e-4, rtol=1e-3)
+    emb, pos = O.eos_gather(hidden, idx, int(z["emb_id"]))
+    _close(emb, torch.from_numpy(z["emb"]), 2e-4, rtol=1e-3)
+    assert pos.tolist() == [47, 30, 12, 1]
