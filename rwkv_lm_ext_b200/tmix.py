@@ -17,7 +17,9 @@ so it can be bound onto the reference's own layers without touching their state_
 The eager chain's ~25 elementwise passes over [B,T,C] become 3 kernels (shift-lerp, ddlerp mix,
 GroupNorm*gate) plus the `silu`; every piece is differentiable (heads.py, ops.py), so the same call
 serves SFT.  Variants: `time_state` attribute present -> state tuning (src/model.py:560-584);
-`last_state` given -> infctx (src/model.py:738-781), returning `(out, (last_token, wkv_state))`.
+`last_state` given -> infctx (src/model.py:738-781): a `TimeMixState` (the reference's or
+rwkv_lm_ext_b200.infctx's) returns `(out, TimeMixState(last_token, wkv_state))`, a plain
+`(shift_state, wkv_state)` tuple returns `(out, (last_token, wkv_state))`.
 """
 import torch
 
@@ -63,7 +65,10 @@ def tmix_x060_forward(layer, x, last_state=None):
         shift_state, wkv_state = (last_state.shift_state, last_state.wkv_state) if hasattr(last_state, "shift_state") else last_state
         r, k, v, g, w = tmix_x060_project(layer, x, shift_state)
         y, new_state = ops.WKV_6STATE_INFCTX.apply(B, T, C, H, r, k, v, w, layer.time_faaaa, wkv_state.clone().contiguous())
-        return tmix_x060_finish(layer, y, g), (x[:, -1], new_state)
+        out = tmix_x060_finish(layer, y, g)
+        if hasattr(last_state, "shift_state"):                  # reference calling convention (src/model.py:781)
+            return out, type(last_state)(x[:, -1], new_state)
+        return out, (x[:, -1], new_state)
     r, k, v, g, w = tmix_x060_project(layer, x)
     if getattr(layer, "time_state", None) is not None:          # state tuning
         y = ops.WKV_6STATE.apply(B, T, C, H, r, k, v, w, layer.time_faaaa, layer.time_state)

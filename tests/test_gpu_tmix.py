@@ -114,3 +114,22 @@ def test_tmix_binds_onto_a_foreign_module():
     x = torch.randn(2, 33, C, device=DEV).bfloat16()
     with torch.no_grad():
         assert torch.equal(f(x), src(x))
+
+
+def test_tmix_infctx_chunks_equal_one_long_pass():
+    """Two infctx calls chained through BlockStateList (fp32 carry) == one plain call on the whole sequence."""
+    import rwkv_lm_ext_b200 as M
+    B, T, H = 2, 256, 2
+    C = H * 64
+    layer = make_layer(M, C, H, 21).to(DEV)
+    x = torch.randn(B, T, C, generator=torch.Generator().manual_seed(22)).bfloat16().to(DEV)
+    states = M.BlockStateList.create(1, B, C, H, DEV, torch.bfloat16, wkv_dtype=torch.float32)
+    with torch.no_grad():
+        full = layer(x)
+        outs = []
+        for lo in (0, 128):
+            out, tms = layer(x[:, lo:lo + 128].contiguous(), states[0].time_mix_state)
+            assert isinstance(tms, M.TimeMixState)
+            states[0] = M.BlockState(tms, states[0].channel_mix_state)
+            outs.append(out)
+    assert relrms(torch.cat(outs, 1), full) < 6e-3
