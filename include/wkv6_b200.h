@@ -200,6 +200,12 @@ WKV6_API int gather_tokens_bf16(int B, int T, int D, const void *x, const int64_
  * shift_state: NULL (zero pad) or bf16 [B,C] (infctx, src/model.py:738-745).  All bf16. */
 WKV6_API int tmix_ddlerp_mix_bf16(int B, int T, int C, const void *x, const void *shift_state,
                          const void *maa, const void *m, void *out, void *stream);
+/* The same with the rank-R LoRA product fused in (src/model.py:442-448): m_n = h_n @ W2_n is computed on
+ * the tensor cores inside the kernel and never written to memory.  h bf16 [B*T, 5*R] = tanh(xxx @ W1)
+ * (row-major, the five R-wide slices side by side), w2 bf16 [5,R,C], out bf16 [5,B,T,C].
+ * R = 32 and C % 64 == 0 only (WKV6_EUNSUPPORTED otherwise: use a bmm + tmix_ddlerp_mix_bf16). */
+WKV6_API int tmix_ddlerp_lora_bf16(int B, int T, int C, int R, const void *x, const void *shift_state,
+                          const void *maa, const void *h, const void *w2, void *out, void *stream);
 /* xxx = x + (shift(x)-x)*maa_x  (src/model.py:439-441), the LoRA input.  bf16. */
 WKV6_API int tmix_shift_lerp_bf16(int B, int T, int C, const void *x, const void *shift_state,
                          const void *maa_x, void *out, void *stream);

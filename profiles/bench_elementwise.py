@@ -79,7 +79,18 @@ def pool_bwd():
     assert lib.pooling_backward_bf16(0, 1, B * 64, 512, 1024, ptr(lens), ptr(goe), ptr(gxe), st) == 0
 
 
+hl = torch.tanh(torch.randn(B * T, 160, device=dev, generator=g)).bfloat16()
+w2 = (torch.randn(5, 32, C, device=dev, generator=g) * 0.1).bfloat16()
+
+
+def lora_unfused():
+    mm = torch.bmm(hl.view(B * T, 5, 32).transpose(0, 1), w2).view(5, B, T, C)
+    return heads.tmix_ddlerp_mix(x, maa, mm)
+
+
 cases = [
+    ("tmix_ddlerp_lora (LoRA product fused, tcgen05)", lambda: heads.tmix_ddlerp_lora(x, maa, hl, w2), E * 12 + B * T * 160 * 2),
+    ("bmm + tmix_ddlerp_mix (unfused equivalent)", lora_unfused, E * 12 + B * T * 160 * 2),
     ("tmix_ddlerp_mix backward", ddlerp_bwd, E * 34),          # x 2 + gout 10 + m 10 -> gx 2 + gm 10 B/elem
     ("tmix_shift_lerp backward", shift_bwd, E * 6),            # x, gout -> gx
     ("groupnorm_gate backward", gn_bwd, E * 10),               # y, g, gout -> gy, gg

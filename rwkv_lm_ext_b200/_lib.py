@@ -44,6 +44,7 @@ SIGNATURES = {
     "create_mask_rev_idx": (c_i, [c_i, c_i, c_p, c_i64, c_i64, c_p, c_p, c_p]),
     "gather_tokens_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "tmix_ddlerp_mix_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "tmix_ddlerp_lora_bf16": (c_i, [c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "tmix_shift_lerp_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "groupnorm_gate_bf16": (c_i, [c_i, c_i, c_i, c_f, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     "elementwise_backward_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i]),

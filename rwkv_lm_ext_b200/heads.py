@@ -255,6 +255,65 @@ def tmix_ddlerp_mix(x, maa_wkvrg, m, shift_state=None):
     return _ddlerp_fwd(x, shift_state, maa, m)
 
 
+class _DdlerpLora(torch.autograd.Function):
+    """Forward: the fused kernel (m never leaves the chip).  Backward: m is recomputed with one bmm, the
+    TMA-fed ddlerp backward gives gx / gm / gmaa, two more bmm carry gm to h and W2."""
+
+    @staticmethod
+    def forward(ctx, x, shift_state, maa, h, w2):
+        ctx.save_for_backward(x, shift_state, maa, h, w2)
+        return tuple(_ddlerp_lora_fwd(x, shift_state, maa, h, w2).unbind(0))
+
+    @staticmethod
+    def backward(ctx, *gouts):
+        x, shift_state, maa, h, w2 = ctx.saved_tensors
+        lib = _lib.load()
+        B, T, C = x.shape
+        R = w2.shape[1]
+        h5 = h.view(B * T, 5, R).transpose(0, 1)                     # [5, BT, R]
+        m = torch.bmm(h5, w2).view(5, B, T, C)
+        gouts = [torch.zeros_like(x) if g is None else g.contiguous() for g in gouts]
+        gx, gm = torch.empty_like(x), torch.empty_like(m)
+        gmaa = torch.empty(5, C, dtype=torch.float32, device=x.device)
+        gshift = torch.empty_like(shift_state) if shift_state is not None else None
+        ws = _ws(lib, B, T, C, 5, x.device)
+        check(lib.tmix_ddlerp_mix_backward_bf16(B, T, C, ptr(x), ptr(shift_state), ptr(maa), ptr(m), *[ptr(g) for g in gouts],
+                                                ptr(gx), ptr(gm), ptr(gmaa), ptr(gshift), ptr(ws), ws.numel(), stream_of(x)),
+              "tmix_ddlerp_mix_backward_bf16")
+        gm5 = gm.view(5, B * T, C)
+        gh = torch.bmm(gm5, w2.transpose(1, 2)).transpose(0, 1).reshape(B * T, 5 * R)
+        gw2 = torch.bmm(h5.transpose(1, 2), gm5)
+        return gx, gshift, gmaa.to(maa.dtype), gh.view_as(h), gw2
+
+
+def _ddlerp_lora_fwd(x, shift_state, maa, h, w2):
+    B, T, C = x.shape
+    out = torch.empty(5, B, T, C, dtype=torch.bfloat16, device=x.device)
+    check(_lib.load().tmix_ddlerp_lora_bf16(B, T, C, w2.shape[1], ptr(x), ptr(shift_state), ptr(maa), ptr(h), ptr(w2), ptr(out),
+                                            stream_of(x)), "tmix_ddlerp_lora_bf16")
+    return out
+
+
+def tmix_ddlerp_lora(x, maa_wkvrg, h, w2, shift_state=None):
+    """xw,xk,xv,xr,xg = x + xx * (time_maa_n + h_n @ W2_n)  (src/model.py:442-448) with the rank-R LoRA
+    product on the tensor cores inside the kernel.  h bf16 [B*T, 5R] or [B,T,5R] = tanh(xxx @ W1);
+    w2 bf16 [5,R,C].  R = 32 and C % 64 == 0; other shapes take the bmm + tmix_ddlerp_mix route.
+    Returns five [B,T,C] tensors (a tuple under autograd, a [5,B,T,C] tensor otherwise)."""
+    _cuda(x)
+    assert x.dtype == torch.bfloat16 and h.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16
+    B, T, C = x.shape
+    R = w2.shape[1]
+    x, maa, w2 = x.contiguous(), maa_wkvrg.contiguous(), w2.contiguous()
+    h = h.contiguous().view(B * T, 5 * R)
+    shift_state = shift_state.contiguous() if shift_state is not None else None
+    if R != 32 or C % 64 != 0:
+        m = torch.bmm(h.view(B * T, 5, R).transpose(0, 1), w2).view(5, B, T, C)
+        return tmix_ddlerp_mix(x, maa, m, shift_state)
+    if _needs_grad(x, maa, h, w2, shift_state):
+        return _DdlerpLora.apply(x, shift_state, maa, h, w2)
+    return _ddlerp_lora_fwd(x, shift_state, maa, h, w2)
+
+
 _GATE_ACT = {None: 0, "none": 0, "silu": 1}
 
 

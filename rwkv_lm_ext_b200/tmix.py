@@ -37,10 +37,8 @@ def tmix_x060_project(layer, x, shift_state=None):
     g_raw is the gate Linear's output BEFORE silu (tmix_x060_finish applies it in-kernel)."""
     B, T, C = x.shape
     xxx = heads.tmix_shift_lerp(x, layer.time_maa_x, shift_state)
-    R = layer.time_maa_w2.shape[1]
-    lora = torch.tanh(xxx.view(B * T, C) @ layer.time_maa_w1).view(B * T, 5, R).transpose(0, 1)
-    m = torch.bmm(lora, layer.time_maa_w2).view(5, B, T, C)
-    xw, xk, xv, xr, xg = heads.tmix_ddlerp_mix(x, _maa5(layer), m, shift_state)
+    h = torch.tanh(xxx.view(B * T, C) @ layer.time_maa_w1)                  # [B*T, 5R]
+    xw, xk, xv, xr, xg = heads.tmix_ddlerp_lora(x, _maa5(layer), h, layer.time_maa_w2, shift_state)
     r = layer.receptance(xr)
     k = layer.key(xk)
     v = layer.value(xv)

@@ -257,3 +257,44 @@ def test_heads_backward(M, O):
     x2 = xb.to(DEV).requires_grad_(True)
     torch.gather(x2, 1, rev.unsqueeze(-1).expand(-1, -1, D)).backward(gor)
     assert torch.equal(x.grad, x2.grad)
+
+
+@pytest.mark.parametrize("B,T,C,with_state", [(2, 37, 256, False), (3, 130, 768, True), (1, 1, 64, True), (2, 300, 2048, False)])
+def test_ddlerp_lora_fused(M, B, T, C, with_state):
+    """tmix_ddlerp_lora (LoRA product on the tensor cores, m never materialised) == bmm + tmix_ddlerp_mix up to
+    the accumulation order of the K=32 product; gradients through the recompute path match too."""
+    g = torch.Generator().manual_seed(23)
+    R = 32
+    x = torch.randn(B, T, C, generator=g).bfloat16().to(DEV)
+    maa = torch.rand(5, C, generator=g).bfloat16().to(DEV)
+    h = torch.tanh(torch.randn(B * T, 5 * R, generator=g)).bfloat16().to(DEV)
+    w2 = (torch.randn(5, R, C, generator=g) * 0.1).bfloat16().to(DEV)
+    st = torch.randn(B, C, generator=g).bfloat16().to(DEV) if with_state else None
+    m = torch.bmm(h.view(B * T, 5, R).transpose(0, 1), w2).view(5, B, T, C)
+    want = M.tmix_ddlerp_mix(x, maa, m, st)
+    got = M.tmix_ddlerp_lora(x, maa, h, w2, st)
+    assert got.shape == want.shape
+    # identical except where the fp32 sum of 32 products rounds to a neighbouring bf16 value
+    diff = (got.float() - want.float()).abs()
+    assert (diff > 0).float().mean().item() < 0.02
+    assert relrms(got, want) < 2e-3
+    # fp64 reference of the whole expression
+    xx = (torch.cat([(st if with_state else torch.zeros(B, C, device=DEV, dtype=torch.bfloat16)).unsqueeze(1), x[:, :-1]], 1).double() - x.double())
+    m64 = torch.bmm(h.double().view(B * T, 5, R).transpose(0, 1), w2.double()).view(5, B, T, C)
+    ref = x.double() + xx * (maa.double().view(5, 1, 1, C) + m64)
+    assert relrms(got, ref) < 1e-2           # four bf16 roundings deep, like the eager chain itself
+    assert abs(relrms(got, ref) - relrms(want, ref)) < 5e-4
+    # gradients
+    leaves = [t.clone().requires_grad_(True) for t in (x, maa, h, w2)] + ([st.clone().requires_grad_(True)] if with_state else [None])
+    outs = M.tmix_ddlerp_lora(leaves[0], leaves[1], leaves[2], leaves[3], leaves[4])
+    go = [torch.randn(B, T, C, generator=g).bfloat16().to(DEV) for _ in range(5)]
+    torch.autograd.backward(list(outs), go)
+    l64 = [t.detach().double().requires_grad_(True) if t is not None else None for t in leaves]
+    prev = torch.zeros(B, 1, C, device=DEV, dtype=torch.float64) if l64[4] is None else l64[4].unsqueeze(1)
+    xx64 = torch.cat([prev, l64[0][:, :-1]], 1) - l64[0]
+    m64 = torch.bmm(l64[2].view(B * T, 5, R).transpose(0, 1), l64[3]).view(5, B, T, C)
+    ref = l64[0] + xx64 * (l64[1].view(5, 1, 1, C) + m64)
+    (ref * torch.stack(go).double()).sum().backward()
+    for name, a, b_ in zip(("gx", "gmaa", "gh", "gw2", "gshift"), leaves, l64):
+        if a is not None:
+            assert relrms(a.grad, b_.grad) < 1.5e-2, name
