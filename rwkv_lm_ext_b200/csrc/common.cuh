@@ -116,7 +116,8 @@ int seg_scan(int B, int nseg, int H, const float *lam, const float *s_loc, const
              long long s0_bstride, float *s_start, void *sT, int sT_f32, int reverse, cudaStream_t stream);
 int seg_flags_merge(int B, int nseg, int H, int *seg_flags, int *stream_flags, cudaStream_t stream);
 // ddlerp_lora.cu: ddlerp forward with the LoRA product on the tensor cores
-bool ddlerp_lora_supported(int B, int T, int C, int R, const void *x, const void *h, const void *w2, const void *out);
+bool ddlerp_lora_supported(int B, int T, int C, int R, const void *x, const void *h, const void *w2, const void *out,
+                           const void *maa);
 int ddlerp_lora_forward(int B, int T, int C, const void *x, const void *shift, const void *maa, const void *h,
                         const void *w2, void *out, cudaStream_t stream);
 }  // namespace wkv6

@@ -27,7 +27,7 @@ constexpr int TM = 128, NC = 64, RANK = 32, NOUT = 5;
 constexpr int EPI_THREADS = 256, THREADS = 288;
 constexpr int H_BOX = TM * 128;                       // one [128 rows][64 cols] bf16 box, 128-byte rows
 constexpr int OFF_H = 0;                              // 3 boxes: columns 0-63, 64-127, 128-191 of h
-constexpr int X_BYTES = 17408;                        // [129 rows][128 B] rounded up to 1024
+constexpr int X_BYTES = 17408;                        // [129 rows][128 B] of x + [5 rows][128 B] of maa, rounded up to 1024
 constexpr int OFF_X = OFF_H + 3 * H_BOX;              // 2 buffers
 constexpr int W_BYTES = RANK * 128;                   // [32 k][64 c] bf16
 constexpr int OFF_W = OFF_X + 2 * X_BYTES;            // ring of 3
@@ -61,7 +61,8 @@ struct Params {
 
 __global__ void __launch_bounds__(THREADS, 2)
 ddlerp_lora_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_w2,
-                   const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_o, const Params p) {
+                   const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_o,
+                   const __grid_constant__ CUtensorMap map_a, const Params p) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     Bars &bar = *reinterpret_cast<Bars *>(sm + OFF_BAR);
@@ -100,8 +101,10 @@ ddlerp_lora_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
             for (int j = 0; j < 3; j++) tma_load_3d(sm + OFF_H + j * H_BOX, &map_h, &bar.h, j * 64, r0, 0);
             auto load_x = [&](int gi) {          // group index inside this CTA
                 const int s = gi & 1;
-                mbar_arrive_expect_tx(&bar.x_full[s], (TM + 1) * 128);
+                mbar_arrive_expect_tx(&bar.x_full[s], (TM + 1 + NOUT) * 128);
                 tma_load_3d(sm + OFF_X + s * X_BYTES, &map_x, &bar.x_full[s], (g0 + gi) * NC, r0 - 1, 0);
+                // the group's 5 x 64 time_maa values ride along as rows 129..133 of the same swizzled tile
+                tma_load_3d(sm + OFF_X + s * X_BYTES + (TM + 1) * 128, &map_a, &bar.x_full[s], (g0 + gi) * NC, 0, 0);
             };
             auto load_w = [&](int item) {
                 const int s = item % 3, gi = item / NOUT, n = item % NOUT;
@@ -180,7 +183,7 @@ ddlerp_lora_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
 #pragma unroll
             for (int q = 0; q < 4; q++) {                     // 4 chunks of 8 channels
                 const uint4 xv = *reinterpret_cast<const uint4 *>(xs + sw128(row + 1, (half * 4 + q) * 16));
-                const uint4 av = __ldg(reinterpret_cast<const uint4 *>(p.maa + (size_t)n * p.C + c + q * 8));
+                const uint4 av = *reinterpret_cast<const uint4 *>(xs + sw128(TM + 1 + n, (half * 4 + q) * 16));
                 const __nv_bfloat162 *x2 = reinterpret_cast<const __nv_bfloat162 *>(&xv);
                 const __nv_bfloat162 *a2 = reinterpret_cast<const __nv_bfloat162 *>(&av);
 #pragma unroll
@@ -229,18 +232,20 @@ inline bool aligned16(const void *q) { return (reinterpret_cast<uintptr_t>(q) & 
 
 }  // namespace
 
-bool ddlerp_lora_supported(int B, int T, int C, int R, const void *x, const void *h, const void *w2, const void *out) {
-    return R == RANK && C % NC == 0 && (long long)B * T > 0 && (long long)B * T < (1ll << 31) - TM && aligned16(x) &&
+bool ddlerp_lora_supported(int B, int T, int C, int R, const void *x, const void *h, const void *w2, const void *out,
+                           const void *maa) {
+    return aligned16(maa) && R == RANK && C % NC == 0 && (long long)B * T > 0 && (long long)B * T < (1ll << 31) - TM && aligned16(x) &&
            aligned16(h) && aligned16(w2) && aligned16(out);
 }
 
 int ddlerp_lora_forward(int B, int T, int C, const void *x, const void *shift, const void *maa, const void *h,
                         const void *w2, void *out, cudaStream_t stream) {
     const long long BT = (long long)B * T;
-    CUtensorMap mh, mw, mx, mo;
+    CUtensorMap mh, mw, mx, mo, ma;
     const auto dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     if (!make_btc_map(&mh, h, 1, (int)BT, NOUT * RANK, TM, dt, 2, 64) || !make_btc_map(&mw, w2, NOUT, RANK, C, RANK, dt, 2, 64) ||
-        !make_btc_map(&mx, x, 1, (int)BT, C, TM + 1, dt, 2, 64) || !make_btc_map(&mo, out, NOUT, (int)BT, C, TM, dt, 2, 64)) {
+        !make_btc_map(&mx, x, 1, (int)BT, C, TM + 1, dt, 2, 64) || !make_btc_map(&mo, out, NOUT, (int)BT, C, TM, dt, 2, 64) ||
+        !make_btc_map(&ma, maa, 1, NOUT, C, NOUT, dt, 2, 64)) {
         set_error("ddlerp_lora: cuTensorMapEncodeTiled failed");
         return WKV6_ECUDA;
     }
@@ -261,7 +266,7 @@ int ddlerp_lora_forward(int B, int T, int C, const void *x, const void *shift, c
         WKV6_CUDA_CHECK(cudaFuncSetAttribute(ddlerp_lora_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
-    ddlerp_lora_kernel<<<dim3(tiles, split), THREADS, SMEM_BYTES, stream>>>(mh, mw, mx, mo, p);
+    ddlerp_lora_kernel<<<dim3(tiles, split), THREADS, SMEM_BYTES, stream>>>(mh, mw, mx, mo, ma, p);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
     return WKV6_OK;
@@ -276,7 +281,7 @@ extern "C" int tmix_ddlerp_lora_bf16(int B, int T, int C, int R, const void *x, 
     if (B < 0 || T < 0 || C <= 0 || R <= 0) { set_error("tmix_ddlerp_lora_bf16: bad shape"); return WKV6_EINVAL; }
     if ((size_t)B * T == 0) return WKV6_OK;
     if (!x || !maa || !h || !w2 || !out) { set_error("tmix_ddlerp_lora_bf16: null pointer"); return WKV6_EINVAL; }
-    if (!ddlerp_lora_supported(B, T, C, R, x, h, w2, out)) {
+    if (!ddlerp_lora_supported(B, T, C, R, x, h, w2, out, maa)) {
         set_error("tmix_ddlerp_lora_bf16: needs R == 32, C %% 64 == 0 and 16-byte aligned tensors (use bmm + tmix_ddlerp_mix_bf16)");
         return WKV6_EUNSUPPORTED;
     }
