@@ -248,6 +248,25 @@ WKV6_API int scatter_rows_bf16(int B, int T, int D, const void *gout, const int6
 WKV6_API int scatter_tokens_bf16(int B, int T, int D, const void *gout, const int64_t *rev_idx, void *gx,
                         void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Channel mix (RWKV_CMix_x060.forward, src/model.py:635-644; infctx :804-812): the elementwise pieces
+ * around its two GEMMs, bit-identical to the eager bf16 chain.
+ * ------------------------------------------------------------------------------------------ */
+/* out[0] = xk, out[1] = xr = x + (shift(x)-x) * time_maa_{k,r};  maa_kr bf16 [2,C];  out bf16 [2,B,T,C]. */
+WKV6_API int cmix_shift_lerp2_bf16(int B, int T, int C, const void *x, const void *shift_state,
+                          const void *maa_kr, void *out, void *stream);
+/* ws: elementwise_backward_workspace_bytes(B, T, C, 3) bytes; gmaa_kr fp32 [2,C]. */
+WKV6_API int cmix_shift_lerp2_backward_bf16(int B, int T, int C, const void *x, const void *shift_state,
+                                   const void *maa_kr, const void *gxk, const void *gxr, void *gx,
+                                   float *gmaa_kr, void *gshift, void *ws, size_t ws_bytes, void *stream);
+/* y = relu(x)^2 and its gradient gx = 2 relu(x) gy;  n elements (n % 8 == 0). */
+WKV6_API int relu_sq_bf16(size_t n, const void *x, void *y, void *stream);
+WKV6_API int relu_sq_backward_bf16(size_t n, const void *x, const void *gy, void *gx, void *stream);
+/* out = sigmoid(r) * kv and its gradients. */
+WKV6_API int sigmoid_mul_bf16(size_t n, const void *r, const void *kv, void *out, void *stream);
+WKV6_API int sigmoid_mul_backward_bf16(size_t n, const void *r, const void *kv, const void *gout, void *gr,
+                              void *gkv, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

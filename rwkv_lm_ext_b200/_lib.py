@@ -53,6 +53,12 @@ SIGNATURES = {
     "groupnorm_gate_backward_bf16": (c_i, [c_i, c_i, c_i, c_f, c_i] + [c_p] * 10 + [c_sz, c_p]),
     "pooling_backward_bf16": (c_i, [c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "scatter_rows_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "cmix_shift_lerp2_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
+    "cmix_shift_lerp2_backward_bf16": (c_i, [c_i, c_i, c_i] + [c_p] * 9 + [c_sz, c_p]),
+    "relu_sq_bf16": (c_i, [c_sz, c_p, c_p, c_p]),
+    "relu_sq_backward_bf16": (c_i, [c_sz, c_p, c_p, c_p, c_p]),
+    "sigmoid_mul_bf16": (c_i, [c_sz, c_p, c_p, c_p, c_p]),
+    "sigmoid_mul_backward_bf16": (c_i, [c_sz, c_p, c_p, c_p, c_p, c_p, c_p]),
     "scatter_tokens_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
 }
 

@@ -256,6 +256,15 @@ int ddlerp_backward_tma(int nout, int B, int T, int C, const void *x, const void
         kern<<<grid, 256, Smem<5, true>::TOTAL, stream>>>(mx, mm, mg, B, T, C, splits, rps, (const bf16 *)shift,
                                                           (const bf16 *)maa, (const bf16 *)m, gp, (bf16 *)gx, (bf16 *)gm,
                                                           (bf16 *)gshift, partial);
+    } else if (nout == 2) {
+        auto kern = ddlerp_bwd_tma_kernel<2, false>;
+        if (dev < 64 && !(attr_done[dev] & 4)) {
+            WKV6_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem<2, false>::TOTAL));
+            attr_done[dev] |= 4;
+        }
+        kern<<<grid, 256, Smem<2, false>::TOTAL, stream>>>(mx, mm, mg, B, T, C, splits, rps, (const bf16 *)shift,
+                                                           (const bf16 *)maa, nullptr, gp, (bf16 *)gx, nullptr,
+                                                           (bf16 *)gshift, partial);
     } else {
         auto kern = ddlerp_bwd_tma_kernel<1, false>;
         if (dev < 64 && !(attr_done[dev] & 2)) {

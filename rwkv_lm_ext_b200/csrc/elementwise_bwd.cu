@@ -377,6 +377,12 @@ __global__ void scatter_tokens_kernel(int BT, int T, int D, const bf16 *__restri
     }
 }
 
+// a += b (bf16, fp32 add): only on the unaligned-pointer fallback of the two-output shift-lerp gradient
+__global__ void add_bf16_kernel(size_t n, bf16 *__restrict__ a, const bf16 *__restrict__ b) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        a[i] = __float2bfloat16_rn(__bfloat162float(a[i]) + __bfloat162float(b[i]));
+}
+
 int grid_for(size_t items, int block) {
     size_t g = (items + block - 1) / block;
     const size_t cap = 148 * 16;
@@ -414,9 +420,10 @@ extern "C" {
 size_t elementwise_backward_workspace_bytes(int B, int T, int C, int nparam) {
     if (B <= 0 || T <= 0 || C <= 0 || nparam <= 0) return 0;
     const long long BT = (long long)B * T;
+    // nparam: 5 ddlerp, 1 shift-lerp, 2 GroupNorm*gate, 3 = the two-output channel-mix shift-lerp (2 rows)
     size_t slots = nparam == 2 ? splits_for(BT, C) : splits_for(BT, C, DD_COLS, DD_LANES);
-    if (nparam != 2) slots = std::max(slots, ddlerp_tma_partial_slots(nparam, B, T, C));
-    return slots * nparam * C * sizeof(float);
+    if (nparam != 2) slots = std::max(slots, ddlerp_tma_partial_slots(nparam == 3 ? 2 : nparam, B, T, C));
+    return slots * (nparam == 3 ? 2 : nparam) * C * sizeof(float);
 }
 
 int tmix_ddlerp_mix_backward_bf16(int B, int T, int C, const void *x, const void *shift_state, const void *maa,
@@ -553,6 +560,49 @@ int scatter_tokens_bf16(int B, int T, int D, const void *gout, const int64_t *re
     const int BT = B * T;
     scatter_tokens_kernel<<<grid_for((size_t)BT * 32, 256), 256, 0, (cudaStream_t)stream>>>(
         BT, T, D, (const bf16 *)gout, rev_idx, (bf16 *)gx);
+    count_launch();
+    WKV6_CUDA_CHECK(cudaGetLastError());
+    return WKV6_OK;
+}
+
+// gradient of cmix_shift_lerp2_bf16: gx [B,T,C], gmaa_kr fp32 [2,C] from gxk, gxr
+int cmix_shift_lerp2_backward_bf16(int B, int T, int C, const void *x, const void *shift_state, const void *maa_kr,
+                                   const void *gxk, const void *gxr, void *gx, float *gmaa_kr, void *gshift, void *ws,
+                                   size_t ws_bytes, void *stream) {
+    if (B < 0 || T < 0 || C <= 0 || (C & 7)) { set_error("cmix_shift_lerp2_backward_bf16: need C %% 8 == 0"); return WKV6_EINVAL; }
+    const long long BT = (long long)B * T;
+    if (BT == 0) return WKV6_OK;
+    if (!x || !maa_kr || !gxk || !gxr || !gx || !gmaa_kr || !ws) { set_error("cmix_shift_lerp2_backward_bf16: null pointer"); return WKV6_EINVAL; }
+    if (ws_bytes < elementwise_backward_workspace_bytes(B, T, C, 3)) { set_error("cmix_shift_lerp2_backward_bf16: workspace too small"); return WKV6_EINVAL; }
+    const void *gs[2] = {gxk, gxr};
+    int slots = 0;
+    int rc = ddlerp_backward_tma(2, B, T, C, x, shift_state, maa_kr, nullptr, gs, gx, nullptr, shift_state ? gshift : nullptr,
+                                 (float *)ws, &slots, (cudaStream_t)stream);
+    if (rc < 0) return rc;
+    if (rc == 1) {          // unaligned pointers: two passes of the register-fed one-output kernel
+        const int S = splits_for(BT, C, DD_COLS, DD_LANES);
+        dim3 grid((C + DD_COLS - 1) / DD_COLS, S);
+        float *part = (float *)ws;
+        bf16 *tmp = nullptr;
+        WKV6_CUDA_CHECK(cudaMallocAsync((void **)&tmp, (size_t)BT * C * 2 + (shift_state ? (size_t)B * C * 2 : 0), (cudaStream_t)stream));
+        bf16 *tmp_shift = shift_state ? tmp + (size_t)BT * C : nullptr;
+        for (int n = 0; n < 2; n++) {
+            Ptr5 g1;
+            for (int i = 0; i < 5; i++) g1.p[i] = (const bf16 *)gs[n];
+            ddlerp_bwd_kernel<1, false, DD_V><<<grid, 256, 0, (cudaStream_t)stream>>>(
+                B, T, C, split_of(BT, S, DD_LANES), (const bf16 *)x, (const bf16 *)shift_state, (const bf16 *)maa_kr + (size_t)n * C,
+                nullptr, g1, n == 0 ? (bf16 *)gx : tmp, nullptr, shift_state ? (n == 0 ? (bf16 *)gshift : tmp_shift) : nullptr, part);
+            sum_partials_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(S, C, (size_t)C, part, gmaa_kr + (size_t)n * C);
+            count_launch(2);
+        }
+        add_bf16_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>((size_t)BT * C, (bf16 *)gx, tmp);
+        if (shift_state) add_bf16_kernel<<<64, 256, 0, (cudaStream_t)stream>>>((size_t)B * C, (bf16 *)gshift, tmp_shift);
+        count_launch(shift_state ? 2 : 1);
+        WKV6_CUDA_CHECK(cudaGetLastError());
+        cudaFreeAsync(tmp, (cudaStream_t)stream);
+        return WKV6_OK;
+    }
+    sum_partials_kernel<<<(2 * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(slots, 2 * C, (size_t)2 * C, (const float *)ws, gmaa_kr);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
     return WKV6_OK;

@@ -14,11 +14,11 @@ Per layer ("semantics 2": a causal pass over the tokens and one over each row's 
     reverse gathers         128-bit gather kernel
     WKV6 (x2)               tcgen05 / TMA chunked kernel
     GroupNorm * silu(gate)  one kernel
-    channel mix             the reference module's own forward (elementwise around two GEMMs)
+    channel mix             cmix_x060_forward: 3 fused elementwise kernels around the two GEMMs
 """
 import torch
 
-from . import heads, ops, tmix
+from . import cmix, heads, ops, tmix
 
 
 def _ids(model):
@@ -49,7 +49,11 @@ def bi_encoder_hidden(model, idx):
         if i == 0 and hasattr(blk, "ln0"):
             x = blk.ln0(x)
         x = x + bi_tmix_forward(blk.att, blk.ln1(x), rev_idx)
-        x = x + blk.ffn(blk.ln2(x))
+        ffn = blk.ffn
+        if all(hasattr(ffn, n) for n in ("time_maa_k", "time_maa_r", "key", "receptance", "value")):
+            x = x + cmix.cmix_x060_forward(ffn, blk.ln2(x))          # x060 channel mix on the fused kernels
+        else:
+            x = x + ffn(blk.ln2(x))
     return model.ln_out(x)
 
 
