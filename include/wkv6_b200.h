@@ -215,6 +215,12 @@ WKV6_API int tmix_shift_lerp_bf16(int B, int T, int C, const void *x, const void
 WKV6_API int groupnorm_gate_bf16(int BT, int C, int H, float eps, int gate_act, const void *y, const void *g,
                         const void *ln_w, const void *ln_b, void *out, void *stream);
 
+/* The same for the bi-directional encoders (src/model_encoder_run.py:72-74): the normalised input is
+ * (y + reverse_x(y_rev, rev_idx)) / 2, gathered and averaged inside the kernel.  rev_idx int64 [B,T]. */
+WKV6_API int groupnorm_gate_pair_bf16(int B, int T, int C, int H, float eps, int gate_act, const void *y,
+                             const void *y_rev, const int64_t *rev_idx, const void *g, const void *ln_w,
+                             const void *ln_b, void *out, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * Gradients of the memory-bound neighbours, so the fused forwards above can replace the eager
  * chains of src/model.py:434-468 / src/model_ext.py:1708-1738 inside a training graph.  Data

@@ -47,6 +47,7 @@ SIGNATURES = {
     "tmix_ddlerp_lora_bf16": (c_i, [c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "tmix_shift_lerp_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "groupnorm_gate_bf16": (c_i, [c_i, c_i, c_i, c_f, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
+    "groupnorm_gate_pair_bf16": (c_i, [c_i, c_i, c_i, c_i, c_f, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "elementwise_backward_workspace_bytes": (c_sz, [c_i, c_i, c_i, c_i]),
     "tmix_ddlerp_mix_backward_bf16": (c_i, [c_i, c_i, c_i] + [c_p] * 14 + [c_sz, c_p]),
     "tmix_shift_lerp_backward_bf16": (c_i, [c_i, c_i, c_i] + [c_p] * 8 + [c_sz, c_p]),

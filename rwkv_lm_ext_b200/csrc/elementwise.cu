@@ -194,10 +194,13 @@ __global__ void __launch_bounds__(256) shift_lerp_kernel(int B, int T, int C, co
 }
 
 // GroupNorm over 64-channel groups, then * g.  8 lanes (8 channels each) per group.
-template <bool SILU>
+// PAIR: the normalised input is (y + y2[b, rev[b,t]]) / 2 -- the two directions of the bi-directional
+// encoders (src/model_encoder_run.py:72-74) -- so the reverse gather and the average cost no pass of their own
+template <bool SILU, bool PAIR>
 __global__ void __launch_bounds__(256) gn_gate_kernel(size_t ngroups, int C, float eps, const bf16 *__restrict__ y,
                                                       const bf16 *__restrict__ g, const bf16 *__restrict__ lw,
-                                                      const bf16 *__restrict__ lb, bf16 *__restrict__ out) {
+                                                      const bf16 *__restrict__ lb, bf16 *__restrict__ out,
+                                                      const bf16 *__restrict__ y2, const int64_t *__restrict__ rev, int T) {
     const size_t nvec = ngroups * 8;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     // all 32 lanes of a warp iterate together (nvec is a multiple of 8, pad the loop to warps)
@@ -206,6 +209,14 @@ __global__ void __launch_bounds__(256) gn_gate_kernel(size_t ngroups, int C, flo
         const size_t i = live ? i0 : nvec - 1;
         float f[8];
         unpack8(ld8(y + i * 8), f);
+        if (PAIR) {
+            const size_t row = (i * 8) / C;                      // b*T + t
+            const size_t src = (row / T) * T + (size_t)rev[row];
+            float f2[8];
+            unpack8(ld8(y2 + src * C + (i * 8) % C), f2);
+#pragma unroll
+            for (int e = 0; e < 8; e++) f[e] = rb(f[e] + f2[e]) * 0.5f;
+        }
         float s = 0.f;
 #pragma unroll
         for (int e = 0; e < 8; e++) s += f[e];
@@ -381,11 +392,31 @@ int groupnorm_gate_bf16(int BT, int C, int H, float eps, int gate_act, const voi
     if (!y || !g || !ln_w || !ln_b || !out) { set_error("groupnorm_gate_bf16: null pointer"); return WKV6_EINVAL; }
     const size_t ngroups = (size_t)BT * H;
     if (gate_act)
-        gn_gate_kernel<true><<<grid_for(ngroups * 8, 256), 256, 0, (cudaStream_t)stream>>>(
-            ngroups, C, eps, (const bf16 *)y, (const bf16 *)g, (const bf16 *)ln_w, (const bf16 *)ln_b, (bf16 *)out);
+        gn_gate_kernel<true, false><<<grid_for(ngroups * 8, 256), 256, 0, (cudaStream_t)stream>>>(
+            ngroups, C, eps, (const bf16 *)y, (const bf16 *)g, (const bf16 *)ln_w, (const bf16 *)ln_b, (bf16 *)out, nullptr, nullptr, 1);
     else
-        gn_gate_kernel<false><<<grid_for(ngroups * 8, 256), 256, 0, (cudaStream_t)stream>>>(
-            ngroups, C, eps, (const bf16 *)y, (const bf16 *)g, (const bf16 *)ln_w, (const bf16 *)ln_b, (bf16 *)out);
+        gn_gate_kernel<false, false><<<grid_for(ngroups * 8, 256), 256, 0, (cudaStream_t)stream>>>(
+            ngroups, C, eps, (const bf16 *)y, (const bf16 *)g, (const bf16 *)ln_w, (const bf16 *)ln_b, (bf16 *)out, nullptr, nullptr, 1);
+    count_launch();
+    WKV6_CUDA_CHECK(cudaGetLastError());
+    return WKV6_OK;
+}
+
+int groupnorm_gate_pair_bf16(int B, int T, int C, int H, float eps, int gate_act, const void *y, const void *y_rev,
+                             const int64_t *rev_idx, const void *g, const void *ln_w, const void *ln_b, void *out,
+                             void *stream) {
+    if (B < 0 || T < 0 || H <= 0 || C != H * 64) { set_error("groupnorm_gate_pair_bf16: need C == H*64"); return WKV6_EINVAL; }
+    if ((size_t)B * T == 0) return WKV6_OK;
+    if (!y || !y_rev || !rev_idx || !g || !ln_w || !ln_b || !out) { set_error("groupnorm_gate_pair_bf16: null pointer"); return WKV6_EINVAL; }
+    const size_t ngroups = (size_t)B * T * H;
+    if (gate_act)
+        gn_gate_kernel<true, true><<<grid_for(ngroups * 8, 256), 256, 0, (cudaStream_t)stream>>>(
+            ngroups, C, eps, (const bf16 *)y, (const bf16 *)g, (const bf16 *)ln_w, (const bf16 *)ln_b, (bf16 *)out,
+            (const bf16 *)y_rev, rev_idx, T);
+    else
+        gn_gate_kernel<false, true><<<grid_for(ngroups * 8, 256), 256, 0, (cudaStream_t)stream>>>(
+            ngroups, C, eps, (const bf16 *)y, (const bf16 *)g, (const bf16 *)ln_w, (const bf16 *)ln_b, (bf16 *)out,
+            (const bf16 *)y_rev, rev_idx, T);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
     return WKV6_OK;

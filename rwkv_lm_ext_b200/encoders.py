@@ -35,8 +35,9 @@ def bi_tmix_forward(att, x, rev_idx):
     r, k, v, g, w = tmix.tmix_x060_project(att, x)
     rr, rk, rv, _, rw = tmix.tmix_x060_project(att, heads.reverse_x(x, rev_idx))
     y = ops.RUN_CUDA_RWKV6(B, T, C, H, r, k, v, w, att.time_faaaa)
-    ry = heads.reverse_x(ops.RUN_CUDA_RWKV6(B, T, C, H, rr, rk, rv, rw, att.time_faaaa), rev_idx)
-    return tmix.tmix_x060_finish(att, (y + ry) / 2, g)
+    ry = ops.RUN_CUDA_RWKV6(B, T, C, H, rr, rk, rv, rw, att.time_faaaa)       # still in reversed token order
+    z = heads.groupnorm_gate_pair(y, ry, rev_idx, g, att.ln_x.weight, att.ln_x.bias, H, att.ln_x.eps, gate_act="silu")
+    return att.output(z)
 
 
 def bi_encoder_hidden(model, idx):

@@ -360,3 +360,20 @@ def groupnorm_gate(y, g, ln_w, ln_b, H, eps, gate_act=None):
     if _needs_grad(y, g, ln_w, ln_b):
         return _GroupNormGate.apply(y, g, ln_w, ln_b, H, eps, act)
     return _gn_fwd(y, g, ln_w, ln_b, H, eps, act)
+
+
+def groupnorm_gate_pair(y, y_rev, rev_idx, g, ln_w, ln_b, H, eps, gate_act=None):
+    """ln_x((y + reverse_x(y_rev, rev_idx)) / 2) * g  -- the tail of bi_att_forward_batch
+    (src/model_encoder_run.py:72-74) with the reverse gather and the average inside the kernel.
+    Under autograd the pieces run separately (each is differentiable)."""
+    _cuda(y)
+    if _needs_grad(y, y_rev, g, ln_w, ln_b):
+        return groupnorm_gate((y + reverse_x(y_rev, rev_idx)) / 2, g, ln_w, ln_b, H, eps, gate_act)
+    assert y.dtype == torch.bfloat16 and y_rev.dtype == torch.bfloat16 and g.dtype == torch.bfloat16 and rev_idx.dtype == torch.int64
+    y, y_rev, g, rev_idx = y.contiguous(), y_rev.contiguous(), g.contiguous(), rev_idx.contiguous()
+    B, T, C = y.shape
+    out = torch.empty_like(y)
+    check(_lib.load().groupnorm_gate_pair_bf16(B, T, C, H, float(eps), _GATE_ACT[gate_act], ptr(y), ptr(y_rev), ptr(rev_idx), ptr(g),
+                                               ptr(ln_w.contiguous()), ptr(ln_b.contiguous()), ptr(out), stream_of(y)),
+          "groupnorm_gate_pair_bf16")
+    return out

@@ -298,3 +298,24 @@ def test_ddlerp_lora_fused(M, B, T, C, with_state):
     for name, a, b_ in zip(("gx", "gmaa", "gh", "gw2", "gshift"), leaves, l64):
         if a is not None:
             assert relrms(a.grad, b_.grad) < 1.5e-2, name
+
+
+def test_groupnorm_gate_pair(M):
+    """Reverse gather + average inside the GroupNorm*gate kernel == the three separate ops."""
+    g = torch.Generator().manual_seed(29)
+    B, T, H = 3, 50, 2
+    C = H * 64
+    y = torch.randn(B, T, C, generator=g).bfloat16().to(DEV)
+    yr = torch.randn(B, T, C, generator=g).bfloat16().to(DEV)
+    gate = torch.randn(B, T, C, generator=g).bfloat16().to(DEV)
+    lw = (torch.rand(C, generator=g) + 0.5).bfloat16().to(DEV)
+    lb = (torch.randn(C, generator=g) * 0.1).bfloat16().to(DEV)
+    idx = torch.randint(2, 50, (B, T), generator=g)
+    for b, n in enumerate((49, 20, 3)):
+        idx[b, n] = 1
+        idx[b, n + 1:] = 0
+    _, rev = M.create_mask_and_rev_idx(idx.to(DEV), 1, 0)
+    for act in (None, "silu"):
+        want = M.groupnorm_gate((y + M.reverse_x(yr, rev)) / 2, gate, lw, lb, H, 64e-5, gate_act=act)
+        got = M.groupnorm_gate_pair(y, yr, rev, gate, lw, lb, H, 64e-5, gate_act=act)
+        assert torch.equal(got, want)
