@@ -319,3 +319,59 @@ def test_groupnorm_gate_pair(M):
         want = M.groupnorm_gate((y + M.reverse_x(yr, rev)) / 2, gate, lw, lb, H, 64e-5, gate_act=act)
         got = M.groupnorm_gate_pair(y, yr, rev, gate, lw, lb, H, 64e-5, gate_act=act)
         assert torch.equal(got, want)
+
+
+def test_no_writes_outside_the_outputs(M):
+    """Ragged shapes (T not a multiple of the 8- / 128-row tiles, C not a multiple of 256): every output of the
+    TMA-fed / tcgen05 kernels sits between sentinel regions that must stay untouched."""
+    from rwkv_lm_ext_b200 import _lib
+    lib = _lib.load()
+    p = _lib.ptr
+    g = torch.Generator().manual_seed(31)
+    B, T, C, R = 3, 77, 320, 32
+    PAD = 4096
+    st = torch.cuda.current_stream().cuda_stream
+
+    def guarded(*shape, dtype=torch.bfloat16):
+        n = 1
+        for s_ in shape:
+            n *= s_
+        buf = torch.full((n + 2 * PAD,), 7.0, dtype=dtype, device=DEV)
+        return buf, buf[PAD:PAD + n].view(*shape)
+
+    def intact(buf):
+        return bool((buf[:PAD] == 7.0).all() and (buf[-PAD:] == 7.0).all())
+
+    x = torch.randn(B, T, C, generator=g).bfloat16().to(DEV)
+    maa = torch.rand(5, C, generator=g).bfloat16().to(DEV)
+    h = torch.tanh(torch.randn(B * T, 5 * R, generator=g)).bfloat16().to(DEV)
+    w2 = (torch.randn(5, R, C, generator=g) * 0.1).bfloat16().to(DEV)
+    m = torch.randn(5, B, T, C, generator=g).bfloat16().to(DEV)
+    gos = [torch.randn(B, T, C, generator=g).bfloat16().to(DEV) for _ in range(5)]
+    # LoRA-fused forward (tcgen05 + TMA stores, 128-row tiles)
+    obuf, out = guarded(5, B, T, C)
+    _lib.check(lib.tmix_ddlerp_lora_bf16(B, T, C, R, p(x), None, p(maa), p(h), p(w2), p(out), st), "lora")
+    torch.cuda.synchronize()
+    assert intact(obuf)
+    mm = torch.bmm(h.view(B * T, 5, R).transpose(0, 1), w2).view(5, B, T, C)
+    assert relrms(out, M.tmix_ddlerp_mix(x, maa, mm)) < 2e-3
+    # TMA-fed backward (8-row tiles, 256-channel column blocks)
+    gxb, gx = guarded(B, T, C)
+    gmb, gm = guarded(5, B, T, C)
+    gab, ga = guarded(5, C, dtype=torch.float32)
+    ws = torch.empty(lib.elementwise_backward_workspace_bytes(B, T, C, 5), dtype=torch.uint8, device=DEV)
+    _lib.check(lib.tmix_ddlerp_mix_backward_bf16(B, T, C, p(x), None, p(maa), p(m), *[p(t) for t in gos], p(gx), p(gm), p(ga),
+                                                 None, p(ws), ws.numel(), st), "ddlerp bwd")
+    torch.cuda.synchronize()
+    assert intact(gxb) and intact(gmb) and intact(gab)
+    assert torch.isfinite(gx.float()).all() and torch.isfinite(gm.float()).all() and torch.isfinite(ga).all()
+    # channel-mix two-output shift-lerp and its gradient
+    o2b, o2 = guarded(2, B, T, C)
+    _lib.check(lib.cmix_shift_lerp2_bf16(B, T, C, p(x), None, p(maa[:2].contiguous()), p(o2), st), "cmix fwd")
+    g2b, g2 = guarded(B, T, C)
+    a2b, a2 = guarded(2, C, dtype=torch.float32)
+    ws3 = torch.empty(lib.elementwise_backward_workspace_bytes(B, T, C, 3), dtype=torch.uint8, device=DEV)
+    _lib.check(lib.cmix_shift_lerp2_backward_bf16(B, T, C, p(x), None, p(maa[:2].contiguous()), p(gos[0]), p(gos[1]), p(g2), p(a2),
+                                                  None, p(ws3), ws3.numel(), st), "cmix bwd")
+    torch.cuda.synchronize()
+    assert intact(o2b) and intact(g2b) and intact(a2b)
