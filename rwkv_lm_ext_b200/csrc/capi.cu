@@ -74,14 +74,15 @@ static void ensure_pool_keeps_memory();
 // Forward over `nseg` time segments run as independent batch rows (seg_scan.cu): state-only pass from
 // zero states, scan over the segment states, ordinary pass with the scanned initial states.
 // flags: [B*H], already holding any pre-set stream flags.
-static int tc3_forward_segmented(const Args &a, int *flags, int nseg) {
+// ckpt / seg_flags: nullptr, or (training pair) where the chunk-start states and the per-segment flags go.
+static int tc3_forward_segmented(const Args &a, int *flags, int nseg, void *ckpt = nullptr, int *seg_flags = nullptr) {
     ensure_pool_keeps_memory();
     const int Bs = a.B * nseg, Tseg = a.T / nseg, C = a.H * 64;
     const size_t st = (size_t)Bs * a.H * 4096, nl = (size_t)Bs * C, nf = (size_t)Bs * a.H;
     float *buf = nullptr;
     WKV6_CUDA_CHECK(cudaMallocAsync((void **)&buf, (2 * st + nl) * sizeof(float) + nf * sizeof(int), a.stream));
     float *s_loc = buf, *s_start = buf + st, *lam = s_start + st;
-    int *sflags = (int *)(lam + nl);
+    int *sflags = seg_flags ? seg_flags : (int *)(lam + nl);
     int rc = cudaMemsetAsync(sflags, 0, nf * sizeof(int), a.stream) == cudaSuccess ? WKV6_OK : WKV6_ECUDA;
     if (rc == WKV6_OK) rc = seg_flags_merge(a.B, nseg, a.H, sflags, flags, a.stream);      // broadcast pre-set flags
     Args a1 = a;
@@ -89,10 +90,10 @@ static int tc3_forward_segmented(const Args &a, int *flags, int nseg) {
     if (rc == WKV6_OK) rc = tc3_forward(a1, nullptr, sflags);
     if (rc == WKV6_OK) rc = seg_flags_merge(a.B, nseg, a.H, sflags, flags, a.stream);
     if (rc == WKV6_OK) rc = seg_decay(Bs, Tseg, C, a.w, lam, a.stream);
-    if (rc == WKV6_OK) rc = seg_scan(a.B, nseg, a.H, lam, s_loc, a.s0, a.s0_f32, a.s0_bstride, s_start, a.sT, a.sT_f32, 0, a.stream);
+    if (rc == WKV6_OK) rc = seg_scan(a.B, nseg, a.H, lam, s_loc, a.s0, a.s0_f32, a.s0_bstride, s_start, a.sT, a.sT_f32, 0, flags, a.stream);
     Args a2 = a;
     a2.B = Bs; a2.T = Tseg; a2.s0 = s_start; a2.s0_f32 = 1; a2.s0_bstride = (long long)a.H * 4096; a2.sT = nullptr; a2.saved = nullptr;
-    if (rc == WKV6_OK) rc = tc3_forward(a2, nullptr, sflags);
+    if (rc == WKV6_OK) rc = tc3_forward(a2, ckpt, sflags);
     if (rc == WKV6_OK) rc = seg_flags_merge(a.B, nseg, a.H, sflags, flags, a.stream);
     cudaFreeAsync(buf, a.stream);
     return rc;
@@ -109,8 +110,10 @@ static int forward3(const Args &a) {
         if (!flags) { set_error("cannot get %zu bytes of flag scratch", nb); return WKV6_ECUDA; }
     }
     WKV6_CUDA_CHECK(cudaMemsetAsync(flags, 0, nb, a.stream));
-    const int nseg = a.saved ? 1 : seg_count(a.B, a.T, a.H);
-    if (int rc = nseg > 1 ? tc3_forward_segmented(a, flags, nseg) : tc3_forward(a, ckpt, flags)) return rc;
+    // the training pair segments forward and backward alike (the saved chunk states are in segment-row order)
+    const int nseg = a.saved ? seg_count_train(a.B, a.T, a.H) : seg_count(a.B, a.T, a.H);
+    if (int rc = nseg > 1 ? tc3_forward_segmented(a, flags, nseg, ckpt, a.saved ? flags + (size_t)a.B * a.H : nullptr)
+                          : tc3_forward(a, ckpt, flags)) return rc;
     Args s = a;                       // exact route, only for the streams the kernel flagged
     s.stream_flags = flags;
     return simt_forward(s);

@@ -111,9 +111,14 @@ int ddlerp_backward_tma(int nout, int B, int T, int C, const void *x, const void
                         cudaStream_t stream);
 // seg_scan.cu: time-axis segmentation for calls with few streams (see the file header)
 int seg_count(int B, int T, int H);
+int seg_count_train(int B, int T, int H);
+int seg_reverse3(size_t rows, int Tseg, int C, const void *a, const void *b, const void *c, void *ra, void *rb, void *rc,
+                 cudaStream_t stream);
+int seg_sum_gu(int B, int nseg, int C, const void *part, void *gu, cudaStream_t stream);
 int seg_decay(int rows, int Tseg, int C, const void *w, float *lam, cudaStream_t stream);
 int seg_scan(int B, int nseg, int H, const float *lam, const float *s_loc, const void *s0, int s0_f32,
-             long long s0_bstride, float *s_start, void *sT, int sT_f32, int reverse, cudaStream_t stream);
+             long long s0_bstride, float *s_start, void *sT, int sT_f32, int reverse, const int *stream_flags,
+             cudaStream_t stream);
 int seg_flags_merge(int B, int nseg, int H, int *seg_flags, int *stream_flags, cudaStream_t stream);
 // ddlerp_lora.cu: ddlerp forward with the LoRA product on the tensor cores
 bool ddlerp_lora_supported(int B, int T, int C, int R, const void *x, const void *h, const void *w2, const void *out,

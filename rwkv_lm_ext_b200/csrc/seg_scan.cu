@@ -57,8 +57,11 @@ __global__ void __launch_bounds__(256) seg_decay_kernel(int Tseg, int C, const b
 __global__ void __launch_bounds__(256) seg_scan_kernel(int nseg, int H, const float *__restrict__ lam,
                                                        const float *__restrict__ s_loc, const void *__restrict__ s0,
                                                        int s0_f32, long long s0_bstride, float *__restrict__ s_start,
-                                                       void *__restrict__ sT, int sT_f32, int reverse) {
+                                                       void *__restrict__ sT, int sT_f32, int reverse,
+                                                       const int *__restrict__ stream_flags) {
     const int b = blockIdx.x / H, h = blockIdx.x % H;
+    // a flagged stream is recomputed by the exact route from the ORIGINAL initial state, which sT may alias
+    const bool write_sT = sT != nullptr && !(stream_flags && stream_flags[blockIdx.x] != 0);
     const size_t C = (size_t)H * 64;
     for (int e = threadIdx.x; e < 4096; e += 256) {
         const int i = e & 63;
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(256) seg_scan_kernel(int nseg, int H, const fl
             s_start[(row * H + h) * 4096 + e] = S;
             S = __expf(lam[row * C + h * 64 + i]) * S + s_loc[(row * H + h) * 4096 + e];
         }
-        if (sT) {
+        if (write_sT) {
             const size_t idx = ((size_t)b * H + h) * 4096 + e;
             if (sT_f32) ((float *)sT)[idx] = S;
             else ((bf16 *)sT)[idx] = __float2bfloat16_rn(S);
@@ -94,6 +97,32 @@ __global__ void seg_flags_kernel(int n, int nseg, int H, int *__restrict__ seg_f
     for (int q = 0; q < nseg; q++) seg_flags[((size_t)b * nseg + q) * H + h] = f;
 }
 
+// out[row, tau, :] = in[row, Tseg-1-tau, :] for three [rows, Tseg, C] tensors at once (the backward's
+// state-gradient chain is the forward state recurrence on time-reversed r, gy, w)
+__global__ void __launch_bounds__(256) seg_reverse3_kernel(size_t nvec, int Tseg, int C, const bf16 *__restrict__ a,
+                                                           const bf16 *__restrict__ b, const bf16 *__restrict__ c,
+                                                           bf16 *__restrict__ ra, bf16 *__restrict__ rb_, bf16 *__restrict__ rc) {
+    const int cv = C / 8;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t tok = i / cv, row = tok / Tseg;
+        const int t = (int)(tok % Tseg);
+        const size_t src = ((row * Tseg + (size_t)(Tseg - 1 - t)) * cv + i % cv) * 8;
+        *reinterpret_cast<uint4 *>(ra + i * 8) = *reinterpret_cast<const uint4 *>(a + src);
+        *reinterpret_cast<uint4 *>(rb_ + i * 8) = *reinterpret_cast<const uint4 *>(b + src);
+        *reinterpret_cast<uint4 *>(rc + i * 8) = *reinterpret_cast<const uint4 *>(c + src);
+    }
+}
+
+// gu[b, c] = sum_seg part[b*nseg + seg, c]   (bf16 in, fp32 sum, bf16 out)
+__global__ void seg_sum_gu_kernel(int B, int nseg, int C, const bf16 *__restrict__ part, bf16 *__restrict__ gu) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * C) return;
+    const int b = i / C, c = i % C;
+    float s = 0.f;
+    for (int q = 0; q < nseg; q++) s += __bfloat162float(part[((size_t)b * nseg + q) * C + c]);
+    gu[i] = __float2bfloat16_rn(s);
+}
+
 }  // namespace
 
 // number of segments for a call with B*H streams of T tokens (1 = do not segment)
@@ -109,6 +138,37 @@ int seg_count(int B, int T, int H) {
     return n < 2 ? 1 : n;
 }
 
+// training pair (forward with a saved buffer + backward): both directions are segmented, which is worth the
+// extra launches from T = 2048 on; at least 8 chunks per segment
+int seg_count_train(int B, int T, int H) {
+    const long long streams = (long long)B * H;
+    static const bool off = getenv("WKV6B200_NO_SEG") != nullptr;
+    if (off || streams <= 0 || streams > 74 || T < 2048) return 1;
+    int n = (int)(296 / streams);
+    if (n > T / 512) n = T / 512;
+    while (n > 1 && T % (n * 64) != 0) n--;
+    return n < 2 ? 1 : n;
+}
+
+int seg_reverse3(size_t rows, int Tseg, int C, const void *a, const void *b, const void *c, void *ra, void *rb, void *rc,
+                 cudaStream_t stream) {
+    const size_t nvec = rows * Tseg * C / 8;
+    size_t g = (nvec + 255) / 256;
+    if (g > 148 * 16) g = 148 * 16;
+    seg_reverse3_kernel<<<(int)g, 256, 0, stream>>>(nvec, Tseg, C, (const bf16 *)a, (const bf16 *)b, (const bf16 *)c, (bf16 *)ra,
+                                                    (bf16 *)rb, (bf16 *)rc);
+    count_launch();
+    WKV6_CUDA_CHECK(cudaGetLastError());
+    return WKV6_OK;
+}
+
+int seg_sum_gu(int B, int nseg, int C, const void *part, void *gu, cudaStream_t stream) {
+    seg_sum_gu_kernel<<<(B * C + 255) / 256, 256, 0, stream>>>(B, nseg, C, (const bf16 *)part, (bf16 *)gu);
+    count_launch();
+    WKV6_CUDA_CHECK(cudaGetLastError());
+    return WKV6_OK;
+}
+
 int seg_decay(int rows, int Tseg, int C, const void *w, float *lam, cudaStream_t stream) {
     dim3 grid((C + 255) / 256, rows);
     seg_decay_kernel<<<grid, 256, 0, stream>>>(Tseg, C, (const bf16 *)w, lam);
@@ -118,8 +178,10 @@ int seg_decay(int rows, int Tseg, int C, const void *w, float *lam, cudaStream_t
 }
 
 int seg_scan(int B, int nseg, int H, const float *lam, const float *s_loc, const void *s0, int s0_f32,
-             long long s0_bstride, float *s_start, void *sT, int sT_f32, int reverse, cudaStream_t stream) {
-    seg_scan_kernel<<<B * H, 256, 0, stream>>>(nseg, H, lam, s_loc, s0, s0_f32, s0_bstride, s_start, sT, sT_f32, reverse);
+             long long s0_bstride, float *s_start, void *sT, int sT_f32, int reverse, const int *stream_flags,
+             cudaStream_t stream) {
+    seg_scan_kernel<<<B * H, 256, 0, stream>>>(nseg, H, lam, s_loc, s0, s0_f32, s0_bstride, s_start, sT, sT_f32, reverse,
+                                               stream_flags);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
     return WKV6_OK;

@@ -66,6 +66,10 @@ struct Params {
     int B, T, H;
     const bf16 *u;
     int has_s0;
+    // time-axis segmentation (seg_scan.cu): batch row b of this launch is segment b % nseg of a longer
+    // sequence; g_init = dL/dS at the end of each row, fp32 [B,H,64(value),64(key)]; nullptr / 1 otherwise
+    const float *g_init;
+    int nseg;
     bf16 *gu, *gs;
     const int *hz_flags;
     long long *dbg;           // nullptr, or [gridDim][NC][8] clock64 stamps of warp 0 at the stage boundaries (profiling aid)
@@ -281,12 +285,24 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         float gu_acc[2] = {0.f, 0.f};
         uint32_t v[16];
 
-        // G = 0 (TMEM) and its bf16 copy
+        // G = dL/dS behind the last token (0, or handed in when this row is a segment) and its bf16 copy
+        const int seg = b % p.nseg;
+        const bool first_has_s0 = p.has_s0 || seg > 0;          // a later segment starts from a non-zero state
+        const bool g_is_zero = p.g_init == nullptr || seg == p.nseg - 1;
 #pragma unroll
         for (int x = 0; x < 16; x++) v[x] = 0u;
+        if (!g_is_zero) {
+#pragma unroll
+            for (int g = 0; g < 4; g++)
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++)
+#pragma unroll
+                    for (int e = 0; e < 2; e++)
+                        v[4 * g + 2 * hh + e] = __float_as_uint(p.g_init[(((size_t)b * p.H + h) * 64 + F.col(g, e)) * 64 + F.row(hh)]);
+        }
         tmem_st_frag(tG, v);
-        stsm_x4(sbase + OFF_GB + F.rc(0), 0u, 0u, 0u, 0u);
-        stsm_x4(sbase + OFF_GB + F.rc(1), 0u, 0u, 0u, 0u);
+        stsm_x4(sbase + OFF_GB + F.rc(0), pack_frag(v, 0, 0), pack_frag(v, 1, 0), pack_frag(v, 2, 0), pack_frag(v, 3, 0));
+        stsm_x4(sbase + OFF_GB + F.rc(1), pack_frag(v, 0, 1), pack_frag(v, 1, 1), pack_frag(v, 2, 1), pack_frag(v, 3, 1));
         tmem_wait_st();
         fence_proxy_async();
         tc_fence_before();
@@ -668,8 +684,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 for (int g = 0; g < 4; g++) {
                     float gw0 = __uint_as_float(lp[4 * g + 2 * hh]) * LN2 * (base + __uint_as_float(v[4 * g + 2 * hh]));
                     float gw1 = __uint_as_float(lp[4 * g + 2 * hh + 1]) * LN2 * (base + __uint_as_float(v[4 * g + 2 * hh + 1]));
-                    if (c == 0 && !p.has_s0 && ch == 0 && g == 0 && q == 0) gw0 = 0.f;   // t = 0 with S_0 = 0
-                    if (c == NC - 1) {      // the last decay feeds no output: exactly 0 like cuda/wkv6_cuda.cu:226
+                    if (c == 0 && !first_has_s0 && ch == 0 && g == 0 && q == 0) gw0 = 0.f;   // t = 0 with S_0 = 0
+                    if (c == NC - 1 && g_is_zero) {      // the last decay feeds no output: exactly 0 like cuda/wkv6_cuda.cu:226
                         if (F.col(g, 0) == nv - 1) gw0 = 0.f;
                         if (F.col(g, 1) == nv - 1) gw1 = 0.f;
                     }
@@ -702,7 +718,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
 
 void *g_tc3_bwd_stamps = nullptr;   // profiling aid, set through wkv6b200_debug_stamps()
 
-size_t tc3_saved_header(int B, int H) { return (((size_t)B * H * sizeof(int)) + 1023) / 1024 * 1024; }
+// per-stream hazard flags [B*H], then (time-axis segmentation, at most 296 segment rows) per-segment flags
+size_t tc3_saved_header(int B, int H) { return ((((size_t)B * H + 512) * sizeof(int)) + 1023) / 1024 * 1024; }
 size_t tc3_saved_bytes(int B, int T, int H) {
     const size_t NC = (size_t)(T + L - 1) / L;
     return tc3_saved_header(B, H) + (size_t)B * H * NC * 8192;
@@ -715,27 +732,10 @@ bool tc3_backward_supported(const Args &a) {
            tc::get_encode_fn() != nullptr;
 }
 
-int tc3_backward(const Args &a, const Args *exact, bool flags_preset, bool run_fallback) {
-    if (a.B * a.H == 0 || a.T == 0) return WKV6_OK;
+// one launch of the backward kernel on `a` viewed as given (B rows of T tokens), chunk-start states in ckpt
+static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const float *g_init, int nseg, bool has_s0) {
     const int C = a.H * 64;
     const size_t NC = (size_t)(a.T + L - 1) / L;
-    const size_t simt_ws = simt_backward_workspace_bytes(a.B, a.T, a.H);
-    const size_t need = tc3_backward_workspace_bytes(a.B, a.T, a.H, a.saved != nullptr);
-    if (!a.workspace || a.workspace_bytes < need) {
-        set_error("workspace too small: need %zu bytes", need);
-        return WKV6_EWORKSPACE;
-    }
-    uint8_t *sv = a.saved ? (uint8_t *)a.saved : (uint8_t *)a.workspace + simt_ws;
-    int *flags = (int *)sv;
-    bf16 *ckpt = (bf16 *)(sv + tc3_saved_header(a.B, a.H));
-    if (!a.saved) {
-        // no training pair: recompute the chunk-start states (and the per-stream hazard flags) first
-        if (!flags_preset) WKV6_CUDA_CHECK(cudaMemsetAsync(flags, 0, (size_t)a.B * a.H * sizeof(int), a.stream));
-        Args f = a;
-        f.y = nullptr;
-        f.sT = nullptr;
-        if (int rc = tc3_forward(f, ckpt, flags)) return rc;
-    }
     CUtensorMap mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw;
     const auto dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     const void *ptrs[10] = {a.r, a.k, a.v, a.w, a.gy, ckpt, a.gr, a.gk, a.gv, a.gw};
@@ -751,7 +751,9 @@ int tc3_backward(const Args &a, const Args *exact, bool flags_preset, bool run_f
     Params p;
     p.B = a.B; p.T = a.T; p.H = a.H;
     p.u = (const bf16 *)a.u;
-    p.has_s0 = a.s0 != nullptr;
+    p.has_s0 = has_s0;
+    p.g_init = g_init;
+    p.nseg = nseg;
     p.gu = (bf16 *)a.gu; p.gs = (bf16 *)a.gs;
     p.hz_flags = flags;
     p.dbg = (long long *)g_tc3_bwd_stamps;
@@ -767,6 +769,73 @@ int tc3_backward(const Args &a, const Args *exact, bool flags_preset, bool run_f
     wkv6_tc3_bwd_kernel<<<a.B * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
+    return WKV6_OK;
+}
+
+// Backward over `nseg` time segments run as independent batch rows (seg_scan.cu).  dL/dS at the end of each
+// segment comes from the SAME recurrence as the forward state, run on time-reversed (r, gy, w):
+//     G_{t-1} = d_t G_t + r_t (x) gy_t      <->      S_{tau+1} = d'_tau S_tau + k'_tau (x) v'_tau
+// so: reverse the three tensors inside every segment, a state-only forward pass (k := r_rev, v := gy_rev) gives
+// each segment's own contribution, a reverse scan over the segments chains them, and the ordinary backward
+// kernel starts every segment from its scanned G.  The forward of the training pair was segmented the same
+// way, so `saved` holds the chunk-start states in segment-row order and the per-segment flags.
+static int tc3_backward_segmented(const Args &a, int nseg) {
+    const int Bs = a.B * nseg, Tseg = a.T / nseg, C = a.H * 64;
+    int *flags = (int *)a.saved, *sflags = flags + (size_t)a.B * a.H;
+    const bf16 *ckpt = (const bf16 *)((uint8_t *)a.saved + tc3_saved_header(a.B, a.H));
+    const size_t n_el = (size_t)a.B * a.T * C, st = (size_t)Bs * a.H * 4096;
+    const size_t bytes = 3 * n_el * 2 + 2 * st * 4 + (size_t)Bs * C * 4 + st * 2 + (size_t)Bs * C * 2;
+    uint8_t *buf = nullptr;
+    WKV6_CUDA_CHECK(cudaMallocAsync((void **)&buf, bytes, a.stream));
+    bf16 *r_rev = (bf16 *)buf, *gy_rev = r_rev + n_el, *w_rev = gy_rev + n_el;
+    float *g_loc = (float *)(w_rev + n_el), *g_end = g_loc + st, *lam = g_end + st;
+    bf16 *gs_tmp = (bf16 *)(lam + (size_t)Bs * C), *gu_tmp = gs_tmp + st;
+    int rc = seg_reverse3(Bs, Tseg, C, a.r, a.gy, a.w, r_rev, gy_rev, w_rev, a.stream);
+    Args f = a;                                   // state-only pass: the "state" it ends with is each segment's own dL/dS_start
+    f.B = Bs; f.T = Tseg; f.r = r_rev; f.k = r_rev; f.v = gy_rev; f.w = w_rev;
+    f.s0 = nullptr; f.s0_bstride = 0; f.s0_f32 = 0; f.sT = g_loc; f.sT_f32 = 1; f.y = nullptr; f.saved = nullptr; f.gy = nullptr;
+    if (rc == WKV6_OK) rc = tc3_forward(f, nullptr, sflags);
+    if (rc == WKV6_OK) rc = seg_decay(Bs, Tseg, C, a.w, lam, a.stream);
+    if (rc == WKV6_OK) rc = seg_scan(a.B, nseg, a.H, lam, g_loc, nullptr, 0, 0, g_end, nullptr, 0, 1, nullptr, a.stream);
+    Args v = a;
+    v.B = Bs; v.T = Tseg; v.gu = gu_tmp; v.gs = a.gs ? gs_tmp : nullptr;
+    if (rc == WKV6_OK) rc = launch_bwd(v, ckpt, sflags, g_end, nseg, a.s0 != nullptr);
+    if (rc == WKV6_OK) rc = seg_sum_gu(a.B, nseg, C, gu_tmp, a.gu, a.stream);
+    if (rc == WKV6_OK && a.gs)                    // dL/dS_0 is what segment 0 of every sequence produced
+        rc = cudaMemcpy2DAsync(a.gs, (size_t)a.H * 4096 * 2, gs_tmp, (size_t)nseg * a.H * 4096 * 2, (size_t)a.H * 4096 * 2, a.B,
+                               cudaMemcpyDeviceToDevice, a.stream) == cudaSuccess ? WKV6_OK : WKV6_ECUDA;
+    cudaFreeAsync(buf, a.stream);
+    if (rc != WKV6_OK) return rc;
+    Args s = a;                                   // exact route for the flagged streams, on the call as it was made
+    s.stream_flags = flags;
+    s.workspace_bytes = simt_backward_workspace_bytes(a.B, a.T, a.H);
+    return simt_backward(s);
+}
+
+int tc3_backward(const Args &a, const Args *exact, bool flags_preset, bool run_fallback) {
+    if (a.B * a.H == 0 || a.T == 0) return WKV6_OK;
+    const size_t simt_ws = simt_backward_workspace_bytes(a.B, a.T, a.H);
+    const size_t need = tc3_backward_workspace_bytes(a.B, a.T, a.H, a.saved != nullptr);
+    if (!a.workspace || a.workspace_bytes < need) {
+        set_error("workspace too small: need %zu bytes", need);
+        return WKV6_EWORKSPACE;
+    }
+    if (a.saved && !exact && run_fallback) {
+        const int nseg = seg_count_train(a.B, a.T, a.H);
+        if (nseg > 1) return tc3_backward_segmented(a, nseg);
+    }
+    uint8_t *sv = a.saved ? (uint8_t *)a.saved : (uint8_t *)a.workspace + simt_ws;
+    int *flags = (int *)sv;
+    bf16 *ckpt = (bf16 *)(sv + tc3_saved_header(a.B, a.H));
+    if (!a.saved) {
+        // no training pair: recompute the chunk-start states (and the per-stream hazard flags) first
+        if (!flags_preset) WKV6_CUDA_CHECK(cudaMemsetAsync(flags, 0, (size_t)a.B * a.H * sizeof(int), a.stream));
+        Args f = a;
+        f.y = nullptr;
+        f.sT = nullptr;
+        if (int rc = tc3_forward(f, ckpt, flags)) return rc;
+    }
+    if (int rc = launch_bwd(a, ckpt, flags, nullptr, 1, a.s0 != nullptr)) return rc;
     if (!run_fallback) return WKV6_OK;      // the caller runs its own exact route on the flags in the workspace
     // exact route for the flagged streams only
     Args s = exact ? *exact : a;
