@@ -71,13 +71,14 @@ static int *flag_slice(size_t n) {
     return ring[dev] + off;
 }
 static void ensure_pool_keeps_memory();
-// Forward over `nseg` time segments run as independent batch rows (seg_scan.cu): state-only pass from
-// zero states, scan over the segment states, ordinary pass with the scanned initial states.
+// Forward over `nseg` time segments that run as separate grid rows (seg_scan.cu): state-only pass from zero
+// states, scan over the segment states, ordinary pass with the scanned initial states.
 // flags: [B*H], already holding any pre-set stream flags.
 // ckpt / seg_flags: nullptr, or (training pair) where the chunk-start states and the per-segment flags go.
-static int tc3_forward_segmented(const Args &a, int *flags, int nseg, void *ckpt = nullptr, int *seg_flags = nullptr) {
+static int tc3_forward_segmented(const Args &a, int *flags, int nseg, int seg_chunks, void *ckpt = nullptr,
+                                 int *seg_flags = nullptr) {
     ensure_pool_keeps_memory();
-    const int Bs = a.B * nseg, Tseg = a.T / nseg, C = a.H * 64;
+    const int Bs = a.B * nseg, C = a.H * 64, seg_tokens = seg_chunks * 64;
     const size_t st = (size_t)Bs * a.H * 4096, nl = (size_t)Bs * C, nf = (size_t)Bs * a.H;
     float *buf = nullptr;
     WKV6_CUDA_CHECK(cudaMallocAsync((void **)&buf, (2 * st + nl) * sizeof(float) + nf * sizeof(int), a.stream));
@@ -86,14 +87,14 @@ static int tc3_forward_segmented(const Args &a, int *flags, int nseg, void *ckpt
     int rc = cudaMemsetAsync(sflags, 0, nf * sizeof(int), a.stream) == cudaSuccess ? WKV6_OK : WKV6_ECUDA;
     if (rc == WKV6_OK) rc = seg_flags_merge(a.B, nseg, a.H, sflags, flags, a.stream);      // broadcast pre-set flags
     Args a1 = a;
-    a1.B = Bs; a1.T = Tseg; a1.s0 = nullptr; a1.s0_bstride = 0; a1.sT = s_loc; a1.sT_f32 = 1; a1.y = nullptr; a1.saved = nullptr;
-    if (rc == WKV6_OK) rc = tc3_forward(a1, nullptr, sflags);
+    a1.s0 = nullptr; a1.s0_bstride = 0; a1.sT = s_loc; a1.sT_f32 = 1; a1.y = nullptr; a1.saved = nullptr;
+    if (rc == WKV6_OK) rc = tc3_forward(a1, nullptr, sflags, nseg, seg_chunks);
     if (rc == WKV6_OK) rc = seg_flags_merge(a.B, nseg, a.H, sflags, flags, a.stream);
-    if (rc == WKV6_OK) rc = seg_decay(Bs, Tseg, C, a.w, lam, a.stream);
+    if (rc == WKV6_OK) rc = seg_decay(a.B, a.T, C, nseg, seg_tokens, a.w, lam, a.stream);
     if (rc == WKV6_OK) rc = seg_scan(a.B, nseg, a.H, lam, s_loc, a.s0, a.s0_f32, a.s0_bstride, s_start, a.sT, a.sT_f32, 0, flags, a.stream);
     Args a2 = a;
-    a2.B = Bs; a2.T = Tseg; a2.s0 = s_start; a2.s0_f32 = 1; a2.s0_bstride = (long long)a.H * 4096; a2.sT = nullptr; a2.saved = nullptr;
-    if (rc == WKV6_OK) rc = tc3_forward(a2, ckpt, sflags);
+    a2.s0 = s_start; a2.s0_f32 = 1; a2.s0_bstride = (long long)a.H * 4096; a2.sT = nullptr; a2.saved = nullptr;
+    if (rc == WKV6_OK) rc = tc3_forward(a2, ckpt, sflags, nseg, seg_chunks);
     if (rc == WKV6_OK) rc = seg_flags_merge(a.B, nseg, a.H, sflags, flags, a.stream);
     cudaFreeAsync(buf, a.stream);
     return rc;
@@ -111,8 +112,10 @@ static int forward3(const Args &a) {
     }
     WKV6_CUDA_CHECK(cudaMemsetAsync(flags, 0, nb, a.stream));
     // the training pair segments forward and backward alike (the saved chunk states are in segment-row order)
-    const int nseg = a.saved ? seg_count_train(a.B, a.T, a.H) : seg_count(a.B, a.T, a.H);
-    if (int rc = nseg > 1 ? tc3_forward_segmented(a, flags, nseg, ckpt, a.saved ? flags + (size_t)a.B * a.H : nullptr)
+    int nseg = 1, seg_chunks = 0;
+    if (a.saved) seg_plan_train(a.B, a.T, a.H, &nseg, &seg_chunks);
+    else seg_plan(a.B, a.T, a.H, &nseg, &seg_chunks);
+    if (int rc = nseg > 1 ? tc3_forward_segmented(a, flags, nseg, seg_chunks, ckpt, a.saved ? flags + (size_t)a.B * a.H : nullptr)
                           : tc3_forward(a, ckpt, flags)) return rc;
     Args s = a;                       // exact route, only for the streams the kernel flagged
     s.stream_flags = flags;
@@ -154,8 +157,9 @@ static int forward3_ew(const Args &a) {
     WKV6_CUDA_CHECK(cudaMallocAsync(&w_raw, (size_t)a.B * a.T * a.H * 64 * 2, a.stream));
     int rc = cudaMemsetAsync(flags, 0, nb, a.stream) == cudaSuccess ? WKV6_OK : WKV6_ECUDA;
     if (rc == WKV6_OK) rc = ew_to_raw_bf16(a.B, a.T, a.H, (const float *)a.w, w_raw, flags, a.stream, a.w_kind == W_DECAY_F32);
-    const int nseg = seg_count(a.B, a.T, a.H);
-    if (rc == WKV6_OK) rc = nseg > 1 ? tc3_forward_segmented(with_raw_w(a, w_raw), flags, nseg) : tc3_forward(with_raw_w(a, w_raw), nullptr, flags);
+    int nseg = 1, seg_chunks = 0;
+    seg_plan(a.B, a.T, a.H, &nseg, &seg_chunks);
+    if (rc == WKV6_OK) rc = nseg > 1 ? tc3_forward_segmented(with_raw_w(a, w_raw), flags, nseg, seg_chunks) : tc3_forward(with_raw_w(a, w_raw), nullptr, flags);
     if (rc == WKV6_OK) {
         Args s = a;
         s.stream_flags = flags;

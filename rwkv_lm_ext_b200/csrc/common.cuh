@@ -54,7 +54,10 @@ int simt_forward(const Args &a);
 int simt_backward(const Args &a);
 size_t simt_backward_workspace_bytes(int B, int T, int H);
 
-int tc3_forward(const Args &a, void *ckpt, int *hz_flags);   // role-uniform tcgen05 forward (per-stream hazard flags)
+// role-uniform tcgen05 forward (per-stream hazard flags).  nseg > 1: every sequence is cut into nseg segments of
+// seg_chunks 64-token chunks (the last may be shorter) that run as separate grid rows; s0 / sT / flags / ckpt
+// are then indexed by row = b*nseg + seg (seg_scan.cu)
+int tc3_forward(const Args &a, void *ckpt, int *hz_flags, int nseg = 1, int seg_chunks = 0);
 bool tc3_forward_supported(const Args &a);
 // role-uniform tcgen05 backward (+ per-stream SIMT fallback, which runs on `exact` when given: the
 // call as the caller made it, e.g. with the fp32 log-decay instead of the converted bf16 logits)
@@ -110,12 +113,12 @@ int ddlerp_backward_tma(int nout, int B, int T, int C, const void *x, const void
                         const void *const *gouts, void *gx, void *gm, void *gshift, float *partial, int *slots,
                         cudaStream_t stream);
 // seg_scan.cu: time-axis segmentation for calls with few streams (see the file header)
-int seg_count(int B, int T, int H);
-int seg_count_train(int B, int T, int H);
-int seg_reverse3(size_t rows, int Tseg, int C, const void *a, const void *b, const void *c, void *ra, void *rb, void *rc,
-                 cudaStream_t stream);
+void seg_plan(int B, int T, int H, int *nseg, int *seg_chunks);
+void seg_plan_train(int B, int T, int H, int *nseg, int *seg_chunks);
+int seg_reverse3(int B, int T, int C, int nseg, int seg_tokens, const void *a, const void *b, const void *c, void *ra, void *rb,
+                 void *rc, cudaStream_t stream);
 int seg_sum_gu(int B, int nseg, int C, const void *part, void *gu, cudaStream_t stream);
-int seg_decay(int rows, int Tseg, int C, const void *w, float *lam, cudaStream_t stream);
+int seg_decay(int B, int T, int C, int nseg, int seg_tokens, const void *w, float *lam, cudaStream_t stream);
 int seg_scan(int B, int nseg, int H, const float *lam, const float *s_loc, const void *s0, int s0_f32,
              long long s0_bstride, float *s_start, void *sT, int sT_f32, int reverse, const int *stream_flags,
              cudaStream_t stream);

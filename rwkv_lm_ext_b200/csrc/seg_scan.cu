@@ -16,15 +16,19 @@ namespace {
 
 typedef __nv_bfloat16 bf16;
 
-// lam[row, c] = sum_t -exp(w[row, t, c])      rows = B*nseg segments of Tseg tokens
+// lam[row, c] = sum over the segment's tokens of -exp(w[b, t, c]);  row = b*nseg + seg covers tokens
+// [seg*seg_tokens, min(T, (seg+1)*seg_tokens)) of sequence b
 // grid (ceil(C/256), rows), block 256 = 32 column lanes (8 channels) x 8 token lanes
-__global__ void __launch_bounds__(256) seg_decay_kernel(int Tseg, int C, const bf16 *__restrict__ w, float *__restrict__ lam) {
+__global__ void __launch_bounds__(256) seg_decay_kernel(int T, int C, int nseg, int seg_tokens, const bf16 *__restrict__ w,
+                                                        float *__restrict__ lam) {
     const int lane = threadIdx.x & 31, tl = threadIdx.x >> 5;
     const int c = (blockIdx.x * 32 + lane) * 8;
     const size_t row = blockIdx.y;
+    const int b = (int)(row / nseg), t0 = (int)(row % nseg) * seg_tokens;
+    const int Tseg = min(seg_tokens, T - t0);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (c < C) {
-        const bf16 *base = w + row * (size_t)Tseg * C + c;
+        const bf16 *base = w + ((size_t)b * T + t0) * C + c;
         for (int t = tl; t < Tseg; t += 8) {
             const uint4 u = *reinterpret_cast<const uint4 *>(base + (size_t)t * C);
             const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
@@ -97,16 +101,18 @@ __global__ void seg_flags_kernel(int n, int nseg, int H, int *__restrict__ seg_f
     for (int q = 0; q < nseg; q++) seg_flags[((size_t)b * nseg + q) * H + h] = f;
 }
 
-// out[row, tau, :] = in[row, Tseg-1-tau, :] for three [rows, Tseg, C] tensors at once (the backward's
-// state-gradient chain is the forward state recurrence on time-reversed r, gy, w)
-__global__ void __launch_bounds__(256) seg_reverse3_kernel(size_t nvec, int Tseg, int C, const bf16 *__restrict__ a,
+// Reverse the token order inside every segment of three [B,T,C] tensors at once (the backward's
+// state-gradient chain is the forward state recurrence on time-reversed r, gy, w): token t of segment
+// [t0, t1) takes the row of token t0 + t1 - 1 - t.
+__global__ void __launch_bounds__(256) seg_reverse3_kernel(size_t nvec, int T, int C, int seg_tokens, const bf16 *__restrict__ a,
                                                            const bf16 *__restrict__ b, const bf16 *__restrict__ c,
                                                            bf16 *__restrict__ ra, bf16 *__restrict__ rb_, bf16 *__restrict__ rc) {
     const int cv = C / 8;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t tok = i / cv, row = tok / Tseg;
-        const int t = (int)(tok % Tseg);
-        const size_t src = ((row * Tseg + (size_t)(Tseg - 1 - t)) * cv + i % cv) * 8;
+        const size_t tok = i / cv, bb = tok / T;
+        const int t = (int)(tok % T);
+        const int t0 = t / seg_tokens * seg_tokens, t1 = min(T, t0 + seg_tokens);
+        const size_t src = ((bb * T + (size_t)(t0 + t1 - 1 - t)) * cv + i % cv) * 8;
         *reinterpret_cast<uint4 *>(ra + i * 8) = *reinterpret_cast<const uint4 *>(a + src);
         *reinterpret_cast<uint4 *>(rb_ + i * 8) = *reinterpret_cast<const uint4 *>(b + src);
         *reinterpret_cast<uint4 *>(rc + i * 8) = *reinterpret_cast<const uint4 *>(c + src);
@@ -125,37 +131,42 @@ __global__ void seg_sum_gu_kernel(int B, int nseg, int C, const bf16 *__restrict
 
 }  // namespace
 
-// number of segments for a call with B*H streams of T tokens (1 = do not segment)
-int seg_count(int B, int T, int H) {
-    const long long streams = (long long)B * H;
-    static const bool off = getenv("WKV6B200_NO_SEG") != nullptr;     // A/B switch for profiles/bench_few_streams.py
-    // the extra launches (state-only pass, decay sums, scan, flag merges: ~40 us of launch latency)
-    // only pay off when a stream keeps its SM busy for a few hundred microseconds: T >= 8192
-    if (off || streams <= 0 || streams >= 148 || T < 8192) return 1;
+// Segment plan: nseg segments of seg_chunks 64-token chunks each (the last one may be shorter), enough of them
+// to fill the 296 CTA slots, none empty.  nseg = 1: do not segment.
+static void plan(long long streams, int T, int min_chunks, int *nseg, int *seg_chunks) {
+    const int NC = (T + 63) / 64;
     int n = (int)(296 / streams);
-    if (n > T / 128) n = T / 128;                 // at least two chunks per segment
-    while (n > 1 && T % (n * 64) != 0) n--;       // segments are whole chunks of the same length
-    return n < 2 ? 1 : n;
+    if (n > NC / min_chunks) n = NC / min_chunks;
+    if (n < 2) { *nseg = 1; *seg_chunks = NC; return; }
+    const int sc = (NC + n - 1) / n;
+    *seg_chunks = sc;
+    *nseg = (NC + sc - 1) / sc;
+    if (*nseg < 2) { *nseg = 1; *seg_chunks = NC; }
 }
-
-// training pair (forward with a saved buffer + backward): both directions are segmented, which is worth the
-// extra launches from T = 2048 on; at least 8 chunks per segment
-int seg_count_train(int B, int T, int H) {
+// forward-only calls: worth the extra launches from T = 8192 on (at least two chunks per segment)
+void seg_plan(int B, int T, int H, int *nseg, int *seg_chunks) {
+    const long long streams = (long long)B * H;
+    static const bool off = getenv("WKV6B200_NO_SEG") != nullptr;     // A/B switch for profiles/bench_few_streams*.py
+    *nseg = 1; *seg_chunks = (T + 63) / 64;
+    if (off || streams <= 0 || streams >= 148 || T < 8192) return;
+    plan(streams, T, 2, nseg, seg_chunks);
+}
+// training pair: forward and backward are both segmented, worth it from T = 2048 on; at least 4 chunks per segment
+void seg_plan_train(int B, int T, int H, int *nseg, int *seg_chunks) {
     const long long streams = (long long)B * H;
     static const bool off = getenv("WKV6B200_NO_SEG") != nullptr;
-    if (off || streams <= 0 || streams > 74 || T < 2048) return 1;
-    int n = (int)(296 / streams);
-    if (n > T / 512) n = T / 512;
-    while (n > 1 && T % (n * 64) != 0) n--;
-    return n < 2 ? 1 : n;
+    *nseg = 1; *seg_chunks = (T + 63) / 64;
+    if (off || streams <= 0 || streams > 74 || T < 2048) return;
+    plan(streams, T, 4, nseg, seg_chunks);
 }
 
-int seg_reverse3(size_t rows, int Tseg, int C, const void *a, const void *b, const void *c, void *ra, void *rb, void *rc,
-                 cudaStream_t stream) {
-    const size_t nvec = rows * Tseg * C / 8;
+int seg_reverse3(int B, int T, int C, int nseg, int seg_tokens, const void *a, const void *b, const void *c, void *ra, void *rb,
+                 void *rc, cudaStream_t stream) {
+    (void)nseg;
+    const size_t nvec = (size_t)B * T * C / 8;
     size_t g = (nvec + 255) / 256;
     if (g > 148 * 16) g = 148 * 16;
-    seg_reverse3_kernel<<<(int)g, 256, 0, stream>>>(nvec, Tseg, C, (const bf16 *)a, (const bf16 *)b, (const bf16 *)c, (bf16 *)ra,
+    seg_reverse3_kernel<<<(int)g, 256, 0, stream>>>(nvec, T, C, seg_tokens, (const bf16 *)a, (const bf16 *)b, (const bf16 *)c, (bf16 *)ra,
                                                     (bf16 *)rb, (bf16 *)rc);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
@@ -169,9 +180,9 @@ int seg_sum_gu(int B, int nseg, int C, const void *part, void *gu, cudaStream_t 
     return WKV6_OK;
 }
 
-int seg_decay(int rows, int Tseg, int C, const void *w, float *lam, cudaStream_t stream) {
-    dim3 grid((C + 255) / 256, rows);
-    seg_decay_kernel<<<grid, 256, 0, stream>>>(Tseg, C, (const bf16 *)w, lam);
+int seg_decay(int B, int T, int C, int nseg, int seg_tokens, const void *w, float *lam, cudaStream_t stream) {
+    dim3 grid((C + 255) / 256, B * nseg);
+    seg_decay_kernel<<<grid, 256, 0, stream>>>(T, C, nseg, seg_tokens, (const bf16 *)w, lam);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
     return WKV6_OK;

@@ -66,10 +66,12 @@ struct Params {
     int B, T, H;
     const bf16 *u;
     int has_s0;
-    // time-axis segmentation (seg_scan.cu): batch row b of this launch is segment b % nseg of a longer
-    // sequence; g_init = dL/dS at the end of each row, fp32 [B,H,64(value),64(key)]; nullptr / 1 otherwise
+    // time-axis segmentation (seg_scan.cu): the grid has B*nseg rows; row = b*nseg + seg covers tokens
+    // [seg*seg_chunks*64, min(T, (seg+1)*seg_chunks*64)) of sequence b; g_init = dL/dS behind the last token of
+    // each row, fp32 [rows,H,64(value),64(key)]; gu, gs, flags and checkpoints are indexed by row.
+    // nseg = 1, seg_chunks = ceil(T/64), g_init = nullptr for an ordinary call.
     const float *g_init;
-    int nseg;
+    int nseg, seg_chunks;
     bf16 *gu, *gs;
     const int *hz_flags;
     long long *dbg;           // nullptr, or [gridDim][NC][8] clock64 stamps of warp 0 at the stage boundaries (profiling aid)
@@ -89,8 +91,10 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
     extern __shared__ __align__(1024) uint8_t sm[];
     Extra &ex = *reinterpret_cast<Extra *>(sm + OFF_TILES_END);
     if ((smem_u32(sm) & 1023u) != 0) __trap();
-    const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
-    const int T = p.T, C = p.H * 64;
+    const int row = blockIdx.x / p.H, h = blockIdx.x % p.H;
+    const int b = row / p.nseg;                                  // batch index inside the [B,T,C] tensors
+    const int t_base = (row % p.nseg) * p.seg_chunks * L;        // first token of this row's segment
+    const int T = min(p.T - t_base, p.seg_chunks * L), C = p.H * 64;
     const int NC = (T + L - 1) / L;
     Frag F;
     F.init();
@@ -125,21 +129,21 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         // =====================================================================================
         auto issue_rk = [&](int c) {
             mbar_arrive_expect_tx(&ex.bar_rk, 2 * 8192);
-            tma_load_3d(sm + OFF_R, &map_r, &ex.bar_rk, h * 64, c * L, b);
-            tma_load_3d(sm + OFF_K, &map_k, &ex.bar_rk, h * 64, c * L, b);
+            tma_load_3d(sm + OFF_R, &map_r, &ex.bar_rk, h * 64, t_base + c * L, b);
+            tma_load_3d(sm + OFF_K, &map_k, &ex.bar_rk, h * 64, t_base + c * L, b);
         };
         auto issue_w = [&](int c) {
             mbar_arrive_expect_tx(&ex.bar_w, 8192);
-            tma_load_3d(sm + OFF_W, &map_w, &ex.bar_w, h * 64, c * L, b);
+            tma_load_3d(sm + OFF_W, &map_w, &ex.bar_w, h * 64, t_base + c * L, b);
         };
         auto issue_vg = [&](int c) {
             mbar_arrive_expect_tx(&ex.bar_vg, 2 * 8192);
-            tma_load_3d(sm + OFF_V, &map_v, &ex.bar_vg, h * 64, c * L, b);
-            tma_load_3d(sm + OFF_GY, &map_gy, &ex.bar_vg, h * 64, c * L, b);
+            tma_load_3d(sm + OFF_V, &map_v, &ex.bar_vg, h * 64, t_base + c * L, b);
+            tma_load_3d(sm + OFF_GY, &map_gy, &ex.bar_vg, h * 64, t_base + c * L, b);
         };
         auto issue_sin = [&](int c) {
             mbar_arrive_expect_tx(&ex.bar_sin, 8192);
-            tma_load_3d(sm + OFF_SIN, &map_ck, &ex.bar_sin, 0, (blockIdx.x * NC + c) * 64, 0);
+            tma_load_3d(sm + OFF_SIN, &map_ck, &ex.bar_sin, 0, (blockIdx.x * p.seg_chunks + c) * 64, 0);
         };
         if (lane == 0) {
             tma_prefetch_desc(&map_r); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
@@ -255,8 +259,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             bar_arrive_all<B_M3>();
             bar_sync_all<B_T2>();                                // gv tile written (under M3)
             if (lane == 0) {
-                tma_store_3d(&map_gv, sm + OFF_GVT, h * 64, c * L, b);
-                tma_store_3d(&map_gr, sm + OFF_GRT, h * 64, c * L, b);
+                tma_store_3d(&map_gv, sm + OFF_GVT, h * 64, t_base + c * L, b);
+                tma_store_3d(&map_gr, sm + OFF_GRT, h * 64, t_base + c * L, b);
                 tma_store_commit();
                 if (c > 0) {                                     // the raw tiles of the next chunk, while T3 runs
                     mbar_wait(&ex.bar_rk, par ^ 1);
@@ -266,8 +270,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             __syncwarp();
             bar_sync_all<B_T3>();                                // gk, gw tiles written; new bf16 G
             if (lane == 0) {
-                tma_store_3d(&map_gk, sm + OFF_GKT, h * 64, c * L, b);
-                tma_store_3d(&map_gw, sm + OFF_GWT, h * 64, c * L, b);
+                tma_store_3d(&map_gk, sm + OFF_GKT, h * 64, t_base + c * L, b);
+                tma_store_3d(&map_gw, sm + OFF_GWT, h * 64, t_base + c * L, b);
                 tma_store_commit();
             }
             __syncwarp();
@@ -286,7 +290,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         uint32_t v[16];
 
         // G = dL/dS behind the last token (0, or handed in when this row is a segment) and its bf16 copy
-        const int seg = b % p.nseg;
+        const int seg = row % p.nseg;
         const bool first_has_s0 = p.has_s0 || seg > 0;          // a later segment starts from a non-zero state
         const bool g_is_zero = p.g_init == nullptr || seg == p.nseg - 1;
 #pragma unroll
@@ -298,7 +302,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 for (int hh = 0; hh < 2; hh++)
 #pragma unroll
                     for (int e = 0; e < 2; e++)
-                        v[4 * g + 2 * hh + e] = __float_as_uint(p.g_init[(((size_t)b * p.H + h) * 64 + F.col(g, e)) * 64 + F.row(hh)]);
+                        v[4 * g + 2 * hh + e] = __float_as_uint(p.g_init[(((size_t)row * p.H + h) * 64 + F.col(g, e)) * 64 + F.row(hh)]);
         }
         tmem_st_frag(tG, v);
         stsm_x4(sbase + OFF_GB + F.rc(0), pack_frag(v, 0, 0), pack_frag(v, 1, 0), pack_frag(v, 2, 0), pack_frag(v, 3, 0));
@@ -308,7 +312,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         tc_fence_before();
         bar_arrive_all<B_T3>();
 
-#define STAMP(k) do { if (p.dbg && threadIdx.x == 0) p.dbg[((size_t)blockIdx.x * NC + it) * 8 + (k)] = clock64(); } while (0)
+#define STAMP(k) do { if (p.dbg && threadIdx.x == 0) p.dbg[((size_t)blockIdx.x * p.seg_chunks + it) * 8 + (k)] = clock64(); } while (0)
         for (int it = 0; it < NC; it++) {
             const int c = NC - 1 - it;
             const int nv = min(L, T - c * L);
@@ -665,7 +669,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     for (int hh = 0; hh < 2; hh++)
 #pragma unroll
                         for (int e = 0; e < 2; e++)   // gs[b,h,j,i] = dL/dS_0[i][j]
-                            p.gs[(((size_t)b * p.H + h) * 64 + F.col(g, e)) * 64 + F.row(hh)] =
+                            p.gs[(((size_t)row * p.H + h) * 64 + F.col(g, e)) * 64 + F.row(hh)] =
                                 __float2bfloat16_rn(__uint_as_float(v[4 * g + 2 * hh + e]));
             }
             tmem_wait_st();
@@ -707,7 +711,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             if (q == 0) atomicAdd(&ex.gu_s[F.row(hh)], x);
         }
         named_bar_sync<B_SCAN, CTHREADS>();
-        if (threadIdx.x < 64) p.gu[(size_t)b * C + h * 64 + threadIdx.x] = __float2bfloat16_rn(ex.gu_s[threadIdx.x]);
+        if (threadIdx.x < 64) p.gu[(size_t)row * C + h * 64 + threadIdx.x] = __float2bfloat16_rn(ex.gu_s[threadIdx.x]);
     }
     tc_fence_before();
     __syncthreads();
@@ -721,7 +725,10 @@ void *g_tc3_bwd_stamps = nullptr;   // profiling aid, set through wkv6b200_debug
 // per-stream hazard flags [B*H], then (time-axis segmentation, at most 296 segment rows) per-segment flags
 size_t tc3_saved_header(int B, int H) { return ((((size_t)B * H + 512) * sizeof(int)) + 1023) / 1024 * 1024; }
 size_t tc3_saved_bytes(int B, int T, int H) {
-    const size_t NC = (size_t)(T + L - 1) / L;
+    size_t NC = (size_t)(T + L - 1) / L;
+    int nseg = 1, seg_chunks = 0;
+    seg_plan_train(B, T, H, &nseg, &seg_chunks);           // uneven segments leave a few checkpoint slots unused
+    if (nseg > 1) NC = (size_t)nseg * seg_chunks;
     return tc3_saved_header(B, H) + (size_t)B * H * NC * 8192;
 }
 size_t tc3_backward_workspace_bytes(int B, int T, int H, bool has_saved) {
@@ -733,9 +740,11 @@ bool tc3_backward_supported(const Args &a) {
 }
 
 // one launch of the backward kernel on `a` viewed as given (B rows of T tokens), chunk-start states in ckpt
-static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const float *g_init, int nseg, bool has_s0) {
+static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const float *g_init, int nseg, int seg_chunks,
+                      bool has_s0) {
     const int C = a.H * 64;
-    const size_t NC = (size_t)(a.T + L - 1) / L;
+    if (nseg <= 1) { nseg = 1; seg_chunks = (a.T + L - 1) / L; }
+    const size_t NC = (size_t)nseg * seg_chunks;
     CUtensorMap mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw;
     const auto dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     const void *ptrs[10] = {a.r, a.k, a.v, a.w, a.gy, ckpt, a.gr, a.gk, a.gv, a.gw};
@@ -753,7 +762,7 @@ static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const f
     p.u = (const bf16 *)a.u;
     p.has_s0 = has_s0;
     p.g_init = g_init;
-    p.nseg = nseg;
+    p.nseg = nseg; p.seg_chunks = seg_chunks;
     p.gu = (bf16 *)a.gu; p.gs = (bf16 *)a.gs;
     p.hz_flags = flags;
     p.dbg = (long long *)g_tc3_bwd_stamps;
@@ -766,7 +775,7 @@ static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const f
                                              cudaSharedmemCarveoutMaxShared));
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
-    wkv6_tc3_bwd_kernel<<<a.B * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
+    wkv6_tc3_bwd_kernel<<<a.B * nseg * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
     return WKV6_OK;
@@ -779,8 +788,8 @@ static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const f
 // each segment's own contribution, a reverse scan over the segments chains them, and the ordinary backward
 // kernel starts every segment from its scanned G.  The forward of the training pair was segmented the same
 // way, so `saved` holds the chunk-start states in segment-row order and the per-segment flags.
-static int tc3_backward_segmented(const Args &a, int nseg) {
-    const int Bs = a.B * nseg, Tseg = a.T / nseg, C = a.H * 64;
+static int tc3_backward_segmented(const Args &a, int nseg, int seg_chunks) {
+    const int Bs = a.B * nseg, C = a.H * 64, seg_tokens = seg_chunks * L;
     int *flags = (int *)a.saved, *sflags = flags + (size_t)a.B * a.H;
     const bf16 *ckpt = (const bf16 *)((uint8_t *)a.saved + tc3_saved_header(a.B, a.H));
     const size_t n_el = (size_t)a.B * a.T * C, st = (size_t)Bs * a.H * 4096;
@@ -790,16 +799,16 @@ static int tc3_backward_segmented(const Args &a, int nseg) {
     bf16 *r_rev = (bf16 *)buf, *gy_rev = r_rev + n_el, *w_rev = gy_rev + n_el;
     float *g_loc = (float *)(w_rev + n_el), *g_end = g_loc + st, *lam = g_end + st;
     bf16 *gs_tmp = (bf16 *)(lam + (size_t)Bs * C), *gu_tmp = gs_tmp + st;
-    int rc = seg_reverse3(Bs, Tseg, C, a.r, a.gy, a.w, r_rev, gy_rev, w_rev, a.stream);
+    int rc = seg_reverse3(a.B, a.T, C, nseg, seg_tokens, a.r, a.gy, a.w, r_rev, gy_rev, w_rev, a.stream);
     Args f = a;                                   // state-only pass: the "state" it ends with is each segment's own dL/dS_start
-    f.B = Bs; f.T = Tseg; f.r = r_rev; f.k = r_rev; f.v = gy_rev; f.w = w_rev;
+    f.r = r_rev; f.k = r_rev; f.v = gy_rev; f.w = w_rev;
     f.s0 = nullptr; f.s0_bstride = 0; f.s0_f32 = 0; f.sT = g_loc; f.sT_f32 = 1; f.y = nullptr; f.saved = nullptr; f.gy = nullptr;
-    if (rc == WKV6_OK) rc = tc3_forward(f, nullptr, sflags);
-    if (rc == WKV6_OK) rc = seg_decay(Bs, Tseg, C, a.w, lam, a.stream);
+    if (rc == WKV6_OK) rc = tc3_forward(f, nullptr, sflags, nseg, seg_chunks);
+    if (rc == WKV6_OK) rc = seg_decay(a.B, a.T, C, nseg, seg_tokens, a.w, lam, a.stream);
     if (rc == WKV6_OK) rc = seg_scan(a.B, nseg, a.H, lam, g_loc, nullptr, 0, 0, g_end, nullptr, 0, 1, nullptr, a.stream);
     Args v = a;
-    v.B = Bs; v.T = Tseg; v.gu = gu_tmp; v.gs = a.gs ? gs_tmp : nullptr;
-    if (rc == WKV6_OK) rc = launch_bwd(v, ckpt, sflags, g_end, nseg, a.s0 != nullptr);
+    v.gu = gu_tmp; v.gs = a.gs ? gs_tmp : nullptr;
+    if (rc == WKV6_OK) rc = launch_bwd(v, ckpt, sflags, g_end, nseg, seg_chunks, a.s0 != nullptr);
     if (rc == WKV6_OK) rc = seg_sum_gu(a.B, nseg, C, gu_tmp, a.gu, a.stream);
     if (rc == WKV6_OK && a.gs)                    // dL/dS_0 is what segment 0 of every sequence produced
         rc = cudaMemcpy2DAsync(a.gs, (size_t)a.H * 4096 * 2, gs_tmp, (size_t)nseg * a.H * 4096 * 2, (size_t)a.H * 4096 * 2, a.B,
@@ -821,8 +830,9 @@ int tc3_backward(const Args &a, const Args *exact, bool flags_preset, bool run_f
         return WKV6_EWORKSPACE;
     }
     if (a.saved && !exact && run_fallback) {
-        const int nseg = seg_count_train(a.B, a.T, a.H);
-        if (nseg > 1) return tc3_backward_segmented(a, nseg);
+        int nseg = 1, seg_chunks = 0;
+        seg_plan_train(a.B, a.T, a.H, &nseg, &seg_chunks);
+        if (nseg > 1) return tc3_backward_segmented(a, nseg, seg_chunks);
     }
     uint8_t *sv = a.saved ? (uint8_t *)a.saved : (uint8_t *)a.workspace + simt_ws;
     int *flags = (int *)sv;
@@ -835,7 +845,7 @@ int tc3_backward(const Args &a, const Args *exact, bool flags_preset, bool run_f
         f.sT = nullptr;
         if (int rc = tc3_forward(f, ckpt, flags)) return rc;
     }
-    if (int rc = launch_bwd(a, ckpt, flags, nullptr, 1, a.s0 != nullptr)) return rc;
+    if (int rc = launch_bwd(a, ckpt, flags, nullptr, 1, 0, a.s0 != nullptr)) return rc;
     if (!run_fallback) return WKV6_OK;      // the caller runs its own exact route on the flags in the workspace
     // exact route for the flagged streams only
     Args s = exact ? *exact : a;

@@ -59,7 +59,11 @@ struct Params {
     void *sT;
     int sT_f32;
     int has_y, has_ckpt;
-    int *hz_flags;            // [B*H]: 1 = this stream needs the exact route
+    int *hz_flags;            // [rows*H]: 1 = this stream needs the exact route
+    // time-axis segmentation (seg_scan.cu): the grid has B*nseg rows; row = b*nseg + seg covers tokens
+    // [seg*seg_chunks*64, min(T, (seg+1)*seg_chunks*64)) of sequence b.  States (s0, sT), flags and the
+    // checkpoints are indexed by row; nseg = 1 and seg_chunks = ceil(T/64) for an ordinary call.
+    int nseg, seg_chunks;
 };
 
 // 9 warps x 2 CTAs = 5 warps on the fullest SM sub-partition (16384 registers): at most 96 per thread
@@ -71,8 +75,10 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
     extern __shared__ __align__(1024) uint8_t sm[];
     Extra &ex = *reinterpret_cast<Extra *>(sm + OFF_TILES_END);
     if ((smem_u32(sm) & 1023u) != 0) __trap();
-    const int b = blockIdx.x / p.H, h = blockIdx.x % p.H;
-    const int T = p.T;
+    const int row = blockIdx.x / p.H, h = blockIdx.x % p.H;
+    const int b = row / p.nseg;                                  // batch index inside the [B,T,C] tensors
+    const int t_base = (row % p.nseg) * p.seg_chunks * L;        // first token of this row's segment
+    const int T = min(p.T - t_base, p.seg_chunks * L);           // tokens of the segment
     const int NC = (T + L - 1) / L;
     Frag F;
     F.init();
@@ -103,13 +109,13 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         // =====================================================================================
         auto issue_rkw = [&](int c) {
             mbar_arrive_expect_tx(&ex.bar_rkw, 3 * 8192);
-            tma_load_3d(sm + OFF_R, &map_r, &ex.bar_rkw, h * 64, c * L, b);
-            tma_load_3d(sm + OFF_K, &map_k, &ex.bar_rkw, h * 64, c * L, b);
-            tma_load_3d(sm + OFF_W, &map_w, &ex.bar_rkw, h * 64, c * L, b);
+            tma_load_3d(sm + OFF_R, &map_r, &ex.bar_rkw, h * 64, t_base + c * L, b);
+            tma_load_3d(sm + OFF_K, &map_k, &ex.bar_rkw, h * 64, t_base + c * L, b);
+            tma_load_3d(sm + OFF_W, &map_w, &ex.bar_rkw, h * 64, t_base + c * L, b);
         };
         auto issue_v = [&](int c) {
             mbar_arrive_expect_tx(&ex.bar_v, 8192);
-            tma_load_3d(sm + OFF_V, &map_v, &ex.bar_v, h * 64, c * L, b);
+            tma_load_3d(sm + OFF_V, &map_v, &ex.bar_v, h * 64, t_base + c * L, b);
         };
         const uint32_t kt = sbase + OFF_KT, rt = sbase + OFF_RT, rh = sbase + OFF_RH, kh = sbase + OFF_KH;
         const uint32_t kl = sbase + OFF_KL, pp = sbase + OFF_P, sb = sbase + OFF_SB, vv = sbase + OFF_V;
@@ -147,7 +153,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         bar_sync_all<B_PB>();
         bar_sync_all<B_T2>();                                    // initial state in TMEM / shared
         if (lane == 0) {
-            if (p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (blockIdx.x * NC) * 64, 0);
+            if (p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (blockIdx.x * p.seg_chunks) * 64, 0);
             tma_store_commit();
         }
         if (lane == 0) mbar_wait(&ex.bar_a, 0);
@@ -210,8 +216,8 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             }
             bar_sync_all<B_T2>();                                // y tile and the new bf16 S written
             if (lane == 0) {
-                if (p.has_y) tma_store_3d(&map_y, sm + OFF_YT, h * 64, c * L, b);
-                if (more && p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (blockIdx.x * NC + c + 1) * 64, 0);
+                if (p.has_y) tma_store_3d(&map_y, sm + OFF_YT, h * 64, t_base + c * L, b);
+                if (more && p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (blockIdx.x * p.seg_chunks + c + 1) * 64, 0);
                 tma_store_commit();
             }
         }
@@ -234,7 +240,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 for (int e = 0; e < 2; e++) {
                     float x = 0.f;
                     if (p.s0) {   // caller layout [.,H,64(value j),64(key i)]
-                        const size_t idx = (size_t)b * p.s0_bstride + ((size_t)h * 64 + F.col(g, e)) * 64 + F.row(hh);
+                        const size_t idx = (size_t)row * p.s0_bstride + ((size_t)h * 64 + F.col(g, e)) * 64 + F.row(hh);
                         x = p.s0_f32 ? ((const float *)p.s0)[idx] : __bfloat162float(((const bf16 *)p.s0)[idx]);
                     }
                     v[4 * g + 2 * hh + e] = __float_as_uint(x);
@@ -469,7 +475,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     for (int hh = 0; hh < 2; hh++)
 #pragma unroll
                         for (int e = 0; e < 2; e++) {
-                            const size_t idx = (((size_t)b * p.H + h) * 64 + F.col(g, e)) * 64 + F.row(hh);
+                            const size_t idx = (((size_t)row * p.H + h) * 64 + F.col(g, e)) * 64 + F.row(hh);
                             const float x = __uint_as_float(v[4 * g + 2 * hh + e]);
                             if (p.sT_f32) ((float *)p.sT)[idx] = x;
                             else ((bf16 *)p.sT)[idx] = __float2bfloat16_rn(x);
@@ -495,10 +501,11 @@ bool tc3_forward_supported(const Args &a) {
 
 // ckpt: nullptr or bf16 [B*H][ceil(T/64)][64 i][64 j] receiving the state at the start of every chunk;
 // hz_flags: device int [B*H], zeroed by the caller; a.y may be nullptr (state-only pass).
-int tc3_forward(const Args &a, void *ckpt, int *hz_flags) {
+int tc3_forward(const Args &a, void *ckpt, int *hz_flags, int nseg, int seg_chunks) {
     if (a.B * a.H == 0 || a.T == 0) return WKV6_OK;
     const int C = a.H * 64;
-    const size_t NC = (size_t)(a.T + L - 1) / L;
+    if (nseg <= 1) { nseg = 1; seg_chunks = (a.T + L - 1) / L; }
+    const size_t NC = (size_t)nseg * seg_chunks;                 // checkpoint slots per (b,h)
     CUtensorMap mr, mk, mv, mw, my, mc;
     const auto dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
     const void *yy = a.y ? a.y : a.r, *cc = ckpt ? ckpt : a.r;    // unused maps still have to encode
@@ -517,6 +524,7 @@ int tc3_forward(const Args &a, void *ckpt, int *hz_flags) {
     p.has_y = a.y != nullptr;
     p.has_ckpt = ckpt != nullptr;
     p.hz_flags = hz_flags;
+    p.nseg = nseg; p.seg_chunks = seg_chunks;
     static bool attr_done[64] = {};          // function attributes are per device
     int dev = 0;
     WKV6_CUDA_CHECK(cudaGetDevice(&dev));
@@ -526,7 +534,7 @@ int tc3_forward(const Args &a, void *ckpt, int *hz_flags) {
                                              cudaSharedmemCarveoutMaxShared));
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
-    wkv6_tc3_fwd_kernel<<<a.B * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
+    wkv6_tc3_fwd_kernel<<<a.B * nseg * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
     return WKV6_OK;
