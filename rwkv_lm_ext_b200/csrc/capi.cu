@@ -70,14 +70,13 @@ static int *flag_slice(size_t n) {
     if (off + n > RING) off = 0;      // wrap: only collides with a call issued ~1M stream-flags ago
     return ring[dev] + off;
 }
-static void ensure_pool_keeps_memory();
 // Forward over `nseg` time segments that run as separate grid rows (seg_scan.cu): state-only pass from zero
 // states, scan over the segment states, ordinary pass with the scanned initial states.
 // flags: [B*H], already holding any pre-set stream flags.
 // ckpt / seg_flags: nullptr, or (training pair) where the chunk-start states and the per-segment flags go.
 static int tc3_forward_segmented(const Args &a, int *flags, int nseg, int seg_chunks, void *ckpt = nullptr,
                                  int *seg_flags = nullptr) {
-    ensure_pool_keeps_memory();
+    wkv6::ensure_pool_keeps_memory();
     const int Bs = a.B * nseg, C = a.H * 64, seg_tokens = seg_chunks * 64;
     const size_t st = (size_t)Bs * a.H * 4096, nl = (size_t)Bs * C, nf = (size_t)Bs * a.H;
     float *buf = nullptr;
@@ -132,24 +131,9 @@ static Args with_raw_w(const Args &a, void *w_raw) {
 static bool ew_convertible(const Args &a) {
     return (a.w_kind == W_LOG_F32 || a.w_kind == W_DECAY_F32) && tc3_forward_supported(with_raw_w(a, const_cast<void *>(a.w)));
 }
-// stream-ordered scratch (cudaMallocAsync) stays cached in the device's default pool instead of going
-// back to the OS at every synchronisation
-static void ensure_pool_keeps_memory() {
-    static bool pool_set[64] = {};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !pool_set[dev]) {
-        cudaMemPool_t pool;
-        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            uint64_t keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-        pool_set[dev] = true;
-    }
-}
 static int forward3_ew(const Args &a) {
     // the reference's entry has no workspace argument: stream-ordered scratch, kept cached in the pool
-    ensure_pool_keeps_memory();
+    wkv6::ensure_pool_keeps_memory();
     const size_t nb = (size_t)a.B * a.H * sizeof(int);
     int *flags = flag_slice((size_t)a.B * a.H);
     if (!flags) { set_error("cannot get %zu bytes of flag scratch", nb); return WKV6_ECUDA; }
@@ -173,7 +157,7 @@ static int dispatch_forward(const Args &a) {
     if (impl != WKV6_IMPL_SIMT && tc3_forward_supported(a)) return forward3(a);
     if (impl != WKV6_IMPL_SIMT && ew_convertible(a) && !a.saved) return forward3_ew(a);
     if (impl != WKV6_IMPL_SIMT && bi_forward_tc_supported(a) && !a.saved) {
-        ensure_pool_keeps_memory();
+        wkv6::ensure_pool_keeps_memory();
         const size_t nb = (size_t)a.B * a.H * sizeof(int);
         int *flags = flag_slice((size_t)a.B * a.H);
         if (!flags) { set_error("cannot get %zu bytes of flag scratch", nb); return WKV6_ECUDA; }
@@ -187,7 +171,7 @@ static int dispatch_backward(const Args &a) {
     const int impl = current_impl();
     if (impl != WKV6_IMPL_SIMT && tc3_backward_supported(a)) return tc3_backward(a);
     if (impl != WKV6_IMPL_SIMT && a.mask && !a.saved && !a.s0 && bi_forward_tc_supported(a)) {
-        ensure_pool_keeps_memory();
+        wkv6::ensure_pool_keeps_memory();
         return bi_backward_tc(a);
     }
     if (impl != WKV6_IMPL_SIMT && a.w_kind == W_LOG_F32 && !a.saved && tc3_backward_supported(with_raw_w(a, const_cast<void *>(a.w)))) {

@@ -113,6 +113,7 @@ int ddlerp_backward_tma(int nout, int B, int T, int C, const void *x, const void
                         const void *const *gouts, void *gx, void *gm, void *gshift, float *partial, int *slots,
                         cudaStream_t stream);
 // seg_scan.cu: time-axis segmentation for calls with few streams (see the file header)
+void ensure_pool_keeps_memory();   // cudaMallocAsync scratch stays cached in the device pool
 void seg_plan(int B, int T, int H, int *nseg, int *seg_chunks);
 void seg_plan_train(int B, int T, int H, int *nseg, int *seg_chunks);
 int seg_reverse3(int B, int T, int C, int nseg, int seg_tokens, const void *a, const void *b, const void *c, void *ra, void *rb,

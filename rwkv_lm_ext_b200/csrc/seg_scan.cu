@@ -131,6 +131,22 @@ __global__ void seg_sum_gu_kernel(int B, int nseg, int C, const bf16 *__restrict
 
 }  // namespace
 
+// stream-ordered scratch (cudaMallocAsync) stays cached in the device's default pool instead of going
+// back to the OS at every synchronisation
+void ensure_pool_keeps_memory() {
+    static bool pool_set[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !pool_set[dev]) {
+        cudaMemPool_t pool;
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = ~0ull;
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+        pool_set[dev] = true;
+    }
+}
+
 // Segment plan: nseg segments of seg_chunks 64-token chunks each (the last one may be shorter), enough of them
 // to fill the 296 CTA slots, none empty.  nseg = 1: do not segment.
 static void plan(long long streams, int T, int min_chunks, int *nseg, int *seg_chunks) {

@@ -81,6 +81,8 @@ __device__ __forceinline__ uint32_t pack_frag(const uint32_t *v, int g, int hh) 
     return pack2(__uint_as_float(v[4 * g + 2 * hh]), __uint_as_float(v[4 * g + 2 * hh + 1]));
 }
 
+// SEG = false: the ordinary call, its own instantiation (see the forward kernel)
+template <bool SEG>
 __global__ void __launch_bounds__(NTHREADS, 2)
 wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_w,
@@ -92,10 +94,11 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
     Extra &ex = *reinterpret_cast<Extra *>(sm + OFF_TILES_END);
     if ((smem_u32(sm) & 1023u) != 0) __trap();
     const int row = blockIdx.x / p.H, h = blockIdx.x % p.H;
-    const int b = row / p.nseg;                                  // batch index inside the [B,T,C] tensors
-    const int t_base = (row % p.nseg) * p.seg_chunks * L;        // first token of this row's segment
-    const int T = min(p.T - t_base, p.seg_chunks * L), C = p.H * 64;
+    const int b = SEG ? row / p.nseg : row;                                  // batch index inside the [B,T,C] tensors
+    const int t_base = SEG ? (row % p.nseg) * p.seg_chunks * L : 0;          // first token of this row's segment
+    const int T = SEG ? min(p.T - t_base, p.seg_chunks * L) : p.T, C = p.H * 64;
     const int NC = (T + L - 1) / L;
+    const int ck_stride = SEG ? p.seg_chunks : NC;                           // checkpoint slots per row
     Frag F;
     F.init();
     const int warp = F.warp, lane = F.lane;
@@ -143,7 +146,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         };
         auto issue_sin = [&](int c) {
             mbar_arrive_expect_tx(&ex.bar_sin, 8192);
-            tma_load_3d(sm + OFF_SIN, &map_ck, &ex.bar_sin, 0, (blockIdx.x * p.seg_chunks + c) * 64, 0);
+            tma_load_3d(sm + OFF_SIN, &map_ck, &ex.bar_sin, 0, (blockIdx.x * ck_stride + c) * 64, 0);
         };
         if (lane == 0) {
             tma_prefetch_desc(&map_r); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
@@ -290,9 +293,9 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         uint32_t v[16];
 
         // G = dL/dS behind the last token (0, or handed in when this row is a segment) and its bf16 copy
-        const int seg = row % p.nseg;
+        const int seg = SEG ? row % p.nseg : 0;
         const bool first_has_s0 = p.has_s0 || seg > 0;          // a later segment starts from a non-zero state
-        const bool g_is_zero = p.g_init == nullptr || seg == p.nseg - 1;
+        const bool g_is_zero = !SEG || p.g_init == nullptr || seg == p.nseg - 1;
 #pragma unroll
         for (int x = 0; x < 16; x++) v[x] = 0u;
         if (!g_is_zero) {
@@ -312,7 +315,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         tc_fence_before();
         bar_arrive_all<B_T3>();
 
-#define STAMP(k) do { if (p.dbg && threadIdx.x == 0) p.dbg[((size_t)blockIdx.x * p.seg_chunks + it) * 8 + (k)] = clock64(); } while (0)
+#define STAMP(k) do { if (p.dbg && threadIdx.x == 0) p.dbg[((size_t)blockIdx.x * ck_stride + it) * 8 + (k)] = clock64(); } while (0)
         for (int it = 0; it < NC; it++) {
             const int c = NC - 1 - it;
             const int nv = min(L, T - c * L);
@@ -770,12 +773,16 @@ static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const f
     int dev = 0;
     WKV6_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_bwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_bwd_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             cudaSharedmemCarveoutMaxShared));
+        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_bwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                              cudaSharedmemCarveoutMaxShared));
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
-    wkv6_tc3_bwd_kernel<<<a.B * nseg * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
+    if (nseg > 1) wkv6_tc3_bwd_kernel<true><<<a.B * nseg * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
+    else wkv6_tc3_bwd_kernel<false><<<a.B * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
     return WKV6_OK;
@@ -795,6 +802,7 @@ static int tc3_backward_segmented(const Args &a, int nseg, int seg_chunks) {
     const size_t n_el = (size_t)a.B * a.T * C, st = (size_t)Bs * a.H * 4096;
     const size_t bytes = 3 * n_el * 2 + 2 * st * 4 + (size_t)Bs * C * 4 + st * 2 + (size_t)Bs * C * 2;
     uint8_t *buf = nullptr;
+    ensure_pool_keeps_memory();
     WKV6_CUDA_CHECK(cudaMallocAsync((void **)&buf, bytes, a.stream));
     bf16 *r_rev = (bf16 *)buf, *gy_rev = r_rev + n_el, *w_rev = gy_rev + n_el;
     float *g_loc = (float *)(w_rev + n_el), *g_end = g_loc + st, *lam = g_end + st;

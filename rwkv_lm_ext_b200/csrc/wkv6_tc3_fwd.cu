@@ -67,6 +67,9 @@ struct Params {
 };
 
 // 9 warps x 2 CTAs = 5 warps on the fullest SM sub-partition (16384 registers): at most 96 per thread
+// SEG = false is the ordinary call (one row per (b,h), the whole sequence): kept as its own instantiation so
+// that the segment arithmetic costs it nothing (with run-time descriptors ptxas scheduled the forward 7 % slower)
+template <bool SEG>
 __global__ void __launch_bounds__(NTHREADS, 2)
 wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_w,
@@ -76,10 +79,11 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
     Extra &ex = *reinterpret_cast<Extra *>(sm + OFF_TILES_END);
     if ((smem_u32(sm) & 1023u) != 0) __trap();
     const int row = blockIdx.x / p.H, h = blockIdx.x % p.H;
-    const int b = row / p.nseg;                                  // batch index inside the [B,T,C] tensors
-    const int t_base = (row % p.nseg) * p.seg_chunks * L;        // first token of this row's segment
-    const int T = min(p.T - t_base, p.seg_chunks * L);           // tokens of the segment
+    const int b = SEG ? row / p.nseg : row;                                  // batch index inside the [B,T,C] tensors
+    const int t_base = SEG ? (row % p.nseg) * p.seg_chunks * L : 0;          // first token of this row's segment
+    const int T = SEG ? min(p.T - t_base, p.seg_chunks * L) : p.T;           // tokens of the segment
     const int NC = (T + L - 1) / L;
+    const int ck_stride = SEG ? p.seg_chunks : NC;                           // checkpoint slots per row
     Frag F;
     F.init();
     const int warp = F.warp, lane = F.lane;
@@ -153,7 +157,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         bar_sync_all<B_PB>();
         bar_sync_all<B_T2>();                                    // initial state in TMEM / shared
         if (lane == 0) {
-            if (p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (blockIdx.x * p.seg_chunks) * 64, 0);
+            if (p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (blockIdx.x * ck_stride) * 64, 0);
             tma_store_commit();
         }
         if (lane == 0) mbar_wait(&ex.bar_a, 0);
@@ -217,7 +221,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             bar_sync_all<B_T2>();                                // y tile and the new bf16 S written
             if (lane == 0) {
                 if (p.has_y) tma_store_3d(&map_y, sm + OFF_YT, h * 64, t_base + c * L, b);
-                if (more && p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (blockIdx.x * p.seg_chunks + c + 1) * 64, 0);
+                if (more && p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (blockIdx.x * ck_stride + c + 1) * 64, 0);
                 tma_store_commit();
             }
         }
@@ -529,12 +533,16 @@ int tc3_forward(const Args &a, void *ckpt, int *hz_flags, int nseg, int seg_chun
     int dev = 0;
     WKV6_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             cudaSharedmemCarveoutMaxShared));
+        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                              cudaSharedmemCarveoutMaxShared));
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
-    wkv6_tc3_fwd_kernel<<<a.B * nseg * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
+    if (nseg > 1) wkv6_tc3_fwd_kernel<true><<<a.B * nseg * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
+    else wkv6_tc3_fwd_kernel<false><<<a.B * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
     return WKV6_OK;
