@@ -541,3 +541,28 @@ def test_segmented_training_pair(M, with_state):
         assert relrms(gs, gs_s) < 8e-3 and relrms(sT, sTs) < 6e-3
     else:
         assert grads[3][:, 0].abs().max().item() == 0.0
+
+
+def test_concurrent_streams_do_not_share_scratch(M):
+    """Calls in flight on different CUDA streams (forward-only path: hazard flags come from the library's static
+    ring; one of the inputs has a hazardous stream so the flags matter) give the same results as serial calls."""
+    B, T, H = 2, 320, 3
+    C = H * 64
+    sets = []
+    for i in range(4):
+        r, k, v, w, u, _ = make_inputs(B, T, H, seed=70 + i, decay="model", device=DEV)
+        if i % 2:
+            w[0, 100:140, :64] = 3.0
+        sets.append((r, k, v, w, u))
+    with torch.no_grad():
+        serial = [M.RUN_CUDA_RWKV6(B, T, C, H, *s) for s in sets]
+        torch.cuda.synchronize()
+        streams = [torch.cuda.Stream() for _ in range(4)]
+        outs = [None] * 4
+        for rep in range(5):
+            for i, st in enumerate(streams):
+                with torch.cuda.stream(st):
+                    outs[i] = M.RUN_CUDA_RWKV6(B, T, C, H, *sets[i])
+        torch.cuda.synchronize()
+    for a, b_ in zip(outs, serial):
+        assert torch.equal(a, b_)
