@@ -17,39 +17,49 @@ namespace {
 typedef __nv_bfloat16 bf16;
 
 // lam[row, c] = sum over the segment's tokens of -exp(w[b, t, c]);  row = b*nseg + seg covers tokens
-// [seg*seg_tokens, min(T, (seg+1)*seg_tokens)) of sequence b
-// grid (ceil(C/256), rows), block 256 = 32 column lanes (8 channels) x 8 token lanes
+// [seg*seg_tokens, min(T, (seg+1)*seg_tokens)) of sequence b.
+// grid (ceil(C/64), rows), block 256 = 8 column lanes (8 channels each: 128 contiguous bytes of a token row)
+// x 32 token lanes; every thread keeps four independent 16-byte loads in flight.  Deterministic.
 __global__ void __launch_bounds__(256) seg_decay_kernel(int T, int C, int nseg, int seg_tokens, const bf16 *__restrict__ w,
                                                         float *__restrict__ lam) {
-    const int lane = threadIdx.x & 31, tl = threadIdx.x >> 5;
-    const int c = (blockIdx.x * 32 + lane) * 8;
+    const int cl = threadIdx.x & 7, tl = threadIdx.x >> 3;
+    const int c = (blockIdx.x * 8 + cl) * 8;
     const size_t row = blockIdx.y;
     const int b = (int)(row / nseg), t0 = (int)(row % nseg) * seg_tokens;
     const int Tseg = min(seg_tokens, T - t0);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (c < C) {
         const bf16 *base = w + ((size_t)b * T + t0) * C + c;
-        for (int t = tl; t < Tseg; t += 8) {
-            const uint4 u = *reinterpret_cast<const uint4 *>(base + (size_t)t * C);
-            const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u);
+        for (int t = tl; t < Tseg; t += 128) {
+            uint4 u[4];
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const float2 f = __bfloat1622float2(h[i]);
-                acc[2 * i] -= __expf(f.x);
-                acc[2 * i + 1] -= __expf(f.y);
+            for (int j = 0; j < 4; j++)
+                u[j] = t + 32 * j < Tseg ? *reinterpret_cast<const uint4 *>(base + (size_t)(t + 32 * j) * C) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                if (t + 32 * j >= Tseg) break;
+                const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&u[j]);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const float2 f = __bfloat1622float2(h[i]);
+                    acc[2 * i] -= __expf(f.x);
+                    acc[2 * i + 1] -= __expf(f.y);
+                }
             }
         }
     }
-    __shared__ float red[8][256 + 8];
+    __shared__ float red[32][64 + 1];
 #pragma unroll
-    for (int e = 0; e < 8; e++) red[tl][lane * 8 + e] = acc[e];
+    for (int e = 0; e < 8; e++) red[tl][cl * 8 + e] = acc[e];
     __syncthreads();
-    const int cc = blockIdx.x * 256 + threadIdx.x;
-    if (cc < C) {
-        float s = 0.f;
-#pragma unroll
-        for (int l = 0; l < 8; l++) s += red[l][threadIdx.x];
-        lam[row * C + cc] = s;
+    if (threadIdx.x < 64) {
+        const int cc = blockIdx.x * 64 + threadIdx.x;
+        if (cc < C) {
+            float s = 0.f;
+#pragma unroll 8
+            for (int l = 0; l < 32; l++) s += red[l][threadIdx.x];
+            lam[row * C + cc] = s;
+        }
     }
 }
 
@@ -57,34 +67,48 @@ __global__ void __launch_bounds__(256) seg_decay_kernel(int T, int C, int nseg, 
 // [value j][key i], the decay acts on the key index = fastest dimension).
 //   S_start[b,0] = s0 (or 0);  S_start[b,seg+1] = exp(lam[b,seg,h,i]) * S_start[b,seg] + S_loc[b,seg]
 // reverse = 1 walks the segments from the last to the first (the backward's state-gradient chain).
-// grid B*H, block 256, 16 elements per thread.
+// grid (16, B*H), block 256: one state element per thread; the loads do not depend on the running value and
+// are issued four segments ahead.
 __global__ void __launch_bounds__(256) seg_scan_kernel(int nseg, int H, const float *__restrict__ lam,
                                                        const float *__restrict__ s_loc, const void *__restrict__ s0,
                                                        int s0_f32, long long s0_bstride, float *__restrict__ s_start,
                                                        void *__restrict__ sT, int sT_f32, int reverse,
                                                        const int *__restrict__ stream_flags) {
-    const int b = blockIdx.x / H, h = blockIdx.x % H;
+    const int stream = blockIdx.y, b = stream / H, h = stream % H;
     // a flagged stream is recomputed by the exact route from the ORIGINAL initial state, which sT may alias
-    const bool write_sT = sT != nullptr && !(stream_flags && stream_flags[blockIdx.x] != 0);
+    const bool write_sT = sT != nullptr && !(stream_flags && stream_flags[stream] != 0);
     const size_t C = (size_t)H * 64;
-    for (int e = threadIdx.x; e < 4096; e += 256) {
-        const int i = e & 63;
-        float S = 0.f;
-        if (s0) {
-            const size_t idx = (size_t)b * s0_bstride + (size_t)h * 4096 + e;
-            S = s0_f32 ? ((const float *)s0)[idx] : __bfloat162float(((const bf16 *)s0)[idx]);
+    const int e = blockIdx.x * 256 + threadIdx.x, i = e & 63;
+    float S = 0.f;
+    if (s0) {
+        const size_t idx = (size_t)b * s0_bstride + (size_t)h * 4096 + e;
+        S = s0_f32 ? ((const float *)s0)[idx] : __bfloat162float(((const bf16 *)s0)[idx]);
+    }
+    for (int q0 = 0; q0 < nseg; q0 += 4) {
+        float l[4], x[4];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int q = q0 + j;
+            if (q < nseg) {
+                const size_t row = (size_t)b * nseg + (reverse ? nseg - 1 - q : q);
+                l[j] = lam[row * C + h * 64 + i];
+                x[j] = s_loc[(row * H + h) * 4096 + e];
+            }
         }
-        for (int q = 0; q < nseg; q++) {
-            const int seg = reverse ? nseg - 1 - q : q;
-            const size_t row = (size_t)b * nseg + seg;
-            s_start[(row * H + h) * 4096 + e] = S;
-            S = __expf(lam[row * C + h * 64 + i]) * S + s_loc[(row * H + h) * 4096 + e];
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int q = q0 + j;
+            if (q < nseg) {
+                const size_t row = (size_t)b * nseg + (reverse ? nseg - 1 - q : q);
+                s_start[(row * H + h) * 4096 + e] = S;
+                S = __expf(l[j]) * S + x[j];
+            }
         }
-        if (write_sT) {
-            const size_t idx = ((size_t)b * H + h) * 4096 + e;
-            if (sT_f32) ((float *)sT)[idx] = S;
-            else ((bf16 *)sT)[idx] = __float2bfloat16_rn(S);
-        }
+    }
+    if (write_sT) {
+        const size_t idx = ((size_t)b * H + h) * 4096 + e;
+        if (sT_f32) ((float *)sT)[idx] = S;
+        else ((bf16 *)sT)[idx] = __float2bfloat16_rn(S);
     }
 }
 
@@ -197,7 +221,7 @@ int seg_sum_gu(int B, int nseg, int C, const void *part, void *gu, cudaStream_t 
 }
 
 int seg_decay(int B, int T, int C, int nseg, int seg_tokens, const void *w, float *lam, cudaStream_t stream) {
-    dim3 grid((C + 255) / 256, B * nseg);
+    dim3 grid((C + 63) / 64, B * nseg);
     seg_decay_kernel<<<grid, 256, 0, stream>>>(T, C, nseg, seg_tokens, (const bf16 *)w, lam);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
@@ -207,7 +231,7 @@ int seg_decay(int B, int T, int C, int nseg, int seg_tokens, const void *w, floa
 int seg_scan(int B, int nseg, int H, const float *lam, const float *s_loc, const void *s0, int s0_f32,
              long long s0_bstride, float *s_start, void *sT, int sT_f32, int reverse, const int *stream_flags,
              cudaStream_t stream) {
-    seg_scan_kernel<<<B * H, 256, 0, stream>>>(nseg, H, lam, s_loc, s0, s0_f32, s0_bstride, s_start, sT, sT_f32, reverse,
+    seg_scan_kernel<<<dim3(16, B * H), 256, 0, stream>>>(nseg, H, lam, s_loc, s0, s0_f32, s0_bstride, s_start, sT, sT_f32, reverse,
                                                stream_flags);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
