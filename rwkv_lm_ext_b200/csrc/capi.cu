@@ -268,7 +268,7 @@ size_t wkv6_saved_bytes(int B, int T, int C, int H) {
 }
 size_t wkv6_train_backward_workspace_bytes(int B, int T, int C, int H, int has_saved) {
     (void)C;
-    return has_saved ? simt_backward_workspace_bytes(B, T, H) : wkv6_backward_workspace_bytes(B, T, C, H);
+    return has_saved ? tc3_backward_workspace_bytes(B, T, H, true) + 1024 : wkv6_backward_workspace_bytes(B, T, C, H);
 }
 int wkv6_train_forward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
                        const void *w, const void *u, const void *s0, int s0_batched, int s0_f32,

@@ -188,7 +188,7 @@ void seg_plan(int B, int T, int H, int *nseg, int *seg_chunks) {
     const long long streams = (long long)B * H;
     static const bool off = getenv("WKV6B200_NO_SEG") != nullptr;     // A/B switch for profiles/bench_few_streams*.py
     *nseg = 1; *seg_chunks = (T + 63) / 64;
-    if (off || streams <= 0 || streams >= 148 || T < 8192) return;
+    if (off || streams <= 0 || streams >= 148 || T < 4096) return;
     plan(streams, T, 2, nseg, seg_chunks);
 }
 // training pair: forward and backward are both segmented, worth it from T = 2048 on; at least 4 chunks per segment

@@ -734,8 +734,17 @@ size_t tc3_saved_bytes(int B, int T, int H) {
     if (nseg > 1) NC = (size_t)nseg * seg_chunks;
     return tc3_saved_header(B, H) + (size_t)B * H * NC * 8192;
 }
+// scratch of the time-segmented backward (seg_scan.cu): r, gy, w reversed inside the segments, the segments'
+// own and scanned state gradients, decay sums, per-row gs and gu
+static size_t seg_backward_scratch_bytes(int B, int T, int H) {
+    int nseg = 1, seg_chunks = 0;
+    seg_plan_train(B, T, H, &nseg, &seg_chunks);
+    if (nseg <= 1) return 0;
+    const size_t C = (size_t)H * 64, Bs = (size_t)B * nseg, n_el = (size_t)B * T * C, st = Bs * H * 4096;
+    return 3 * n_el * 2 + 2 * st * 4 + Bs * C * 4 + st * 2 + Bs * C * 2 + 1024;
+}
 size_t tc3_backward_workspace_bytes(int B, int T, int H, bool has_saved) {
-    return simt_backward_workspace_bytes(B, T, H) + (has_saved ? 0 : tc3_saved_bytes(B, T, H));
+    return simt_backward_workspace_bytes(B, T, H) + (has_saved ? seg_backward_scratch_bytes(B, T, H) : tc3_saved_bytes(B, T, H));
 }
 bool tc3_backward_supported(const Args &a) {
     return a.io_dtype == WKV6_BF16 && a.w_kind == W_RAW_BF16 && a.mask == nullptr && a.T >= 1 && !a.s0_f32 &&
@@ -800,10 +809,9 @@ static int tc3_backward_segmented(const Args &a, int nseg, int seg_chunks) {
     int *flags = (int *)a.saved, *sflags = flags + (size_t)a.B * a.H;
     const bf16 *ckpt = (const bf16 *)((uint8_t *)a.saved + tc3_saved_header(a.B, a.H));
     const size_t n_el = (size_t)a.B * a.T * C, st = (size_t)Bs * a.H * 4096;
-    const size_t bytes = 3 * n_el * 2 + 2 * st * 4 + (size_t)Bs * C * 4 + st * 2 + (size_t)Bs * C * 2;
-    uint8_t *buf = nullptr;
-    ensure_pool_keeps_memory();
-    WKV6_CUDA_CHECK(cudaMallocAsync((void **)&buf, bytes, a.stream));
+    // scratch lives in the caller's workspace, behind the part the exact route uses
+    const size_t simt_ws = (simt_backward_workspace_bytes(a.B, a.T, a.H) + 1023) / 1024 * 1024;
+    uint8_t *buf = (uint8_t *)a.workspace + simt_ws;
     bf16 *r_rev = (bf16 *)buf, *gy_rev = r_rev + n_el, *w_rev = gy_rev + n_el;
     float *g_loc = (float *)(w_rev + n_el), *g_end = g_loc + st, *lam = g_end + st;
     bf16 *gs_tmp = (bf16 *)(lam + (size_t)Bs * C), *gu_tmp = gs_tmp + st;
@@ -821,7 +829,6 @@ static int tc3_backward_segmented(const Args &a, int nseg, int seg_chunks) {
     if (rc == WKV6_OK && a.gs)                    // dL/dS_0 is what segment 0 of every sequence produced
         rc = cudaMemcpy2DAsync(a.gs, (size_t)a.H * 4096 * 2, gs_tmp, (size_t)nseg * a.H * 4096 * 2, (size_t)a.H * 4096 * 2, a.B,
                                cudaMemcpyDeviceToDevice, a.stream) == cudaSuccess ? WKV6_OK : WKV6_ECUDA;
-    cudaFreeAsync(buf, a.stream);
     if (rc != WKV6_OK) return rc;
     Args s = a;                                   // exact route for the flagged streams, on the call as it was made
     s.stream_flags = flags;
