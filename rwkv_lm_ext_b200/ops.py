@@ -50,6 +50,30 @@ def _train_forward(ctx, lib, B, T, C, H, r, k, v, w, u, s0, s0_batched, sT, y):
                                  s0_f32, ptr(sT), sT_f32, ptr(y), ptr(saved), ctypes.byref(valid), stream_of(r)),
           "wkv6_train_forward")
     ctx.saved_state = saved if valid.value else None
+    if _diag["collect"] and ctx.saved_state is not None:
+        _diag["flags"].append(saved[: B * H * 4].view(torch.int32).view(B, H))    # a view, no synchronisation
+
+
+# Diagnostics: which (b,h) streams left the tensor-core kernels for the exact SIMT route (their decay is
+# stronger than the block references allow) -- e.g. to see what a real checkpoint does.
+_diag = {"collect": False, "flags": []}
+
+
+class exact_route_report:
+    """with exact_route_report() as rep: ...training forwards...;  rep.streams() -> (flagged, total)"""
+
+    def __enter__(self):
+        _diag["collect"], _diag["flags"] = True, []
+        return self
+
+    def __exit__(self, *exc):
+        self._flags = _diag["flags"]
+        _diag["collect"], _diag["flags"] = False, []
+        return False
+
+    def streams(self):
+        flagged = sum(int((f != 0).sum().item()) for f in self._flags)
+        return flagged, sum(f.numel() for f in self._flags)
 
 
 def _train_backward(ctx, lib, B, T, C, H, r, k, v, w, u, s0, s0_batched, gy, gr, gk, gv, gw, gu, gs):

@@ -121,6 +121,18 @@ def test_mixed_hazard_streams(M, O):
     assert_bf16_close(s, s_ref, "infctx final state")
 
 
+def test_exact_route_report(M):
+    """Diagnostics: how many streams of the training forwards went to the exact route."""
+    B, T, H = 2, 200, 2
+    r, k, v, w, u, gy = make_inputs(B, T, H, seed=12, decay="model", device=DEV)
+    w[1, 40:120, 64:128] = 3.0
+    leaves = [t.clone().requires_grad_(True) for t in (r, k, v, w, u)]
+    with M.exact_route_report() as rep:
+        M.RUN_CUDA_RWKV6(B, T, H * 64, H, *leaves)
+        M.RUN_CUDA_RWKV6(B, T, H * 64, H, *leaves)
+    assert rep.streams() == (2, 8)
+
+
 def test_native_raww_backward_without_saved_state(M):
     """wkv6_backward_raww (no training pair): the library recomputes the chunk-start states itself."""
     import ctypes
