@@ -41,23 +41,12 @@ struct Bars {
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ float rb(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
-__device__ __forceinline__ float lo(uint32_t u) { return __uint_as_float(u << 16); }
-__device__ __forceinline__ float hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
-__device__ __forceinline__ uint32_t pack(float a, float b) {
-    __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t *>(&t);
-}
 
 struct Params {
     int BT, T, C, groups_per_cta;
     const bf16 *shift;      // nullptr or [B, C]
     const bf16 *maa;        // [5, C]
-    bf16 *out;              // [5, BT, C]
 };
-#ifndef LORA_DIRECT_STORE
-#define LORA_DIRECT_STORE 0   // measured: plain per-thread stores 0.30 ms, staging + TMA store 0.22 ms
-#endif
 
 __global__ void __launch_bounds__(THREADS, 2)
 ddlerp_lora_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_constant__ CUtensorMap map_w2,
@@ -194,16 +183,6 @@ ddlerp_lora_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
                 }
             }
             if (n == NOUT - 1) mbar_arrive(&bar.x_free[gi & 1]);
-#if LORA_DIRECT_STORE
-            // each thread owns 64 contiguous bytes of its row (two full 32-byte sectors): plain stores,
-            // fire and forget -- no staging buffer, no barrier, nothing to wait for
-            if (rlive) {
-                bf16 *dst = p.out + ((size_t)n * p.BT + (size_t)rg) * p.C + c;
-#pragma unroll
-                for (int q = 0; q < 4; q++)
-                    *reinterpret_cast<uint4 *>(dst + q * 8) = make_uint4(outp[q * 4], outp[q * 4 + 1], outp[q * 4 + 2], outp[q * 4 + 3]);
-            }
-#else
             // staging buffer free?  (thread 0 issued the previous store)
             if (threadIdx.x == 0) tma_store_wait_read<0>();
             named_bar_sync<1, EPI_THREADS>();
@@ -217,11 +196,8 @@ ddlerp_lora_kernel(const __grid_constant__ CUtensorMap map_h, const __grid_const
                 tma_store_3d(&map_o, sm + OFF_STG, (g0 + gi) * NC, r0, n);
                 tma_store_commit();
             }
-#endif
         }
-#if !LORA_DIRECT_STORE
         if (threadIdx.x == 0) tma_store_wait_all<0>();
-#endif
     }
     tc_fence_before();
     __syncthreads();
@@ -258,7 +234,7 @@ int ddlerp_lora_forward(int B, int T, int C, const void *x, const void *shift, c
     split = (groups + gpc - 1) / gpc;
     Params p;
     p.BT = (int)BT; p.T = T; p.C = C; p.groups_per_cta = gpc;
-    p.shift = (const bf16 *)shift; p.maa = (const bf16 *)maa; p.out = (bf16 *)out;
+    p.shift = (const bf16 *)shift; p.maa = (const bf16 *)maa;
     static thread_local bool attr_done[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
