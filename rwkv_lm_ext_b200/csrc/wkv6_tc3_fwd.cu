@@ -69,7 +69,9 @@ struct Params {
 // 9 warps x 2 CTAs = 5 warps on the fullest SM sub-partition (16384 registers): at most 96 per thread
 // SEG = false is the ordinary call (one row per (b,h), the whole sequence): kept as its own instantiation so
 // that the segment arithmetic costs it nothing (with run-time descriptors ptxas scheduled the forward 7 % slower)
-template <bool SEG>
+// SO = true: a state-only pass known at compile time (the two extra passes of the segmented routes): no r tile,
+// no Rt / Kt versions, no diag(u) term, no A / Y products -- about half of the operand preparation.
+template <bool SEG, bool SO = false>
 __global__ void __launch_bounds__(NTHREADS, 2)
 wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_w,
@@ -112,8 +114,8 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         // named barriers
         // =====================================================================================
         auto issue_rkw = [&](int c) {
-            mbar_arrive_expect_tx(&ex.bar_rkw, 3 * 8192);
-            tma_load_3d(sm + OFF_R, &map_r, &ex.bar_rkw, h * 64, t_base + c * L, b);
+            mbar_arrive_expect_tx(&ex.bar_rkw, (SO ? 2 : 3) * 8192);
+            if constexpr (!SO) tma_load_3d(sm + OFF_R, &map_r, &ex.bar_rkw, h * 64, t_base + c * L, b);
             tma_load_3d(sm + OFF_K, &map_k, &ex.bar_rkw, h * 64, t_base + c * L, b);
             tma_load_3d(sm + OFF_W, &map_w, &ex.bar_rkw, h * 64, t_base + c * L, b);
         };
@@ -127,7 +129,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         constexpr uint32_t ID_KM = idesc_bf16(64, 64, 0, 1);
         constexpr uint32_t ID_MM = idesc_bf16(64, 64, 1, 1);
         auto issue_A = [&]() {                               // A^T[s, t in q] = Kt_q Rt_own^T   (not in a state-only pass)
-            if (p.has_y)
+            if (!SO && p.has_y)
 #pragma unroll
             for (int qq = 0; qq < 2; qq++)
 #pragma unroll
@@ -174,13 +176,13 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             bar_sync_all<B_T1>();                                // P written, S decayed
             if (elect_one()) {
                 tc_fence_after();
-                if (p.has_y)
+                if (!SO && p.has_y)
 #pragma unroll
                 for (int k = 0; k < 4; k++)                      // Y = Rh * S_in      (S tile is [i][j]: MN-major B)
                     mma_bf16_ss(tmem + TM_Y, smem_desc_sw128(rh + 32 * k, 8192, 1024),
                                 smem_desc_sw128(sb + 2048 * k, 8192, 1024), ID_KM, k > 0);
                 mbar_wait(&ex.bar_v, par);
-                if (p.has_y)
+                if (!SO && p.has_y)
 #pragma unroll
                 for (int k = 0; k < 4; k++)                      // Y += P * V
                     mma_bf16_ss(tmem + TM_Y, smem_desc_sw128(pp + 32 * k, 8192, 1024),
@@ -220,7 +222,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             }
             bar_sync_all<B_T2>();                                // y tile and the new bf16 S written
             if (lane == 0) {
-                if (p.has_y) tma_store_3d(&map_y, sm + OFF_YT, h * 64, t_base + c * L, b);
+                if (!SO && p.has_y) tma_store_3d(&map_y, sm + OFF_YT, h * 64, t_base + c * L, b);
                 if (more && p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (blockIdx.x * ck_stride + c + 1) * 64, 0);
                 tma_store_commit();
             }
@@ -303,9 +305,11 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             }
             named_bar_sync<B_SCAN, CTHREADS>();
 
-            uint32_t rr[2][4], kk[2][4];
-            ldsm_x4_t(sbase + OFF_R + F.ti(0), rr[0][0], rr[0][1], rr[0][2], rr[0][3]);
-            ldsm_x4_t(sbase + OFF_R + F.ti(1), rr[1][0], rr[1][1], rr[1][2], rr[1][3]);
+            uint32_t rr[2][4] = {}, kk[2][4];
+            if constexpr (!SO) {
+                ldsm_x4_t(sbase + OFF_R + F.ti(0), rr[0][0], rr[0][1], rr[0][2], rr[0][3]);
+                ldsm_x4_t(sbase + OFF_R + F.ti(1), rr[1][0], rr[1][1], rr[1][2], rr[1][3]);
+            }
             ldsm_x4_t(sbase + OFF_K + F.ti(0), kk[0][0], kk[0][1], kk[0][2], kk[0][3]);
             ldsm_x4_t(sbase + OFF_K + F.ti(1), kk[1][0], kk[1][1], kk[1][2], kk[1][3]);
             float du[4][2];
@@ -332,18 +336,21 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 for (int g = 0; g < 4; g++) {
                     const float e0 = gb[g] + exq[hh][g], c0 = e0 + l[hh][g][0], c1 = c0 + l[hh][g][1];
                     const float r0 = bf_lo(rr[hh][g]), r1 = bf_hi(rr[hh][g]), k0 = bf_lo(kk[hh][g]), k1 = bf_hi(kk[hh][g]);
-                    const float rt0 = r0 * fast_ex2(e0 - rq), rt1 = r1 * fast_ex2(c0 - rq);
                     const float kf0 = k0 * fast_ex2(rq - c0), kf1 = k1 * fast_ex2(rq - c1);
-                    rto[g] = pack2(rt0, rt1);
-                    kto[g] = pack2(kf0, kf1);
-                    rhp[hh][g] = hmul2(rto[g], erq);                      // Rh = Rt * 2^rho (exact)
+                    if constexpr (!SO) {
+                        const float rt0 = r0 * fast_ex2(e0 - rq), rt1 = r1 * fast_ex2(c0 - rq);
+                        rto[g] = pack2(rt0, rt1);
+                        kto[g] = pack2(kf0, kf1);
+                        rhp[hh][g] = hmul2(rto[g], erq);                  // Rh = Rt * 2^rho (exact)
+                        du[g][0] = fmaf(r0 * u_h[hh], k0, du[g][0]);
+                        du[g][1] = fmaf(r1 * u_h[hh], k1, du[g][1]);
+                    }
                     const float kh0 = kf0 * el, kh1 = kf1 * el;           // Kh = k * 2^(Lam - cum)
                     khp[hh][g] = pack2(kh0, kh1);
                     klp[hh][g] = pack2(kh0 - bf_lo(khp[hh][g]), kh1 - bf_hi(khp[hh][g]));
-                    du[g][0] = fmaf(r0 * u_h[hh], k0, du[g][0]);
-                    du[g][1] = fmaf(r1 * u_h[hh], k1, du[g][1]);
                 }
                 const uint32_t ti = F.ti(hh);
+                if constexpr (!SO) {
                 stsm_x4_t(sbase + OFF_RT + ti, rto[0], rto[1], rto[2], rto[3]);
                 if (ch == 0) {      // block 0: own in Kt_0, scaled to the later reference in Kt_1 (2^(rho1-rho0) spans 32
                                     // tokens and may leave the bf16 range although the products do not: two exact factors)
@@ -354,9 +361,10 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 } else {
                     stsm_x4_t(sbase + OFF_KT + kt_ver(1) + ti, kto[0], kto[1], kto[2], kto[3]);
                 }
+                }
             }
             // ---- diag(u) term: sum over channels of r u k per token; reduce-scatter over the 8 lanes ri
-            {
+            if constexpr (!SO) {
                 const bool b2 = lane & 16, b1 = lane & 8, b0 = lane & 4;
                 float a4[2][2], a2[2], a1;
 #pragma unroll
@@ -384,7 +392,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
                 const uint32_t ti = F.ti(hh);
-                stsm_x4_t(sbase + OFF_RH + ti, rhp[hh][0], rhp[hh][1], rhp[hh][2], rhp[hh][3]);
+                if constexpr (!SO) stsm_x4_t(sbase + OFF_RH + ti, rhp[hh][0], rhp[hh][1], rhp[hh][2], rhp[hh][3]);
                 stsm_x4_t(sbase + OFF_KH + ti, khp[hh][0], khp[hh][1], khp[hh][2], khp[hh][3]);
                 stsm_x4_t(sbase + OFF_KL + ti, klp[hh][0], klp[hh][1], klp[hh][2], klp[hh][3]);
             }
@@ -402,7 +410,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             // ================================================================== T1: A^T -> P, decay S
             bar_sync_all<B_A>();
             tc_fence_after();
-            if (p.has_y) {
+            if (!SO && p.has_y) {
             tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_A + 32 * ch), v);
             tmem_wait_ld();
 #pragma unroll
@@ -454,7 +462,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 elam[1] = elam_nx[1];
             }
             // ================================================================== T2: y tile, new bf16 S
-            if (p.has_y) {
+            if (!SO && p.has_y) {
                 tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_Y + 32 * ch), v);
                 tmem_wait_ld();
 #pragma unroll
@@ -539,9 +547,14 @@ int tc3_forward(const Args &a, void *ckpt, int *hz_flags, int nseg, int seg_chun
         WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                              cudaSharedmemCarveoutMaxShared));
+        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             cudaSharedmemCarveoutMaxShared));
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
-    if (nseg > 1) wkv6_tc3_fwd_kernel<true><<<a.B * nseg * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
+    if (nseg > 1 && !p.has_y && !p.has_ckpt)
+        wkv6_tc3_fwd_kernel<true, true><<<a.B * nseg * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
+    else if (nseg > 1) wkv6_tc3_fwd_kernel<true><<<a.B * nseg * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
     else wkv6_tc3_fwd_kernel<false><<<a.B * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
