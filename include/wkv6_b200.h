@@ -52,6 +52,10 @@ extern "C" {
 #define WKV6_IMPL_TC   2       /* tcgen05/TMA chunked kernels only; WKV6_EUNSUPPORTED otherwise  */
 
 WKV6_API int         wkv6b200_abi_version(void);
+/* How a call with B*H streams of T tokens is cut along the time axis when it has too few streams to fill the
+ * GPU (csrc/seg_scan.cu): nseg segments of seg_chunks 64-token chunks, the last one possibly shorter;
+ * nseg = 1 = not segmented.  training != 0: the forward/backward pair.  Host logic only. */
+WKV6_API void        wkv6b200_seg_plan(int B, int T, int H, int training, int *nseg, int *seg_chunks);
 WKV6_API const char *wkv6b200_last_error(void);              /* host string, thread-local */
 WKV6_API int         wkv6b200_set_impl(int impl);            /* returns the previous value */
 WKV6_API int         wkv6b200_get_impl(void);

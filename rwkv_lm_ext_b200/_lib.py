@@ -15,6 +15,7 @@ c_p, c_i, c_sz, c_i64, c_f = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, cty
 _BTCH = [c_i, c_i, c_i, c_i]
 SIGNATURES = {
     "wkv6b200_abi_version": (c_i, []),
+    "wkv6b200_seg_plan": (None, [c_i, c_i, c_i, c_i, ctypes.POINTER(c_i), ctypes.POINTER(c_i)]),
     "wkv6b200_last_error": (ctypes.c_char_p, []),
     "wkv6b200_set_impl": (c_i, [c_i]),
     "wkv6b200_get_impl": (c_i, []),

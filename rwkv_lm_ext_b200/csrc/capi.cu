@@ -197,6 +197,14 @@ using namespace wkv6;
 extern "C" {
 
 int wkv6b200_abi_version(void) { return 1; }
+// host logic only (no device access): the time-segmentation plan of a call, for tests and diagnostics
+void wkv6b200_seg_plan(int B, int T, int H, int training, int *nseg, int *seg_chunks) {
+    int n = 1, sc = 0;
+    if (training) seg_plan_train(B, T, H, &n, &sc);
+    else seg_plan(B, T, H, &n, &sc);
+    if (nseg) *nseg = n;
+    if (seg_chunks) *seg_chunks = sc;
+}
 const char *wkv6b200_last_error(void) { return g_err; }
 int wkv6b200_set_impl(int impl) {
     int prev = current_impl();
