@@ -61,6 +61,13 @@ WKV6_API int         wkv6b200_set_impl(int impl);            /* returns the prev
 WKV6_API int         wkv6b200_get_impl(void);
 /* number of kernels this library launched since process start (bench.py's gpu_launches) */
 WKV6_API uint64_t    wkv6b200_launch_count(void);
+/* Opt-in: floor the per-token log-decay at -nats_per_token, i.e. compute with w' = min(w, log(nats_per_token))
+ * (and a zero w-gradient where the floor is active).  A channel that decays faster than e^-3.7 per token keeps
+ * < 2.5 % of the previous token; with a floor of 3.7 no stream can exceed what the tensor-core kernels' block
+ * references allow, so none is handed to the (much slower) exact kernels.  This CHANGES the function for such
+ * channels: it is off by default (0 turns it off again).  Returns the previous setting (0 = off).  Process-wide;
+ * applies to every entry point, the exact kernels included. */
+WKV6_API float       wkv6b200_set_decay_clamp(float nats_per_token);
 
 /* ------------------------------------------------------------------------------------------
  * (a1/a2) wkv6 -- replaces cuda_forward / cuda_backward of cuda/wkv6_cuda.cu:229-242, bound by

@@ -20,6 +20,7 @@ SIGNATURES = {
     "wkv6b200_set_impl": (c_i, [c_i]),
     "wkv6b200_get_impl": (c_i, []),
     "wkv6b200_launch_count": (ctypes.c_uint64, []),
+    "wkv6b200_set_decay_clamp": (c_f, [c_f]),
     "wkv6_forward": (c_i, _BTCH + [c_p] * 7),
     "wkv6_forward_raww": (c_i, _BTCH + [c_p] * 7),
     "wkv6_backward_workspace_bytes": (c_sz, _BTCH),
@@ -111,6 +112,11 @@ def launch_count() -> int:
 
 
 IMPL = {"auto": 0, "simt": 1, "tc": 2}
+
+
+def set_decay_clamp(nats_per_token: float) -> float:
+    """Opt-in floor of the per-token log-decay (include/wkv6_b200.h); 0 = off.  Returns the previous value."""
+    return float(load().wkv6b200_set_decay_clamp(float(nats_per_token)))
 
 
 def set_impl(name: str) -> str:

@@ -1,5 +1,6 @@
 // extern "C" entry points of libwkv6_b200.so -- see include/wkv6_b200.h for the contract.
 #include <atomic>
+#include <cmath>
 #include <cstdarg>
 #include <cstdlib>
 #include <cstring>
@@ -12,6 +13,8 @@ extern void *g_tc3_bwd_stamps;
 static thread_local char g_err[512] = "";
 static std::atomic<int> g_impl{-1};
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<float> g_lmin{-INFINITY};
+float decay_clamp_nats() { return g_lmin.load(std::memory_order_relaxed); }
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -89,7 +92,7 @@ static int tc3_forward_segmented(const Args &a, int *flags, int nseg, int seg_ch
     a1.s0 = nullptr; a1.s0_bstride = 0; a1.sT = s_loc; a1.sT_f32 = 1; a1.y = nullptr; a1.saved = nullptr;
     if (rc == WKV6_OK) rc = tc3_forward(a1, nullptr, sflags, nseg, seg_chunks);
     if (rc == WKV6_OK) rc = seg_flags_merge(a.B, nseg, a.H, sflags, flags, a.stream);
-    if (rc == WKV6_OK) rc = seg_decay(a.B, a.T, C, nseg, seg_tokens, a.w, lam, a.stream);
+    if (rc == WKV6_OK) rc = seg_decay(a.B, a.T, C, nseg, seg_tokens, a.w, lam, a.lmin, a.stream);
     if (rc == WKV6_OK) rc = seg_scan(a.B, nseg, a.H, lam, s_loc, a.s0, a.s0_f32, a.s0_bstride, s_start, a.sT, a.sT_f32, 0, flags, a.stream);
     Args a2 = a;
     a2.s0 = s_start; a2.s0_f32 = 1; a2.s0_bstride = (long long)a.H * 4096; a2.sT = nullptr; a2.saved = nullptr;
@@ -197,6 +200,11 @@ using namespace wkv6;
 extern "C" {
 
 int wkv6b200_abi_version(void) { return 1; }
+float wkv6b200_set_decay_clamp(float nats_per_token) {
+    const float prev = -g_lmin.load();
+    g_lmin.store(nats_per_token > 0.f ? -nats_per_token : -INFINITY);
+    return prev == INFINITY ? 0.f : prev;
+}
 // host logic only (no device access): the time-segmentation plan of a call, for tests and diagnostics
 void wkv6b200_seg_plan(int B, int T, int H, int training, int *nseg, int *seg_chunks) {
     int n = 1, sc = 0;

@@ -19,9 +19,14 @@ enum WKind : int {
     W_DECAY_F32 = 2,  // d = exp(-exp(w)), fp32       (rwkv6 inference entry, src/model_run.py:64)
 };
 
+// Opt-in decay clamp (wkv6b200_set_decay_clamp): the per-token log-decay is floored at this many nats
+// (a negative number; -inf = off).  Every Args picks up the setting current at its construction.
+float decay_clamp_nats();
+
 // One generic description of a WKV6 call; every C-ABI entry point fills one of these.
 struct Args {
     int B = 0, T = 0, H = 0;
+    float lmin = decay_clamp_nats();
     int io_dtype = WKV6_BF16;         // element type of r,k,v,u,y,(gy,g*)
     const void *r = nullptr, *k = nullptr, *v = nullptr, *u = nullptr;
     const void *w = nullptr;
@@ -100,10 +105,12 @@ template <> __device__ __forceinline__ __half from_f32<__half>(float x) { return
 template <> __device__ __forceinline__ float from_f32<float>(float x) { return x; }
 
 // log-decay l = log d (<= 0) from whatever the boundary carries
-template <int WK> __device__ __forceinline__ float load_logdecay(const void *w, size_t idx) {
-    if (WK == W_RAW_BF16) return -__expf(__bfloat162float(((const __nv_bfloat16 *)w)[idx]));
-    if (WK == W_LOG_F32) return ((const float *)w)[idx];
-    return __logf(fmaxf(((const float *)w)[idx], 1e-38f));
+template <int WK> __device__ __forceinline__ float load_logdecay(const void *w, size_t idx, float lmin) {
+    float l;
+    if (WK == W_RAW_BF16) l = -__expf(__bfloat162float(((const __nv_bfloat16 *)w)[idx]));
+    else if (WK == W_LOG_F32) l = ((const float *)w)[idx];
+    else l = __logf(fmaxf(((const float *)w)[idx], 1e-38f));
+    return fmaxf(l, lmin);
 }
 
 // ddlerp_tma.cu: TMA-fed token-shift ddlerp backward (nout = 5 with m, or 1 without).  Returns 1 when
@@ -119,7 +126,7 @@ void seg_plan_train(int B, int T, int H, int *nseg, int *seg_chunks);
 int seg_reverse3(int B, int T, int C, int nseg, int seg_tokens, const void *a, const void *b, const void *c, void *ra, void *rb,
                  void *rc, cudaStream_t stream);
 int seg_sum_gu(int B, int nseg, int C, const void *part, void *gu, cudaStream_t stream);
-int seg_decay(int B, int T, int C, int nseg, int seg_tokens, const void *w, float *lam, cudaStream_t stream);
+int seg_decay(int B, int T, int C, int nseg, int seg_tokens, const void *w, float *lam, float lmin, cudaStream_t stream);
 int seg_scan(int B, int nseg, int H, const float *lam, const float *s_loc, const void *s0, int s0_f32,
              long long s0_bstride, float *s_start, void *sT, int sT_f32, int reverse, const int *stream_flags,
              cudaStream_t stream);

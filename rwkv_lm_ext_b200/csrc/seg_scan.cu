@@ -21,7 +21,7 @@ typedef __nv_bfloat16 bf16;
 // grid (ceil(C/64), rows), block 256 = 8 column lanes (8 channels each: 128 contiguous bytes of a token row)
 // x 32 token lanes; every thread keeps four independent 16-byte loads in flight.  Deterministic.
 __global__ void __launch_bounds__(256) seg_decay_kernel(int T, int C, int nseg, int seg_tokens, const bf16 *__restrict__ w,
-                                                        float *__restrict__ lam) {
+                                                        float *__restrict__ lam, float lmin) {
     const int cl = threadIdx.x & 7, tl = threadIdx.x >> 3;
     const int c = (blockIdx.x * 8 + cl) * 8;
     const size_t row = blockIdx.y;
@@ -42,8 +42,8 @@ __global__ void __launch_bounds__(256) seg_decay_kernel(int T, int C, int nseg, 
 #pragma unroll
                 for (int i = 0; i < 4; i++) {
                     const float2 f = __bfloat1622float2(h[i]);
-                    acc[2 * i] -= __expf(f.x);
-                    acc[2 * i + 1] -= __expf(f.y);
+                    acc[2 * i] += fmaxf(-__expf(f.x), lmin);
+                    acc[2 * i + 1] += fmaxf(-__expf(f.y), lmin);
                 }
             }
         }
@@ -220,9 +220,9 @@ int seg_sum_gu(int B, int nseg, int C, const void *part, void *gu, cudaStream_t 
     return WKV6_OK;
 }
 
-int seg_decay(int B, int T, int C, int nseg, int seg_tokens, const void *w, float *lam, cudaStream_t stream) {
+int seg_decay(int B, int T, int C, int nseg, int seg_tokens, const void *w, float *lam, float lmin, cudaStream_t stream) {
     dim3 grid((C + 63) / 64, B * nseg);
-    seg_decay_kernel<<<grid, 256, 0, stream>>>(T, C, nseg, seg_tokens, (const bf16 *)w, lam);
+    seg_decay_kernel<<<grid, 256, 0, stream>>>(T, C, nseg, seg_tokens, (const bf16 *)w, lam, lmin);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
     return WKV6_OK;

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(NT) fwd_kernel(Args a, int mode) {
                 const int t = rev ? (Teff - 1 - tau) : tau;
                 const size_t o = base + (size_t)t * C + c;
                 pr[q] = to_f32(R[o]); pk[q] = to_f32(K[o]); pv[q] = to_f32(V[o]);
-                pd[q] = __expf(load_logdecay<WK>(a.w, o));
+                pd[q] = __expf(load_logdecay<WK>(a.w, o, a.lmin));
             } else { pr[q] = 0.f; pk[q] = 0.f; pv[q] = 0.f; pd[q] = 1.f; }
         }
     };
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(NT) bwd_f_kernel(Args a, int mode, float *Abuf
                 const int t = rev ? (Teff - 1 - tau) : tau;
                 const size_t o = base + (size_t)t * C + c;
                 pr[q] = to_f32(R[o]); pk[q] = to_f32(K[o]); pv[q] = to_f32(V[o]); pg[q] = to_f32(GY[o]);
-                pd[q] = __expf(load_logdecay<WK>(a.w, o));
+                pd[q] = __expf(load_logdecay<WK>(a.w, o, a.lmin));
             } else { pr[q] = 0.f; pk[q] = 0.f; pv[q] = 0.f; pg[q] = 0.f; pd[q] = 1.f; }
         }
     };
@@ -290,7 +290,7 @@ __global__ void __launch_bounds__(NT) bwd_r_kernel(Args a, int mode, const float
                 const int t = rev ? (Teff - 1 - tau) : tau;
                 const size_t o = base + (size_t)t * C + c;
                 pr[q] = to_f32(R[o]); pk[q] = to_f32(K[o]); pv[q] = to_f32(V[o]); pg[q] = to_f32(GY[o]);
-                pl[q] = load_logdecay<WK>(a.w, o);
+                pl[q] = load_logdecay<WK>(a.w, o, a.lmin);
                 pa[q] = Abuf[((size_t)blockIdx.x * T + tau) * N + c];
             } else { pr[q] = 0.f; pk[q] = 0.f; pv[q] = 0.f; pg[q] = 0.f; pl[q] = 0.f; pa[q] = 0.f; }
         }
@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(NT) bwd_r_kernel(Args a, int mode, const float
                 const float vg = pvg[tt][0] + pvg[tt][1] + pvg[tt][2] + pvg[tt][3];
                 float gkv = fmaf(ui * sr[tt][x], vg, gvd);
                 const float Bt = sk[tt][x] * gvd;
-                float gwv = sl[tt][x] * (Q - Bt);
+                float gwv = sl[tt][x] > a.lmin ? sl[tt][x] * (Q - Bt) : 0.f;   // a clamped decay no longer depends on w
                 if (tau == Teff - 1 || (tau == 0 && zero_gw0)) gwv = 0.f;
                 Q += sA[tt][x] - Bt;
                 if (rev) { gkv += to_f32(GK[o]); gwv += to_f32(GW[o]); }

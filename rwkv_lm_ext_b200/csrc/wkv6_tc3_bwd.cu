@@ -27,6 +27,7 @@
 //
 // Streams whose forward raised the hazard flag are skipped here; the exact SIMT backward, enqueued
 // behind this kernel and predicated per stream on the same flag, handles them.
+#include <cmath>
 #include "common.cuh"
 #include "tc3_common.cuh"
 
@@ -72,6 +73,7 @@ struct Params {
     // nseg = 1, seg_chunks = ceil(T/64), g_init = nullptr for an ordinary call.
     const float *g_init;
     int nseg, seg_chunks;
+    float lmin;               // floor of the per-token log2-decay (opt-in clamp; -inf = off)
     bf16 *gu, *gs;
     const int *hz_flags;
     long long *dbg;           // nullptr, or [gridDim][NC][8] clock64 stamps of warp 0 at the stage boundaries (profiling aid)
@@ -81,8 +83,9 @@ __device__ __forceinline__ uint32_t pack_frag(const uint32_t *v, int g, int hh) 
     return pack2(__uint_as_float(v[4 * g + 2 * hh]), __uint_as_float(v[4 * g + 2 * hh + 1]));
 }
 
-// SEG = false: the ordinary call, its own instantiation (see the forward kernel)
-template <bool SEG>
+// SEG = false: the ordinary call, its own instantiation (see the forward kernel).  CLAMP: the opt-in decay floor
+// (two FMNMX per element pair in the hot path cost 1.4 % when always compiled in)
+template <bool SEG, bool CLAMP = false>
 __global__ void __launch_bounds__(NTHREADS, 2)
 wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_w,
@@ -336,6 +339,10 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     for (int g = 0; g < 4; g++) {
                         float l0 = -fast_ex2(fmaf(bf_lo(wp[hh][g]), LOG2E, LOG2_LOG2E));   // -exp(w) * log2(e)
                         float l1 = -fast_ex2(fmaf(bf_hi(wp[hh][g]), LOG2E, LOG2_LOG2E));
+                        if constexpr (CLAMP) {
+                            l0 = fmaxf(l0, p.lmin);
+                            l1 = fmaxf(l1, p.lmin);
+                        }
                         if (nv < L) {                                   // ragged last chunk: no decay on the padded rows
                             const int t0 = F.col(g, 0);
                             if (t0 >= nv) l0 = 0.f;
@@ -751,6 +758,27 @@ bool tc3_backward_supported(const Args &a) {
            tc::get_encode_fn() != nullptr;
 }
 
+// gw = 0 where the opt-in decay clamp is active (w > log(clamp)), for the streams the tensor-core kernel computed
+// (flags index rows of the launch: stream = row / nseg when the call was segmented)
+__global__ void __launch_bounds__(256) clamp_gw_kernel(size_t n8, const bf16 *__restrict__ w, bf16 *__restrict__ gw, float wmax,
+                                                       const int *__restrict__ flags, int T, int H, int nseg) {
+    const size_t C = (size_t)H * 64;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t e0 = 8 * i, bt = e0 / C, b = bt / T, h = (e0 % C) / 64;
+        if (flags[(b * nseg) * H + h] != 0) continue;             // the exact route writes its own gw
+        const uint4 wv = *reinterpret_cast<const uint4 *>(w + e0);
+        uint4 gv = *reinterpret_cast<const uint4 *>(gw + e0);
+        const __nv_bfloat16 *wp = reinterpret_cast<const __nv_bfloat16 *>(&wv);
+        __nv_bfloat16 *gp = reinterpret_cast<__nv_bfloat16 *>(&gv);
+        bool any = false;
+#pragma unroll
+        for (int e = 0; e < 8; e++)
+            if (__bfloat162float(wp[e]) > wmax) { gp[e] = __float2bfloat16_rn(0.f); any = true; }
+        if (any) *reinterpret_cast<uint4 *>(gw + e0) = gv;
+    }
+}
+static inline float __logf_host(float x) { return logf(x); }
+
 // one launch of the backward kernel on `a` viewed as given (B rows of T tokens), chunk-start states in ckpt
 static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const float *g_init, int nseg, int seg_chunks,
                       bool has_s0) {
@@ -775,6 +803,7 @@ static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const f
     p.has_s0 = has_s0;
     p.g_init = g_init;
     p.nseg = nseg; p.seg_chunks = seg_chunks;
+    p.lmin = a.lmin * 1.4426950408889634f;
     p.gu = (bf16 *)a.gu; p.gs = (bf16 *)a.gs;
     p.hz_flags = flags;
     p.dbg = (long long *)g_tc3_bwd_stamps;
@@ -782,18 +811,30 @@ static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const f
     int dev = 0;
     WKV6_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_bwd_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                             cudaSharedmemCarveoutMaxShared));
-        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_bwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                             cudaSharedmemCarveoutMaxShared));
+        const void *kerns[4] = {(const void *)wkv6_tc3_bwd_kernel<false, false>, (const void *)wkv6_tc3_bwd_kernel<true, false>,
+                                (const void *)wkv6_tc3_bwd_kernel<false, true>, (const void *)wkv6_tc3_bwd_kernel<true, true>};
+        for (const void *kf : kerns) {
+            WKV6_CUDA_CHECK(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+            WKV6_CUDA_CHECK(cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
-    if (nseg > 1) wkv6_tc3_bwd_kernel<true><<<a.B * nseg * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
-    else wkv6_tc3_bwd_kernel<false><<<a.B * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
+    const bool clamp = a.lmin > -INFINITY;
+    const dim3 grid(a.B * nseg * a.H);
+    if (nseg > 1 && clamp) wkv6_tc3_bwd_kernel<true, true><<<grid, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
+    else if (nseg > 1) wkv6_tc3_bwd_kernel<true, false><<<grid, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
+    else if (clamp) wkv6_tc3_bwd_kernel<false, true><<<grid, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
+    else wkv6_tc3_bwd_kernel<false, false><<<grid, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
+    if (clamp) {                       // opt-in decay clamp: a clamped decay no longer depends on w (kept out of the hot kernel)
+        const size_t n8 = (size_t)a.B * a.T * C / 8;
+        size_t g = (n8 + 255) / 256;
+        if (g > 148 * 16) g = 148 * 16;
+        clamp_gw_kernel<<<(int)g, 256, 0, a.stream>>>(n8, (const bf16 *)a.w, (bf16 *)a.gw, __logf_host(-a.lmin), flags, a.T, a.H, nseg);
+        count_launch();
+        WKV6_CUDA_CHECK(cudaGetLastError());
+    }
     return WKV6_OK;
 }
 
@@ -820,7 +861,7 @@ static int tc3_backward_segmented(const Args &a, int nseg, int seg_chunks) {
     f.r = r_rev; f.k = r_rev; f.v = gy_rev; f.w = w_rev;
     f.s0 = nullptr; f.s0_bstride = 0; f.s0_f32 = 0; f.sT = g_loc; f.sT_f32 = 1; f.y = nullptr; f.saved = nullptr; f.gy = nullptr;
     if (rc == WKV6_OK) rc = tc3_forward(f, nullptr, sflags, nseg, seg_chunks);
-    if (rc == WKV6_OK) rc = seg_decay(a.B, a.T, C, nseg, seg_tokens, a.w, lam, a.stream);
+    if (rc == WKV6_OK) rc = seg_decay(a.B, a.T, C, nseg, seg_tokens, a.w, lam, a.lmin, a.stream);
     if (rc == WKV6_OK) rc = seg_scan(a.B, nseg, a.H, lam, g_loc, nullptr, 0, 0, g_end, nullptr, 0, 1, nullptr, a.stream);
     Args v = a;
     v.gu = gu_tmp; v.gs = a.gs ? gs_tmp : nullptr;

@@ -64,6 +64,7 @@ struct Params {
     // [seg*seg_chunks*64, min(T, (seg+1)*seg_chunks*64)) of sequence b.  States (s0, sT), flags and the
     // checkpoints are indexed by row; nseg = 1 and seg_chunks = ceil(T/64) for an ordinary call.
     int nseg, seg_chunks;
+    float lmin;               // floor of the per-token log2-decay (opt-in clamp; -inf = off)
 };
 
 // 9 warps x 2 CTAs = 5 warps on the fullest SM sub-partition (16384 registers): at most 96 per thread
@@ -282,6 +283,8 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     for (int g = 0; g < 4; g++) {
                         float l0 = -fast_ex2(fmaf(bf_lo(wp[hh][g]), LOG2E, LOG2_LOG2E));   // -exp(w) * log2(e)
                         float l1 = -fast_ex2(fmaf(bf_hi(wp[hh][g]), LOG2E, LOG2_LOG2E));
+                        l0 = fmaxf(l0, p.lmin);
+                        l1 = fmaxf(l1, p.lmin);
                         if (nv < L) {                                   // ragged last chunk: no decay on the padded rows
                             const int t0 = F.col(g, 0);
                             if (t0 >= nv) l0 = 0.f;
@@ -537,6 +540,7 @@ int tc3_forward(const Args &a, void *ckpt, int *hz_flags, int nseg, int seg_chun
     p.has_ckpt = ckpt != nullptr;
     p.hz_flags = hz_flags;
     p.nseg = nseg; p.seg_chunks = seg_chunks;
+    p.lmin = a.lmin * 1.4426950408889634f;
     static bool attr_done[64] = {};          // function attributes are per device
     int dev = 0;
     WKV6_CUDA_CHECK(cudaGetDevice(&dev));

@@ -578,3 +578,37 @@ def test_concurrent_streams_do_not_share_scratch(M):
         torch.cuda.synchronize()
     for a, b_ in zip(outs, serial):
         assert torch.equal(a, b_)
+
+
+def test_decay_clamp_opt_in(M, O):
+    """wkv6b200_set_decay_clamp(3.7): the op computes with w' = min(w, log 3.7) (zero w-gradient where the floor is
+    active), on the tensor-core kernels for EVERY stream -- the one that would otherwise be handed to the exact
+    route included -- and on the exact kernels alike.  Off again afterwards: the default semantics are untouched."""
+    import math
+    B, T, H = 2, 200, 2
+    r, k, v, w, u, gy = make_inputs(B, T, H, seed=81, decay="model")
+    w[1, 40:120, 64:128] = 3.0                     # exp(3) = 20 nats per token: far beyond the block references
+    wc = torch.clamp(w.float(), max=math.log(3.7)).double().requires_grad_(True)
+    leaves = [t.double().requires_grad_(True) for t in (r, k, v)] + [wc, u.double().requires_grad_(True)]
+    y_ref, _ = O.wkv6_recurrence(*leaves)
+    (y_ref * gy.double()).sum().backward()
+    gw_ref = wc.grad * (w.float() <= math.log(3.7)).double()      # d/dw of min(w, c)
+    assert M.set_decay_clamp(3.7) == 0.0
+    try:
+        for impl in ("auto", "simt"):
+            M.set_impl(impl)
+            with M.exact_route_report() as rep:
+                y, grads = _run_fwd_bwd(M, r, k, v, w, u, gy)
+            if impl == "auto":
+                assert rep.streams() == (0, B * H)                 # nobody left the tensor-core kernels
+            assert_bf16_close(y, y_ref, f"clamped y ({impl})")
+            for g, ref, name in zip(grads, (leaves[0].grad, leaves[1].grad, leaves[2].grad, gw_ref, leaves[4].grad),
+                                    ("gr", "gk", "gv", "gw", "gu")):
+                assert_bf16_close(g, ref, f"clamped {name} ({impl})")
+            assert grads[3][1, 41:119, 64:128].abs().max().item() == 0.0
+    finally:
+        M.set_impl("auto")
+        assert abs(M.set_decay_clamp(0.0) - 3.7) < 1e-6
+    with M.exact_route_report() as rep:
+        _run_fwd_bwd(M, r, k, v, w, u, gy)
+    assert rep.streams() == (1, B * H)                             # default: that stream takes the exact route
