@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(NT) bwd_f_kernel(Args a, int mode, float *Abuf
 //   gl_t = Q - B_t ;  Q += A_t - B_t   (Q = sum_{s>t}(A_s - B_s));  gw_t = l_t * gl_t
 // ---------------------------------------------------------------------------------------------
 template <typename IO, int WK>
-__global__ void __launch_bounds__(NT) bwd_r_kernel(Args a, int mode, const float *Abuf) {
+__global__ void __launch_bounds__(NT, 2) bwd_r_kernel(Args a, int mode, const float *Abuf) {   // 2 blocks per SM: at most 128 registers
     if (a.stream_flags && a.stream_flags[blockIdx.x] == 0) return;
     const int b = blockIdx.x / a.H, h = blockIdx.x % a.H;
     const int x = threadIdx.x & (N - 1), g = threadIdx.x >> 6;
