@@ -66,7 +66,7 @@ WKV6_API uint64_t    wkv6b200_launch_count(void);
  * < 2.5 % of the previous token; with a floor of 3.7 no stream can exceed what the tensor-core kernels' block
  * references allow, so none is handed to the (much slower) exact kernels.  This CHANGES the function for such
  * channels: it is off by default (0 turns it off again).  Returns the previous setting (0 = off).  Process-wide;
- * applies to every entry point, the exact kernels included. */
+ * applies to every entry point, the exact kernels included.  Environment: WKV6_B200_DECAY_CLAMP=3.7. */
 WKV6_API float       wkv6b200_set_decay_clamp(float nats_per_token);
 
 /* ------------------------------------------------------------------------------------------

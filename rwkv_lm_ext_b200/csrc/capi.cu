@@ -14,7 +14,16 @@ static thread_local char g_err[512] = "";
 static std::atomic<int> g_impl{-1};
 static std::atomic<uint64_t> g_launches{0};
 static std::atomic<float> g_lmin{-INFINITY};
-float decay_clamp_nats() { return g_lmin.load(std::memory_order_relaxed); }
+float decay_clamp_nats() {
+    static const bool env_read = [] {          // WKV6_B200_DECAY_CLAMP=3.7 in the environment == wkv6b200_set_decay_clamp(3.7)
+        const char *e = getenv("WKV6_B200_DECAY_CLAMP");
+        const float v = e ? (float)atof(e) : 0.f;
+        if (v > 0.f) g_lmin.store(-v);
+        return true;
+    }();
+    (void)env_read;
+    return g_lmin.load(std::memory_order_relaxed);
+}
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -201,7 +210,7 @@ extern "C" {
 
 int wkv6b200_abi_version(void) { return 1; }
 float wkv6b200_set_decay_clamp(float nats_per_token) {
-    const float prev = -g_lmin.load();
+    const float prev = -decay_clamp_nats();
     g_lmin.store(nats_per_token > 0.f ? -nats_per_token : -INFINITY);
     return prev == INFINITY ? 0.f : prev;
 }
