@@ -249,7 +249,7 @@ def main():
         barrier()
         # three consecutive blocks of steps inside one timed region; the per-block times are reported as well,
         # because the host-memory path of a shared box is the one noisy part of this measurement
-        kblock = max(2, min(args.steps, 24) // 3)
+        kblock = max(2, min(args.steps, 48) // 3)            # the fill and drain of the 3-stage pipeline are inside the timed region
         ksteps = 3 * kblock
         marks = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         marks[0].record()
