@@ -245,7 +245,7 @@ def main():
             for st in (s_in, s_cmp, s_out):
                 torch.cuda.current_stream().wait_stream(st)
 
-        e2e_steps(12)               # warm-up: the first passes over the pinned buffers are slower (more so with 8 ranks)
+        e2e_steps(40)               # warm-up: the copy path takes ~0.6 s of traffic to reach its steady rate on this box
         barrier()
         # three consecutive blocks of steps inside one timed region; the per-block times are reported as well,
         # because the host-memory path of a shared box is the one noisy part of this measurement
