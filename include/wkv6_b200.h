@@ -108,6 +108,9 @@ WKV6_API int wkv6_backward_raww(int B, int T, int C, int H, const void *r, const
  *       out (may alias s0).  *saved_valid (host int) is set to 1 when `saved` was filled; pass
  *       saved = NULL to wkv6_train_backward otherwise (it then recomputes, needing the larger
  *       workspace of wkv6_backward_workspace_bytes).  gs: NULL iff s0 is NULL, else bf16 [B,H,64,64].
+ * `saved` is opaque: its layout depends on how the pair schedules the call (few (b,h) streams and T >= 2048:
+ * both directions run as time segments, wkv6b200_seg_plan), so it must go to the backward of the same
+ * B, T, H and the same library; the workspace then also holds the segmented backward's scratch.
  * ------------------------------------------------------------------------------------------ */
 WKV6_API size_t wkv6_saved_bytes(int B, int T, int C, int H);
 WKV6_API size_t wkv6_train_backward_workspace_bytes(int B, int T, int C, int H, int has_saved);
