@@ -86,8 +86,9 @@ static int *flag_slice(size_t n) {
 // states, scan over the segment states, ordinary pass with the scanned initial states.
 // flags: [B*H], already holding any pre-set stream flags.
 // ckpt / seg_flags: nullptr, or (training pair) where the chunk-start states and the per-segment flags go.
+// presets: `flags` may already hold non-zero entries (streams whose fp32 decay did not convert exactly).
 static int tc3_forward_segmented(const Args &a, int *flags, int nseg, int seg_chunks, void *ckpt = nullptr,
-                                 int *seg_flags = nullptr) {
+                                 int *seg_flags = nullptr, bool presets = false) {
     wkv6::ensure_pool_keeps_memory();
     const int Bs = a.B * nseg, C = a.H * 64, seg_tokens = seg_chunks * 64;
     const size_t st = (size_t)Bs * a.H * 4096, nl = (size_t)Bs * C, nf = (size_t)Bs * a.H;
@@ -96,7 +97,7 @@ static int tc3_forward_segmented(const Args &a, int *flags, int nseg, int seg_ch
     float *s_loc = buf, *s_start = buf + st, *lam = s_start + st;
     int *sflags = seg_flags ? seg_flags : (int *)(lam + nl);
     int rc = cudaMemsetAsync(sflags, 0, nf * sizeof(int), a.stream) == cudaSuccess ? WKV6_OK : WKV6_ECUDA;
-    if (rc == WKV6_OK) rc = seg_flags_merge(a.B, nseg, a.H, sflags, flags, a.stream);      // broadcast pre-set flags
+    if (rc == WKV6_OK && presets) rc = seg_flags_merge(a.B, nseg, a.H, sflags, flags, a.stream);      // broadcast pre-set flags
     Args a1 = a;
     a1.s0 = nullptr; a1.s0_bstride = 0; a1.sT = s_loc; a1.sT_f32 = 1; a1.y = nullptr; a1.saved = nullptr;
     if (rc == WKV6_OK) rc = tc3_forward(a1, nullptr, sflags, nseg, seg_chunks);
@@ -105,8 +106,8 @@ static int tc3_forward_segmented(const Args &a, int *flags, int nseg, int seg_ch
     if (rc == WKV6_OK) rc = seg_scan(a.B, nseg, a.H, lam, s_loc, a.s0, a.s0_f32, a.s0_bstride, s_start, a.sT, a.sT_f32, 0, flags, a.stream);
     Args a2 = a;
     a2.s0 = s_start; a2.s0_f32 = 1; a2.s0_bstride = (long long)a.H * 4096; a2.sT = nullptr; a2.saved = nullptr;
+    // (this pass sees the same decays as the first one: it cannot raise a flag the merge above has not seen)
     if (rc == WKV6_OK) rc = tc3_forward(a2, ckpt, sflags, nseg, seg_chunks);
-    if (rc == WKV6_OK) rc = seg_flags_merge(a.B, nseg, a.H, sflags, flags, a.stream);
     cudaFreeAsync(buf, a.stream);
     return rc;
 }
@@ -155,7 +156,7 @@ static int forward3_ew(const Args &a) {
     if (rc == WKV6_OK) rc = ew_to_raw_bf16(a.B, a.T, a.H, (const float *)a.w, w_raw, flags, a.stream, a.w_kind == W_DECAY_F32);
     int nseg = 1, seg_chunks = 0;
     seg_plan(a.B, a.T, a.H, &nseg, &seg_chunks);
-    if (rc == WKV6_OK) rc = nseg > 1 ? tc3_forward_segmented(with_raw_w(a, w_raw), flags, nseg, seg_chunks) : tc3_forward(with_raw_w(a, w_raw), nullptr, flags);
+    if (rc == WKV6_OK) rc = nseg > 1 ? tc3_forward_segmented(with_raw_w(a, w_raw), flags, nseg, seg_chunks, nullptr, nullptr, true) : tc3_forward(with_raw_w(a, w_raw), nullptr, flags);
     if (rc == WKV6_OK) {
         Args s = a;
         s.stream_flags = flags;
