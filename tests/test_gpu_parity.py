@@ -612,3 +612,30 @@ def test_decay_clamp_opt_in(M, O):
     with M.exact_route_report() as rep:
         _run_fwd_bwd(M, r, k, v, w, u, gy)
     assert rep.streams() == (1, B * H)                             # default: that stream takes the exact route
+
+
+def test_long_prefill_through_the_fp32_decay_entries(M):
+    """The pybind-shaped entries that receive fp32 decays (rwkv6 inference: exp(-exp(w)); wkv6: -exp(w)) with a long
+    sequence and few streams: logits are recovered, the call is time-segmented, one stream whose decays do not
+    survive the bf16 round trip goes to the exact route -- all in one call, equal to the exact kernels."""
+    B, T, H = 1, 4096 + 64, 3
+    C = H * 64
+    r, k, v, w, u, _ = make_inputs(B, T, H, seed=91, decay="model", device=DEV)
+    ew = -torch.exp(w.float())
+    ew[0, :, 128:] = -torch.exp(w.float()[0, :, 128:] + 0.001)          # stream h=2: not representable as bf16 logits
+    decay = torch.exp(ew)[0].contiguous()
+    st0 = (torch.randn(H, 64, 64, generator=torch.Generator().manual_seed(5)) * 0.3).to(DEV)
+    outs = {}
+    for impl in ("auto", "simt"):
+        M.set_impl(impl)
+        try:
+            st = st0.clone()
+            y, _ = M.RUN_RWKV_6(1, T, C, H, st, r[0].contiguous(), k[0].contiguous(), v[0].contiguous(), decay, u)
+            y2 = torch.empty_like(r)
+            M.wkv6_cuda.forward(B, T, C, H, r, k, v, ew.contiguous(), u, y2)
+            outs[impl] = (y, st, y2)
+        finally:
+            M.set_impl("auto")
+    (y, st, y2), (ys, sts, y2s) = outs["auto"], outs["simt"]
+    assert relrms(y, ys) < 6e-3 and relrms(st, sts) < 2e-3 and relrms(y2, y2s) < 6e-3
+    assert torch.equal(y[..., 128:], ys[..., 128:])                     # the inexact stream ran on the exact kernels
