@@ -554,12 +554,16 @@ int tc3_forward(const Args &a, void *ckpt, int *hz_flags, int nseg, int seg_chun
         WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
         WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                              cudaSharedmemCarveoutMaxShared));
+        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             cudaSharedmemCarveoutMaxShared));
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
-    if (nseg > 1 && !p.has_y && !p.has_ckpt)
-        wkv6_tc3_fwd_kernel<true, true><<<a.B * nseg * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
-    else if (nseg > 1) wkv6_tc3_fwd_kernel<true><<<a.B * nseg * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
-    else wkv6_tc3_fwd_kernel<false><<<a.B * a.H, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
+    const dim3 grid(a.B * nseg * a.H);
+    if (nseg > 1 && !p.has_y) wkv6_tc3_fwd_kernel<true, true><<<grid, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
+    else if (nseg > 1) wkv6_tc3_fwd_kernel<true><<<grid, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
+    else if (!p.has_y) wkv6_tc3_fwd_kernel<false, true><<<grid, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
+    else wkv6_tc3_fwd_kernel<false><<<grid, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
     return WKV6_OK;
