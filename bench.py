@@ -62,16 +62,23 @@ class ClockSampler(threading.Thread):
         super().__init__(daemon=True)
         self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
         self._stop_evt = threading.Event()
-
-    def run(self):
-        try:
+        self._nv = self._h = None
+        try:            # NVML is initialised here, before the timed region, so that sampling starts with it
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
-                     "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80, "sync_boost": 0x10,
-                     "applications_clocks": 0x2}
+            self._nv, self._h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(self._h, nv.NVML_CLOCK_SM)
+        except Exception as e:  # no NVML: report that instead of inventing numbers
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def run(self):
+        nv, h = self._nv, self._h
+        if nv is None:
+            return
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20,
+                 "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80, "sync_boost": 0x10,
+                 "applications_clocks": 0x2}
+        try:
             while not self._stop_evt.is_set():
                 self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
                 try:
@@ -81,9 +88,9 @@ class ClockSampler(threading.Thread):
                 for k, b in names.items():
                     if bits & b:
                         self.reasons.add(k)
-                time.sleep(0.01)
-        except Exception as e:  # no NVML: report that instead of inventing numbers
-            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+                time.sleep(0.005)
+        except Exception as e:
+            self.reasons.add(f"nvml_error:{type(e).__name__}")
 
     def stop(self):
         self._stop_evt.set()
