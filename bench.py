@@ -211,6 +211,30 @@ def main():
         ms = float(tms.item())
     value = world * B * T / (ms * 1e-3)
 
+    # ---- SURVEY 8(d)'s second run of this config: the reference tests' own decay distribution, w ~ N(0,1)
+    # (tests/test_cpu.py:266), same shapes, same call; how many (b,h) streams left the tensor-core kernels
+    w_randn = make_inputs(B, T, H, seed=1000 + rank, decay="randn")[3].to(dev)
+    with M.exact_route_report() as rep:
+        for _ in range(3):
+            step(r, k, v, w_randn, u, gy)
+    rn_steps = max(3, min(args.steps, 20))
+    barrier()
+    a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a_.record()
+    for _ in range(rn_steps):
+        step(r, k, v, w_randn, u, gy)
+    b_.record()
+    barrier()
+    rn_ms = a_.elapsed_time(b_) / rn_steps
+    if world > 1:
+        tms = torch.tensor([rn_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        rn_ms = float(tms.item())
+    randn_decay = {"ms_per_step": rn_ms, "value": world * B * T / (rn_ms * 1e-3), "unit": UNIT, "steps": rn_steps,
+                   "exact_route_streams": rep.streams()[0], "streams": rep.streams()[1] // 3,
+                   "slowdown_vs_model_decay": rn_ms / ms, "what": "same op and shape with w ~ N(0,1)"}
+    del w_randn
+
     # ---- end to end: host buffers in, results out, inside the timed region.  Three CUDA streams form
     # the pipeline a data-parallel worker would run: copy-in of step i+1 and copy-out of step i-1
     # overlap the kernels of step i (PCIe is full duplex); every step still moves all of its inputs
@@ -320,7 +344,7 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "config": config(world),
-            "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline}
+            "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "randn_decay": randn_decay}
     if e2e:
         line["e2e"] = e2e
 

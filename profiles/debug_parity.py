@@ -1,6 +1,6 @@
 """GPU debugging aid (not a pytest module): per-gradient error of the tensor-core backward against the
 fp64 oracle on a few shapes, with the error located by chunk / token, plus a quick timing at the
-1B6 shape.  Usage on the GPU box:  python -m tests.debug_bwd [--time]"""
+1B6 shape.  Usage on the GPU box:  python -m profiles.debug_parity [--time]"""
 import sys
 
 import torch
@@ -52,8 +52,9 @@ def timing(M):
     B, T, H = 8, 4096, 32
     C = H * 64
     r, k, v, w, u, gy = make_inputs(B, T, H, seed=1, decay="model", device="cuda")
-    for impl in ("auto", "simt"):
+    for impl, decay in (("tc", "model"), ("tc", "randn"), ("simt", "model")):
         M.set_impl(impl)
+        r, k, v, w, u, gy = make_inputs(B, T, H, seed=1, decay=decay, device="cuda")
         leaves = [t.clone().requires_grad_(True) for t in (r, k, v, w, u)]
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         for it in range(4):
@@ -65,7 +66,7 @@ def timing(M):
             y.backward(gy)
             ev[2].record()
             torch.cuda.synchronize()
-        print(f"{impl}: fwd {ev[0].elapsed_time(ev[1]):.3f} ms  bwd {ev[1].elapsed_time(ev[2]):.3f} ms", flush=True)
+        print(f"{impl} {decay}: fwd {ev[0].elapsed_time(ev[1]):.3f} ms  bwd {ev[1].elapsed_time(ev[2]):.3f} ms", flush=True)
     M.set_impl("auto")
 
 
@@ -75,7 +76,7 @@ def main():
     for (B, T, H, decay) in ((1, 17, 1, "model"), (1, 64, 1, "model"), (2, 64, 2, "model"), (1, 65, 1, "model"),
                              (1, 130, 3, "model"), (1, 257, 1, "model"), (1, 1024, 2, "model"),
                              (1, 17, 1, "randn"), (2, 64, 2, "randn"), (1, 257, 1, "randn")):
-        run(M, B, T, H, decay, seed=B * 1000 + T)
+        run(M, B, T, H, decay, seed=B * 1000 + T, impl="tc")
     s0 = (torch.randn(2, 2, 64, 64, generator=torch.Generator().manual_seed(1)) * 0.5).bfloat16()
     run(M, 2, 96, 2, "model", 77, state=s0)
     run(M, 2, 200, 2, "model", 78, state=s0)

@@ -54,6 +54,11 @@ struct Args {
     cudaStream_t stream = nullptr;
 };
 
+// The tensor-core kernels floor the per-token log2-decay at -13 (tc3_common.cuh LCLAMP2); an opt-in clamp
+// that is tighter wins.  Returned in log2 units (kernels) / nats (seg_decay).
+inline float tc_lmin_nats(const Args &a) { return a.lmin > -13.0f * 0.6931471805599453f ? a.lmin : -13.0f * 0.6931471805599453f; }
+inline float tc_lmin_log2(const Args &a) { return tc_lmin_nats(a) * 1.4426950408889634f; }
+
 // implementations (each returns a WKV6_* code)
 int simt_forward(const Args &a);
 int simt_backward(const Args &a);

@@ -24,7 +24,11 @@ constexpr int L = 64;
 constexpr int CWARPS = 8, CTHREADS = 256, NTHREADS = CTHREADS + 32;
 constexpr float LOG2E = 1.4426950408889634f, LN2 = 0.6931471805599453f;
 constexpr float LOG2_LOG2E = 0.5287663729448977f;   // log2(log2(e)): exp(w) * log2(e) = 2^(w log2(e) + log2(log2(e)))
-constexpr float HAZARD2 = 60.0f * LOG2E;   // log2 units per aligned 16-token span
+// Built-in floor of the per-token log2-decay.  A factor 2^-13 = 1.2e-4 per token is below bf16 resolution
+// (2^-9), so the floor changes no output beyond the stated tolerance (checked against the UNCLAMPED fp64
+// recurrence at w ~ N(0,1) and hotter, tests/test_gpu_parity.py), and it bounds every scaled operand: a 16-token
+// block has its reference in the middle, so exponents stay within 8 x 13 = 104 < 127 binary orders.
+constexpr float LCLAMP2 = 13.0f;
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
@@ -42,6 +46,8 @@ __device__ __forceinline__ float pow2i_le0(float n) {
     const int e = min(max((int)n, -127), 0);
     return __int_as_float((e + 127) << 23);
 }
+// 2^e for an integer e <= 0, exact; 0 below the normal range
+__device__ __forceinline__ float pow2i(int e) { return __int_as_float((max(e, -127) + 127) << 23); }
 // packed bf16 pair (x, x) of an exact power of two given as fp32
 __device__ __forceinline__ uint32_t bfpair(float x) {
     const uint32_t hi = __float_as_uint(x) & 0xffff0000u;   // a power of two has no low mantissa bits
@@ -94,6 +100,18 @@ __device__ __forceinline__ void bar_sync_all() { asm volatile("bar.sync %0, %1;"
 __device__ __forceinline__ uint32_t bfpow2pair(int d) {
     const uint32_t x = (uint32_t)(max(d, -127) + 127) << 7;
     return x | (x << 16);
+}
+// exact scaling of packed bf16 pairs by 2^d, -254 <= d <= 0, as two factors (2^d alone may leave the bf16
+// range although the scaled values do not)
+__device__ __forceinline__ void scale2(uint32_t &a, uint32_t &b, int d) {
+    const uint32_t fa = bfpow2pair(d >> 1), fb = bfpow2pair(d - (d >> 1));
+    a = hmul2(hmul2(a, fa), fb);
+    b = hmul2(hmul2(b, fa), fb);
+}
+__device__ __forceinline__ void scale4(uint32_t (&x)[4], int d) {
+    const uint32_t fa = bfpow2pair(d >> 1), fb = bfpow2pair(d - (d >> 1));
+#pragma unroll
+    for (int g = 0; g < 4; g++) x[g] = hmul2(hmul2(x[g], fa), fb);
 }
 
 }  // namespace tc3

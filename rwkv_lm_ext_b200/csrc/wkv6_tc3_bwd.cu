@@ -1,32 +1,39 @@
 // WKV6 backward, chunked, on tcgen05 tensor cores fed by TMA -- role-uniform version (reverse sweep
 // over 64-token chunks; 2 CTAs per SM; thread <-> data mapping of tc3_common.cuh).
 //
-// Notation as in wkv6_tc3_fwd.cu, with TWO 32-token blocks per chunk (block p = tokens 32p..32p+31,
-// reference rho_p = exc at the block middle on the integer log2 grid; a warp's column half `ch` IS
-// its block).  Inputs per chunk: r,k,v,w,gy tiles, S_in = bf16 state at the chunk start ([i][j],
-// saved by the forward), G = dL/dS at the chunk end, fp32 in TMEM as [key i][value j].
+// Notation as in wkv6_tc3_fwd.cu, with FOUR 16-token blocks per chunk (block b = tokens 16b..16b+15,
+// reference rho_b = exc at the block middle on the integer log2 grid; the per-token log2-decay is floored
+// at -13, so every scaled operand stays within 8 x 13 binary orders of 1 and no stream needs an exact
+// fallback).  Inputs per chunk: r,k,v,w,gy tiles, S_in = bf16 state at the chunk start ([i][j], saved by
+// the forward), G = dL/dS at the chunk end, fp32 in TMEM as [key i][value j].
+//
+//   E = 2^(exc - rho_b(t)), F = 2^(rho_b(s) - cum);  Rt = r E, Kt_own = k F  (bf16)
+//   Kt_q[s] = Kt_own[s] 2^(rho_q - rho_b(s)), q >= b(s);   Rp_p[t] = Rt[t] 2^(rho_b(t) - rho_p), p <= b(t)
+//       exact power-of-two multiples (<= 1): every pair product r k 2^(exc_t - cum_s) has ONE bf16 value
 //
 //   M1  Bm[t,s]  = gy_t . v_s                               -> dA = strict-lower(Bm), bd[t] = Bm[t,t]
-//       A^T[s,t] = sum_i Kt_q[s,i] Rt[t,i]                  -> P^T = strict-upper + diag(sum_i r u k)
+//       A^T[s,t] = sum_i Kt_q[s,i] Rt[t,i]   (q = b(t))      -> P^T = strict-upper + diag(sum_i r u k)
 //       Drs[i,t] = sum_j S_in[i,j] gy_t[j]
-//   T1  dA, P^T tiles (bf16);  q0_i = <S_in, G>_i;  G *= 2^Lam_i
-//   M2  gv[s,j]  = sum_t P^T[s,t] gy_t[j] + sum_i Kh[s,i] G[i,j]
-//       Dr[i,t]  = sum_{s<t} Kt_q[s,i] dA[t,s]              (q = block of t)
-//       G[i,j]  += sum_t Rh[t,i] gy_t[j]
-//   T2  gv tile;  gr_t[i] = E (Dr + 2^rho_q Drs) + u_i k_t[i] bd[t];   XA = Rt_own Dr + r E 2^rho_q Drs
-//   M3  Dk[i,s]  = sum_{t>s} Rp_p[t,i] dA[t,s]  (p = block of s);   Dks[i,s] = sum_j G_old[i,j] v_s[j]
-//   T3  gk_s[i] = F (Dk + 2^(Lam-rho_p) Dks) + u_i r_s[i] bd[s];   bf16 copy of the new G;
-//       gl_t[i] = 2^Lam_i q0_i + sum_{s<t} Be_s + sum_{t'>t} (Ae + Ai - Bi)_t' - Bi_t,   gw = l * gl
-//          Ae = r E 2^rho (S_in gy),  Be = k F 2^(Lam-rho) (G v)   (terms through the states)
-//          Ai = Rt_own * Dr,  Bi = Kt_own * Dk                     (intra-chunk pair terms)
+//   T1  dA, P^T tiles (bf16);  q0_i = <S_in, G>_i;  Gb = bf16(G 2^(Lam - rho_3));  G <- G 2^(Lam - rho_0)
+//   M2  gv[s,j]  = sum_t P^T[s,t] gy_t[j] + sum_i Kt_3[s,i] Gb[i,j]       (Kt_3 2^(Lam - rho_3) = k 2^(Lam - cum))
+//       Dr[i,t]  = sum_{s<t} Kt_q[s,i] dA[t,s]              (q = b(t))
+//       G[i,j]  += sum_t Rp_0[t,i] gy_t[j]                  (G is carried as G_true 2^(-rho_0): Rp_0 2^rho_0 = r 2^exc)
+//   T2  Z = Dr + 2^rho_q Drs;   gr_t[i] = E Z + u_i k_t[i] bd[t];   XA = Rt Z        (XA parked in TMEM)
+//   M3  Dk[i,s]  = sum_{t>s} Rp_p[t,i] dA[t,s]  (p = b(s));   Dks[i,s] = sum_j Gb[i,j] v_s[j]
+//   T3  Zk = Dk + 2^(rho_3 - rho_p) Dks;   gk_s[i] = F Zk + u_i r_s[i] bd[s];
+//       X = XA - Kt_own Dk,  D = Kt_own Zk - XA
+//       gl_t[i] = 2^Lam_i q0_i + sum_all X + sum_{s<t} D_s - XA_t,   gw = l * gl
 //       This is d_t <S_t, G_t>_i expanded so that no two large quantities are
-//       subtracted: with integer references all Kt_q / Rp_p versions are exact power-of-two multiples of
-//       one another, so Ai and Bi are sums of bit-identical pair products r k dA and their difference
-//       telescopes exactly, like the reference's fp32 suffix trick (cuda/wkv6_cuda.cu:161-227).
-//   E = 2^(exc - rho_q), F = 2^(rho_p - cum);  gr, gk, gw, gv leave through swizzled tiles + TMA stores.
+//       subtracted: the intra-chunk pair terms Rt Dr and Kt_own Dk are sums of bit-identical pair products
+//       r k dA, so their difference telescopes like the reference's fp32 suffix trick
+//       (cuda/wkv6_cuda.cu:161-227).
+//   gr, gk, gw, gv leave through swizzled tiles + TMA stores.
 //
-// Streams whose forward raised the hazard flag are skipped here; the exact SIMT backward, enqueued
-// behind this kernel and predicated per stream on the same flag, handles them.
+// What the output stages need per element (Rt, Kt_own, E, F as bf16, the raw r, k, and l) is parked by the
+// operand preparation in the unused half of TMEM (see PARK_* below) instead of being recomputed.
+//
+// The per-stream flags only mark streams the CALLER routed to the exact SIMT kernels (fp32 decay entries
+// whose values are not bf16 logits); the kernels never raise one.
 #include <cmath>
 #include "common.cuh"
 #include "tc3_common.cuh"
@@ -38,20 +45,23 @@ using namespace tc3;
 
 constexpr uint32_t OFF_R = 0, OFF_K = 8192, OFF_V = 16384, OFF_GY = 24576, OFF_W = 32768, OFF_PT = OFF_W;
 constexpr uint32_t OFF_SIN = 40960, OFF_GB = 49152;
-constexpr uint32_t OFF_KT = 57344;     // version 1 (rows 0..63) at +0, version 0 (rows 0..31) at +8192
-constexpr uint32_t OFF_RP = 69632;     // version 0 (rows 0..63) at +0, version 1 (rows 32..63, stored from row 0) at +8192
-constexpr uint32_t OFF_RH = 81920, OFF_KH = 90112, OFF_DA = 98304, OFF_TILES_END = 106496;
-// output tiles reuse operand tiles that are dead by the time they are written
-constexpr uint32_t OFF_GVT = OFF_RH, OFF_GRT = OFF_KT, OFF_GKT = OFF_DA, OFF_GWT = OFF_RP;
-__host__ __device__ constexpr uint32_t kt_ver(int q) { return q ? 0u : 8192u; }
-__host__ __device__ constexpr uint32_t rp_ver(int p) { return p ? 8192u : 0u; }
+// Kt versions: version q = rows s 0..16q+15 in reference rho_q (64 + 48 + 32 + 16 rows)
+constexpr uint32_t OFF_KT = 57344;
+// Rp versions: version p = rows t 16p..63 (stored from row 0) in reference rho_p (64 + 48 + 32 + 16 rows)
+constexpr uint32_t OFF_RP = 77824;
+constexpr uint32_t OFF_DA = 98304, OFF_TILES_END = 106496;
+__host__ __device__ constexpr uint32_t kt_ver(int q) { return q == 3 ? 0u : q == 2 ? 8192u : q == 1 ? 14336u : 18432u; }
+__host__ __device__ constexpr uint32_t rp_ver(int p) { return p == 0 ? 0u : p == 1 ? 8192u : p == 2 ? 14336u : 18432u; }
+// output tiles reuse operand tiles that are dead by the time they are written: gr the Kt versions 0-2 (dead
+// once Dr is done), gv Kt_3 (dead once gv is done), gk the dA tile, gw the Rp versions (dead once M3 is done)
+constexpr uint32_t OFF_GRT = OFF_KT + 8192, OFF_GVT = OFF_KT, OFF_GKT = OFF_DA, OFF_GWT = OFF_RP;
 
 struct Extra {
     float gtot[8][64];        // decay total of every 8-token group, per channel (log2 units)
     float pdu[4][64];         // per channel-quarter partial sums of r u k, per token
     float bd[64];             // Bm[t,t]
     float q0p[2][64];         // <S_in, G>_i, partial over each half of j
-    float htY[2][64], htX[2][64];   // per token-half totals of D = Be - X and of X = Ae + Ai - Bi, per channel
+    float htY[2][64], htX[2][64];   // per token-half totals of D and of X, per channel
     float gu_s[64];
     uint64_t bar_rk, bar_w, bar_vg, bar_sin, bar_bm, bar_m1, bar_dr, bar_m2, bar_m3;
     uint32_t tmem_base;
@@ -59,9 +69,12 @@ struct Extra {
 constexpr uint32_t SMEM_BYTES = OFF_TILES_END + sizeof(Extra);
 constexpr uint32_t TM_G = 0, TM_X0 = 64, TM_X1 = 128, TM_X2 = 192, TM_COLS = 256;
 // An M = 64 accumulator only occupies lanes 0-15 of each 32-lane TMEM sub-partition; lanes 16-31 of the
-// same columns are used as per-thread scratch ("parking") for what the operand preparation hands to the
-// output stages, so that it does not sit in registers across the three MMA round trips.
-constexpr uint32_t PARK_L = 0, PARK_RK = 64, PARK_E = 128, PARK_X = 192;
+// same columns are per-thread scratch ("parking"): 4 regions x 2 registers per token pair.
+//   PARK_A: (Rt, Kt_own) packed bf16 pairs   -> T2 replaces Rt by XA(e=0), T3 replaces both by its part of gl
+//   PARK_B: (r, k) raw packed bf16 pairs
+//   PARK_C: (E, F) packed bf16 pairs         -> T2 replaces E by XA(e=1)
+//   PARK_L: l (fp32, e = 0,1)
+constexpr uint32_t PARK_A = 0, PARK_B = 64, PARK_C = 128, PARK_L = 192;
 
 struct Params {
     int B, T, H;
@@ -73,7 +86,7 @@ struct Params {
     // nseg = 1, seg_chunks = ceil(T/64), g_init = nullptr for an ordinary call.
     const float *g_init;
     int nseg, seg_chunks;
-    float lmin;               // floor of the per-token log2-decay (opt-in clamp; -inf = off)
+    float lmin;               // floor of the per-token log2-decay (>= -LCLAMP2)
     bf16 *gu, *gs;
     const int *hz_flags;
     long long *dbg;           // nullptr, or [gridDim][NC][8] clock64 stamps of warp 0 at the stage boundaries (profiling aid)
@@ -83,9 +96,8 @@ __device__ __forceinline__ uint32_t pack_frag(const uint32_t *v, int g, int hh) 
     return pack2(__uint_as_float(v[4 * g + 2 * hh]), __uint_as_float(v[4 * g + 2 * hh + 1]));
 }
 
-// SEG = false: the ordinary call, its own instantiation (see the forward kernel).  CLAMP: the opt-in decay floor
-// (two FMNMX per element pair in the hot path cost 1.4 % when always compiled in)
-template <bool SEG, bool CLAMP = false>
+// SEG = false: the ordinary call, its own instantiation (see the forward kernel).
+template <bool SEG>
 __global__ void __launch_bounds__(NTHREADS, 2)
 wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_w,
@@ -159,12 +171,12 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             issue_vg(NC - 1);
             issue_sin(NC - 1);
         }
-        const uint32_t kt = sbase + OFF_KT, rp = sbase + OFF_RP, rh = sbase + OFF_RH, kh = sbase + OFF_KH;
+        const uint32_t kt = sbase + OFF_KT, rp = sbase + OFF_RP;
         const uint32_t da = sbase + OFF_DA, pt = sbase + OFF_PT, gb = sbase + OFF_GB, sin = sbase + OFF_SIN;
         const uint32_t vv = sbase + OFF_V, gy = sbase + OFF_GY;
         constexpr uint32_t ID_KK = idesc_bf16(64, 64, 0, 0), ID_KM = idesc_bf16(64, 64, 0, 1), ID_MM = idesc_bf16(64, 64, 1, 1);
-        constexpr uint32_t ID32_KK = idesc_bf16(64, 32, 0, 0), ID32_MK = idesc_bf16(64, 32, 1, 0), ID32_MM = idesc_bf16(64, 32, 1, 1);
-        bar_sync_all<B_T3>();                                    // G = 0 written (TMEM + bf16 copy)
+        constexpr uint32_t ID16_KK = idesc_bf16(64, 16, 0, 0), ID16_MK = idesc_bf16(64, 16, 1, 0), ID16_MM = idesc_bf16(64, 16, 1, 1);
+        bar_sync_all<B_T3>();                                    // G = 0 written (TMEM)
         if (lane == 0) {
             mbar_wait(&ex.bar_rk, 0);
             mbar_wait(&ex.bar_w, 0);
@@ -176,7 +188,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             const uint32_t par = it & 1;
             if (lane == 0 && it > 0) tma_store_wait_read<0>();   // every output tile of the previous chunk has left shared memory
             __syncwarp();
-            bar_arrive_all<B_FREE>();                            // ... so the preparation may overwrite RH, KT, RP (and T1 DA)
+            bar_arrive_all<B_FREE>();                            // ... so the preparation may overwrite KT, RP (and T1 DA)
             // ---- products that need nothing from the operand preparation run under it
             if (elect_one()) {
                 mbar_wait(&ex.bar_vg, par);
@@ -197,11 +209,11 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             if (elect_one()) {
                 tc_fence_after();
 #pragma unroll
-                for (int q = 0; q < 2; q++)   // A^T[s, t in q] = Kt_q Rt_own^T            (runs under T1a)
+                for (int q = 0; q < 4; q++)   // A^T[s, t in q] = Kt_q Rt_own^T            (runs under T1a)
 #pragma unroll
                     for (int k = 0; k < 4; k++)
-                        mma_bf16_ss(tmem + TM_X1 + 32 * q, smem_desc_sw128(kt + kt_ver(q) + 32 * k, 8192, 1024),
-                                    smem_desc_sw128(rp + rp_ver(q) + 32 * k, 8192, 1024), ID32_KK, k > 0);
+                        mma_bf16_ss(tmem + TM_X1 + 16 * q, smem_desc_sw128(kt + kt_ver(q) + 32 * k, 8192, 1024),
+                                    smem_desc_sw128(rp + rp_ver(q) + 32 * k, 8192, 1024), ID16_KK, k > 0);
                 mma_commit(&ex.bar_m1);
                 mbar_wait(&ex.bar_m1, par);
             }
@@ -212,30 +224,30 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             if (elect_one()) {
                 tc_fence_after();
 #pragma unroll
-                for (int q = 0; q < 2; q++)   // Dr[i, t in q] = sum_{s in blocks <= q} Kt_q[s,i] dA[t,s]     (runs under T1b)
+                for (int q = 0; q < 4; q++)   // Dr[i, t in q] = sum_{s in blocks <= q} Kt_q[s,i] dA[t,s]     (runs under T1b)
 #pragma unroll
                     for (int ks = 0; ks < 4; ks++)
-                        if (ks < 2 * q + 2)
-                            mma_bf16_ss(tmem + TM_X0 + 32 * q, smem_desc_sw128(kt + kt_ver(q) + 2048 * ks, 8192, 1024),
-                                        smem_desc_sw128(da + 4096 * q + 32 * ks, 8192, 1024), ID32_MK, ks > 0);
+                        if (ks <= q)
+                            mma_bf16_ss(tmem + TM_X0 + 16 * q, smem_desc_sw128(kt + kt_ver(q) + 2048 * ks, 8192, 1024),
+                                        smem_desc_sw128(da + 2048 * q + 32 * ks, 8192, 1024), ID16_MK, ks > 0);
                 mma_commit(&ex.bar_dr);
                 mbar_wait(&ex.bar_dr, par);
             }
             __syncwarp();
             bar_arrive_all<B_DR>();
-            bar_sync_all<B_T1>();                                // P^T written; <S_in,G> taken; G decayed
+            bar_sync_all<B_T1>();                                // P^T, Gb written; <S_in,G> taken; G decayed
             if (elect_one()) {
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 4; k++)   // gv[s,j] = P^T GY ...                               (runs under T2a)
                     mma_bf16_ss(tmem + TM_X1, smem_desc_sw128(pt + 32 * k, 8192, 1024), smem_desc_sw128(gy + 2048 * k, 8192, 1024), ID_KM, k > 0);
 #pragma unroll
-                for (int k = 0; k < 4; k++)   // ... + Kh G
-                    mma_bf16_ss(tmem + TM_X1, smem_desc_sw128(kh + 32 * k, 8192, 1024), smem_desc_sw128(gb + 2048 * k, 8192, 1024), ID_KM, 1);
+                for (int k = 0; k < 4; k++)   // ... + Kt_3 Gb
+                    mma_bf16_ss(tmem + TM_X1, smem_desc_sw128(kt + kt_ver(3) + 32 * k, 8192, 1024), smem_desc_sw128(gb + 2048 * k, 8192, 1024), ID_KM, 1);
                 mma_commit(&ex.bar_m2);
 #pragma unroll
-                for (int k = 0; k < 4; k++)   // G[i,j] += Rh^T GY                    (first read in T3: covered by the M3 commit)
-                    mma_bf16_ss(tmem + TM_G, smem_desc_sw128(rh + 2048 * k, 8192, 1024), smem_desc_sw128(gy + 2048 * k, 8192, 1024), ID_MM, 1);
+                for (int k = 0; k < 4; k++)   // G[i,j] += Rp_0^T GY                  (first read in the next T1: covered by the M3 commit)
+                    mma_bf16_ss(tmem + TM_G, smem_desc_sw128(rp + rp_ver(0) + 2048 * k, 8192, 1024), smem_desc_sw128(gy + 2048 * k, 8192, 1024), ID_MM, 1);
                 mbar_wait(&ex.bar_m2, par);
             }
             __syncwarp();
@@ -248,14 +260,14 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             if (elect_one()) {
                 tc_fence_after();
 #pragma unroll
-                for (int pb = 0; pb < 2; pb++)   // Dk[i, s in p] = sum_{t >= 32p} Rp_p[t,i] dA[t,s]   (dA read MN-major; under T2b)
+                for (int pb = 0; pb < 4; pb++)   // Dk[i, s in p] = sum_{t >= 16p} Rp_p[t,i] dA[t,s]   (dA read MN-major; under T2b)
 #pragma unroll
                     for (int kk = 0; kk < 4; kk++)
-                        if (kk < 4 - 2 * pb)
-                            mma_bf16_ss(tmem + TM_X0 + 32 * pb, smem_desc_sw128(rp + rp_ver(pb) + 2048 * kk, 8192, 1024),
-                                        smem_desc_sw128(da + 4096 * pb + 2048 * kk + 64 * pb, 8192, 1024), ID32_MM, kk > 0);
+                        if (kk < 4 - pb)
+                            mma_bf16_ss(tmem + TM_X0 + 16 * pb, smem_desc_sw128(rp + rp_ver(pb) + 2048 * kk, 8192, 1024),
+                                        smem_desc_sw128(da + 2048 * (pb + kk) + 32 * pb, 8192, 1024), ID16_MM, kk > 0);
 #pragma unroll
-                for (int k = 0; k < 4; k++)   // Dks[i,s] = G_old V^T
+                for (int k = 0; k < 4; k++)   // Dks[i,s] = Gb V^T
                     mma_bf16_ss(tmem + TM_X2, smem_desc_sw128(gb + 32 * k, 8192, 1024), smem_desc_sw128(vv + 32 * k, 8192, 1024), ID_KK, k > 0);
                 mma_commit(&ex.bar_m3);
                 mbar_wait(&ex.bar_m3, par);
@@ -274,7 +286,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 }
             }
             __syncwarp();
-            bar_sync_all<B_T3>();                                // gk, gw tiles written; new bf16 G
+            bar_sync_all<B_T3>();                                // gk, gw tiles written
             if (lane == 0) {
                 tma_store_3d(&map_gk, sm + OFF_GKT, h * 64, t_base + c * L, b);
                 tma_store_3d(&map_gw, sm + OFF_GWT, h * 64, t_base + c * L, b);
@@ -292,10 +304,13 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         const float u_h[2] = {__bfloat162float(p.u[h * 64 + F.row(0)]), __bfloat162float(p.u[h * 64 + F.row(1)])};
         const uint32_t tG = tmem_addr(tmem, 32 * sp, TM_G + 32 * ch);
         const uint32_t tPark = tmem_addr(tmem, 32 * sp + 16, 32 * ch);
+        // x2 transposing stores of one 8-token group: lanes 0-7 address the rows of channel half 0, lanes 8-15 of half 1
+        const uint32_t ti2_off = F.ti1_off ^ ((lane & 8) ? 16u : 0u);
         float gu_acc[2] = {0.f, 0.f};
+        int sig[2] = {0, 0};              // G in TMEM = G_true 2^(-sig) per key row: rho_0 of the chunk processed last
         uint32_t v[16];
 
-        // G = dL/dS behind the last token (0, or handed in when this row is a segment) and its bf16 copy
+        // G = dL/dS behind the last token (0, or handed in when this row is a segment)
         const int seg = SEG ? row % p.nseg : 0;
         const bool first_has_s0 = p.has_s0 || seg > 0;          // a later segment starts from a non-zero state
         const bool g_is_zero = !SEG || p.g_init == nullptr || seg == p.nseg - 1;
@@ -311,10 +326,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                         v[4 * g + 2 * hh + e] = __float_as_uint(p.g_init[(((size_t)row * p.H + h) * 64 + F.col(g, e)) * 64 + F.row(hh)]);
         }
         tmem_st_frag(tG, v);
-        stsm_x4(sbase + OFF_GB + F.rc(0), pack_frag(v, 0, 0), pack_frag(v, 1, 0), pack_frag(v, 2, 0), pack_frag(v, 3, 0));
-        stsm_x4(sbase + OFF_GB + F.rc(1), pack_frag(v, 0, 1), pack_frag(v, 1, 1), pack_frag(v, 2, 1), pack_frag(v, 3, 1));
         tmem_wait_st();
-        fence_proxy_async();
         tc_fence_before();
         bar_arrive_all<B_T3>();
 
@@ -326,7 +338,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             bar_sync_all<B_RAW>();
             asm volatile("fence.acq_rel.cta;" ::: "memory");
             STAMP(0);
-            float rqf[2], elam[2], elr[2], erho[2];
+            float lamf[2];                    // Lam (log2 units)
+            int irb[2][2], ir0[2], ir3[2];    // block references (integers, log2 units): my two blocks, block 0, block 3
             {   // ---- everything per element lives only inside this block
             float l[2][4][2], exq[2][4];
             {
@@ -339,10 +352,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     for (int g = 0; g < 4; g++) {
                         float l0 = -fast_ex2(fmaf(bf_lo(wp[hh][g]), LOG2E, LOG2_LOG2E));   // -exp(w) * log2(e)
                         float l1 = -fast_ex2(fmaf(bf_hi(wp[hh][g]), LOG2E, LOG2_LOG2E));
-                        if constexpr (CLAMP) {
-                            l0 = fmaxf(l0, p.lmin);
-                            l1 = fmaxf(l1, p.lmin);
-                        }
+                        l0 = fmaxf(l0, p.lmin);
+                        l1 = fmaxf(l1, p.lmin);
                         if (nv < L) {                                   // ragged last chunk: no decay on the padded rows
                             const int t0 = F.col(g, 0);
                             if (t0 >= nv) l0 = 0.f;
@@ -360,69 +371,100 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                         if (q == 3) ex.gtot[4 * ch + g][F.row(hh)] = x;
                     }
             }
+            {   // park l in the shadow lanes (fragment order [4g + 2h + e])
+                uint32_t pk[16];
+#pragma unroll
+                for (int g = 0; g < 4; g++)
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        pk[4 * g + 2 * hh] = __float_as_uint(l[hh][g][0]);
+                        pk[4 * g + 2 * hh + 1] = __float_as_uint(l[hh][g][1]);
+                    }
+                tmem_st_frag(tPark + PARK_L, pk);
+            }
             named_bar_sync<B_SCAN, CTHREADS>();
-            bar_sync_all<B_FREE>();              // the output tiles of the previous chunk (RH, KT, RP, DA space) have been stored
+            bar_sync_all<B_FREE>();              // the output tiles of the previous chunk (KT, RP, DA space) have been stored
 
             uint32_t rr[2][4], kk[2][4];
             ldsm_x4_t(sbase + OFF_R + F.ti(0), rr[0][0], rr[0][1], rr[0][2], rr[0][3]);
             ldsm_x4_t(sbase + OFF_R + F.ti(1), rr[1][0], rr[1][1], rr[1][2], rr[1][3]);
             ldsm_x4_t(sbase + OFF_K + F.ti(0), kk[0][0], kk[0][1], kk[0][2], kk[0][3]);
             ldsm_x4_t(sbase + OFF_K + F.ti(1), kk[1][0], kk[1][1], kk[1][2], kk[1][3]);
-            float exc0[2][4];                       // exclusive decay prefix of the first token of each pair
+            {
+                uint32_t pk[16];
+#pragma unroll
+                for (int g = 0; g < 4; g++)
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        pk[4 * g + 2 * hh] = rr[hh][g];
+                        pk[4 * g + 2 * hh + 1] = kk[hh][g];
+                    }
+                tmem_st_frag(tPark + PARK_B, pk);
+            }
+            uint32_t pa[16], pc[16];                // (Rt, Kt_own) and (E, F) in fragment order
             float du[4][2];
 #pragma unroll
             for (int g = 0; g < 4; g++) du[g][0] = du[g][1] = 0.f;
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
-                float run = 0.f, gb[4], rho0 = 0.f, rho1 = 0.f;
+                float run = 0.f, gb[4];
+                int ir[4];
 #pragma unroll
                 for (int x8 = 0; x8 < 8; x8++) {
-                    if (x8 == 2) rho0 = rintf(run);                       // middle of block 0, integer log2 grid
-                    if (x8 == 6) rho1 = rintf(run);                       // middle of block 1
+                    if (x8 & 1) ir[x8 >> 1] = __float2int_rn(run);        // middle of block x8/2, integer log2 grid
                     if ((x8 >> 2) == ch) gb[x8 & 3] = run;
                     run += ex.gtot[x8][F.row(hh)];
                 }
-                const float lam = run, rq = ch ? rho1 : rho0;
-                const int ir0 = (int)rho0, ir1 = (int)rho1;
-                // 2^(rho1 - rho0) spans 32 tokens and may leave the bf16 range although the scaled values do
-                // not: apply it as two exact factors
-                const int d10 = ir1 - ir0;
-                const uint32_t f10a = bfpow2pair(d10 >> 1), f10b = bfpow2pair(d10 - (d10 >> 1)), erq = bfpow2pair(ch ? ir1 : ir0);
-                const float el = fast_ex2(lam - rq);
-                rqf[hh] = rq;
-                elam[hh] = fast_ex2(lam);
-                elr[hh] = el;
-                erho[hh] = fast_ex2(rq);
-                uint32_t rto[4], kto[4], rhp[4], khp[4];
+                lamf[hh] = run;
+                irb[hh][0] = ch ? ir[2] : ir[0];                           // my groups 0,1 are block 2ch, groups 2,3 block 2ch+1
+                irb[hh][1] = ch ? ir[3] : ir[1];
+                ir0[hh] = ir[0];
+                ir3[hh] = ir[3];
+                uint32_t rto[4], kto[4];
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
+                    const float rq = (float)irb[hh][g >> 1];
                     const float e0 = gb[g] + exq[hh][g], c0 = e0 + l[hh][g][0], c1 = c0 + l[hh][g][1];
-                    exc0[hh][g] = e0;
                     const float r0 = bf_lo(rr[hh][g]), r1 = bf_hi(rr[hh][g]), k0 = bf_lo(kk[hh][g]), k1 = bf_hi(kk[hh][g]);
-                    const float rt0 = r0 * fast_ex2(e0 - rq), rt1 = r1 * fast_ex2(c0 - rq);
-                    const float kf0 = k0 * fast_ex2(rq - c0), kf1 = k1 * fast_ex2(rq - c1);
-                    rto[g] = pack2(rt0, rt1);
-                    kto[g] = pack2(kf0, kf1);
-                    rhp[g] = hmul2(rto[g], erq);                          // Rh = Rt * 2^rho (exact)
-                    khp[g] = pack2(kf0 * el, kf1 * el);                   // Kh = k * 2^(Lam - cum)
+                    const float E0 = fast_ex2(e0 - rq), E1 = fast_ex2(c0 - rq), F0 = fast_ex2(rq - c0), F1 = fast_ex2(rq - c1);
+                    rto[g] = pack2(r0 * E0, r1 * E1);
+                    kto[g] = pack2(k0 * F0, k1 * F1);
+                    pa[4 * g + 2 * hh] = rto[g];
+                    pa[4 * g + 2 * hh + 1] = kto[g];
+                    pc[4 * g + 2 * hh] = pack2(E0, E1);
+                    pc[4 * g + 2 * hh + 1] = pack2(F0, F1);
                     du[g][0] = fmaf(r0 * u_h[hh], k0, du[g][0]);
                     du[g][1] = fmaf(r1 * u_h[hh], k1, du[g][1]);
                 }
+                // versions: my rows in their own reference, then scaled (exactly, by powers of two <= 1) to the
+                // reference of every later block (Kt) / earlier block (Rp)
                 const uint32_t ti = F.ti(hh);
-                stsm_x4_t(sbase + OFF_RH + ti, rhp[0], rhp[1], rhp[2], rhp[3]);
-                stsm_x4_t(sbase + OFF_KH + ti, khp[0], khp[1], khp[2], khp[3]);
-                if (ch == 0) {      // block 0: own in Kt_0 / Rp_0, scaled to the later reference in Kt_1
-                    stsm_x4_t(sbase + OFF_KT + kt_ver(0) + ti, kto[0], kto[1], kto[2], kto[3]);
-                    stsm_x4_t(sbase + OFF_KT + kt_ver(1) + ti, hmul2(hmul2(kto[0], f10a), f10b), hmul2(hmul2(kto[1], f10a), f10b),
-                              hmul2(hmul2(kto[2], f10a), f10b), hmul2(hmul2(kto[3], f10a), f10b));
+                if (ch == 0) {
+                    stsm_x2_t(sbase + OFF_RP + rp_ver(1) + ti, rto[2], rto[3]);                    // t 16..31 -> rows 0..15
+                    scale2(rto[2], rto[3], ir[1] - ir[0]);
                     stsm_x4_t(sbase + OFF_RP + rp_ver(0) + ti, rto[0], rto[1], rto[2], rto[3]);
-                } else {            // block 1: own in Kt_1 / Rp_1 (stored from row 0), scaled to the earlier reference in Rp_0
+                    stsm_x2_t(sbase + OFF_KT + kt_ver(0) + ti, kto[0], kto[1]);
+                    scale2(kto[0], kto[1], ir[1] - ir[0]);
                     stsm_x4_t(sbase + OFF_KT + kt_ver(1) + ti, kto[0], kto[1], kto[2], kto[3]);
-                    stsm_x4_t(sbase + OFF_RP + rp_ver(0) + ti, hmul2(hmul2(rto[0], f10a), f10b), hmul2(hmul2(rto[1], f10a), f10b),
-                              hmul2(hmul2(rto[2], f10a), f10b), hmul2(hmul2(rto[3], f10a), f10b));
-                    stsm_x4_t(sbase + OFF_RP + rp_ver(1) + ti - 4096u, rto[0], rto[1], rto[2], rto[3]);
+                    scale4(kto, ir[2] - ir[1]);
+                    stsm_x4_t(sbase + OFF_KT + kt_ver(2) + ti, kto[0], kto[1], kto[2], kto[3]);
+                    scale4(kto, ir[3] - ir[2]);
+                    stsm_x4_t(sbase + OFF_KT + kt_ver(3) + ti, kto[0], kto[1], kto[2], kto[3]);
+                } else {
+                    stsm_x2_t(sbase + OFF_KT + kt_ver(2) + ti, kto[0], kto[1]);                    // s 32..47
+                    scale2(kto[0], kto[1], ir[3] - ir[2]);
+                    stsm_x4_t(sbase + OFF_KT + kt_ver(3) + ti, kto[0], kto[1], kto[2], kto[3]);
+                    stsm_x2_t(sbase + OFF_RP + rp_ver(3) + ti - 4096u, rto[2], rto[3]);            // t 48..63 -> rows 0..15
+                    scale2(rto[2], rto[3], ir[3] - ir[2]);
+                    stsm_x4_t(sbase + OFF_RP + rp_ver(2) + ti - 4096u, rto[0], rto[1], rto[2], rto[3]);   // t 32..63 -> rows 0..31
+                    scale4(rto, ir[2] - ir[1]);
+                    stsm_x4_t(sbase + OFF_RP + rp_ver(1) + ti - 2048u, rto[0], rto[1], rto[2], rto[3]);   // rows 16..47
+                    scale4(rto, ir[1] - ir[0]);
+                    stsm_x4_t(sbase + OFF_RP + rp_ver(0) + ti, rto[0], rto[1], rto[2], rto[3]);
                 }
             }
+            tmem_st_frag(tPark + PARK_A, pa);
+            tmem_st_frag(tPark + PARK_C, pc);
             {   // diag(u) term: reduce-scatter over the 8 lanes ri, then one partial per channel quarter
                 const bool b2 = lane & 16, b1 = lane & 8, b0 = lane & 4;
                 float a4[2][2], a2[2], a1;
@@ -444,34 +486,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 }
                 ex.pdu[sp][32 * ch + 8 * ((b2 ? 2 : 0) + (b1 ? 1 : 0)) + 2 * q + (b0 ? 1 : 0)] = a1;
             }
-            {   // park l, (r,k), exc in the shadow lanes (fragment order [4g + 2h + e])
-                uint32_t pk[16];
-#pragma unroll
-                for (int g = 0; g < 4; g++)
-#pragma unroll
-                    for (int hh = 0; hh < 2; hh++) {
-                        pk[4 * g + 2 * hh] = __float_as_uint(l[hh][g][0]);
-                        pk[4 * g + 2 * hh + 1] = __float_as_uint(l[hh][g][1]);
-                    }
-                tmem_st_frag(tPark + PARK_L, pk);
-#pragma unroll
-                for (int g = 0; g < 4; g++)
-#pragma unroll
-                    for (int hh = 0; hh < 2; hh++) {
-                        pk[4 * g + 2 * hh] = rr[hh][g];
-                        pk[4 * g + 2 * hh + 1] = kk[hh][g];
-                    }
-                tmem_st_frag(tPark + PARK_RK, pk);
-#pragma unroll
-                for (int g = 0; g < 4; g++)
-#pragma unroll
-                    for (int hh = 0; hh < 2; hh++) {
-                        pk[4 * g + 2 * hh] = __float_as_uint(exc0[hh][g]);
-                        pk[4 * g + 2 * hh + 1] = 0u;
-                    }
-                tmem_st_frag(tPark + PARK_E, pk);
-                tmem_wait_st();
-            }
+            tmem_wait_st();
             }
             fence_proxy_async();
             STAMP(1);
@@ -530,27 +545,32 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 }
                 stsm_x4(sbase + OFF_PT + F.rc(hh), pk[0], pk[1], pk[2], pk[3]);
             }
-            // ---- G rows (key channel i): q0_i = <S_in, G>_i (partial over my half of j), then decay by 2^Lam_i
+            // ---- G rows (key channel i): G_old = G' 2^sig;  q0_i = <S_in, G_old>_i (partial over my half of j);
+            //      Gb = bf16(G_old 2^(Lam - rho_3)) (operand of gv and Dks);  G' <- G_old 2^(Lam - rho_0)
+            //      (factors applied one after the other: their product may leave the fp32 range although the result does not)
             tmem_ld_frag(tG, v);
             tmem_wait_ld();
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
-                uint32_t s4[4];
+                const float es = pow2i(sig[hh]);
+                const float f3 = fast_ex2(lamf[hh] - (float)ir3[hh]), f0 = fast_ex2(lamf[hh] - (float)ir0[hh]);
+                uint32_t s4[4], gbp[4];
                 ldsm_x4(sbase + OFF_SIN + F.rc(hh), s4[0], s4[1], s4[2], s4[3]);
                 float qs = 0.f;
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
-                    qs = fmaf(bf_lo(s4[g]), __uint_as_float(v[4 * g + 2 * hh]), qs);
-                    qs = fmaf(bf_hi(s4[g]), __uint_as_float(v[4 * g + 2 * hh + 1]), qs);
+                    const float g0 = __uint_as_float(v[4 * g + 2 * hh]) * es, g1 = __uint_as_float(v[4 * g + 2 * hh + 1]) * es;
+                    qs = fmaf(bf_lo(s4[g]), g0, qs);
+                    qs = fmaf(bf_hi(s4[g]), g1, qs);
+                    gbp[g] = pack2(g0 * f3, g1 * f3);
+                    v[4 * g + 2 * hh] = __float_as_uint(g0 * f0);
+                    v[4 * g + 2 * hh + 1] = __float_as_uint(g1 * f0);
                 }
+                stsm_x4(sbase + OFF_GB + F.rc(hh), gbp[0], gbp[1], gbp[2], gbp[3]);
                 qs += __shfl_xor_sync(0xffffffffu, qs, 1);
                 qs += __shfl_xor_sync(0xffffffffu, qs, 2);
                 if (q == 0) ex.q0p[ch][F.row(hh)] = qs;
-#pragma unroll
-                for (int g = 0; g < 4; g++)
-#pragma unroll
-                    for (int e = 0; e < 2; e++)
-                        v[4 * g + 2 * hh + e] = __float_as_uint(__uint_as_float(v[4 * g + 2 * hh + e]) * elam[hh]);
+                sig[hh] = ir0[hh];
             }
             tmem_st_frag(tG, v);
             tmem_wait_st();
@@ -559,37 +579,36 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             STAMP(3);
             bar_arrive_all<B_T1>();
 
-            // ================================================================== T2: gv tile, gr tile, XA
+            // ================================================================== T2: gr tile, XA
             bar_sync_all<B_DR>();                        // Dr ran under T1b; gv is not needed yet
             tc_fence_after();
             STAMP(4);
-            // per 8-token group: Dr, Drs -> gr (tile) and XA, which is parked in the shadow lanes until T3
+            // per 8-token group: Dr, Drs -> gr (tile) and XA, which replaces Rt / E in the shadow lanes until T3
 #pragma unroll
             for (int g = 0; g < 4; g++) {
-                uint32_t d4[4], s4[4], x4[4];
-                uint32_t pl[4], prk[4], pe[4];
+                uint32_t d4[4], s4[4], a4[4], b4[4], c4[4];
                 tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch + 8 * g), d4);
                 tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 8 * g), s4);
-                tmem_ld_frag1(tPark + PARK_L + 8 * g, pl);
-                tmem_ld_frag1(tPark + PARK_RK + 8 * g, prk);
-                tmem_ld_frag1(tPark + PARK_E + 8 * g, pe);
+                tmem_ld_frag1(tPark + PARK_A + 8 * g, a4);
+                tmem_ld_frag1(tPark + PARK_B + 8 * g, b4);
+                tmem_ld_frag1(tPark + PARK_C + 8 * g, c4);
                 tmem_wait_ld();
                 const float2 bd2 = *reinterpret_cast<const float2 *>(&ex.bd[F.col(g, 0)]);
+                uint32_t grp[2];
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++) {
-                    const float e0 = __uint_as_float(pe[2 * hh]), c0 = e0 + __uint_as_float(pl[2 * hh]);
-                    const float E0 = fast_ex2(e0 - rqf[hh]), E1 = fast_ex2(c0 - rqf[hh]);
-                    const float r0 = bf_lo(prk[2 * hh]), r1 = bf_hi(prk[2 * hh]), k0 = bf_lo(prk[2 * hh + 1]), k1 = bf_hi(prk[2 * hh + 1]);
-                    const float dr0 = __uint_as_float(d4[2 * hh]), dr1 = __uint_as_float(d4[2 * hh + 1]);
-                    const float ds0 = erho[hh] * __uint_as_float(s4[2 * hh]), ds1 = erho[hh] * __uint_as_float(s4[2 * hh + 1]);
-                    const float re0 = r0 * E0, re1 = r1 * E1;
-                    const uint32_t rtp = pack2(re0, re1);                 // Rt_own exactly as the MMAs saw it
-                    x4[2 * hh] = __float_as_uint(fmaf(re0, ds0, bf_lo(rtp) * dr0));
-                    x4[2 * hh + 1] = __float_as_uint(fmaf(re1, ds1, bf_hi(rtp) * dr1));
-                    const float ub = u_h[hh] * bd2.x, ub1 = u_h[hh] * bd2.y;
-                    stsm_x1_t(sbase + OFF_GRT + F.ti1(g, hh), pack2(fmaf(E0, dr0 + ds0, ub * k0), fmaf(E1, dr1 + ds1, ub1 * k1)));
+                    const float erho = pow2i(irb[hh][g >> 1]);     // 2^rho of this block (0 when out of range)
+                    const float z0 = fmaf(erho, __uint_as_float(s4[2 * hh]), __uint_as_float(d4[2 * hh]));
+                    const float z1 = fmaf(erho, __uint_as_float(s4[2 * hh + 1]), __uint_as_float(d4[2 * hh + 1]));
+                    const uint32_t rtp = a4[2 * hh], epk = c4[2 * hh], kkp = b4[2 * hh + 1];
+                    a4[2 * hh] = __float_as_uint(bf_lo(rtp) * z0);           // XA = Rt Z, with Rt exactly as the MMAs saw it
+                    c4[2 * hh] = __float_as_uint(bf_hi(rtp) * z1);
+                    const float ub0 = u_h[hh] * bd2.x, ub1 = u_h[hh] * bd2.y;
+                    grp[hh] = pack2(fmaf(bf_lo(epk), z0, ub0 * bf_lo(kkp)), fmaf(bf_hi(epk), z1, ub1 * bf_hi(kkp)));
                 }
-                tmem_st_frag1(tPark + PARK_X + 8 * g, x4);
+                stsm_x2_t(sbase + OFF_GRT + ti2_off + 1024u * g, grp[0], grp[1]);
+                tmem_st_frag1(tPark + PARK_A + 8 * g, a4);
+                tmem_st_frag1(tPark + PARK_C + 8 * g, c4);
             }
             tmem_wait_st();
             fence_proxy_async();
@@ -607,42 +626,39 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             tc_fence_before();
             bar_arrive_all<B_T2>();
 
-            // ================================================================== T3: gk tile, gw tile, new bf16 G
+            // ================================================================== T3: gk tile, gw tile
             bar_sync_all<B_M3>();
             tc_fence_after();
             STAMP(6);
             // per 8-token group: Dk, Dks, XA -> gk (tile), running scans; the part of gl that does not need the
-            // other token half replaces XA in TMEM
-            // With D = Be - X:  gl_t = 2^Lam q0 + sum_all X + sum_{s<t} D_s - XA_t   (X_t + Bi_t = XA_t), so one
-            // exclusive prefix scan of D plus the totals of X are enough.
+            // other token half replaces (XA, Kt_own) in the shadow lanes.
+            // With X = XA - Kt_own Dk and D = Kt_own Zk - XA:  gl_t = 2^Lam q0 + sum_all X + sum_{s<t} D_s - XA_t,
+            // so one exclusive prefix scan of D plus the totals of X are enough.
             float runD[2] = {0.f, 0.f}, runX[2] = {0.f, 0.f};
 #pragma unroll
             for (int g = 0; g < 4; g++) {
-                uint32_t d4[4], s4[4], x4[4];
+                uint32_t d4[4], s4[4], a4[4], b4[4], c4[4];
                 tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch + 8 * g), d4);
                 tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 8 * g), s4);
-                tmem_ld_frag1(tPark + PARK_X + 8 * g, x4);
-                uint32_t pl[4], prk[4], pe[4];
-                tmem_ld_frag1(tPark + PARK_L + 8 * g, pl);
-                tmem_ld_frag1(tPark + PARK_RK + 8 * g, prk);
-                tmem_ld_frag1(tPark + PARK_E + 8 * g, pe);
+                tmem_ld_frag1(tPark + PARK_A + 8 * g, a4);
+                tmem_ld_frag1(tPark + PARK_B + 8 * g, b4);
+                tmem_ld_frag1(tPark + PARK_C + 8 * g, c4);
                 tmem_wait_ld();
                 const float2 bd2 = *reinterpret_cast<const float2 *>(&ex.bd[F.col(g, 0)]);
+                uint32_t gkp[2];
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++) {
-                    const float c0 = __uint_as_float(pe[2 * hh]) + __uint_as_float(pl[2 * hh]), c1 = c0 + __uint_as_float(pl[2 * hh + 1]);
-                    const float F0 = fast_ex2(rqf[hh] - c0), F1 = fast_ex2(rqf[hh] - c1);
-                    const float r0 = bf_lo(prk[2 * hh]), r1 = bf_hi(prk[2 * hh]), k0 = bf_lo(prk[2 * hh + 1]), k1 = bf_hi(prk[2 * hh + 1]);
+                    const float elr = pow2i(ir3[hh] - irb[hh][g >> 1]);   // 2^(rho_3 - rho_p)
                     const float dk0 = __uint_as_float(d4[2 * hh]), dk1 = __uint_as_float(d4[2 * hh + 1]);
-                    const float ds0 = elr[hh] * __uint_as_float(s4[2 * hh]), ds1 = elr[hh] * __uint_as_float(s4[2 * hh + 1]);
-                    const float kf0 = k0 * F0, kf1 = k1 * F1;
-                    const uint32_t ktp = pack2(kf0, kf1);                 // Kt_own exactly as the MMAs saw it
-                    const float xa0 = __uint_as_float(x4[2 * hh]), xa1 = __uint_as_float(x4[2 * hh + 1]);
-                    const float x0 = fmaf(-bf_lo(ktp), dk0, xa0), x1 = fmaf(-bf_hi(ktp), dk1, xa1);      // X = XA - Bi
-                    const float d0 = fmaf(kf0, ds0, -x0), d1 = fmaf(kf1, ds1, -x1);                      // D = Be - X
-                    const float br0 = bd2.x * r0, br1 = bd2.y * r1;
-                    stsm_x1_t(sbase + OFF_GKT + F.ti1(g, hh), pack2(fmaf(F0, dk0 + ds0, u_h[hh] * br0), fmaf(F1, dk1 + ds1, u_h[hh] * br1)));
-                    gu_acc[hh] = fmaf(br0, k0, fmaf(br1, k1, gu_acc[hh]));
+                    const float z0 = fmaf(elr, __uint_as_float(s4[2 * hh]), dk0), z1 = fmaf(elr, __uint_as_float(s4[2 * hh + 1]), dk1);
+                    const uint32_t ktp = a4[2 * hh + 1], fpk = c4[2 * hh + 1], rrp = b4[2 * hh], kkp = b4[2 * hh + 1];
+                    const float xa0 = __uint_as_float(a4[2 * hh]), xa1 = __uint_as_float(c4[2 * hh]);
+                    const float kt0 = bf_lo(ktp), kt1 = bf_hi(ktp);          // Kt_own exactly as the MMAs saw it
+                    const float x0 = fmaf(-kt0, dk0, xa0), x1 = fmaf(-kt1, dk1, xa1);             // X = XA - Bi
+                    const float d0 = fmaf(kt0, z0, -xa0), d1 = fmaf(kt1, z1, -xa1);               // D = Be + Bi - XA
+                    const float br0 = bd2.x * bf_lo(rrp), br1 = bd2.y * bf_hi(rrp);
+                    gkp[hh] = pack2(fmaf(bf_lo(fpk), z0, u_h[hh] * br0), fmaf(bf_hi(fpk), z1, u_h[hh] * br1));
+                    gu_acc[hh] = fmaf(br0, bf_lo(kkp), fmaf(br1, bf_hi(kkp), gu_acc[hh]));
                     // exclusive prefix of D over the 4 lanes of the group; total of X
                     const float pd = d0 + d1;
                     float y = pd, z = x0 + x1, tmp;
@@ -653,12 +669,13 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     if (q >= 2) y += tmp;
                     z += __shfl_xor_sync(0xffffffffu, z, 2);
                     const float ex0 = runD[hh] + (y - pd);
-                    x4[2 * hh] = __float_as_uint(ex0 - xa0);
-                    x4[2 * hh + 1] = __float_as_uint(ex0 + d0 - xa1);
+                    a4[2 * hh] = __float_as_uint(ex0 - xa0);
+                    a4[2 * hh + 1] = __float_as_uint(ex0 + d0 - xa1);
                     runD[hh] += __shfl_sync(0xffffffffu, y, 3, 4);
                     runX[hh] += z;
                 }
-                tmem_st_frag1(tPark + PARK_X + 8 * g, x4);
+                stsm_x2_t(sbase + OFF_GKT + ti2_off + 1024u * g, gkp[0], gkp[1]);
+                tmem_st_frag1(tPark + PARK_A + 8 * g, a4);
             }
             if (q == 0) {
 #pragma unroll
@@ -667,32 +684,31 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     ex.htX[ch][F.row(hh)] = runX[hh];
                 }
             }
-            // ---- new G -> bf16 operand copy [i][j]; after chunk 0 it is dL/dS_0
-            tmem_ld_frag(tG, v);
-            tmem_wait_ld();
-            stsm_x4(sbase + OFF_GB + F.rc(0), pack_frag(v, 0, 0), pack_frag(v, 1, 0), pack_frag(v, 2, 0), pack_frag(v, 3, 0));
-            stsm_x4(sbase + OFF_GB + F.rc(1), pack_frag(v, 0, 1), pack_frag(v, 1, 1), pack_frag(v, 2, 1), pack_frag(v, 3, 1));
-            if (c == 0 && p.gs) {
+            if (c == 0 && p.gs) {        // after chunk 0, G' 2^rho_0 is dL/dS_0 (the G update of M2 is covered by the M3 commit)
+                tmem_ld_frag(tG, v);
+                tmem_wait_ld();
 #pragma unroll
-                for (int g = 0; g < 4; g++)
+                for (int hh = 0; hh < 2; hh++) {
+                    const float es = pow2i(sig[hh]);
 #pragma unroll
-                    for (int hh = 0; hh < 2; hh++)
+                    for (int g = 0; g < 4; g++)
 #pragma unroll
                         for (int e = 0; e < 2; e++)   // gs[b,h,j,i] = dL/dS_0[i][j]
                             p.gs[(((size_t)row * p.H + h) * 64 + F.col(g, e)) * 64 + F.row(hh)] =
-                                __float2bfloat16_rn(__uint_as_float(v[4 * g + 2 * hh + e]));
+                                __float2bfloat16_rn(__uint_as_float(v[4 * g + 2 * hh + e]) * es);
+                }
             }
             tmem_wait_st();
             named_bar_sync<B_SCAN, CTHREADS>();          // token-half totals of both scans are in shared memory
             uint32_t lp[16];
-            tmem_ld_frag(tPark + PARK_X, v);
+            tmem_ld_frag(tPark + PARK_A, v);
             tmem_ld_frag(tPark + PARK_L, lp);
             tmem_wait_ld();
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
                 const int i = F.row(hh);
                 // 2^Lam <S_in,G> + total X of both halves + D of the earlier half
-                const float base = (ex.q0p[0][i] + ex.q0p[1][i]) * elam[hh] + runX[hh] + (ch ? ex.htY[0][i] + ex.htX[0][i] : ex.htX[1][i]);
+                const float base = (ex.q0p[0][i] + ex.q0p[1][i]) * fast_ex2(lamf[hh]) + runX[hh] + (ch ? ex.htY[0][i] + ex.htX[0][i] : ex.htX[1][i]);
                 uint32_t gwp[4];
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
@@ -758,7 +774,7 @@ bool tc3_backward_supported(const Args &a) {
            tc::get_encode_fn() != nullptr;
 }
 
-// gw = 0 where the opt-in decay clamp is active (w > log(clamp)), for the streams the tensor-core kernel computed
+// gw = 0 where the OPT-IN decay clamp is active (w > log(clamp)), for the streams the tensor-core kernel computed
 // (flags index rows of the launch: stream = row / nseg when the call was segmented)
 __global__ void __launch_bounds__(256) clamp_gw_kernel(size_t n8, const bf16 *__restrict__ w, bf16 *__restrict__ gw, float wmax,
                                                        const int *__restrict__ flags, int T, int H, int nseg) {
@@ -803,7 +819,7 @@ static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const f
     p.has_s0 = has_s0;
     p.g_init = g_init;
     p.nseg = nseg; p.seg_chunks = seg_chunks;
-    p.lmin = a.lmin * 1.4426950408889634f;
+    p.lmin = tc_lmin_log2(a);
     p.gu = (bf16 *)a.gu; p.gs = (bf16 *)a.gs;
     p.hz_flags = flags;
     p.dbg = (long long *)g_tc3_bwd_stamps;
@@ -811,8 +827,7 @@ static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const f
     int dev = 0;
     WKV6_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-        const void *kerns[4] = {(const void *)wkv6_tc3_bwd_kernel<false, false>, (const void *)wkv6_tc3_bwd_kernel<true, false>,
-                                (const void *)wkv6_tc3_bwd_kernel<false, true>, (const void *)wkv6_tc3_bwd_kernel<true, true>};
+        const void *kerns[2] = {(const void *)wkv6_tc3_bwd_kernel<false>, (const void *)wkv6_tc3_bwd_kernel<true>};
         for (const void *kf : kerns) {
             WKV6_CUDA_CHECK(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
             WKV6_CUDA_CHECK(cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -821,10 +836,8 @@ static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const f
     }
     const bool clamp = a.lmin > -INFINITY;
     const dim3 grid(a.B * nseg * a.H);
-    if (nseg > 1 && clamp) wkv6_tc3_bwd_kernel<true, true><<<grid, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
-    else if (nseg > 1) wkv6_tc3_bwd_kernel<true, false><<<grid, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
-    else if (clamp) wkv6_tc3_bwd_kernel<false, true><<<grid, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
-    else wkv6_tc3_bwd_kernel<false, false><<<grid, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
+    if (nseg > 1) wkv6_tc3_bwd_kernel<true><<<grid, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
+    else wkv6_tc3_bwd_kernel<false><<<grid, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
     if (clamp) {                       // opt-in decay clamp: a clamped decay no longer depends on w (kept out of the hot kernel)
@@ -861,7 +874,7 @@ static int tc3_backward_segmented(const Args &a, int nseg, int seg_chunks) {
     f.r = r_rev; f.k = r_rev; f.v = gy_rev; f.w = w_rev;
     f.s0 = nullptr; f.s0_bstride = 0; f.s0_f32 = 0; f.sT = g_loc; f.sT_f32 = 1; f.y = nullptr; f.saved = nullptr; f.gy = nullptr;
     if (rc == WKV6_OK) rc = tc3_forward(f, nullptr, sflags, nseg, seg_chunks);
-    if (rc == WKV6_OK) rc = seg_decay(a.B, a.T, C, nseg, seg_tokens, a.w, lam, a.lmin, a.stream);
+    if (rc == WKV6_OK) rc = seg_decay(a.B, a.T, C, nseg, seg_tokens, a.w, lam, tc_lmin_nats(a), a.stream);
     if (rc == WKV6_OK) rc = seg_scan(a.B, nseg, a.H, lam, g_loc, nullptr, 0, 0, g_end, nullptr, 0, 1, nullptr, a.stream);
     Args v = a;
     v.gu = gu_tmp; v.gs = a.gs ? gs_tmp : nullptr;

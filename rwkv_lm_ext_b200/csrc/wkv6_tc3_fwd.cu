@@ -2,13 +2,15 @@
 //
 // One CTA owns one (batch, head) stream and walks its T tokens in chunks of L = 64; 2 CTAs per SM.
 // Per chunk (i = key channel, j = value channel, l_t = -exp(w_t), cum =
-// inclusive prefix sum of l inside the chunk, exc = cum - l, Lam = cum at the chunk end), with two
-// 32-token blocks q (reference rho_q = exc at the block middle rounded to the INTEGER log2 grid, so
-// every scaled operand stays within 16 decay steps of 1 and the two versions of Kt are exact
-// power-of-two multiples of one another -- bf16 mul.rn, no second exp):
+// inclusive prefix sum of l inside the chunk, exc = cum - l, Lam = cum at the chunk end), with FOUR
+// 16-token blocks q (reference rho_q = exc at the block middle rounded to the INTEGER log2 grid).  The
+// per-token log2-decay is floored at -13 (a factor 2^-13 is below bf16 resolution), so every scaled
+// operand stays within 8 x 13 binary orders of 1: nothing overflows whatever the decays are, and no
+// stream ever needs an exact fallback.  The versions of Kt are exact power-of-two multiples (<= 1) of
+// one another -- bf16 mul.rn, no second exp:
 //
-//   A    A^T[s,t] = sum_i Kt_q[s,i] * Rt[t,i]        2 x (64 x 32 x 64), one per target block q
-//         Rt[t] = r_t * 2^(exc_t - rho_q),   Kt_q[s] = k_s * 2^(rho_q - cum_s)
+//   A    A^T[s,t] = sum_i Kt_q[s,i] * Rt[t,i]        4 x (64 x 16 x 64), one per target block q
+//         Rt[t] = r_t * 2^(exc_t - rho_q),   Kt_q[s] = k_s * 2^(rho_q - cum_s)   (s in blocks <= q)
 //   T1   P = strict-lower(A) + diag(sum_i r u k)  (bf16),   S[i,j] *= 2^Lam_i  (fp32, in TMEM)
 //   M2   Y[t,j]  = sum_i Rh[t,i] * S_in[i,j] + sum_s P[t,s] * V[s,j]          Rh = r * 2^exc
 //        S[i,j] += sum_s Kh[s,i] * V[s,j]     Kh = k * 2^(Lam - cum), split into bf16 hi + lo so that the
@@ -21,9 +23,8 @@
 // The operand preparation of chunk c+1 runs while the tensor cores work on M2 of chunk c (only the
 // tiles M2 still reads -- Rh, Kh -- are written after it), and A of chunk c+1 is queued behind M2, so
 // the compute warps never wait for a full MMA round trip; the co-resident CTA fills what is left.
-// Streams whose decay is too strong for the block references (more than e^-60 inside an aligned
-// 16-token span) raise their hazard flag: the exact SIMT kernel, enqueued behind this one and
-// predicated per stream on that flag, redoes them.
+// The per-stream flags only mark streams the CALLER routed to the exact SIMT kernels (fp32 decay
+// entries whose values are not bf16 logits); this kernel never raises one.
 #include "common.cuh"
 #include "tc3_common.cuh"
 
@@ -33,16 +34,16 @@ namespace {
 using namespace tc3;
 
 constexpr uint32_t OFF_R = 0, OFF_K = 8192, OFF_W = 16384, OFF_V = 24576;
-constexpr uint32_t OFF_KT = 32768;                       // version 1 (rows 0..63) at +0, version 0 (rows 0..31) at +8192
-__host__ __device__ constexpr uint32_t kt_ver(int q) { return q ? 0u : 8192u; }
-constexpr uint32_t OFF_RT = 45056, OFF_P = 53248, OFF_RH = 61440, OFF_KH = 69632, OFF_KL = 77824, OFF_SB = 86016, OFF_YT = 94208;
-constexpr uint32_t OFF_TILES_END = 102400;
+// Kt versions: version q holds rows s = 0 .. 16q+15 (reference rho_q); 64 + 48 + 32 + 16 rows, 1024-byte aligned
+constexpr uint32_t OFF_KT = 32768;
+__host__ __device__ constexpr uint32_t kt_ver(int q) { return q == 3 ? 0u : q == 2 ? 8192u : q == 1 ? 14336u : 18432u; }
+constexpr uint32_t OFF_RT = 53248, OFF_P = 61440, OFF_RH = 69632, OFF_KH = 77824, OFF_KL = 86016, OFF_SB = 94208, OFF_YT = 102400;
+constexpr uint32_t OFF_TILES_END = 110592;
 struct Extra {
     float gtot[8][64];        // decay total of every 8-token group, per channel (log2 units)
     float pdu[4][64];         // per channel-quarter partial sums of r u k, per token
     uint64_t bar_rkw, bar_v, bar_a, bar_m2;
     uint32_t tmem_base;
-    int hz;
 };
 constexpr uint32_t SMEM_BYTES = OFF_TILES_END + sizeof(Extra);
 constexpr uint32_t TM_A = 0, TM_Y = 64, TM_S = 128, TM_COLS = 256;
@@ -96,7 +97,6 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         mbar_init(&ex.bar_v, 1);
         mbar_init(&ex.bar_a, 1);
         mbar_init(&ex.bar_m2, 1);
-        ex.hz = 0;
         fence_barrier_init();
     }
     if (warp == 0) {
@@ -126,17 +126,17 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         };
         const uint32_t kt = sbase + OFF_KT, rt = sbase + OFF_RT, rh = sbase + OFF_RH, kh = sbase + OFF_KH;
         const uint32_t kl = sbase + OFF_KL, pp = sbase + OFF_P, sb = sbase + OFF_SB, vv = sbase + OFF_V;
-        constexpr uint32_t ID32_KK = idesc_bf16(64, 32, 0, 0);
+        constexpr uint32_t ID16_KK = idesc_bf16(64, 16, 0, 0);
         constexpr uint32_t ID_KM = idesc_bf16(64, 64, 0, 1);
         constexpr uint32_t ID_MM = idesc_bf16(64, 64, 1, 1);
         auto issue_A = [&]() {                               // A^T[s, t in q] = Kt_q Rt_own^T   (not in a state-only pass)
             if (!SO && p.has_y)
 #pragma unroll
-            for (int qq = 0; qq < 2; qq++)
+            for (int qq = 0; qq < 4; qq++)                   // rows s past block qq are never read (strictly lower part only)
 #pragma unroll
                 for (int k = 0; k < 4; k++)
-                    mma_bf16_ss(tmem + TM_A + 32 * qq, smem_desc_sw128(kt + kt_ver(qq) + 32 * k, 8192, 1024),
-                                smem_desc_sw128(rt + 4096 * qq + 32 * k, 8192, 1024), ID32_KK, k > 0);
+                    mma_bf16_ss(tmem + TM_A + 16 * qq, smem_desc_sw128(kt + kt_ver(qq) + 32 * k, 8192, 1024),
+                                smem_desc_sw128(rt + 2048 * qq + 32 * k, 8192, 1024), ID16_KK, k > 0);
             mma_commit(&ex.bar_a);
         };
         if (lane == 0) {
@@ -275,8 +275,6 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 uint32_t wp[2][4];
                 ldsm_x4_t(sbase + OFF_W + F.ti(0), wp[0][0], wp[0][1], wp[0][2], wp[0][3]);
                 ldsm_x4_t(sbase + OFF_W + F.ti(1), wp[1][0], wp[1][1], wp[1][2], wp[1][3]);
-                bool hazard = false;
-                float prev = 0.f;
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++)
 #pragma unroll
@@ -300,11 +298,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                         if (q >= 2) x += y;
                         exq[hh][g] = x - ps;
                         if (q == 3) ex.gtot[4 * ch + g][F.row(hh)] = x;
-                        // exactness guard: total decay of every aligned 16-token span (two groups)
-                        if (g & 1) hazard |= (-(x + prev) > HAZARD2);
-                        prev = x;
                     }
-                if (hazard && q == 3) ex.hz = 1;
             }
             named_bar_sync<B_SCAN, CTHREADS>();
 
@@ -320,23 +314,24 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             for (int g = 0; g < 4; g++) du[g][0] = du[g][1] = 0.f;
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
-                // prefix over the 8 groups of this channel: start of my groups, block references, total
-                float run = 0.f, gb[4], rho0 = 0.f, rho1 = 0.f;
+                // prefix over the 8 groups of this channel: start of my groups, the four block references, total
+                float run = 0.f, gb[4];
+                int ir[4];
 #pragma unroll
                 for (int x8 = 0; x8 < 8; x8++) {
-                    if (x8 == 2) rho0 = rintf(run);                       // middle of block 0, integer log2 grid
-                    if (x8 == 6) rho1 = rintf(run);                       // middle of block 1
+                    if (x8 & 1) ir[x8 >> 1] = __float2int_rn(run);        // middle of block x8/2, integer log2 grid
                     if ((x8 >> 2) == ch) gb[x8 & 3] = run;
                     run += ex.gtot[x8][F.row(hh)];
                 }
-                const float lam = run, rq = ch ? rho1 : rho0;
-                const int ir0 = (int)rho0, ir1 = (int)rho1, d10 = ir1 - ir0;
-                const uint32_t erq = bfpow2pair(ch ? ir1 : ir0);
-                const float el = fast_ex2(lam - rq);
+                const float lam = run;
                 elam_nx[hh] = fast_ex2(lam);
+                // my tokens: groups g = 0,1 are block 2ch, g = 2,3 block 2ch + 1
+                const int irb[2] = {ch ? ir[2] : ir[0], ch ? ir[3] : ir[1]};
                 uint32_t rto[4], kto[4];
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
+                    const float rq = (float)irb[g >> 1];
+                    const float el = fast_ex2(lam - rq);
                     const float e0 = gb[g] + exq[hh][g], c0 = e0 + l[hh][g][0], c1 = c0 + l[hh][g][1];
                     const float r0 = bf_lo(rr[hh][g]), r1 = bf_hi(rr[hh][g]), k0 = bf_lo(kk[hh][g]), k1 = bf_hi(kk[hh][g]);
                     const float kf0 = k0 * fast_ex2(rq - c0), kf1 = k1 * fast_ex2(rq - c1);
@@ -344,7 +339,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                         const float rt0 = r0 * fast_ex2(e0 - rq), rt1 = r1 * fast_ex2(c0 - rq);
                         rto[g] = pack2(rt0, rt1);
                         kto[g] = pack2(kf0, kf1);
-                        rhp[hh][g] = hmul2(rto[g], erq);                  // Rh = Rt * 2^rho (exact)
+                        rhp[hh][g] = hmul2(rto[g], bfpow2pair(irb[g >> 1]));   // Rh = Rt * 2^rho (exact)
                         du[g][0] = fmaf(r0 * u_h[hh], k0, du[g][0]);
                         du[g][1] = fmaf(r1 * u_h[hh], k1, du[g][1]);
                     }
@@ -355,14 +350,21 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 const uint32_t ti = F.ti(hh);
                 if constexpr (!SO) {
                 stsm_x4_t(sbase + OFF_RT + ti, rto[0], rto[1], rto[2], rto[3]);
-                if (ch == 0) {      // block 0: own in Kt_0, scaled to the later reference in Kt_1 (2^(rho1-rho0) spans 32
-                                    // tokens and may leave the bf16 range although the products do not: two exact factors)
-                    const uint32_t fa = bfpow2pair(d10 >> 1), fb = bfpow2pair(d10 - (d10 >> 1));
-                    stsm_x4_t(sbase + OFF_KT + kt_ver(0) + ti, kto[0], kto[1], kto[2], kto[3]);
-                    stsm_x4_t(sbase + OFF_KT + kt_ver(1) + ti, hmul2(hmul2(kto[0], fa), fb), hmul2(hmul2(kto[1], fa), fb),
-                              hmul2(hmul2(kto[2], fa), fb), hmul2(hmul2(kto[3], fa), fb));
-                } else {
+                // Kt versions: my rows in their own reference, then scaled down to every later block's reference.
+                // 2^(rho_q - rho_(q-1)) spans 16 tokens and may leave the bf16 range although the products it is
+                // meant for do not: two exact factors.
+                if (ch == 0) {
+                    stsm_x2_t(sbase + OFF_KT + kt_ver(0) + ti, kto[0], kto[1]);
+                    scale2(kto[0], kto[1], ir[1] - ir[0]);
                     stsm_x4_t(sbase + OFF_KT + kt_ver(1) + ti, kto[0], kto[1], kto[2], kto[3]);
+                    scale4(kto, ir[2] - ir[1]);
+                    stsm_x4_t(sbase + OFF_KT + kt_ver(2) + ti, kto[0], kto[1], kto[2], kto[3]);
+                    scale4(kto, ir[3] - ir[2]);
+                    stsm_x4_t(sbase + OFF_KT + kt_ver(3) + ti, kto[0], kto[1], kto[2], kto[3]);
+                } else {
+                    stsm_x2_t(sbase + OFF_KT + kt_ver(2) + ti, kto[0], kto[1]);
+                    scale2(kto[0], kto[1], ir[3] - ir[2]);
+                    stsm_x4_t(sbase + OFF_KT + kt_ver(3) + ti, kto[0], kto[1], kto[2], kto[3]);
                 }
                 }
             }
@@ -483,7 +485,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                         pack2(__uint_as_float(v[4 + 2 * hh]), __uint_as_float(v[5 + 2 * hh])),
                         pack2(__uint_as_float(v[8 + 2 * hh]), __uint_as_float(v[9 + 2 * hh])),
                         pack2(__uint_as_float(v[12 + 2 * hh]), __uint_as_float(v[13 + 2 * hh])));
-            if (c == NC - 1 && p.sT && !ex.hz) {
+            if (c == NC - 1 && p.sT) {
 #pragma unroll
                 for (int g = 0; g < 4; g++)
 #pragma unroll
@@ -503,7 +505,6 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
     }
     tc_fence_before();
     __syncthreads();
-    if (threadIdx.x == 0 && ex.hz) p.hz_flags[blockIdx.x] = 1;
     if (warp == 0) tmem_dealloc(tmem, TM_COLS);
 }
 
@@ -540,7 +541,7 @@ int tc3_forward(const Args &a, void *ckpt, int *hz_flags, int nseg, int seg_chun
     p.has_ckpt = ckpt != nullptr;
     p.hz_flags = hz_flags;
     p.nseg = nseg; p.seg_chunks = seg_chunks;
-    p.lmin = a.lmin * 1.4426950408889634f;
+    p.lmin = tc_lmin_log2(a);
     static bool attr_done[64] = {};          // function attributes are per device
     int dev = 0;
     WKV6_CUDA_CHECK(cudaGetDevice(&dev));
