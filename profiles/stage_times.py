@@ -7,14 +7,17 @@ import rwkv_lm_ext_b200 as M
 from rwkv_lm_ext_b200 import _lib
 from rwkv_lm_ext_b200.synthetic import make_inputs
 
-B, T, H = 8, 4096, 32
+FINE = "--fine" in sys.argv          # needs a library built with -DWKV6_FINE_STAMPS (WKV6_B200_LIB=...)
+_a = [a for a in sys.argv[1:] if not a.startswith("--")]
+B, T, H = int(_a[0]) if _a else 8, 4096, 32
+NS = 32 if FINE else 8
 lib = M.load()
 lib = _lib.load()
 fn = lib.wkv6b200_debug_stamps
 fn.argtypes = [ctypes.c_void_p]
 r, k, v, w, u, gy = make_inputs(B, T, H, seed=0, decay="model", device="cuda")
 NC = T // 64
-buf = torch.zeros(B * H, NC, 8, dtype=torch.int64, device="cuda")
+buf = torch.zeros(B * H, NC, NS, dtype=torch.int64, device="cuda")
 for it in range(3):
     leaves = [t.detach().requires_grad_(True) for t in (r, k, v, w, u)]
     y = M.RUN_CUDA_RWKV6(B, T, H * 64, H, *leaves)
@@ -35,3 +38,14 @@ print(f"  {names[-1]:10s} {nxt.mean():8.0f}   (min {nxt.min():6.0f}  max {nxt.ma
 per_chunk = (s[:, 1:, 0] - s[:, :-1, 0])[:, 2:-2]
 print(f"  chunk period {per_chunk.mean():8.0f}")
 
+
+if FINE:
+    order = [0, 8, 9, 10, 24, 11, 12, 13, 1, 2, 14, 25, 26, 15, 16, 17, 18, 19, 3, 4, 5, 6, 20, 21, 22, 23, 7]
+    label = {0: "P start", 8: "P scan done", 9: "P scan barrier", 10: "P free barrier", 24: "P r,k loaded + parked", 11: "P math+versions done",
+             12: "P parks+diag issued", 13: "P wait::st", 1: "P end", 2: "T1 start (Bm ready)", 14: "T1 Bm,G loaded", 25: "T1 dA converted", 26: "T1 dA fence.proxy", 15: "T1 dA stored",
+             16: "T1 G done", 17: "T1 M1 barrier", 18: "T1 A^T loaded", 19: "T1 P^T stored", 3: "T1 end", 4: "T2 start (Dr ready)",
+             5: "T2a end", 6: "T3 start (M3 ready)", 20: "T3 loop done", 21: "T3 gs/wait::st", 22: "T3 scan barrier", 23: "T3 parks loaded", 7: "T3 end"}
+    print("fine timeline (mean cycles since the previous point):")
+    for a, b in zip(order[:-1], order[1:]):
+        dd = (s[:, :, b] - s[:, :, a])[:, 2:-2]
+        print(f"  -> {label[b]:28s} {dd.mean():8.0f}")

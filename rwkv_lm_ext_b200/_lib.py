@@ -7,7 +7,8 @@ import ctypes
 import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libwkv6_b200.so")
+# WKV6_B200_LIB: load another build of the same library instead (A/B timing of kernel variants, profiles/variants.py)
+LIB_PATH = os.environ.get("WKV6_B200_LIB") or os.path.join(_PKG, "libwkv6_b200.so")
 
 c_p, c_i, c_sz, c_i64, c_f = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t, ctypes.c_int64, ctypes.c_float
 
@@ -66,6 +67,7 @@ SIGNATURES = {
 }
 
 _lib = None
+ABI_VERSION = 2   # == wkv6b200_abi_version() of the library this signature table was written for
 
 
 class Wkv6B200Error(RuntimeError):
@@ -77,17 +79,19 @@ def load(build_if_missing: bool = True):
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        if build_if_missing and os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")):
-            from .build import build_library
-            build_library()
-        else:
-            raise Wkv6B200Error(f"{LIB_PATH} is missing: run `python -m rwkv_lm_ext_b200.build` "
-                                "(there is no CPU or eager fallback)")
+    have_nvcc = os.path.exists(os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc"))
+    if build_if_missing and have_nvcc and not os.environ.get("WKV6_B200_LIB"):
+        from .build import build_library
+        build_library()                  # returns at once unless a source or the header is newer than the library
+    elif not os.path.exists(LIB_PATH):
+        raise Wkv6B200Error(f"{LIB_PATH} is missing: run `python -m rwkv_lm_ext_b200.build` "
+                            "(there is no CPU or eager fallback)")
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)          # AttributeError here = header and library disagree
         fn.restype, fn.argtypes = res, args
+    if lib.wkv6b200_abi_version() != ABI_VERSION:
+        raise Wkv6B200Error(f"{LIB_PATH} has ABI version {lib.wkv6b200_abi_version()}, this package needs {ABI_VERSION}: rebuild it")
     _lib = lib
     return lib
 

@@ -24,18 +24,20 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force: bool = False, verbose: bool = False) -> str:
-    """Compile every .cu under csrc/ into one shared library.  Objects are built in parallel."""
-    if not force and not _stale():
+def build_library(force: bool = False, verbose: bool = False, defines=(), out: str = None) -> str:
+    """Compile every .cu under csrc/ into one shared library.  Objects are built in parallel.
+    defines / out: an experimental variant (-DNAME[=V] ...) written to another file (profiles/variants.py)."""
+    if out is None and not force and not _stale():
         return LIB
-    objdir = os.path.join(PKG, "build")
+    lib_out = out or LIB
+    objdir = os.path.join(PKG, "build" if out is None else "build_" + os.path.basename(out).replace(".so", ""))
     os.makedirs(objdir, exist_ok=True)
     procs = []
     objs = []
     for src in sources():
         obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
         objs.append(obj)
-        cmd = [NVCC, *FLAGS, "-c", src, "-o", obj]
+        cmd = [NVCC, *FLAGS, *[f"-D{d}" for d in defines], "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
@@ -50,8 +52,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
             sys.stderr.write(out)
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([NVCC, "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
-    return LIB
+    subprocess.check_call([NVCC, "-shared", "-o", lib_out, *objs, "-gencode", "arch=compute_100a,code=sm_100a"])
+    return lib_out
 
 
 if __name__ == "__main__":

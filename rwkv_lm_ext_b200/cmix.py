@@ -15,7 +15,7 @@ import torch
 
 from . import _lib
 from ._lib import check, ptr, stream_of
-from .heads import _cuda, _needs_grad, _ws
+from .heads import _bf16_param, _cuda, _needs_grad, _ws
 
 
 class _ShiftLerp2(torch.autograd.Function):
@@ -55,8 +55,8 @@ def cmix_shift_lerp2(x, maa_k, maa_r, shift_state=None):
     assert x.dtype == torch.bfloat16
     x = x.contiguous()
     C = x.shape[-1]
-    maa_kr = torch.cat([maa_k.reshape(1, C), maa_r.reshape(1, C)], 0)
-    shift_state = shift_state.contiguous() if shift_state is not None else None
+    maa_kr = _bf16_param(torch.cat([maa_k.reshape(1, C), maa_r.reshape(1, C)], 0))
+    shift_state = _bf16_param(shift_state)
     if _needs_grad(x, maa_kr, shift_state):
         return _ShiftLerp2.apply(x, shift_state, maa_kr)
     return tuple(_shift_lerp2_fwd(x, shift_state, maa_kr).unbind(0))

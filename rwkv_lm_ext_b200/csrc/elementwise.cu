@@ -50,6 +50,7 @@ __global__ void gather_rows_kernel(int T, int D, const bf16 *__restrict__ x, con
     const int b = blockIdx.x;
     int64_t p = pos[b];
     p = p < 0 ? p + T : p;  // python-style negative index, like torch advanced indexing
+    if (p < 0 || p >= T) __trap();   // torch raises an IndexError here; never read out of bounds
     const bf16 *src = x + ((size_t)b * T + (size_t)p) * D;
     bf16 *dst = out + (size_t)b * D;
     if ((D & 7) == 0) {

@@ -60,6 +60,26 @@ __device__ __forceinline__ uint32_t hmul2(uint32_t a, uint32_t b) {
     return d;
 }
 
+// ---- packed fp32 pairs (sm_100 FFMA2 / FMUL2 / FADD2: two fp32 operations per issue slot).  A pair lives in an
+// aligned 64-bit register; lo = the even element (e = 0), hi = the odd one.
+typedef unsigned long long f2;
+__device__ __forceinline__ f2 f2pack(float lo, float hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f2 f2packu(uint32_t lo, uint32_t hi) { f2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
+__device__ __forceinline__ void f2unpack(f2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ void f2unpacku(f2 v, uint32_t &lo, uint32_t &hi) { asm("mov.b64 {%0, %1}, %2;" : "=r"(lo), "=r"(hi) : "l"(v)); }
+__device__ __forceinline__ f2 f2bcast(float x) { return f2pack(x, x); }
+__device__ __forceinline__ f2 f2fma(f2 a, f2 b, f2 c) { f2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f2 f2mul(f2 a, f2 b) { f2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 f2add(f2 a, f2 b) { f2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f2 f2sub(f2 a, f2 b) { f2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+// packed bf16 pair -> packed fp32 pair (exact), and back (round to nearest even)
+__device__ __forceinline__ f2 bf2f2(uint32_t x) { return f2packu(x << 16, x & 0xffff0000u); }
+__device__ __forceinline__ uint32_t f2tobf(f2 v) {
+    float lo, hi;
+    f2unpack(v, lo, hi);
+    return pack2(lo, hi);
+}
+
 struct Frag {
     int warp, lane, sp, ch, ri, q;
     uint32_t ti_off;     // byte offset (within a [token][channel] tile) this lane supplies to ldmatrix/stmatrix .x4:

@@ -70,9 +70,9 @@ constexpr uint32_t SMEM_BYTES = OFF_TILES_END + sizeof(Extra);
 constexpr uint32_t TM_G = 0, TM_X0 = 64, TM_X1 = 128, TM_X2 = 192, TM_COLS = 256;
 // An M = 64 accumulator only occupies lanes 0-15 of each 32-lane TMEM sub-partition; lanes 16-31 of the
 // same columns are per-thread scratch ("parking"): 4 regions x 2 registers per token pair.
-//   PARK_A: (Rt, Kt_own) packed bf16 pairs   -> T2 replaces Rt by XA(e=0), T3 replaces both by its part of gl
+//   PARK_A: (Rt, E) packed bf16 pairs        -> T2 replaces them by XA (fp32, e = 0,1), T3 by its part of gl
 //   PARK_B: (r, k) raw packed bf16 pairs
-//   PARK_C: (E, F) packed bf16 pairs         -> T2 replaces E by XA(e=1)
+//   PARK_C: (Kt_own, F) packed bf16 pairs
 //   PARK_L: l (fp32, e = 0,1)
 constexpr uint32_t PARK_A = 0, PARK_B = 64, PARK_C = 128, PARK_L = 192;
 
@@ -89,7 +89,7 @@ struct Params {
     float lmin;               // floor of the per-token log2-decay (>= -LCLAMP2)
     bf16 *gu, *gs;
     const int *hz_flags;
-    long long *dbg;           // nullptr, or [gridDim][NC][8] clock64 stamps of warp 0 at the stage boundaries (profiling aid)
+    long long *dbg;           // nullptr, or [gridDim][NC][8 (32 in the profiling build)] clock64 stamps of warp 0 at the stage boundaries (profiling aid)
 };
 
 __device__ __forceinline__ uint32_t pack_frag(const uint32_t *v, int g, int hh) {
@@ -208,12 +208,14 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             bar_sync_all<B_PREP>();                              // operands written, raw r,k,w consumed
             if (elect_one()) {
                 tc_fence_after();
+#ifndef EXP_NO_AT
 #pragma unroll
                 for (int q = 0; q < 4; q++)   // A^T[s, t in q] = Kt_q Rt_own^T            (runs under T1a)
 #pragma unroll
                     for (int k = 0; k < 4; k++)
                         mma_bf16_ss(tmem + TM_X1 + 16 * q, smem_desc_sw128(kt + kt_ver(q) + 32 * k, 8192, 1024),
                                     smem_desc_sw128(rp + rp_ver(q) + 32 * k, 8192, 1024), ID16_KK, k > 0);
+#endif
                 mma_commit(&ex.bar_m1);
                 mbar_wait(&ex.bar_m1, par);
             }
@@ -306,7 +308,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         const uint32_t tPark = tmem_addr(tmem, 32 * sp + 16, 32 * ch);
         // x2 transposing stores of one 8-token group: lanes 0-7 address the rows of channel half 0, lanes 8-15 of half 1
         const uint32_t ti2_off = F.ti1_off ^ ((lane & 8) ? 16u : 0u);
-        float gu_acc[2] = {0.f, 0.f};
+        const int dcol = (32 * ch + 2 * q) - (16 * sp + ri);     // column(g, e = 0) - row(hh) at g = hh
+        f2 gu2[2] = {0ull, 0ull};
         int sig[2] = {0, 0};              // G in TMEM = G_true 2^(-sig) per key row: rho_0 of the chunk processed last
         uint32_t v[16];
 
@@ -330,7 +333,14 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         tc_fence_before();
         bar_arrive_all<B_T3>();
 
-#define STAMP(k) do { if (p.dbg && threadIdx.x == 0) p.dbg[((size_t)blockIdx.x * ck_stride + it) * 8 + (k)] = clock64(); } while (0)
+#ifdef WKV6_FINE_STAMPS      // profiling build (profiles/stage_times.py --fine): 32 stamps per chunk, extra points inside the stages
+#define STAMP_N 32
+#define STAMPX(k) STAMP(k)
+#else
+#define STAMP_N 8
+#define STAMPX(k) do { } while (0)
+#endif
+#define STAMP(k) do { if (p.dbg && threadIdx.x == 0) p.dbg[((size_t)blockIdx.x * ck_stride + it) * STAMP_N + (k)] = clock64(); } while (0)
         for (int it = 0; it < NC; it++) {
             const int c = NC - 1 - it;
             const int nv = min(L, T - c * L);
@@ -382,8 +392,11 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     }
                 tmem_st_frag(tPark + PARK_L, pk);
             }
+            STAMPX(8);
             named_bar_sync<B_SCAN, CTHREADS>();
+            STAMPX(9);
             bar_sync_all<B_FREE>();              // the output tiles of the previous chunk (KT, RP, DA space) have been stored
+            STAMPX(10);
 
             uint32_t rr[2][4], kk[2][4];
             ldsm_x4_t(sbase + OFF_R + F.ti(0), rr[0][0], rr[0][1], rr[0][2], rr[0][3]);
@@ -401,10 +414,11 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     }
                 tmem_st_frag(tPark + PARK_B, pk);
             }
-            uint32_t pa[16], pc[16];                // (Rt, Kt_own) and (E, F) in fragment order
-            float du[4][2];
+            STAMPX(24);
+            uint32_t pa[16], pc[16];                // (Rt, E) and (Kt_own, F) in fragment order
+            f2 du2[4];
 #pragma unroll
-            for (int g = 0; g < 4; g++) du[g][0] = du[g][1] = 0.f;
+            for (int g = 0; g < 4; g++) du2[g] = 0ull;
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
                 float run = 0.f, gb[4];
@@ -421,20 +435,20 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 ir0[hh] = ir[0];
                 ir3[hh] = ir[3];
                 uint32_t rto[4], kto[4];
+                const f2 uu = f2bcast(u_h[hh]);
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
-                    const float rq = (float)irb[hh][g >> 1];
-                    const float e0 = gb[g] + exq[hh][g], c0 = e0 + l[hh][g][0], c1 = c0 + l[hh][g][1];
-                    const float r0 = bf_lo(rr[hh][g]), r1 = bf_hi(rr[hh][g]), k0 = bf_lo(kk[hh][g]), k1 = bf_hi(kk[hh][g]);
-                    const float E0 = fast_ex2(e0 - rq), E1 = fast_ex2(c0 - rq), F0 = fast_ex2(rq - c0), F1 = fast_ex2(rq - c1);
-                    rto[g] = pack2(r0 * E0, r1 * E1);
-                    kto[g] = pack2(k0 * F0, k1 * F1);
+                    // a0 = exc_0 - rho, a1 = cum_0 - rho = exc_1 - rho, a2 = cum_1 - rho
+                    const float a0 = (gb[g] - (float)irb[hh][g >> 1]) + exq[hh][g], a1 = a0 + l[hh][g][0], a2 = a1 + l[hh][g][1];
+                    const f2 E2 = f2pack(fast_ex2(a0), fast_ex2(a1)), F2 = f2pack(fast_ex2(-a1), fast_ex2(-a2));
+                    const f2 r2 = bf2f2(rr[hh][g]), k2 = bf2f2(kk[hh][g]);
+                    rto[g] = f2tobf(f2mul(r2, E2));
+                    kto[g] = f2tobf(f2mul(k2, F2));
                     pa[4 * g + 2 * hh] = rto[g];
-                    pa[4 * g + 2 * hh + 1] = kto[g];
-                    pc[4 * g + 2 * hh] = pack2(E0, E1);
-                    pc[4 * g + 2 * hh + 1] = pack2(F0, F1);
-                    du[g][0] = fmaf(r0 * u_h[hh], k0, du[g][0]);
-                    du[g][1] = fmaf(r1 * u_h[hh], k1, du[g][1]);
+                    pa[4 * g + 2 * hh + 1] = f2tobf(E2);
+                    pc[4 * g + 2 * hh] = kto[g];
+                    pc[4 * g + 2 * hh + 1] = f2tobf(F2);
+                    du2[g] = f2fma(f2mul(r2, uu), k2, du2[g]);
                 }
                 // versions: my rows in their own reference, then scaled (exactly, by powers of two <= 1) to the
                 // reference of every later block (Kt) / earlier block (Rp)
@@ -463,10 +477,14 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     stsm_x4_t(sbase + OFF_RP + rp_ver(0) + ti, rto[0], rto[1], rto[2], rto[3]);
                 }
             }
+            STAMPX(11);
             tmem_st_frag(tPark + PARK_A, pa);
             tmem_st_frag(tPark + PARK_C, pc);
             {   // diag(u) term: reduce-scatter over the 8 lanes ri, then one partial per channel quarter
                 const bool b2 = lane & 16, b1 = lane & 8, b0 = lane & 4;
+                float du[4][2];
+#pragma unroll
+                for (int g = 0; g < 4; g++) f2unpack(du2[g], du[g][0], du[g][1]);
                 float a4[2][2], a2[2], a1;
 #pragma unroll
                 for (int gg = 0; gg < 2; gg++)
@@ -486,8 +504,10 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 }
                 ex.pdu[sp][32 * ch + 8 * ((b2 ? 2 : 0) + (b1 ? 1 : 0)) + 2 * q + (b0 ? 1 : 0)] = a1;
             }
+            STAMPX(12);
             tmem_wait_st();
             }
+            STAMPX(13);
             fence_proxy_async();
             STAMP(1);
             bar_arrive_all<B_PREP>();
@@ -496,83 +516,83 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             bar_sync_all<B_BM>();                        // Bm and Drs were issued before the preparation started
             tc_fence_after();
             STAMP(2);
-            // ---- Bm[t rows][s cols] -> dA[t][s] = Bm for s < t; bd[t] = Bm[t,t]
+            // ---- Bm[t rows][s cols] -> dA[t][s] = Bm for s < t; bd[t] = Bm[t,t]   (G is fetched along with it)
+            uint32_t vg[16];
             tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch), v);
+            tmem_ld_frag(tG, vg);
             tmem_wait_ld();
+            STAMPX(14);
+            // branch-free: dcol = (column of e = 0) - row for g = hh; 8 more per group
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
-                const int rb8 = 2 * sp + hh;
                 uint32_t pk[4];
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
-                    const int cb8 = 4 * ch + g;
+                    const int d = dcol + 8 * (g - hh);                    // (s - t) for e = 0
                     const float a0 = __uint_as_float(v[4 * g + 2 * hh]), a1 = __uint_as_float(v[4 * g + 2 * hh + 1]);
-                    if (cb8 < rb8) pk[g] = pack2(a0, a1);
-                    else if (cb8 > rb8) pk[g] = 0u;
-                    else {
-                        const int d = 2 * q - ri;                         // (s - t) for e = 0
-                        pk[g] = pack2(d < 0 ? a0 : 0.f, d + 1 < 0 ? a1 : 0.f);
-                        if (d == 0) ex.bd[F.row(hh)] = a0;
-                        if (d + 1 == 0) ex.bd[F.row(hh)] = a1;
-                    }
+                    pk[g] = pack2(d < 0 ? a0 : 0.f, d < -1 ? a1 : 0.f);
+#ifndef EXP_NO_BD
+                    if (d == 0) ex.bd[F.row(hh)] = a0;
+                    if (d == -1) ex.bd[F.row(hh)] = a1;
+#endif
                 }
                 stsm_x4(sbase + OFF_DA + F.rc(hh), pk[0], pk[1], pk[2], pk[3]);
             }
+            STAMPX(25);
             fence_proxy_async();
+            STAMPX(26);
             tc_fence_before();
-            bar_arrive_all<B_T1A>();                     // Dr (into the Bm columns) can start while P^T and G are handled
-            bar_sync_all<B_M1>();                        // A^T ran under the conversion above
-            tc_fence_after();
-            // ---- A^T[s rows][t cols] -> P^T[s][t] = A^T for t > s, diag = sum_i r u k
-            tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X1 + 32 * ch), v);
-            tmem_wait_ld();
-#pragma unroll
-            for (int hh = 0; hh < 2; hh++) {
-                const int rb8 = 2 * sp + hh;
-                uint32_t pk[4];
-#pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    const int cb8 = 4 * ch + g;
-                    const float a0 = __uint_as_float(v[4 * g + 2 * hh]), a1 = __uint_as_float(v[4 * g + 2 * hh + 1]);
-                    if (cb8 > rb8) pk[g] = pack2(a0, a1);
-                    else if (cb8 < rb8) pk[g] = 0u;
-                    else {
-                        const int s = F.row(hh);
-                        const float dg = ex.pdu[0][s] + ex.pdu[1][s] + ex.pdu[2][s] + ex.pdu[3][s];
-                        const int d = 2 * q - ri;                         // (t - s) for e = 0
-                        pk[g] = pack2(d > 0 ? a0 : (d == 0 ? dg : 0.f), d + 1 > 0 ? a1 : (d + 1 == 0 ? dg : 0.f));
-                    }
-                }
-                stsm_x4(sbase + OFF_PT + F.rc(hh), pk[0], pk[1], pk[2], pk[3]);
-            }
+            STAMPX(15);
+            bar_arrive_all<B_T1A>();                     // Dr (into the Bm columns) can start while G and P^T are handled
             // ---- G rows (key channel i): G_old = G' 2^sig;  q0_i = <S_in, G_old>_i (partial over my half of j);
             //      Gb = bf16(G_old 2^(Lam - rho_3)) (operand of gv and Dks);  G' <- G_old 2^(Lam - rho_0)
             //      (factors applied one after the other: their product may leave the fp32 range although the result does not)
-            tmem_ld_frag(tG, v);
-            tmem_wait_ld();
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
-                const float es = pow2i(sig[hh]);
-                const float f3 = fast_ex2(lamf[hh] - (float)ir3[hh]), f0 = fast_ex2(lamf[hh] - (float)ir0[hh]);
+                const f2 es = f2bcast(pow2i(sig[hh]));
+                const f2 f3 = f2bcast(fast_ex2(lamf[hh] - (float)ir3[hh])), f0 = f2bcast(fast_ex2(lamf[hh] - (float)ir0[hh]));
                 uint32_t s4[4], gbp[4];
                 ldsm_x4(sbase + OFF_SIN + F.rc(hh), s4[0], s4[1], s4[2], s4[3]);
-                float qs = 0.f;
+                f2 qs2 = 0ull;
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
-                    const float g0 = __uint_as_float(v[4 * g + 2 * hh]) * es, g1 = __uint_as_float(v[4 * g + 2 * hh + 1]) * es;
-                    qs = fmaf(bf_lo(s4[g]), g0, qs);
-                    qs = fmaf(bf_hi(s4[g]), g1, qs);
-                    gbp[g] = pack2(g0 * f3, g1 * f3);
-                    v[4 * g + 2 * hh] = __float_as_uint(g0 * f0);
-                    v[4 * g + 2 * hh + 1] = __float_as_uint(g1 * f0);
+                    const f2 gold = f2mul(f2packu(vg[4 * g + 2 * hh], vg[4 * g + 2 * hh + 1]), es);
+                    qs2 = f2fma(bf2f2(s4[g]), gold, qs2);
+                    gbp[g] = f2tobf(f2mul(gold, f3));
+                    f2unpacku(f2mul(gold, f0), vg[4 * g + 2 * hh], vg[4 * g + 2 * hh + 1]);
                 }
                 stsm_x4(sbase + OFF_GB + F.rc(hh), gbp[0], gbp[1], gbp[2], gbp[3]);
+                float qa, qb;
+                f2unpack(qs2, qa, qb);
+                float qs = qa + qb;
                 qs += __shfl_xor_sync(0xffffffffu, qs, 1);
                 qs += __shfl_xor_sync(0xffffffffu, qs, 2);
                 if (q == 0) ex.q0p[ch][F.row(hh)] = qs;
                 sig[hh] = ir0[hh];
             }
-            tmem_st_frag(tG, v);
+            tmem_st_frag(tG, vg);
+            STAMPX(16);
+            bar_sync_all<B_M1>();                        // A^T ran under the conversions above
+            tc_fence_after();
+            STAMPX(17);
+            // ---- A^T[s rows][t cols] -> P^T[s][t] = A^T for t > s, diag = sum_i r u k
+            tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X1 + 32 * ch), v);
+            tmem_wait_ld();
+            STAMPX(18);
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                const int sr = F.row(hh);
+                const float dg = (ex.pdu[0][sr] + ex.pdu[1][sr]) + (ex.pdu[2][sr] + ex.pdu[3][sr]);
+                uint32_t pk[4];
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const int d = dcol + 8 * (g - hh);                    // (t - s) for e = 0
+                    const float a0 = __uint_as_float(v[4 * g + 2 * hh]), a1 = __uint_as_float(v[4 * g + 2 * hh + 1]);
+                    pk[g] = pack2(d > 0 ? a0 : (d == 0 ? dg : 0.f), d > -1 ? a1 : (d == -1 ? dg : 0.f));
+                }
+                stsm_x4(sbase + OFF_PT + F.rc(hh), pk[0], pk[1], pk[2], pk[3]);
+            }
+            STAMPX(19);
             tmem_wait_st();
             fence_proxy_async();
             tc_fence_before();
@@ -583,32 +603,27 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             bar_sync_all<B_DR>();                        // Dr ran under T1b; gv is not needed yet
             tc_fence_after();
             STAMP(4);
-            // per 8-token group: Dr, Drs -> gr (tile) and XA, which replaces Rt / E in the shadow lanes until T3
+            // per 8-token group: Dr, Drs -> gr (tile) and XA, which replaces (Rt, E) in the shadow lanes until T3
 #pragma unroll
             for (int g = 0; g < 4; g++) {
-                uint32_t d4[4], s4[4], a4[4], b4[4], c4[4];
+                uint32_t d4[4], s4[4], a4[4], b4[4];
                 tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch + 8 * g), d4);
                 tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 8 * g), s4);
                 tmem_ld_frag1(tPark + PARK_A + 8 * g, a4);
                 tmem_ld_frag1(tPark + PARK_B + 8 * g, b4);
-                tmem_ld_frag1(tPark + PARK_C + 8 * g, c4);
                 tmem_wait_ld();
-                const float2 bd2 = *reinterpret_cast<const float2 *>(&ex.bd[F.col(g, 0)]);
+                const f2 bd2 = *reinterpret_cast<const f2 *>(&ex.bd[F.col(g, 0)]);
                 uint32_t grp[2];
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++) {
-                    const float erho = pow2i(irb[hh][g >> 1]);     // 2^rho of this block (0 when out of range)
-                    const float z0 = fmaf(erho, __uint_as_float(s4[2 * hh]), __uint_as_float(d4[2 * hh]));
-                    const float z1 = fmaf(erho, __uint_as_float(s4[2 * hh + 1]), __uint_as_float(d4[2 * hh + 1]));
-                    const uint32_t rtp = a4[2 * hh], epk = c4[2 * hh], kkp = b4[2 * hh + 1];
-                    a4[2 * hh] = __float_as_uint(bf_lo(rtp) * z0);           // XA = Rt Z, with Rt exactly as the MMAs saw it
-                    c4[2 * hh] = __float_as_uint(bf_hi(rtp) * z1);
-                    const float ub0 = u_h[hh] * bd2.x, ub1 = u_h[hh] * bd2.y;
-                    grp[hh] = pack2(fmaf(bf_lo(epk), z0, ub0 * bf_lo(kkp)), fmaf(bf_hi(epk), z1, ub1 * bf_hi(kkp)));
+                    const f2 erho = f2bcast(pow2i(irb[hh][g >> 1]));                       // 2^rho of this block (0 when out of range)
+                    const f2 z = f2fma(erho, f2packu(s4[2 * hh], s4[2 * hh + 1]), f2packu(d4[2 * hh], d4[2 * hh + 1]));
+                    const f2 ubk = f2mul(f2mul(bd2, f2bcast(u_h[hh])), bf2f2(b4[2 * hh + 1]));
+                    grp[hh] = f2tobf(f2fma(bf2f2(a4[2 * hh + 1]), z, ubk));                // E Z + u bd k
+                    f2unpacku(f2mul(bf2f2(a4[2 * hh]), z), a4[2 * hh], a4[2 * hh + 1]);    // XA = Rt Z, Rt exactly as the MMAs saw it
                 }
                 stsm_x2_t(sbase + OFF_GRT + ti2_off + 1024u * g, grp[0], grp[1]);
                 tmem_st_frag1(tPark + PARK_A + 8 * g, a4);
-                tmem_st_frag1(tPark + PARK_C + 8 * g, c4);
             }
             tmem_wait_st();
             fence_proxy_async();
@@ -633,7 +648,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             // per 8-token group: Dk, Dks, XA -> gk (tile), running scans; the part of gl that does not need the
             // other token half replaces (XA, Kt_own) in the shadow lanes.
             // With X = XA - Kt_own Dk and D = Kt_own Zk - XA:  gl_t = 2^Lam q0 + sum_all X + sum_{s<t} D_s - XA_t,
-            // so one exclusive prefix scan of D plus the totals of X are enough.
+            // so one exclusive prefix scan of D plus the totals of X are enough (the scan runs on -D).
             float runD[2] = {0.f, 0.f}, runX[2] = {0.f, 0.f};
 #pragma unroll
             for (int g = 0; g < 4; g++) {
@@ -644,39 +659,42 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 tmem_ld_frag1(tPark + PARK_B + 8 * g, b4);
                 tmem_ld_frag1(tPark + PARK_C + 8 * g, c4);
                 tmem_wait_ld();
-                const float2 bd2 = *reinterpret_cast<const float2 *>(&ex.bd[F.col(g, 0)]);
+                const f2 bd2 = *reinterpret_cast<const f2 *>(&ex.bd[F.col(g, 0)]);
                 uint32_t gkp[2];
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++) {
-                    const float elr = pow2i(ir3[hh] - irb[hh][g >> 1]);   // 2^(rho_3 - rho_p)
-                    const float dk0 = __uint_as_float(d4[2 * hh]), dk1 = __uint_as_float(d4[2 * hh + 1]);
-                    const float z0 = fmaf(elr, __uint_as_float(s4[2 * hh]), dk0), z1 = fmaf(elr, __uint_as_float(s4[2 * hh + 1]), dk1);
-                    const uint32_t ktp = a4[2 * hh + 1], fpk = c4[2 * hh + 1], rrp = b4[2 * hh], kkp = b4[2 * hh + 1];
-                    const float xa0 = __uint_as_float(a4[2 * hh]), xa1 = __uint_as_float(c4[2 * hh]);
-                    const float kt0 = bf_lo(ktp), kt1 = bf_hi(ktp);          // Kt_own exactly as the MMAs saw it
-                    const float x0 = fmaf(-kt0, dk0, xa0), x1 = fmaf(-kt1, dk1, xa1);             // X = XA - Bi
-                    const float d0 = fmaf(kt0, z0, -xa0), d1 = fmaf(kt1, z1, -xa1);               // D = Be + Bi - XA
-                    const float br0 = bd2.x * bf_lo(rrp), br1 = bd2.y * bf_hi(rrp);
-                    gkp[hh] = pack2(fmaf(bf_lo(fpk), z0, u_h[hh] * br0), fmaf(bf_hi(fpk), z1, u_h[hh] * br1));
-                    gu_acc[hh] = fmaf(br0, bf_lo(kkp), fmaf(br1, bf_hi(kkp), gu_acc[hh]));
-                    // exclusive prefix of D over the 4 lanes of the group; total of X
-                    const float pd = d0 + d1;
-                    float y = pd, z = x0 + x1, tmp;
+                    const f2 elr = f2bcast(pow2i(ir3[hh] - irb[hh][g >> 1]));              // 2^(rho_3 - rho_p)
+                    const f2 dk = f2packu(d4[2 * hh], d4[2 * hh + 1]), xa = f2packu(a4[2 * hh], a4[2 * hh + 1]);
+                    const f2 z = f2fma(elr, f2packu(s4[2 * hh], s4[2 * hh + 1]), dk);
+                    const f2 nkt = bf2f2(c4[2 * hh] ^ 0x80008000u);          // -Kt_own, exactly as the MMAs saw it
+                    const f2 x2 = f2fma(nkt, dk, xa);                          // X = XA - Bi
+                    const f2 nd2 = f2fma(nkt, z, xa);                          // -D = XA - Kt_own Zk
+                    const f2 br = f2mul(bd2, bf2f2(b4[2 * hh]));
+                    gkp[hh] = f2tobf(f2fma(bf2f2(c4[2 * hh + 1]), z, f2mul(br, f2bcast(u_h[hh]))));   // F Zk + u bd r
+                    gu2[hh] = f2fma(br, bf2f2(b4[2 * hh + 1]), gu2[hh]);
+                    float x0, x1, nd0, nd1, xa0, xa1;
+                    f2unpack(x2, x0, x1);
+                    f2unpack(nd2, nd0, nd1);
+                    f2unpack(xa, xa0, xa1);
+                    // exclusive prefix of -D over the 4 lanes of the group; total of X
+                    const float pd = nd0 + nd1;
+                    float y = pd, z1 = x0 + x1, tmp;
                     tmp = __shfl_up_sync(0xffffffffu, y, 1, 4);
                     if (q >= 1) y += tmp;
-                    z += __shfl_xor_sync(0xffffffffu, z, 1);
+                    z1 += __shfl_xor_sync(0xffffffffu, z1, 1);
                     tmp = __shfl_up_sync(0xffffffffu, y, 2, 4);
                     if (q >= 2) y += tmp;
-                    z += __shfl_xor_sync(0xffffffffu, z, 2);
-                    const float ex0 = runD[hh] + (y - pd);
-                    a4[2 * hh] = __float_as_uint(ex0 - xa0);
-                    a4[2 * hh + 1] = __float_as_uint(ex0 + d0 - xa1);
+                    z1 += __shfl_xor_sync(0xffffffffu, z1, 2);
+                    const float ex0 = runD[hh] + (y - pd);                     // sum_{s<t} (-D_s) for e = 0
+                    a4[2 * hh] = __float_as_uint(ex0 + xa0);                   // gl_t = base - (this)
+                    a4[2 * hh + 1] = __float_as_uint(ex0 + nd0 + xa1);
                     runD[hh] += __shfl_sync(0xffffffffu, y, 3, 4);
-                    runX[hh] += z;
+                    runX[hh] += z1;
                 }
                 stsm_x2_t(sbase + OFF_GKT + ti2_off + 1024u * g, gkp[0], gkp[1]);
                 tmem_st_frag1(tPark + PARK_A + 8 * g, a4);
             }
+            STAMPX(20);
             if (q == 0) {
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++) {
@@ -699,21 +717,26 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 }
             }
             tmem_wait_st();
+            STAMPX(21);
             named_bar_sync<B_SCAN, CTHREADS>();          // token-half totals of both scans are in shared memory
+            STAMPX(22);
             uint32_t lp[16];
             tmem_ld_frag(tPark + PARK_A, v);
             tmem_ld_frag(tPark + PARK_L, lp);
             tmem_wait_ld();
+            STAMPX(23);
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
                 const int i = F.row(hh);
-                // 2^Lam <S_in,G> + total X of both halves + D of the earlier half
-                const float base = (ex.q0p[0][i] + ex.q0p[1][i]) * fast_ex2(lamf[hh]) + runX[hh] + (ch ? ex.htY[0][i] + ex.htX[0][i] : ex.htX[1][i]);
+                // 2^Lam <S_in,G> + total X of both halves + D of the earlier half (runD / htY hold sums of -D)
+                const float base = (ex.q0p[0][i] + ex.q0p[1][i]) * fast_ex2(lamf[hh]) + runX[hh] + (ch ? ex.htX[0][i] - ex.htY[0][i] : ex.htX[1][i]);
+                const f2 base2 = f2bcast(base), ln2 = f2bcast(LN2);
                 uint32_t gwp[4];
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
-                    float gw0 = __uint_as_float(lp[4 * g + 2 * hh]) * LN2 * (base + __uint_as_float(v[4 * g + 2 * hh]));
-                    float gw1 = __uint_as_float(lp[4 * g + 2 * hh + 1]) * LN2 * (base + __uint_as_float(v[4 * g + 2 * hh + 1]));
+                    const f2 gl = f2sub(base2, f2packu(v[4 * g + 2 * hh], v[4 * g + 2 * hh + 1]));
+                    float gw0, gw1;
+                    f2unpack(f2mul(f2mul(f2packu(lp[4 * g + 2 * hh], lp[4 * g + 2 * hh + 1]), ln2), gl), gw0, gw1);
                     if (c == 0 && !first_has_s0 && ch == 0 && g == 0 && q == 0) gw0 = 0.f;   // t = 0 with S_0 = 0
                     if (c == NC - 1 && g_is_zero) {      // the last decay feeds no output: exactly 0 like cuda/wkv6_cuda.cu:226
                         if (F.col(g, 0) == nv - 1) gw0 = 0.f;
@@ -731,7 +754,9 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         // gu[b, i] = sum_t r k bd: reduce over the 4 lanes q and the two token halves
 #pragma unroll
         for (int hh = 0; hh < 2; hh++) {
-            float x = gu_acc[hh];
+            float xa_, xb_;
+            f2unpack(gu2[hh], xa_, xb_);
+            float x = xa_ + xb_;
             x += __shfl_xor_sync(0xffffffffu, x, 1);
             x += __shfl_xor_sync(0xffffffffu, x, 2);
             if (q == 0) atomicAdd(&ex.gu_s[F.row(hh)], x);

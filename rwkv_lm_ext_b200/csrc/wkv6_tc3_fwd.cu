@@ -236,6 +236,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         const int sp = F.sp, ch = F.ch, q = F.q;
         const float u_h[2] = {__bfloat162float(p.u[h * 64 + F.row(0)]), __bfloat162float(p.u[h * 64 + F.row(1)])};
         const uint32_t tS = tmem_addr(tmem, 32 * sp, TM_S + 32 * ch);
+        const int dcol = (32 * ch + 2 * q) - (16 * sp + F.ri);     // column(g, e = 0) - row(hh) at g = hh
         uint32_t v[16];
 
         // ---- initial state -> TMEM (fp32 master, [i][j]) and shared (bf16 operand copy)
@@ -309,9 +310,9 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             }
             ldsm_x4_t(sbase + OFF_K + F.ti(0), kk[0][0], kk[0][1], kk[0][2], kk[0][3]);
             ldsm_x4_t(sbase + OFF_K + F.ti(1), kk[1][0], kk[1][1], kk[1][2], kk[1][3]);
-            float du[4][2];
+            f2 du2[4];
 #pragma unroll
-            for (int g = 0; g < 4; g++) du[g][0] = du[g][1] = 0.f;
+            for (int g = 0; g < 4; g++) du2[g] = 0ull;
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
                 // prefix over the 8 groups of this channel: start of my groups, the four block references, total
@@ -328,24 +329,25 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 // my tokens: groups g = 0,1 are block 2ch, g = 2,3 block 2ch + 1
                 const int irb[2] = {ch ? ir[2] : ir[0], ch ? ir[3] : ir[1]};
                 uint32_t rto[4], kto[4];
+                const f2 uu = f2bcast(u_h[hh]);
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
                     const float rq = (float)irb[g >> 1];
-                    const float el = fast_ex2(lam - rq);
-                    const float e0 = gb[g] + exq[hh][g], c0 = e0 + l[hh][g][0], c1 = c0 + l[hh][g][1];
-                    const float r0 = bf_lo(rr[hh][g]), r1 = bf_hi(rr[hh][g]), k0 = bf_lo(kk[hh][g]), k1 = bf_hi(kk[hh][g]);
-                    const float kf0 = k0 * fast_ex2(rq - c0), kf1 = k1 * fast_ex2(rq - c1);
+                    const f2 el = f2bcast(fast_ex2(lam - rq));
+                    // a0 = exc_0 - rho, a1 = cum_0 - rho = exc_1 - rho, a2 = cum_1 - rho
+                    const float a0 = (gb[g] - rq) + exq[hh][g], a1 = a0 + l[hh][g][0], a2 = a1 + l[hh][g][1];
+                    const f2 k2 = bf2f2(kk[hh][g]);
+                    const f2 kf = f2mul(k2, f2pack(fast_ex2(-a1), fast_ex2(-a2)));
                     if constexpr (!SO) {
-                        const float rt0 = r0 * fast_ex2(e0 - rq), rt1 = r1 * fast_ex2(c0 - rq);
-                        rto[g] = pack2(rt0, rt1);
-                        kto[g] = pack2(kf0, kf1);
+                        const f2 r2 = bf2f2(rr[hh][g]);
+                        rto[g] = f2tobf(f2mul(r2, f2pack(fast_ex2(a0), fast_ex2(a1))));
+                        kto[g] = f2tobf(kf);
                         rhp[hh][g] = hmul2(rto[g], bfpow2pair(irb[g >> 1]));   // Rh = Rt * 2^rho (exact)
-                        du[g][0] = fmaf(r0 * u_h[hh], k0, du[g][0]);
-                        du[g][1] = fmaf(r1 * u_h[hh], k1, du[g][1]);
+                        du2[g] = f2fma(f2mul(r2, uu), k2, du2[g]);
                     }
-                    const float kh0 = kf0 * el, kh1 = kf1 * el;           // Kh = k * 2^(Lam - cum)
-                    khp[hh][g] = pack2(kh0, kh1);
-                    klp[hh][g] = pack2(kh0 - bf_lo(khp[hh][g]), kh1 - bf_hi(khp[hh][g]));
+                    const f2 kh = f2mul(kf, el);                          // Kh = k * 2^(Lam - cum)
+                    khp[hh][g] = f2tobf(kh);
+                    klp[hh][g] = f2tobf(f2sub(kh, bf2f2(khp[hh][g])));
                 }
                 const uint32_t ti = F.ti(hh);
                 if constexpr (!SO) {
@@ -371,6 +373,9 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             // ---- diag(u) term: sum over channels of r u k per token; reduce-scatter over the 8 lanes ri
             if constexpr (!SO) {
                 const bool b2 = lane & 16, b1 = lane & 8, b0 = lane & 4;
+                float du[4][2];
+#pragma unroll
+                for (int g = 0; g < 4; g++) f2unpack(du2[g], du[g][0], du[g][1]);
                 float a4[2][2], a2[2], a1;
 #pragma unroll
                 for (int gg = 0; gg < 2; gg++)
@@ -418,23 +423,17 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             if (!SO && p.has_y) {
             tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_A + 32 * ch), v);
             tmem_wait_ld();
+            // branch-free: dcol = (t of e = 0) - s at g = hh; 8 more per column group
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
-                // 8x8 blocks: rows s in block 2sp+hh, columns t in block 4ch+g; only the diagonal block is mixed
-                const int sb8 = 2 * sp + hh;
+                const int sr = F.row(hh);
+                const float dg = (ex.pdu[0][sr] + ex.pdu[1][sr]) + (ex.pdu[2][sr] + ex.pdu[3][sr]);
                 uint32_t pk[4];
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
-                    const int tb8 = 4 * ch + g;
+                    const int d = dcol + 8 * (g - hh);                    // (t - s) for e = 0
                     const float a0 = __uint_as_float(v[4 * g + 2 * hh]), a1 = __uint_as_float(v[4 * g + 2 * hh + 1]);
-                    if (tb8 > sb8) pk[g] = pack2(a0, a1);
-                    else if (tb8 < sb8) pk[g] = 0u;
-                    else {
-                        const int s = F.row(hh);
-                        const float dg = ex.pdu[0][s] + ex.pdu[1][s] + ex.pdu[2][s] + ex.pdu[3][s];
-                        const int d = 2 * q - F.ri;                       // (t - s) for e = 0
-                        pk[g] = pack2(d > 0 ? a0 : (d == 0 ? dg : 0.f), d + 1 > 0 ? a1 : (d + 1 == 0 ? dg : 0.f));
-                    }
+                    pk[g] = pack2(d > 0 ? a0 : (d == 0 ? dg : 0.f), d > -1 ? a1 : (d == -1 ? dg : 0.f));
                 }
                 stsm_x4_t(sbase + OFF_P + F.ti(hh), pk[0], pk[1], pk[2], pk[3]);       // P[t][s]
             }
@@ -442,12 +441,12 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             tmem_ld_frag(tS, v);
             tmem_wait_ld();
 #pragma unroll
-            for (int g = 0; g < 4; g++)
+            for (int hh = 0; hh < 2; hh++) {
+                const f2 el2 = f2bcast(elam[hh]);
 #pragma unroll
-                for (int hh = 0; hh < 2; hh++)
-#pragma unroll
-                    for (int e = 0; e < 2; e++)
-                        v[4 * g + 2 * hh + e] = __float_as_uint(__uint_as_float(v[4 * g + 2 * hh + e]) * elam[hh]);
+                for (int g = 0; g < 4; g++)
+                    f2unpacku(f2mul(f2packu(v[4 * g + 2 * hh], v[4 * g + 2 * hh + 1]), el2), v[4 * g + 2 * hh], v[4 * g + 2 * hh + 1]);
+            }
             tmem_st_frag(tS, v);
             tmem_wait_st();
             fence_proxy_async();

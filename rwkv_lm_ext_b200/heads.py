@@ -14,6 +14,14 @@ def _cuda(t):
         raise _lib.Wkv6B200Error("rwkv_lm_ext_b200 kernels run on CUDA tensors only (no CPU fallback)")
 
 
+def _bf16_param(t):
+    """Parameters reach the kernels as bf16.  A model kept in fp32 ('bf16-mixed', ln_x in fp32, ...) is cast here --
+    differentiably, so the gradient returns in the parameter's own dtype -- instead of being reinterpreted."""
+    if t is None:
+        return None
+    return (t if t.dtype == torch.bfloat16 else t.to(torch.bfloat16)).contiguous()
+
+
 def eos_index(idx: torch.Tensor, token_id: int) -> torch.Tensor:
     """== torch.eq(idx, token_id).int().argmax(-1): first occurrence, 0 if absent.  int64 [B]."""
     _cuda(idx)
@@ -61,8 +69,10 @@ def gather_rows(x: torch.Tensor, pos: torch.Tensor) -> torch.Tensor:
     """== x[torch.arange(B), pos]  for x bf16 [B,T,D]  (differentiable w.r.t. x)."""
     _cuda(x)
     assert x.dtype == torch.bfloat16 and x.dim() == 3 and pos.dtype == torch.int64
+    assert pos.numel() == x.shape[0], "one position per batch row"
     x, pos = x.contiguous(), pos.contiguous()
     if _needs_grad(x):
+        assert x.shape[-1] % 8 == 0, "gather_rows under autograd needs D % 8 == 0 (scatter_rows_bf16)"
         return _GatherRows.apply(x, pos)
     return _gather_rows_fwd(x, pos)
 
@@ -202,7 +212,9 @@ def tmix_shift_lerp(x, maa_x, shift_state=None):
     assert x.dtype == torch.bfloat16
     x = x.contiguous()
     shift_state = shift_state.contiguous() if shift_state is not None else None
-    flat = maa_x.contiguous().view(-1)
+    flat = _bf16_param(maa_x).view(-1)
+    assert flat.numel() == x.shape[-1]
+    shift_state = _bf16_param(shift_state)
     if _needs_grad(x, maa_x, shift_state):
         return _ShiftLerp.apply(x, shift_state, flat)
     return _shift_lerp_fwd(x, shift_state, flat)
@@ -248,8 +260,9 @@ def tmix_ddlerp_mix(x, maa_wkvrg, m, shift_state=None):
     it either way.  Differentiable w.r.t. x, maa_wkvrg, m and the shift state."""
     _cuda(x)
     assert x.dtype == torch.bfloat16 and m.dtype == torch.bfloat16
-    x, m, maa = x.contiguous(), m.contiguous(), maa_wkvrg.contiguous()
-    shift_state = shift_state.contiguous() if shift_state is not None else None
+    x, m, maa = x.contiguous(), m.contiguous(), _bf16_param(maa_wkvrg)
+    assert tuple(maa.shape) == (5, x.shape[-1]) and tuple(m.shape) == (5,) + tuple(x.shape)
+    shift_state = _bf16_param(shift_state)
     if _needs_grad(x, maa, m, shift_state):
         return _DdlerpMix.apply(x, shift_state, maa, m)
     return _ddlerp_fwd(x, shift_state, maa, m)
@@ -300,12 +313,13 @@ def tmix_ddlerp_lora(x, maa_wkvrg, h, w2, shift_state=None):
     w2 bf16 [5,R,C].  R = 32 and C % 64 == 0; other shapes take the bmm + tmix_ddlerp_mix route.
     Returns five [B,T,C] tensors (a tuple under autograd, a [5,B,T,C] tensor otherwise)."""
     _cuda(x)
-    assert x.dtype == torch.bfloat16 and h.dtype == torch.bfloat16 and w2.dtype == torch.bfloat16
+    assert x.dtype == torch.bfloat16 and h.dtype == torch.bfloat16
     B, T, C = x.shape
     R = w2.shape[1]
-    x, maa, w2 = x.contiguous(), maa_wkvrg.contiguous(), w2.contiguous()
+    x, maa, w2 = x.contiguous(), _bf16_param(maa_wkvrg), _bf16_param(w2)
+    assert tuple(maa.shape) == (5, C) and tuple(w2.shape) == (5, R, C)
     h = h.contiguous().view(B * T, 5 * R)
-    shift_state = shift_state.contiguous() if shift_state is not None else None
+    shift_state = _bf16_param(shift_state)
     if R != 32 or C % 64 != 0:
         m = torch.bmm(h.view(B * T, 5, R).transpose(0, 1), w2).view(5, B, T, C)
         return tmix_ddlerp_mix(x, maa, m, shift_state)
@@ -355,7 +369,8 @@ def groupnorm_gate(y, g, ln_w, ln_b, H, eps, gate_act=None):
     inside the kernel.  Differentiable w.r.t. y, g and the GroupNorm affine parameters."""
     _cuda(y)
     assert y.dtype == torch.bfloat16 and g.dtype == torch.bfloat16
-    y, g, ln_w, ln_b = y.contiguous(), g.contiguous(), ln_w.contiguous(), ln_b.contiguous()
+    y, g, ln_w, ln_b = y.contiguous(), g.contiguous(), _bf16_param(ln_w), _bf16_param(ln_b)
+    assert ln_w.numel() == y.shape[-1] and ln_b.numel() == y.shape[-1] and y.shape[-1] == H * 64
     act = _GATE_ACT[gate_act]
     if _needs_grad(y, g, ln_w, ln_b):
         return _GroupNormGate.apply(y, g, ln_w, ln_b, H, eps, act)
@@ -374,6 +389,6 @@ def groupnorm_gate_pair(y, y_rev, rev_idx, g, ln_w, ln_b, H, eps, gate_act=None)
     B, T, C = y.shape
     out = torch.empty_like(y)
     check(_lib.load().groupnorm_gate_pair_bf16(B, T, C, H, float(eps), _GATE_ACT[gate_act], ptr(y), ptr(y_rev), ptr(rev_idx), ptr(g),
-                                               ptr(ln_w.contiguous()), ptr(ln_b.contiguous()), ptr(out), stream_of(y)),
+                                               ptr(_bf16_param(ln_w)), ptr(_bf16_param(ln_b)), ptr(out), stream_of(y)),
           "groupnorm_gate_pair_bf16")
     return out

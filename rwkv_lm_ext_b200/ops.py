@@ -224,6 +224,7 @@ class RWKV_6(torch.autograd.Function):
             assert HEAD_SIZE == C // H
             ctx.B, ctx.T, ctx.C, ctx.H = B, T, C, H
             assert state.dtype == torch.float32
+            assert state.numel() == B * H * HEAD_SIZE * HEAD_SIZE, "state must be [B,H,64,64] ([H,64,64] when B == 1)"
             assert r.is_contiguous() and k.is_contiguous() and v.is_contiguous()
             assert w.is_contiguous() and u.is_contiguous() and state.is_contiguous()
             _require_cuda(r)

@@ -36,16 +36,17 @@ def tmix_x060_project(layer, x, shift_state=None):
     """jit_func (src/model.py:434-459 / :738-762): x [B,T,C] bf16 -> r, k, v, g_raw, w (each [B,T,C]);
     g_raw is the gate Linear's output BEFORE silu (tmix_x060_finish applies it in-kernel)."""
     B, T, C = x.shape
+    bf = heads._bf16_param          # fp32 parameters (mixed-precision modules) are cast, never reinterpreted
     xxx = heads.tmix_shift_lerp(x, layer.time_maa_x, shift_state)
-    h = torch.tanh(xxx.view(B * T, C) @ layer.time_maa_w1)                  # [B*T, 5R]
+    h = torch.tanh(xxx.view(B * T, C) @ bf(layer.time_maa_w1))               # [B*T, 5R]
     xw, xk, xv, xr, xg = heads.tmix_ddlerp_lora(x, _maa5(layer), h, layer.time_maa_w2, shift_state)
     r = layer.receptance(xr)
     k = layer.key(xk)
     v = layer.value(xv)
     g = layer.gate(xg)                      # raw: silu is applied inside the GroupNorm*gate kernel
     # time_decay + tanh(xw @ W1) @ W2 with the bias add as the GEMM epilogue
-    w = torch.addmm(layer.time_decay.view(-1), torch.tanh(xw.view(B * T, C) @ layer.time_decay_w1),
-                    layer.time_decay_w2).view(B, T, -1)
+    w = torch.addmm(bf(layer.time_decay).view(-1), torch.tanh(xw.view(B * T, C) @ bf(layer.time_decay_w1)),
+                    bf(layer.time_decay_w2)).view(B, T, -1)
     return r, k, v, g, w
 
 
@@ -62,16 +63,17 @@ def tmix_x060_forward(layer, x, last_state=None):
     if last_state is not None:                                  # infctx: (shift_state [B,C], wkv_state [B,H,64,64])
         shift_state, wkv_state = (last_state.shift_state, last_state.wkv_state) if hasattr(last_state, "shift_state") else last_state
         r, k, v, g, w = tmix_x060_project(layer, x, shift_state)
-        y, new_state = ops.WKV_6STATE_INFCTX.apply(B, T, C, H, r, k, v, w, layer.time_faaaa, wkv_state.clone().contiguous())
+        y, new_state = ops.WKV_6STATE_INFCTX.apply(B, T, C, H, r, k, v, w, heads._bf16_param(layer.time_faaaa),
+                                                   wkv_state.clone().contiguous())
         out = tmix_x060_finish(layer, y, g)
         if hasattr(last_state, "shift_state"):                  # reference calling convention (src/model.py:781)
             return out, type(last_state)(x[:, -1], new_state)
         return out, (x[:, -1], new_state)
     r, k, v, g, w = tmix_x060_project(layer, x)
     if getattr(layer, "time_state", None) is not None:          # state tuning
-        y = ops.WKV_6STATE.apply(B, T, C, H, r, k, v, w, layer.time_faaaa, layer.time_state)
+        y = ops.WKV_6STATE.apply(B, T, C, H, r, k, v, w, heads._bf16_param(layer.time_faaaa), heads._bf16_param(layer.time_state))
     else:
-        y = ops.RUN_CUDA_RWKV6(B, T, C, H, r, k, v, w, layer.time_faaaa)
+        y = ops.RUN_CUDA_RWKV6(B, T, C, H, r, k, v, w, heads._bf16_param(layer.time_faaaa))
     return tmix_x060_finish(layer, y, g)
 
 

@@ -22,7 +22,7 @@ def test_header_and_library_agree():
     out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
     assert declared <= exported, declared - exported
-    assert lib.wkv6b200_abi_version() == 1
+    assert lib.wkv6b200_abi_version() == 2
 
 
 def test_argument_validation_without_gpu():
