@@ -1,5 +1,7 @@
 #!/usr/bin/env python
-"""bench.py -- WKV6 fwd+bwd tokens/s at the RWKV-6 1B6 shape (BASELINE.json configs[1]).
+"""bench.py -- WKV6 fwd+bwd tokens/s at the RWKV-6 1B6 shape (BASELINE.json configs[1]), and -- in the
+same JSON line, key "bi_encoder" -- BASELINE metric (ii): bi-encoder passages/s at the 1B6 shape (configs[2]),
+batch-sharded over the ranks with one NCCL all_gather of the [B_local, D] embeddings per step.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
@@ -120,6 +122,98 @@ def run_cpu(steps, warmup, budget_s=20.0):
     return s["B"] * s["T"] / sec, cores, sec, len(ts)
 
 
+BI = dict(layers=24, D=2048, H=32, ffn=7168, vocab=65536, micro_batch=64, T=512)
+
+
+def run_bi_encoder(args, M, torch, dist, dev, rank, world, barrier):
+    """BASELINE metric (ii): corpus embedding with the bidirectional 1B6 encoder (src/model_encoder_run.py:296-350,
+    semantics 2 of SURVEY.md 2.3), 512-token padded passages, micro-batch 64 per GPU, forward only.
+    value  : passages/s, ids resident on the device, all_gather of the embeddings inside the timed region
+    e2e    : the call a user makes: token ids in pinned host memory -> embeddings of ALL ranks in pinned host memory
+    accuracy (1 GPU only): the same 1024 passages on the exact SIMT route; min cosine and top-1 neighbour agreement"""
+    from rwkv_lm_ext_b200.synthetic import make_bi_encoder, make_passages
+    c = BI
+    model = make_bi_encoder(c["layers"], c["D"], c["H"], c["ffn"], c["vocab"], seed=0, device=dev)
+    Bm, T, D = c["micro_batch"], c["T"], c["D"]
+    ids_host = make_passages(Bm, T, c["vocab"], seed=100 + rank).pin_memory()
+    ids = ids_host.to(dev)
+    gathered = torch.empty(world * Bm, D, dtype=torch.bfloat16, device=dev)
+    out_host = torch.empty(world * Bm, D, dtype=torch.bfloat16).pin_memory()
+
+    def step(idx_dev):
+        with torch.no_grad():
+            e = M.bi_encoder_encode(model, idx_dev)                 # [Bm, D] bf16
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, e.contiguous())   # the one data-path collective of this config
+            return gathered
+        return e
+
+    def step_e2e():
+        d = ids_host.to(dev, non_blocking=True)
+        e = step(d)
+        out_host[: e.size(0)].copy_(e, non_blocking=True)
+
+    def timed(fn, n):
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(n):
+            fn()
+        b.record()
+        barrier()
+        ms = a.elapsed_time(b) / n
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    steps = max(3, min(args.steps, 10))
+    for _ in range(3):
+        step(ids)
+    n0 = M.launch_count()
+    ms = timed(lambda: step(ids), steps)
+    launches = M.launch_count() - n0
+    for _ in range(2):
+        step_e2e()
+    ems = timed(step_e2e, steps)
+    lin_flops = 2 * Bm * T * c["layers"] * (2 * 5 * D * D + 2 * D * c["ffn"] + D * D)   # Linears (time-mix ones run twice)
+    res = {"metric": "bi-encoder passages/s (1B6 shape)", "value": world * Bm / (ms * 1e-3), "unit": "passages/s",
+           "ms_per_step": ms, "steps": steps, "micro_batch_per_gpu": [Bm, T], "global_batch": world * Bm,
+           "model": f"RWKV-6 1B6 shape L{c['layers']} D{D} H{c['H']} FFN{c['ffn']}, random init, bf16",
+           "scaling": "weak", "collective": "none" if world == 1 else f"all_gather [{Bm},{D}] bf16 per rank per step (NCCL)",
+           "all_gather_bytes_per_step": 0 if world == 1 else world * Bm * D * 2,
+           "linear_tflops_per_gpu": lin_flops / (ms * 1e-3) / 1e12, "gpu_launches": int(launches),
+           "e2e": {"value": world * Bm / (ems * 1e-3), "unit": "passages/s", "ms_per_step": ems,
+                   "h2d_bytes_per_step": Bm * T * 8, "d2h_bytes_per_step": world * Bm * D * 2,
+                   "api": "rwkv_lm_ext_b200.bi_encoder_encode(model, idx): token ids in pinned host memory -> "
+                          "embeddings of the whole global batch in pinned host memory"}}
+    if world == 1:
+        # accuracy gate of SURVEY 8(d) config 3 on 1024 passages: fused tensor-core route vs the exact SIMT WKV6 route
+        n_mb = 16
+        batches = [make_passages(Bm, T, c["vocab"], seed=500 + i).to(dev) for i in range(n_mb)]
+        with torch.no_grad():
+            ef = torch.cat([M.bi_encoder_encode(model, b) for b in batches]).float()
+            M.set_impl("simt")
+            try:
+                es = torch.cat([M.bi_encoder_encode(model, b) for b in batches]).float()
+            finally:
+                M.set_impl(args.kernel_impl)
+        cos = torch.nn.functional.cosine_similarity(ef, es, dim=-1)
+
+        def top1(e):
+            e = torch.nn.functional.normalize(e - e.mean(0, keepdim=True), dim=-1)     # centred: random-init embeddings share a large common component
+            sim = e @ e.t()
+            sim.fill_diagonal_(-2.0)
+            return sim.argmax(-1)
+        res["accuracy"] = {"passages": n_mb * Bm, "min_cosine_vs_exact_route": float(cos.min().item()),
+                           "top1_neighbour_agreement": float((top1(ef) == top1(es)).float().mean().item()),
+                           "what": "fused kernels + tcgen05 WKV6 vs the same forward with the exact fp32 SIMT WKV6 kernels"}
+    del model
+    torch.cuda.empty_cache()
+    return res
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -129,6 +223,8 @@ def main():
     ap.add_argument("--kernel-impl", default="auto", choices=["auto", "simt", "tc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-bi-encoder", action="store_true")
+    ap.add_argument("--no-sft", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -316,6 +412,24 @@ def main():
                "api": "rwkv_lm_ext_b200.RUN_CUDA_RWKV6 + .backward; pinned host tensors in, all results out, "
                       "copy-in / kernels / copy-out of consecutive steps pipelined on 3 CUDA streams"}
 
+    # ---- BASELINE metric (ii) on every rank (its all_gather is a collective)
+    bi = None
+    if not args.no_bi_encoder:
+        bi = run_bi_encoder(args, M, torch, dist, dev, rank, world, barrier)
+
+    # ---- BASELINE configs[3]: data-parallel LoRA SFT step (fwd + bwd + NCCL gradient all-reduce + AdamW) on every rank
+    sft_res = None
+    if not args.no_sft:
+        sys.path.insert(0, os.path.join(ROOT, "profiles"))
+        import bench_sft
+        sft_res = {}
+        for mode, graphs in (("eager", False), ("cuda_graphs", True)):
+            try:
+                sft_res[mode], _ = bench_sft.run(layers=24, graphs=graphs, steps_per_bucket=2)
+            except Exception as e:      # an extra key must never take the headline measurement down with it
+                sft_res[mode] = {"failed": f"{type(e).__name__}: {e}"[:300]}
+            barrier()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -347,6 +461,10 @@ def main():
             "clocks": clocks, "gpu_launches": int(launches), "roofline": roofline, "randn_decay": randn_decay}
     if e2e:
         line["e2e"] = e2e
+    if bi:
+        line["bi_encoder"] = bi
+    if sft_res:
+        line["sft"] = sft_res
 
     # ---- the reference's own CUDA kernels on the same inputs (not part of the contract; context)
     try:

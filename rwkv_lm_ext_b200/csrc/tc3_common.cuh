@@ -41,6 +41,12 @@ __device__ __forceinline__ float fast_ex2(float x) {
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
     return y;
 }
+// (d == c) ? a : b as one compare + one select (the compiler turns chains of ?: over runtime ints into branches)
+__device__ __forceinline__ float sel_eq(int d, int c, float a, float b) {
+    float r;
+    asm("{\n\t.reg .pred p;\n\tsetp.eq.s32 p, %1, %2;\n\tselp.f32 %0, %3, %4, p;\n\t}" : "=f"(r) : "r"(d), "r"(c), "f"(a), "f"(b));
+    return r;
+}
 // 2^n for an integer-valued n, exact; 0 below the normal range, clamped at 2^0 above
 __device__ __forceinline__ float pow2i_le0(float n) {
     const int e = min(max((int)n, -127), 0);
@@ -97,6 +103,9 @@ struct Frag {
         ti_off = sw128(32 * ch + 8 * (lane >> 3) + (lane & 7), 32 * sp);
         ti1_off = sw128(32 * ch + (lane & 7), 32 * sp);
         rc_off = sw128(16 * sp + (lane & 7), 64 * ch + 16 * (lane >> 3));
+        // opaque to the optimiser: otherwise, under register pressure, ptxas re-derives these from SR_TID inside the
+        // chunk loop (S2R + ~10 integer instructions per use, 6 % of all instructions executed) instead of keeping them
+        asm volatile("" : "+r"(ti_off), "+r"(ti1_off), "+r"(rc_off));
     }
     // h = 1 moves the 16-byte chunk (ti) / the row by 8 (rc); both keep row % 8, so the swizzle XOR is unchanged
     __device__ __forceinline__ uint32_t ti(int h) const { return ti_off ^ (h ? 16u : 0u); }

@@ -307,8 +307,16 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         const uint32_t tG = tmem_addr(tmem, 32 * sp, TM_G + 32 * ch);
         const uint32_t tPark = tmem_addr(tmem, 32 * sp + 16, 32 * ch);
         // x2 transposing stores of one 8-token group: lanes 0-7 address the rows of channel half 0, lanes 8-15 of half 1
-        const uint32_t ti2_off = F.ti1_off ^ ((lane & 8) ? 16u : 0u);
-        const int dcol = (32 * ch + 2 * q) - (16 * sp + ri);     // column(g, e = 0) - row(hh) at g = hh
+        uint32_t ti2_off = F.ti1_off ^ ((lane & 8) ? 16u : 0u);
+        int dcol = (32 * ch + 2 * q) - (16 * sp + ri);           // column(g, e = 0) - row(hh) at g = hh
+        asm volatile("" : "+r"(dcol), "+r"(ti2_off));
+        bool diag_hit[2];                                        // this thread holds the diagonal element of row(hh)
+#pragma unroll
+        for (int hh = 0; hh < 2; hh++) {
+            diag_hit[hh] = false;
+#pragma unroll
+            for (int g = 0; g < 4; g++) diag_hit[hh] |= (dcol + 8 * (g - hh) == 0) | (dcol + 8 * (g - hh) == -1);
+        }
         f2 gu2[2] = {0ull, 0ull};
         int sig[2] = {0, 0};              // G in TMEM = G_true 2^(-sig) per key row: rho_0 of the chunk processed last
         uint32_t v[16];
@@ -522,21 +530,22 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             tmem_ld_frag(tG, vg);
             tmem_wait_ld();
             STAMPX(14);
-            // branch-free: dcol = (column of e = 0) - row for g = hh; 8 more per group
+            // branch-free: dcol = (column of e = 0) - row for g = hh; 8 more per group.  The diagonal element (if this
+            // thread holds it) is picked with selects and stored once per row half (divergent stores per element were
+            // 700 cycles of this stage)
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
                 uint32_t pk[4];
+                float dv = 0.f;
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
                     const int d = dcol + 8 * (g - hh);                    // (s - t) for e = 0
                     const float a0 = __uint_as_float(v[4 * g + 2 * hh]), a1 = __uint_as_float(v[4 * g + 2 * hh + 1]);
                     pk[g] = pack2(d < 0 ? a0 : 0.f, d < -1 ? a1 : 0.f);
-#ifndef EXP_NO_BD
-                    if (d == 0) ex.bd[F.row(hh)] = a0;
-                    if (d == -1) ex.bd[F.row(hh)] = a1;
-#endif
+                    dv = sel_eq(d, 0, a0, sel_eq(d, -1, a1, dv));
                 }
                 stsm_x4(sbase + OFF_DA + F.rc(hh), pk[0], pk[1], pk[2], pk[3]);
+                if (diag_hit[hh]) ex.bd[F.row(hh)] = dv;
             }
             STAMPX(25);
             fence_proxy_async();

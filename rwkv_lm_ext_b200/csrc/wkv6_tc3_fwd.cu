@@ -236,7 +236,8 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         const int sp = F.sp, ch = F.ch, q = F.q;
         const float u_h[2] = {__bfloat162float(p.u[h * 64 + F.row(0)]), __bfloat162float(p.u[h * 64 + F.row(1)])};
         const uint32_t tS = tmem_addr(tmem, 32 * sp, TM_S + 32 * ch);
-        const int dcol = (32 * ch + 2 * q) - (16 * sp + F.ri);     // column(g, e = 0) - row(hh) at g = hh
+        int dcol = (32 * ch + 2 * q) - (16 * sp + F.ri);           // column(g, e = 0) - row(hh) at g = hh
+        asm volatile("" : "+r"(dcol));
         uint32_t v[16];
 
         // ---- initial state -> TMEM (fp32 master, [i][j]) and shared (bf16 operand copy)

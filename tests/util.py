@@ -23,12 +23,12 @@ def relrms(a, b):
     return ((a - b).norm() / (b.norm() + 1e-300)).item()
 
 
-def assert_bf16_close(got, ref, what="", relrms_tol=BF16_RELRMS):
+def assert_bf16_close(got, ref, what="", relrms_tol=BF16_RELRMS, maxabs_rel=BF16_MAXABS_REL):
     got, ref = got.detach().double().cpu(), ref.detach().double().cpu()
     assert got.shape == ref.shape, f"{what}: shape {tuple(got.shape)} vs {tuple(ref.shape)}"
     assert torch.isfinite(got).all(), f"{what}: non-finite values"
     err = (got - ref).abs().max().item()
-    bound = BF16_MAXABS_REL * ref.abs().max().item() + BF16_MAXABS_ABS
+    bound = maxabs_rel * ref.abs().max().item() + BF16_MAXABS_ABS
     rr = relrms(got, ref)
     assert err <= bound, f"{what}: max abs err {err:.4g} > {bound:.4g} (relrms {rr:.3g})"
     assert rr <= relrms_tol or ref.norm().item() < 1e-6, f"{what}: rel-RMS {rr:.4g} > {relrms_tol}"
