@@ -1,0 +1,2 @@
+// Intentionally empty: the reference lists cuda/wkv6_bi_cuda.cu in its load() call (e.g. src/model.py:188), but the kernels
+// live in libwkv6_b200.so, built by plain nvcc for sm_100a (rwkv_lm_ext_b200/build.py) and opened by the *_op.cpp next to this file.
