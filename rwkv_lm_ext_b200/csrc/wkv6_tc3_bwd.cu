@@ -70,10 +70,13 @@ constexpr uint32_t SMEM_BYTES = OFF_TILES_END + sizeof(Extra);
 constexpr uint32_t TM_G = 0, TM_X0 = 64, TM_X1 = 128, TM_X2 = 192, TM_COLS = 256;
 // An M = 64 accumulator only occupies lanes 0-15 of each 32-lane TMEM sub-partition; lanes 16-31 of the
 // same columns are per-thread scratch ("parking"): 4 regions x 2 registers per token pair.
-//   PARK_A: (Rt, E) packed bf16 pairs        -> T2 replaces them by XA (fp32, e = 0,1), T3 by its part of gl
+//   PARK_A: Rt (packed bf16 pair), E of e = 0 (fp32; E_1 = E_0 2^l_0)   -> T2 replaces them by XA (fp32, e = 0,1),
+//           T3 by its part of gl
 //   PARK_B: (r, k) raw packed bf16 pairs
-//   PARK_C: (Kt_own, F) packed bf16 pairs
+//   PARK_C: Kt_own (packed bf16 pair), F of e = 0 (fp32; F_1 = F_0 2^-l_1)
 //   PARK_L: l (fp32, e = 0,1)
+// (E and F stay fp32: as bf16 they put 2^-9 of relative error on whole output elements, which showed in the max-abs
+// bound of gk at the full benchmark shape)
 constexpr uint32_t PARK_A = 0, PARK_B = 64, PARK_C = 128, PARK_L = 192;
 
 struct Params {
@@ -423,7 +426,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 tmem_st_frag(tPark + PARK_B, pk);
             }
             STAMPX(24);
-            uint32_t pa[16], pc[16];                // (Rt, E) and (Kt_own, F) in fragment order
+            uint32_t pa[16], pc[16];                // (Rt, E_0) and (Kt_own, F_0) in fragment order
             f2 du2[4];
 #pragma unroll
             for (int g = 0; g < 4; g++) du2[g] = 0ull;
@@ -448,14 +451,15 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 for (int g = 0; g < 4; g++) {
                     // a0 = exc_0 - rho, a1 = cum_0 - rho = exc_1 - rho, a2 = cum_1 - rho
                     const float a0 = (gb[g] - (float)irb[hh][g >> 1]) + exq[hh][g], a1 = a0 + l[hh][g][0], a2 = a1 + l[hh][g][1];
-                    const f2 E2 = f2pack(fast_ex2(a0), fast_ex2(a1)), F2 = f2pack(fast_ex2(-a1), fast_ex2(-a2));
+                    const float E0 = fast_ex2(a0), F0 = fast_ex2(-a1);
+                    const f2 E2 = f2pack(E0, fast_ex2(a1)), F2 = f2pack(F0, fast_ex2(-a2));
                     const f2 r2 = bf2f2(rr[hh][g]), k2 = bf2f2(kk[hh][g]);
                     rto[g] = f2tobf(f2mul(r2, E2));
                     kto[g] = f2tobf(f2mul(k2, F2));
                     pa[4 * g + 2 * hh] = rto[g];
-                    pa[4 * g + 2 * hh + 1] = f2tobf(E2);
+                    pa[4 * g + 2 * hh + 1] = __float_as_uint(E0);
                     pc[4 * g + 2 * hh] = kto[g];
-                    pc[4 * g + 2 * hh + 1] = f2tobf(F2);
+                    pc[4 * g + 2 * hh + 1] = __float_as_uint(F0);
                     du2[g] = f2fma(f2mul(r2, uu), k2, du2[g]);
                 }
                 // versions: my rows in their own reference, then scaled (exactly, by powers of two <= 1) to the
@@ -612,15 +616,24 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             bar_sync_all<B_DR>();                        // Dr ran under T1b; gv is not needed yet
             tc_fence_after();
             STAMP(4);
-            // per 8-token group: Dr, Drs -> gr (tile) and XA, which replaces (Rt, E) in the shadow lanes until T3
+            // per 8-token group: Dr, Drs -> gr (tile) and XA, which replaces (Rt, E) in the shadow lanes until T3.
+            // The TMEM loads of group g+1 are in flight while group g is computed (tcgen05.wait::ld waits for ALL
+            // outstanding loads, so they are issued right after the wait).
+            {
+            uint32_t tb[2][5][4];
+            auto t2_load = [&](int g, uint32_t (&b)[5][4]) {
+                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch + 8 * g), b[0]);
+                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 8 * g), b[1]);
+                tmem_ld_frag1(tPark + PARK_A + 8 * g, b[2]);
+                tmem_ld_frag1(tPark + PARK_B + 8 * g, b[3]);
+                tmem_ld_frag1(tPark + PARK_L + 8 * g, b[4]);
+            };
+            t2_load(0, tb[0]);
 #pragma unroll
             for (int g = 0; g < 4; g++) {
-                uint32_t d4[4], s4[4], a4[4], b4[4];
-                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch + 8 * g), d4);
-                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 8 * g), s4);
-                tmem_ld_frag1(tPark + PARK_A + 8 * g, a4);
-                tmem_ld_frag1(tPark + PARK_B + 8 * g, b4);
+                uint32_t (&d4)[4] = tb[g & 1][0], (&s4)[4] = tb[g & 1][1], (&a4)[4] = tb[g & 1][2], (&b4)[4] = tb[g & 1][3], (&l4)[4] = tb[g & 1][4];
                 tmem_wait_ld();
+                if (g < 3) t2_load(g + 1, tb[(g + 1) & 1]);
                 const f2 bd2 = *reinterpret_cast<const f2 *>(&ex.bd[F.col(g, 0)]);
                 uint32_t grp[2];
 #pragma unroll
@@ -628,11 +641,13 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     const f2 erho = f2bcast(pow2i(irb[hh][g >> 1]));                       // 2^rho of this block (0 when out of range)
                     const f2 z = f2fma(erho, f2packu(s4[2 * hh], s4[2 * hh + 1]), f2packu(d4[2 * hh], d4[2 * hh + 1]));
                     const f2 ubk = f2mul(f2mul(bd2, f2bcast(u_h[hh])), bf2f2(b4[2 * hh + 1]));
-                    grp[hh] = f2tobf(f2fma(bf2f2(a4[2 * hh + 1]), z, ubk));                // E Z + u bd k
+                    const float E0 = __uint_as_float(a4[2 * hh + 1]);
+                    grp[hh] = f2tobf(f2fma(f2pack(E0, E0 * fast_ex2(__uint_as_float(l4[2 * hh]))), z, ubk));     // E Z + u bd k
                     f2unpacku(f2mul(bf2f2(a4[2 * hh]), z), a4[2 * hh], a4[2 * hh + 1]);    // XA = Rt Z, Rt exactly as the MMAs saw it
                 }
                 stsm_x2_t(sbase + OFF_GRT + ti2_off + 1024u * g, grp[0], grp[1]);
                 tmem_st_frag1(tPark + PARK_A + 8 * g, a4);
+            }
             }
             tmem_wait_st();
             fence_proxy_async();
@@ -659,15 +674,23 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             // With X = XA - Kt_own Dk and D = Kt_own Zk - XA:  gl_t = 2^Lam q0 + sum_all X + sum_{s<t} D_s - XA_t,
             // so one exclusive prefix scan of D plus the totals of X are enough (the scan runs on -D).
             float runD[2] = {0.f, 0.f}, runX[2] = {0.f, 0.f};
+            {
+            uint32_t tb[2][6][4];
+            auto t3_load = [&](int g, uint32_t (&b)[6][4]) {
+                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch + 8 * g), b[0]);
+                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 8 * g), b[1]);
+                tmem_ld_frag1(tPark + PARK_A + 8 * g, b[2]);
+                tmem_ld_frag1(tPark + PARK_B + 8 * g, b[3]);
+                tmem_ld_frag1(tPark + PARK_C + 8 * g, b[4]);
+                tmem_ld_frag1(tPark + PARK_L + 8 * g, b[5]);
+            };
+            t3_load(0, tb[0]);
 #pragma unroll
             for (int g = 0; g < 4; g++) {
-                uint32_t d4[4], s4[4], a4[4], b4[4], c4[4];
-                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch + 8 * g), d4);
-                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 8 * g), s4);
-                tmem_ld_frag1(tPark + PARK_A + 8 * g, a4);
-                tmem_ld_frag1(tPark + PARK_B + 8 * g, b4);
-                tmem_ld_frag1(tPark + PARK_C + 8 * g, c4);
+                uint32_t (&d4)[4] = tb[g & 1][0], (&s4)[4] = tb[g & 1][1], (&a4)[4] = tb[g & 1][2], (&b4)[4] = tb[g & 1][3];
+                uint32_t (&c4)[4] = tb[g & 1][4], (&l4)[4] = tb[g & 1][5];
                 tmem_wait_ld();
+                if (g < 3) t3_load(g + 1, tb[(g + 1) & 1]);
                 const f2 bd2 = *reinterpret_cast<const f2 *>(&ex.bd[F.col(g, 0)]);
                 uint32_t gkp[2];
 #pragma unroll
@@ -679,7 +702,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     const f2 x2 = f2fma(nkt, dk, xa);                          // X = XA - Bi
                     const f2 nd2 = f2fma(nkt, z, xa);                          // -D = XA - Kt_own Zk
                     const f2 br = f2mul(bd2, bf2f2(b4[2 * hh]));
-                    gkp[hh] = f2tobf(f2fma(bf2f2(c4[2 * hh + 1]), z, f2mul(br, f2bcast(u_h[hh]))));   // F Zk + u bd r
+                    const float F0 = __uint_as_float(c4[2 * hh + 1]);
+                    gkp[hh] = f2tobf(f2fma(f2pack(F0, F0 * fast_ex2(-__uint_as_float(l4[2 * hh + 1]))), z, f2mul(br, f2bcast(u_h[hh]))));   // F Zk + u bd r
                     gu2[hh] = f2fma(br, bf2f2(b4[2 * hh + 1]), gu2[hh]);
                     float x0, x1, nd0, nd1, xa0, xa1;
                     f2unpack(x2, x0, x1);
@@ -702,6 +726,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 }
                 stsm_x2_t(sbase + OFF_GKT + ti2_off + 1024u * g, gkp[0], gkp[1]);
                 tmem_st_frag1(tPark + PARK_A + 8 * g, a4);
+            }
             }
             STAMPX(20);
             if (q == 0) {

@@ -16,11 +16,20 @@ MODULES = {      # name -> sources, as the reference's load() calls list them
 REF_CUDA_CFLAGS = ["-res-usage", "--use_fast_math", "-O3", "-Xptxas -O3", "--extra-device-vectorization", "-D_N_=64", "-D_T_=4096"]
 
 
-def load_shim(name, verbose=False):
-    """The reference's own call, with a fixed build directory so that a prebuilt module is reused."""
+def load_shim(name, verbose=False, rebuild=False):
+    """The reference's own call, with a fixed build directory.  A module already built there (by `python
+    shim/build_shims.py`, e.g. in the build container) is imported as it is unless `rebuild` is set."""
+    import torch  # noqa: F401  (the extension links against libtorch)
+    bd = os.path.join(HERE, "_build", name)
+    so = os.path.join(bd, name + ".so")
+    if os.path.exists(so) and not rebuild:
+        import importlib.util
+        spec = importlib.util.spec_from_file_location(name, so)
+        mod = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(mod)
+        return mod
     os.environ.setdefault("TORCH_CUDA_ARCH_LIST", "10.0")
     from torch.utils.cpp_extension import load
-    bd = os.path.join(HERE, "_build", name)
     os.makedirs(bd, exist_ok=True)
     return load(name=name, sources=[os.path.join(HERE, s) for s in MODULES[name]], verbose=verbose,
                 extra_cuda_cflags=REF_CUDA_CFLAGS, build_directory=bd)
@@ -28,5 +37,5 @@ def load_shim(name, verbose=False):
 
 if __name__ == "__main__":
     for n in (sys.argv[1:] or list(MODULES)):
-        m = load_shim(n, verbose=True)
+        m = load_shim(n, verbose=True, rebuild=True)
         print("built", n, "->", m.__file__)

@@ -27,7 +27,7 @@ LCLAMP = 13.0
 
 NOROUND = set()   # experiment switch: operand names whose rounding is skipped
 REAL_RHO = False  # experiment switch: real-valued references (shows why the integer grid matters)
-BF16_EF = True    # E and F reach the output stages as bf16 (parked in TMEM)
+BF16_EF = False   # experiment switch: E and F reach the output stages as bf16 (costs the max-abs bound of gk at full shape)
 
 
 def rb(x, on=True, name=None):

@@ -16,6 +16,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def _model(sft, seed=0, **kw):
+    torch.manual_seed(seed)                        # lora_A keeps its kaiming init (global RNG), like the reference's
     m = sft.RwkvSft(layers=2, D=128, H=2, ffn=448, vocab=512, lora_r=4, lora_alpha=16, **kw)
     return sft.init_like_reference(m, seed).to(DEV).bfloat16()
 
