@@ -7,7 +7,9 @@ import rwkv_lm_ext_b200 as M
 from rwkv_lm_ext_b200 import _lib
 from rwkv_lm_ext_b200.synthetic import make_inputs
 
-FINE = "--fine" in sys.argv          # needs a library built with -DWKV6_FINE_STAMPS (WKV6_B200_LIB=...)
+# needs a library built with -DWKV6_FINE_STAMPS:  python -c "from rwkv_lm_ext_b200.build import build_library as b; b(defines=['WKV6_FINE_STAMPS'], out='rwkv_lm_ext_b200/libwkv6_b200_stamps.so')"
+# and WKV6_B200_LIB pointing at it (the product library has no stamps)
+FINE = True
 _a = [a for a in sys.argv[1:] if not a.startswith("--")]
 B, T, H = int(_a[0]) if _a else 8, 4096, 32
 NS = 32 if FINE else 8

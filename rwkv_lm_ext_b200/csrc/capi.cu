@@ -9,7 +9,9 @@
 
 namespace wkv6 {
 
+#ifdef WKV6_FINE_STAMPS
 extern void *g_tc3_bwd_stamps;
+#endif
 static thread_local char g_err[512] = "";
 static std::atomic<int> g_impl{-1};
 static std::atomic<uint64_t> g_launches{0};
@@ -231,9 +233,11 @@ int wkv6b200_set_impl(int impl) {
 }
 int wkv6b200_get_impl(void) { return current_impl(); }
 uint64_t wkv6b200_launch_count(void) { return g_launches.load(); }
-// Profiling aid (not part of the reference-facing ABI): device buffer [B*H][chunks][8] of int64 that the
-// backward kernel fills with clock64() stamps at its stage boundaries; NULL switches it off.
+#ifdef WKV6_FINE_STAMPS
+// Profiling BUILD only (-DWKV6_FINE_STAMPS, profiles/stage_times.py; not in the product library): device buffer
+// [B*H][chunks][32] of int64 that the backward kernel fills with clock64() stamps inside its stages; NULL = off.
 __attribute__((visibility("default"))) void wkv6b200_debug_stamps(void *dev_buf) { wkv6::g_tc3_bwd_stamps = dev_buf; }
+#endif
 
 // ------------------------------------------------------------------------------------ wkv6
 static int wkv6_fwd_common(int B, int T, int C, int H, const void *r, const void *k, const void *v,

@@ -132,6 +132,9 @@ __device__ __forceinline__ uint32_t bfpow2pair(int d) {
 }
 // exact scaling of packed bf16 pairs by 2^d, -254 <= d <= 0, as two factors (2^d alone may leave the bf16
 // range although the scaled values do not)
+__device__ __forceinline__ void scale1(uint32_t &a, int d) {
+    a = hmul2(hmul2(a, bfpow2pair(d >> 1)), bfpow2pair(d - (d >> 1)));
+}
 __device__ __forceinline__ void scale2(uint32_t &a, uint32_t &b, int d) {
     const uint32_t fa = bfpow2pair(d >> 1), fb = bfpow2pair(d - (d >> 1));
     a = hmul2(hmul2(a, fa), fb);

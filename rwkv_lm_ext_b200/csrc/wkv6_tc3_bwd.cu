@@ -344,14 +344,13 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         tc_fence_before();
         bar_arrive_all<B_T3>();
 
-#ifdef WKV6_FINE_STAMPS      // profiling build (profiles/stage_times.py --fine): 32 stamps per chunk, extra points inside the stages
+#ifdef WKV6_FINE_STAMPS      // profiling build only (profiles/stage_times.py): 32 clock64 stamps per chunk; the product has none
 #define STAMP_N 32
-#define STAMPX(k) STAMP(k)
-#else
-#define STAMP_N 8
-#define STAMPX(k) do { } while (0)
-#endif
 #define STAMP(k) do { if (p.dbg && threadIdx.x == 0) p.dbg[((size_t)blockIdx.x * ck_stride + it) * STAMP_N + (k)] = clock64(); } while (0)
+#else
+#define STAMP(k) do { } while (0)
+#endif
+#define STAMPX(k) STAMP(k)
         for (int it = 0; it < NC; it++) {
             const int c = NC - 1 - it;
             const int nv = min(L, T - c * L);
@@ -805,7 +804,9 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
 
 }  // namespace
 
-void *g_tc3_bwd_stamps = nullptr;   // profiling aid, set through wkv6b200_debug_stamps()
+#ifdef WKV6_FINE_STAMPS
+void *g_tc3_bwd_stamps = nullptr;   // profiling build: set through wkv6b200_debug_stamps()
+#endif
 
 // per-stream hazard flags [B*H], then (time-axis segmentation, at most 296 segment rows) per-segment flags
 size_t tc3_saved_header(int B, int H) { return ((((size_t)B * H + 512) * sizeof(int)) + 1023) / 1024 * 1024; }
@@ -881,7 +882,11 @@ static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const f
     p.lmin = tc_lmin_log2(a);
     p.gu = (bf16 *)a.gu; p.gs = (bf16 *)a.gs;
     p.hz_flags = flags;
+#ifdef WKV6_FINE_STAMPS
     p.dbg = (long long *)g_tc3_bwd_stamps;
+#else
+    p.dbg = nullptr;
+#endif
     static bool attr_done[64] = {};          // function attributes are per device
     int dev = 0;
     WKV6_CUDA_CHECK(cudaGetDevice(&dev));

@@ -270,13 +270,20 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         // lo) and 2^Lam stay in registers until the MMAs of the previous chunk no longer read those tiles.
         uint32_t rhp[2][4], khp[2][4], klp[2][4];
         float elam_nx[2];
+        // Token groups of the operand preparation: thread (ch, lane) owns the 8-token groups 2g + ch, g = 0..3, i.e.
+        // ONE group of each 16-token reference block (block g = groups 2g and 2g + 1).  With the natural mapping
+        // (groups 4ch + g) the warps of ch = 0 would scale and store ten Kt group-versions and those of ch = 1 three.
+        // ldmatrix / stmatrix take one row address per lane, so any group assignment costs the same there.
+        const uint32_t tg_off = sw128(16 * (lane >> 3) + 8 * ch + (lane & 7), 32 * sp);    // .x4: matrix m = group 2m + ch
+        const uint32_t tg1_off = sw128(8 * ch + (lane & 7), 32 * sp);                       // .x1 of group 2m + ch: + 2048 m
+        auto tg = [&](int hh) { return tg_off ^ (hh ? 16u : 0u); };
         auto prepare = [&](int c) {
             const int nv = min(L, T - c * L);
             float l[2][4][2], exq[2][4];
             {
                 uint32_t wp[2][4];
-                ldsm_x4_t(sbase + OFF_W + F.ti(0), wp[0][0], wp[0][1], wp[0][2], wp[0][3]);
-                ldsm_x4_t(sbase + OFF_W + F.ti(1), wp[1][0], wp[1][1], wp[1][2], wp[1][3]);
+                ldsm_x4_t(sbase + OFF_W + tg(0), wp[0][0], wp[0][1], wp[0][2], wp[0][3]);
+                ldsm_x4_t(sbase + OFF_W + tg(1), wp[1][0], wp[1][1], wp[1][2], wp[1][3]);
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++)
 #pragma unroll
@@ -286,7 +293,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                         l0 = fmaxf(l0, p.lmin);
                         l1 = fmaxf(l1, p.lmin);
                         if (nv < L) {                                   // ragged last chunk: no decay on the padded rows
-                            const int t0 = F.col(g, 0);
+                            const int t0 = 8 * (2 * g + ch) + 2 * q;
                             if (t0 >= nv) l0 = 0.f;
                             if (t0 + 1 >= nv) l1 = 0.f;
                         }
@@ -299,18 +306,18 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                         y = __shfl_up_sync(0xffffffffu, x, 2, 4);
                         if (q >= 2) x += y;
                         exq[hh][g] = x - ps;
-                        if (q == 3) ex.gtot[4 * ch + g][F.row(hh)] = x;
+                        if (q == 3) ex.gtot[2 * g + ch][F.row(hh)] = x;
                     }
             }
             named_bar_sync<B_SCAN, CTHREADS>();
 
             uint32_t rr[2][4] = {}, kk[2][4];
             if constexpr (!SO) {
-                ldsm_x4_t(sbase + OFF_R + F.ti(0), rr[0][0], rr[0][1], rr[0][2], rr[0][3]);
-                ldsm_x4_t(sbase + OFF_R + F.ti(1), rr[1][0], rr[1][1], rr[1][2], rr[1][3]);
+                ldsm_x4_t(sbase + OFF_R + tg(0), rr[0][0], rr[0][1], rr[0][2], rr[0][3]);
+                ldsm_x4_t(sbase + OFF_R + tg(1), rr[1][0], rr[1][1], rr[1][2], rr[1][3]);
             }
-            ldsm_x4_t(sbase + OFF_K + F.ti(0), kk[0][0], kk[0][1], kk[0][2], kk[0][3]);
-            ldsm_x4_t(sbase + OFF_K + F.ti(1), kk[1][0], kk[1][1], kk[1][2], kk[1][3]);
+            ldsm_x4_t(sbase + OFF_K + tg(0), kk[0][0], kk[0][1], kk[0][2], kk[0][3]);
+            ldsm_x4_t(sbase + OFF_K + tg(1), kk[1][0], kk[1][1], kk[1][2], kk[1][3]);
             f2 du2[4];
 #pragma unroll
             for (int g = 0; g < 4; g++) du2[g] = 0ull;
@@ -322,18 +329,16 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
 #pragma unroll
                 for (int x8 = 0; x8 < 8; x8++) {
                     if (x8 & 1) ir[x8 >> 1] = __float2int_rn(run);        // middle of block x8/2, integer log2 grid
-                    if ((x8 >> 2) == ch) gb[x8 & 3] = run;
+                    if ((x8 & 1) == ch) gb[x8 >> 1] = run;
                     run += ex.gtot[x8][F.row(hh)];
                 }
                 const float lam = run;
                 elam_nx[hh] = fast_ex2(lam);
-                // my tokens: groups g = 0,1 are block 2ch, g = 2,3 block 2ch + 1
-                const int irb[2] = {ch ? ir[2] : ir[0], ch ? ir[3] : ir[1]};
                 uint32_t rto[4], kto[4];
                 const f2 uu = f2bcast(u_h[hh]);
 #pragma unroll
-                for (int g = 0; g < 4; g++) {
-                    const float rq = (float)irb[g >> 1];
+                for (int g = 0; g < 4; g++) {                             // my group g lies in block g
+                    const float rq = (float)ir[g];
                     const f2 el = f2bcast(fast_ex2(lam - rq));
                     // a0 = exc_0 - rho, a1 = cum_0 - rho = exc_1 - rho, a2 = cum_1 - rho
                     const float a0 = (gb[g] - rq) + exq[hh][g], a1 = a0 + l[hh][g][0], a2 = a1 + l[hh][g][1];
@@ -343,32 +348,29 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                         const f2 r2 = bf2f2(rr[hh][g]);
                         rto[g] = f2tobf(f2mul(r2, f2pack(fast_ex2(a0), fast_ex2(a1))));
                         kto[g] = f2tobf(kf);
-                        rhp[hh][g] = hmul2(rto[g], bfpow2pair(irb[g >> 1]));   // Rh = Rt * 2^rho (exact)
+                        rhp[hh][g] = hmul2(rto[g], bfpow2pair(ir[g]));    // Rh = Rt * 2^rho (exact)
                         du2[g] = f2fma(f2mul(r2, uu), k2, du2[g]);
                     }
                     const f2 kh = f2mul(kf, el);                          // Kh = k * 2^(Lam - cum)
                     khp[hh][g] = f2tobf(kh);
                     klp[hh][g] = f2tobf(f2sub(kh, bf2f2(khp[hh][g])));
                 }
-                const uint32_t ti = F.ti(hh);
                 if constexpr (!SO) {
+                const uint32_t ti = tg(hh), t1 = tg1_off ^ (hh ? 16u : 0u);
                 stsm_x4_t(sbase + OFF_RT + ti, rto[0], rto[1], rto[2], rto[3]);
-                // Kt versions: my rows in their own reference, then scaled down to every later block's reference.
-                // 2^(rho_q - rho_(q-1)) spans 16 tokens and may leave the bf16 range although the products it is
-                // meant for do not: two exact factors.
-                if (ch == 0) {
-                    stsm_x2_t(sbase + OFF_KT + kt_ver(0) + ti, kto[0], kto[1]);
-                    scale2(kto[0], kto[1], ir[1] - ir[0]);
-                    stsm_x4_t(sbase + OFF_KT + kt_ver(1) + ti, kto[0], kto[1], kto[2], kto[3]);
-                    scale4(kto, ir[2] - ir[1]);
-                    stsm_x4_t(sbase + OFF_KT + kt_ver(2) + ti, kto[0], kto[1], kto[2], kto[3]);
-                    scale4(kto, ir[3] - ir[2]);
-                    stsm_x4_t(sbase + OFF_KT + kt_ver(3) + ti, kto[0], kto[1], kto[2], kto[3]);
-                } else {
-                    stsm_x2_t(sbase + OFF_KT + kt_ver(2) + ti, kto[0], kto[1]);
-                    scale2(kto[0], kto[1], ir[3] - ir[2]);
-                    stsm_x4_t(sbase + OFF_KT + kt_ver(3) + ti, kto[0], kto[1], kto[2], kto[3]);
-                }
+                // Kt versions: version q holds the groups of blocks <= q in the reference of block q.  My group g
+                // enters version g as it is and is then scaled down (exactly, by powers of two <= 1) for every later
+                // version.  2^(rho_q - rho_(q-1)) spans 16 tokens and may leave the bf16 range although the products
+                // it is meant for do not: two exact factors.
+                stsm_x1_t(sbase + OFF_KT + kt_ver(0) + t1, kto[0]);
+                scale1(kto[0], ir[1] - ir[0]);
+                stsm_x2_t(sbase + OFF_KT + kt_ver(1) + ti, kto[0], kto[1]);
+                scale2(kto[0], kto[1], ir[2] - ir[1]);
+                stsm_x2_t(sbase + OFF_KT + kt_ver(2) + ti, kto[0], kto[1]);
+                stsm_x1_t(sbase + OFF_KT + kt_ver(2) + t1 + 4096u, kto[2]);
+                scale2(kto[0], kto[1], ir[3] - ir[2]);
+                scale1(kto[2], ir[3] - ir[2]);
+                stsm_x4_t(sbase + OFF_KT + kt_ver(3) + ti, kto[0], kto[1], kto[2], kto[3]);
                 }
             }
             // ---- diag(u) term: sum over channels of r u k per token; reduce-scatter over the 8 lanes ri
@@ -394,7 +396,8 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     const float keep = b0 ? a2[1] : a2[0], send = b0 ? a2[0] : a2[1];
                     a1 = keep + __shfl_xor_sync(0xffffffffu, send, 4);
                 }
-                ex.pdu[sp][32 * ch + 8 * ((b2 ? 2 : 0) + (b1 ? 1 : 0)) + 2 * q + (b0 ? 1 : 0)] = a1;
+                // the partial of my group gsel = (b2 ? 2 : 0) + (b1 ? 1 : 0), token 8 (2 gsel + ch) + 2q + e
+                ex.pdu[sp][8 * (2 * ((b2 ? 2 : 0) + (b1 ? 1 : 0)) + ch) + 2 * q + (b0 ? 1 : 0)] = a1;
             }
             fence_proxy_async();
             bar_arrive_all<B_PA>();
@@ -402,7 +405,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         auto store_deferred = [&]() {
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
-                const uint32_t ti = F.ti(hh);
+                const uint32_t ti = tg(hh);
                 if constexpr (!SO) stsm_x4_t(sbase + OFF_RH + ti, rhp[hh][0], rhp[hh][1], rhp[hh][2], rhp[hh][3]);
                 stsm_x4_t(sbase + OFF_KH + ti, khp[hh][0], khp[hh][1], khp[hh][2], khp[hh][3]);
                 stsm_x4_t(sbase + OFF_KL + ti, klp[hh][0], klp[hh][1], klp[hh][2], klp[hh][3]);

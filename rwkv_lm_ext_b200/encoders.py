@@ -63,3 +63,102 @@ def bi_encoder_encode(model, idx):
     emb_id, _ = _ids(model)
     hidden = bi_encoder_hidden(model, idx)
     return heads.eos_gather(hidden.contiguous(), idx, emb_id)[0]
+
+
+# ------------------------------------------------------------------------------------------------
+# uni-directional task models (src/model_ext.py:172-212, :1690-1769; src/model_run.py:760-883)
+# ------------------------------------------------------------------------------------------------
+def _base(wrapper):
+    return getattr(wrapper, "rwkvModel", wrapper)
+
+
+def causal_hidden(model, idx):
+    """ln_out(blocks(emb(idx)))  [B,T,D] of the plain (causal) RWKV-6 model -- the body shared by
+    `RwkvForSequenceEmbedding.forward` (src/model_ext.py:1739-1762) and `RwkvForClassification.forward`
+    (src/model_ext.py:183-205) -- with every block on the fused kernels.  Right padding never reaches a position
+    before it, so a padded batch gives each row what the reference's one-sentence-at-a-time inference classes
+    (src/model_run.py:815-848) compute for it."""
+    base = _base(model)
+    x = base.emb(idx.contiguous())
+    for i, blk in enumerate(base.blocks):
+        if i == 0 and hasattr(blk, "ln0"):
+            x = blk.ln0(x)
+        x = x + tmix.tmix_x060_forward(blk.att, blk.ln1(x))
+        ffn = blk.ffn
+        if all(hasattr(ffn, n) for n in ("time_maa_k", "time_maa_r", "key", "receptance", "value")):
+            x = x + cmix.cmix_x060_forward(ffn, blk.ln2(x))
+        else:
+            x = x + ffn(blk.ln2(x))
+    return base.ln_out(x)
+
+
+def sequence_embedding(wrapper, idx, variant="train"):
+    """`RwkvForSequenceEmbedding.forward`: hidden states -> position of the first `embedding_id` token (bit-exact
+    index kernel) -> pooling (`weightedmean` / `lasttoken` / `avg`; variant "train" = src/model_ext.py:1708-1738,
+    "infer" = src/model_run.py:777-797) -> optional dense + tanh head.  `wrapper` carries the reference's
+    attribute names: rwkvModel, embedding_id, pooling_type, add_mlp, dense, activation."""
+    emb_id = int(getattr(wrapper, "embedding_id", 1))
+    hidden = causal_hidden(wrapper, idx).contiguous()
+    pos = heads.eos_index(idx, emb_id)
+    x = heads.pooling(hidden, pos, getattr(wrapper, "pooling_type", "weightedmean"), variant)
+    if getattr(wrapper, "add_mlp", False):
+        x = wrapper.activation(wrapper.dense(x.to(wrapper.dense.weight.dtype)))
+    return x
+
+
+def classification_logits(wrapper, idx):
+    """`RwkvForClassification.forward` (src/model_ext.py:183-211): score(hidden)[b, first class_id token].  The row is
+    gathered BEFORE the score Linear (same numbers, T times fewer FLOPs than scoring every token).  This is also the
+    reference's cross-encoder: rows are "query [sep] document [cls]" (see `cross_encoder_rows`)."""
+    cls_id = int(getattr(wrapper, "class_id", 1))
+    hidden = causal_hidden(wrapper, idx).contiguous()
+    row, _ = heads.eos_gather(hidden, idx, cls_id)
+    return wrapper.score(row.to(wrapper.score.weight.dtype))
+
+
+def cross_encoder_rows(queries, documents, max_len, sep_id=2, class_id=1, pad_id=0):
+    """Token rows of the cross-encoder (peft_train/data_collators.py / data/custom_datasets.py
+    `cross_encoder_pad_and_truncated_according_data`): query + [sep] + document, truncated to max_len - 1, then the
+    class token, right-padded.  queries / documents: lists of token-id lists.  Returns int64 [B, max_len] (CPU)."""
+    rows = []
+    for q, d in zip(queries, documents):
+        ids = (list(q) + [sep_id] + list(d))[: max_len - 1] + [class_id]
+        rows.append(ids + [pad_id] * (max_len - len(ids)))
+    return torch.tensor(rows, dtype=torch.long)
+
+
+def length_buckets(lengths, max_tokens, multiple=64):
+    """Batches of sequence indices for a corpus of ragged sequences: sorted by length, each batch padded to its longest
+    member (rounded up to `multiple`) with at most `max_tokens` padded tokens -- the batched, GPU-resident replacement
+    of the reference's one-sentence-at-a-time loops (tests/TestBiEncoder.py:22-36, src/model_run.py:954-968)."""
+    order = sorted(range(len(lengths)), key=lambda i: lengths[i])
+    batches, cur, width = [], [], 0
+    for i in order:
+        w = -(-max(1, lengths[i]) // multiple) * multiple
+        if cur and max(width, w) * (len(cur) + 1) > max_tokens:
+            batches.append((cur, width))
+            cur, width = [], 0
+        cur.append(i)
+        width = max(width, w)
+    if cur:
+        batches.append((cur, width))
+    return batches
+
+
+def encode_corpus(model, sequences, fn=None, max_tokens=32768, end_id=1, pad_id=0):
+    """Embeds (or scores) a list of token-id lists of any lengths.  Each sequence gets `end_id` appended if it does not
+    end with it; batches come from `length_buckets`; `fn(model, idx)` defaults to `bi_encoder_encode` for a bare
+    encoder and `sequence_embedding` for a wrapper with `rwkvModel`.  Results are returned in input order."""
+    if fn is None:
+        fn = sequence_embedding if hasattr(model, "rwkvModel") else bi_encoder_encode
+    seqs = [list(s) if len(s) and s[-1] == end_id else list(s) + [end_id] for s in sequences]
+    dev = next(model.parameters()).device
+    out = [None] * len(seqs)
+    for members, width in length_buckets([len(s) for s in seqs], max_tokens):
+        idx = torch.full((len(members), width), pad_id, dtype=torch.long)
+        for r, i in enumerate(members):
+            idx[r, : len(seqs[i])] = torch.tensor(seqs[i], dtype=torch.long)
+        res = fn(model, idx.to(dev, non_blocking=True))
+        for r, i in enumerate(members):
+            out[i] = res[r]
+    return torch.stack(out)

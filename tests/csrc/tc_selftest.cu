@@ -3,8 +3,20 @@
 // the real kernels (descriptor mistakes produce silent garbage, not faults).
 #include <cuda_bf16.h>
 
-#include "common.cuh"
-#include "tc_common.cuh"
+#include <stdio.h>
+
+#include "../../rwkv_lm_ext_b200/csrc/tc_common.cuh"
+
+// TEST CODE: built into tests/libwkv6_b200_selftest.so by tests/test_gpu_tc_selftest.py (plain nvcc), not into the
+// product library.  It only shares the header of building blocks with the product kernels.
+#define WKV6_OK 0
+#define WKV6_EINVAL (-1)
+#define WKV6_ECUDA (-2)
+static char g_selftest_err[256];
+static void set_error(const char *msg) { snprintf(g_selftest_err, sizeof(g_selftest_err), "%s", msg); }
+static void count_launch() {}
+#define WKV6_CUDA_CHECK(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { set_error(cudaGetErrorString(_e)); return WKV6_ECUDA; } } while (0)
+extern "C" __attribute__((visibility("default"))) const char *wkv6b200_selftest_last_error(void) { return g_selftest_err; }
 
 namespace wkv6 {
 namespace {

@@ -22,6 +22,8 @@ def test_header_and_library_agree():
     out = subprocess.check_output(["nm", "-D", "--defined-only", _lib.LIB_PATH], text=True)
     exported = {l.split()[-1] for l in out.splitlines() if " T " in l}
     assert declared <= exported, declared - exported
+    # ... and nothing else: no test kernels, no profiling hooks in the product library
+    assert exported <= declared, exported - declared
     assert lib.wkv6b200_abi_version() == 2
 
 
