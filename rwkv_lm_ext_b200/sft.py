@@ -388,6 +388,9 @@ class SftTrainer:
     def __init__(self, model, lr=3e-4, betas=(0.9, 0.99), eps=1e-8, weight_decay=0.001, n_buckets=4, graphs=False):
         self.model = model
         self.params = model.mark_trainable() if hasattr(model, "mark_trainable") else [p for p in model.parameters() if p.requires_grad]
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            for p in self.params:                      # every rank starts from rank 0's adapter (what DDP does at wrap time)
+                dist.broadcast(p.data, src=0)
         self.grads = GradBuckets(self.params, n_buckets)
         dev = self.params[0].device
         self.opt = torch.optim.AdamW(self.params, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,

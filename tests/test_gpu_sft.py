@@ -75,6 +75,7 @@ from rwkv_lm_ext_b200 import sft
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(rank)
 dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+torch.manual_seed(11)                  # same lora_A (kaiming, global RNG) in the 1-rank and the 2-rank run
 m = sft.init_like_reference(sft.RwkvSft(layers=2, D=128, H=2, ffn=448, vocab=512, lora_r=4, lora_alpha=16), 5).cuda().bfloat16()
 tr = sft.SftTrainer(m, lr=1e-3, n_buckets=3)
 g = torch.Generator().manual_seed(9)
