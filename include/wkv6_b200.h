@@ -184,6 +184,12 @@ WKV6_API int wkv6_bi_backward_raww(int B, int T, int C, int H, const int *mask, 
 WKV6_API int rwkv6_forward(int dtype, int B, int T, int C, int H, float *state, const void *r,
                   const void *k, const void *v, const float *w_decay, const void *u, void *y,
                   void *stream);
+/* The same op for a caller that still holds the raw bf16 decay logits w (what `RWKV_6.forward`,
+ * src/model_run.py:58-66, starts from before it materialises exp(-exp(w.float()))): no fp32 decay tensor is
+ * built (2 eager passes and 4 B/element saved) and nothing has to be recovered from it.  bf16 r,k,v,w,u,y. */
+WKV6_API int rwkv6_forward_raww(int B, int T, int C, int H, float *state, const void *r,
+                       const void *k, const void *v, const void *w, const void *u, void *y,
+                       void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * Memory-bound neighbours of the recurrence.
@@ -273,6 +279,17 @@ WKV6_API int scatter_tokens_bf16(int B, int T, int D, const void *gout, const in
  * around its two GEMMs, bit-identical to the eager bf16 chain.
  * ------------------------------------------------------------------------------------------ */
 /* out[0] = xk, out[1] = xr = x + (shift(x)-x) * time_maa_{k,r};  maa_kr bf16 [2,C];  out bf16 [2,B,T,C]. */
+/* Residual add + LayerNorm (the glue of `Block.forward`, src/model.py:904-933), rows = B*T, D % 256 == 0:
+ *   x_new = bf16(x + delta);  y = LayerNorm(x_new; w, b, eps)   (fp32 statistics, bf16 result)
+ * delta == NULL: plain LayerNorm of x (x_new unused).  stats: NULL or fp32 [rows][2] receiving (mean, rstd) for the backward. */
+WKV6_API int add_layernorm_bf16(long long rows, int D, float eps, const void *x, const void *delta, const void *w,
+                       const void *b, void *x_new, void *y, float *stats, void *stream);
+WKV6_API size_t add_layernorm_backward_workspace_bytes(long long rows, int D);
+/* g = g_xnew + dLN(g_y): the gradient of BOTH x and delta (g_xnew may be NULL).  gw / gb: fp32 [D] or both NULL
+ * (frozen affine parameters: the column pass is skipped); workspace only needed for gw / gb. */
+WKV6_API int add_layernorm_backward_bf16(long long rows, int D, const void *x_new, const float *stats, const void *w,
+                                const void *g_y, const void *g_xnew, void *g, float *gw, float *gb,
+                                void *workspace, size_t workspace_bytes, void *stream);
 WKV6_API int cmix_shift_lerp2_bf16(int B, int T, int C, const void *x, const void *shift_state,
                           const void *maa_kr, void *out, void *stream);
 /* ws: elementwise_backward_workspace_bytes(B, T, C, 3) bytes; gmaa_kr fp32 [2,C]. */

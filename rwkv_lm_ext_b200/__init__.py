@@ -6,10 +6,10 @@ from ._lib import LIB_PATH, Wkv6B200Error, launch_count, load, set_decay_clamp, 
 from .ops import (HEAD_SIZE, RUN_CUDA_RWKV6, RUN_CUDA_RWKV6_BI, RUN_CUDA_RWKV6_STATE, RUN_RWKV_6, RWKV_6,  # noqa: F401
                   WKV_6, WKV_6_BI, WKV_6STATE, WKV_6STATE_INFCTX, exact_route_report, install, rwkv6, wkv6_bi_cuda, wkv6_cuda,
                   wkv6infctx_cuda, wkv6state_cuda)
-from .heads import (create_mask_and_rev_idx, eos_gather, eos_index, gather_rows, groupnorm_gate, groupnorm_gate_pair, pooling,  # noqa: F401
+from .heads import (add_layernorm, create_mask_and_rev_idx, eos_gather, eos_index, gather_rows, groupnorm_gate, groupnorm_gate_pair, pooling,  # noqa: F401
                     reverse_x, tmix_ddlerp_lora, tmix_ddlerp_mix, tmix_shift_lerp)
 from .cmix import cmix_shift_lerp2, cmix_x060_forward, relu_sq, sigmoid_mul  # noqa: F401
-from .encoders import (bi_encoder_encode, bi_encoder_hidden, bi_tmix_forward, causal_hidden, classification_logits,  # noqa: F401
+from .encoders import (bi_encoder_encode, bi_encoder_hidden, bi_tmix_forward, blocks_forward, causal_hidden, classification_logits,  # noqa: F401
                        cross_encoder_rows, encode_corpus, length_buckets, sequence_embedding)
 from .infctx import BlockState, BlockStateList, ChannelMixState, TimeMixState  # noqa: F401
 from .tmix import Tmix_x060, tmix_x060_finish, tmix_x060_forward, tmix_x060_project  # noqa: F401

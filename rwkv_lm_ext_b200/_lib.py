@@ -41,6 +41,7 @@ SIGNATURES = {
     "wkv6_bi_backward": (c_i, _BTCH + [c_p] * 13 + [c_sz, c_p]),
     "wkv6_bi_backward_raww": (c_i, _BTCH + [c_p] * 13 + [c_sz, c_p]),
     "rwkv6_forward": (c_i, [c_i] + _BTCH + [c_p] * 8),
+    "rwkv6_forward_raww": (c_i, _BTCH + [c_p] * 8),
     "eos_index_i64": (c_i, [c_i, c_i, c_p, c_i64, c_p, c_p]),
     "gather_rows_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "pooling_bf16": (c_i, [c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
@@ -57,6 +58,9 @@ SIGNATURES = {
     "groupnorm_gate_backward_bf16": (c_i, [c_i, c_i, c_i, c_f, c_i] + [c_p] * 10 + [c_sz, c_p]),
     "pooling_backward_bf16": (c_i, [c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "scatter_rows_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "add_layernorm_bf16": (c_i, [ctypes.c_longlong, c_i, c_f] + [c_p] * 8),
+    "add_layernorm_backward_workspace_bytes": (c_sz, [ctypes.c_longlong, c_i]),
+    "add_layernorm_backward_bf16": (c_i, [ctypes.c_longlong, c_i] + [c_p] * 9 + [c_sz, c_p]),
     "cmix_shift_lerp2_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     "cmix_shift_lerp2_backward_bf16": (c_i, [c_i, c_i, c_i] + [c_p] * 9 + [c_sz, c_p]),
     "relu_sq_bf16": (c_i, [c_sz, c_p, c_p, c_p]),

@@ -428,4 +428,16 @@ int rwkv6_forward(int dtype, int B, int T, int C, int H, float *state, const voi
     return dispatch_forward(a);
 }
 
+int rwkv6_forward_raww(int B, int T, int C, int H, float *state, const void *r, const void *k,
+                       const void *v, const void *w, const void *u, void *y, void *stream) {
+    if (int rc = check_shape(B, T, C, H)) return rc;
+    if ((size_t)B * T == 0) return WKV6_OK;
+    REQUIRE_PTRS(state, r, k, v, w, u, y);
+    Args a;
+    a.B = B; a.T = T; a.H = H; a.io_dtype = WKV6_BF16; a.r = r; a.k = k; a.v = v; a.w = w;
+    a.w_kind = W_RAW_BF16; a.u = u; a.s0 = state; a.s0_f32 = 1; a.s0_bstride = (long long)H * N * N;
+    a.sT = state; a.sT_f32 = 1; a.y = y; a.stream = (cudaStream_t)stream;
+    return dispatch_forward(a);
+}
+
 }  // extern "C"

@@ -40,22 +40,38 @@ def bi_tmix_forward(att, x, rev_idx):
     return att.output(z)
 
 
+def _ffn(ffn, h):
+    if all(hasattr(ffn, n) for n in ("time_maa_k", "time_maa_r", "key", "receptance", "value")):
+        return cmix.cmix_x060_forward(ffn, h)                         # x060 channel mix on the fused kernels
+    return ffn(h)
+
+
+def blocks_forward(blocks, x, ln_out, att):
+    """ln_out(block_L(... block_1(x))) for `Block.forward` of src/model.py:904-933 (x = ln0(x) in block 0;
+    x = x + att(ln1(x)); x = x + ffn(ln2(x))), with every residual add fused with the LayerNorm that follows it
+    (heads.add_layernorm: one pass over the residual stream instead of an add pass and a LayerNorm pass).
+    `att(blk, h)` computes the time-mix output of a block from its normalised input."""
+    def ln(mod, x_, delta=None):
+        return heads.add_layernorm(x_, delta, mod.weight, mod.bias, mod.eps)
+    h = None
+    n = len(blocks)
+    for i, blk in enumerate(blocks):
+        if i == 0 and hasattr(blk, "ln0"):
+            x = ln(blk.ln0, x)[1]
+        if h is None:
+            h = ln(blk.ln1, x)[1]
+        x, h = ln(blk.ln2, x, att(blk, h))                            # x += att(ln1(x));  h = ln2(x)
+        nxt = blocks[i + 1].ln1 if i + 1 < n else ln_out
+        x, h = ln(nxt, x, _ffn(blk.ffn, h))                           # x += ffn(ln2(x));  h = next ln1(x) / ln_out(x)
+    return h
+
+
 def bi_encoder_hidden(model, idx):
     """ln_out(blocks(emb(idx)))  [B,T,D] in the model's dtype (bf16 weights expected)."""
     emb_id, pad_id = _ids(model)
     idx = idx.contiguous()
     _, rev_idx = heads.create_mask_and_rev_idx(idx, emb_id, pad_id)
-    x = model.emb(idx)
-    for i, blk in enumerate(model.blocks):
-        if i == 0 and hasattr(blk, "ln0"):
-            x = blk.ln0(x)
-        x = x + bi_tmix_forward(blk.att, blk.ln1(x), rev_idx)
-        ffn = blk.ffn
-        if all(hasattr(ffn, n) for n in ("time_maa_k", "time_maa_r", "key", "receptance", "value")):
-            x = x + cmix.cmix_x060_forward(ffn, blk.ln2(x))          # x060 channel mix on the fused kernels
-        else:
-            x = x + ffn(blk.ln2(x))
-    return model.ln_out(x)
+    return blocks_forward(model.blocks, model.emb(idx), model.ln_out, lambda blk, h: bi_tmix_forward(blk.att, h, rev_idx))
 
 
 def bi_encoder_encode(model, idx):
@@ -79,17 +95,8 @@ def causal_hidden(model, idx):
     before it, so a padded batch gives each row what the reference's one-sentence-at-a-time inference classes
     (src/model_run.py:815-848) compute for it."""
     base = _base(model)
-    x = base.emb(idx.contiguous())
-    for i, blk in enumerate(base.blocks):
-        if i == 0 and hasattr(blk, "ln0"):
-            x = blk.ln0(x)
-        x = x + tmix.tmix_x060_forward(blk.att, blk.ln1(x))
-        ffn = blk.ffn
-        if all(hasattr(ffn, n) for n in ("time_maa_k", "time_maa_r", "key", "receptance", "value")):
-            x = x + cmix.cmix_x060_forward(ffn, blk.ln2(x))
-        else:
-            x = x + ffn(blk.ln2(x))
-    return base.ln_out(x)
+    return blocks_forward(base.blocks, base.emb(idx.contiguous()), base.ln_out,
+                          lambda blk, h: tmix.tmix_x060_forward(blk.att, h))
 
 
 def sequence_embedding(wrapper, idx, variant="train"):

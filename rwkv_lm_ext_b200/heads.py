@@ -392,3 +392,88 @@ def groupnorm_gate_pair(y, y_rev, rev_idx, g, ln_w, ln_b, H, eps, gate_act=None)
                                                ptr(_bf16_param(ln_w)), ptr(_bf16_param(ln_b)), ptr(out), stream_of(y)),
           "groupnorm_gate_pair_bf16")
     return out
+
+
+def _add_ln_fwd(x, delta, w, b, eps, want_stats):
+    D = x.shape[-1]
+    rows = x.numel() // D
+    y = torch.empty_like(x)
+    x_new = torch.empty_like(x) if delta is not None else None
+    stats = torch.empty(rows, 2, dtype=torch.float32, device=x.device) if want_stats else None
+    check(_lib.load().add_layernorm_bf16(rows, D, float(eps), ptr(x), ptr(delta), ptr(w), ptr(b), ptr(x_new), ptr(y),
+                                         ptr(stats), stream_of(x)), "add_layernorm_bf16")
+    return (x if delta is None else x_new), y, stats
+
+
+def _add_ln_bwd(ctx, g_xnew, g_y):
+    x_new, stats, w = ctx.saved_tensors
+    lib = _lib.load()
+    D = x_new.shape[-1]
+    rows = x_new.numel() // D
+    if g_y is None:                              # only the residual stream carried a gradient
+        return g_xnew, None, None
+    g_y = g_y.contiguous()
+    g_xnew = g_xnew.contiguous() if g_xnew is not None else None
+    g = torch.empty_like(x_new)
+    need_p = ctx.needs_input_grad[ctx.w_index] or ctx.needs_input_grad[ctx.w_index + 1]
+    gw = torch.empty(D, dtype=torch.float32, device=x_new.device) if need_p else None
+    gb = torch.empty(D, dtype=torch.float32, device=x_new.device) if need_p else None
+    n = lib.add_layernorm_backward_workspace_bytes(rows, D) if need_p else 0
+    ws = torch.empty(max(n, 1), dtype=torch.uint8, device=x_new.device) if need_p else None
+    check(lib.add_layernorm_backward_bf16(rows, D, ptr(x_new), ptr(stats), ptr(w), ptr(g_y), ptr(g_xnew), ptr(g), ptr(gw),
+                                          ptr(gb), ptr(ws), n, stream_of(x_new)), "add_layernorm_backward_bf16")
+    return g, (gw.to(w.dtype) if need_p else None), (gb.to(w.dtype) if need_p else None)
+
+
+class _AddLayerNorm(torch.autograd.Function):
+    """(x, delta) -> (x + delta, LayerNorm(x + delta)); one gradient tensor serves x and delta."""
+
+    @staticmethod
+    def forward(ctx, x, delta, w, b, eps):
+        x_new, y, stats = _add_ln_fwd(x, delta, w, b, eps, True)
+        ctx.save_for_backward(x_new, stats, w)
+        ctx.w_index = 2
+        return x_new, y
+
+    @staticmethod
+    def backward(ctx, g_xnew, g_y):
+        g, gw, gb = _add_ln_bwd(ctx, g_xnew, g_y)
+        return g, g, gw, gb, None
+
+
+class _LayerNorm(torch.autograd.Function):
+    """x -> LayerNorm(x) on the same kernels (no residual operand)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b, eps):
+        _, y, stats = _add_ln_fwd(x, None, w, b, eps, True)
+        ctx.save_for_backward(x, stats, w)
+        ctx.w_index = 1
+        return y
+
+    @staticmethod
+    def backward(ctx, g_y):
+        g, gw, gb = _add_ln_bwd(ctx, None, g_y)
+        return g, gw, gb, None
+
+
+def add_layernorm(x, delta, ln_w, ln_b, eps=1e-5):
+    """(x_new, y) with x_new = x + delta and y = LayerNorm(x_new) -- the residual add and the next LayerNorm of
+    `Block.forward` (src/model.py:904-933) in one pass over the residual stream.  delta = None: y = LayerNorm(x),
+    x_new is x.  bf16 [..., D], D % 256 == 0 (other widths take the eager route).  Differentiable w.r.t. x, delta
+    and the affine parameters (their column pass is skipped when they are frozen)."""
+    _cuda(x)
+    assert x.dtype == torch.bfloat16
+    D = x.shape[-1]
+    if D % 256 != 0:
+        x_new = x if delta is None else x + delta
+        return x_new, torch.nn.functional.layer_norm(x_new, (D,), ln_w, ln_b, eps)
+    x = x.contiguous()
+    delta = delta.contiguous() if delta is not None else None
+    w, b = _bf16_param(ln_w), _bf16_param(ln_b)
+    if _needs_grad(x, delta, w, b):
+        if delta is None:
+            return x, _LayerNorm.apply(x, w, b, eps)
+        return _AddLayerNorm.apply(x, delta, w, b, eps)
+    x_new, y, _ = _add_ln_fwd(x, delta, w, b, eps, False)
+    return x_new, y

@@ -229,12 +229,17 @@ class RWKV_6(torch.autograd.Function):
             assert w.is_contiguous() and u.is_contiguous() and state.is_contiguous()
             _require_cuda(r)
             y = torch.empty((B, T, C), device=w.device, dtype=r.dtype, memory_format=torch.contiguous_format)
-            # the reference computes eew = exp(-exp(w.float())) in PyTorch first (src/model_run.py:64)
-            eew = torch.exp(-torch.exp(w.float())).contiguous()
-            code = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}[r.dtype]
             lib = _lib.load()
-            check(lib.rwkv6_forward(code, B, T, C, H, ptr(state), ptr(r), ptr(k), ptr(v), ptr(eew), ptr(u),
-                                    ptr(y), stream_of(r)), "rwkv6_forward")
+            if r.dtype == torch.bfloat16 and all(t.dtype == torch.bfloat16 for t in (k, v, w, u)):
+                # bf16 models: the kernels read the raw logits themselves -- no exp(-exp(w.float())) passes
+                check(lib.rwkv6_forward_raww(B, T, C, H, ptr(state), ptr(r), ptr(k), ptr(v), ptr(w), ptr(u), ptr(y),
+                                             stream_of(r)), "rwkv6_forward_raww")
+            else:
+                # the reference computes eew = exp(-exp(w.float())) in PyTorch first (src/model_run.py:64)
+                eew = torch.exp(-torch.exp(w.float())).contiguous()
+                code = {torch.bfloat16: 0, torch.float16: 1, torch.float32: 2}[r.dtype]
+                check(lib.rwkv6_forward(code, B, T, C, H, ptr(state), ptr(r), ptr(k), ptr(v), ptr(eew), ptr(u),
+                                        ptr(y), stream_of(r)), "rwkv6_forward")
             ctx.mark_dirty(state)
             return y, state
 

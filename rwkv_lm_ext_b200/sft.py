@@ -127,10 +127,9 @@ class RwkvSft(nn.Module):
         self.train_type = train_type
 
     def forward(self, idx):
-        x = self.emb(idx)
-        for blk in self.blocks:
-            x = blk(x)
-        return self.head(self.ln_out(x))
+        from .encoders import blocks_forward      # residual adds fused with the LayerNorms that follow them
+        h = blocks_forward(self.blocks, self.emb(idx), self.ln_out, lambda blk, x: blk.att(x))
+        return self.head(h)
 
     def mark_trainable(self):
         """peft_train_sft.py:330-387: LoRA / PiSSA train the `lora_` parameters, state tuning the `state` ones."""

@@ -375,3 +375,43 @@ def test_no_writes_outside_the_outputs(M):
                                                   None, p(ws3), ws3.numel(), st), "cmix bwd")
     torch.cuda.synchronize()
     assert intact(o2b) and intact(g2b) and intact(a2b)
+
+
+@pytest.mark.parametrize("D", [768, 2048, 2560, 4096])
+@pytest.mark.parametrize("with_delta", [True, False])
+def test_add_layernorm_matches_the_eager_chain(D, with_delta):
+    """x_new = x + delta, y = LayerNorm(x_new) (the residual glue of Block.forward, src/model.py:904-933) in one kernel:
+    forward equal to torch's bf16 add + layer_norm up to one bf16 ulp of y, backward against fp32 autograd, including the
+    affine-parameter gradients and the case where they are frozen."""
+    import rwkv_lm_ext_b200 as M
+    torch.manual_seed(D)
+    B, T = 3, 37
+    x = torch.randn(B, T, D, device=DEV).bfloat16()
+    delta = (torch.randn(B, T, D, device=DEV) * 0.5).bfloat16() if with_delta else None
+    w = (1 + 0.3 * torch.randn(D, device=DEV)).bfloat16()
+    b = (0.2 * torch.randn(D, device=DEV)).bfloat16()
+    xs = x + delta if with_delta else x
+    y_ref = torch.nn.functional.layer_norm(xs, (D,), w, b, 1e-5)
+    x_new, y = M.add_layernorm(x, delta, w, b, 1e-5)
+    assert torch.equal(x_new, xs)
+    assert (y.float() - y_ref.float()).abs().max().item() <= 2.0 ** -7 * y_ref.float().abs().max().item()
+    assert relrms(y, y_ref) < 3e-3
+    # backward
+    go_x = torch.randn(B, T, D, device=DEV).bfloat16()
+    go_y = torch.randn(B, T, D, device=DEV).bfloat16()
+    leaves32 = [t.float().detach().requires_grad_(True) for t in ([x, delta] if with_delta else [x]) + [w, b]]
+    xs32 = leaves32[0] + leaves32[1] if with_delta else leaves32[0]
+    y32 = torch.nn.functional.layer_norm(xs32, (D,), leaves32[-2], leaves32[-1], 1e-5)
+    (y32 * go_y.float()).sum().backward() if not with_delta else ((y32 * go_y.float()).sum() + (xs32 * go_x.float()).sum()).backward()
+    leaves = [t.detach().clone().requires_grad_(True) for t in ([x, delta] if with_delta else [x]) + [w, b]]
+    xn, yy = M.add_layernorm(leaves[0], leaves[1] if with_delta else None, leaves[-2], leaves[-1], 1e-5)
+    ((yy.float() * go_y.float()).sum() if not with_delta else (yy.float() * go_y.float()).sum() + (xn.float() * go_x.float()).sum()).backward()
+    for a, r_, name in zip(leaves, leaves32, (["x", "delta"] if with_delta else ["x"]) + ["w", "b"]):
+        assert relrms(a.grad, r_.grad) < 6e-3, (name, relrms(a.grad, r_.grad))
+    # frozen affine parameters (LoRA / state tuning): no column pass, same input gradient
+    xf = x.detach().clone().requires_grad_(True)
+    _, y2 = M.add_layernorm(xf, delta, w, b, 1e-5)
+    (y2.float() * go_y.float()).sum().backward()
+    ref_gx = torch.autograd.grad((torch.nn.functional.layer_norm((xf.float() + (delta.float() if with_delta else 0)), (D,), w.float(), b.float(), 1e-5)
+                                  * go_y.float()).sum(), xf)[0]
+    assert relrms(xf.grad, ref_gx) < 6e-3
