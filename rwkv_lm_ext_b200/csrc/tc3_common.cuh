@@ -29,6 +29,7 @@ constexpr float LOG2_LOG2E = 0.5287663729448977f;   // log2(log2(e)): exp(w) * l
 // recurrence at w ~ N(0,1) and hotter, tests/test_gpu_parity.py), and it bounds every scaled operand: a 16-token
 // block has its reference in the middle, so exponents stay within 8 x 13 = 104 < 127 binary orders.
 constexpr float LCLAMP2 = 13.0f;
+constexpr int B_SCAN_ID = 1;   // == B_SCAN below (named barrier of the 256 compute threads)
 
 __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 t = __floats2bfloat162_rn(a, b);
@@ -115,11 +116,80 @@ struct Frag {
     __device__ __forceinline__ int col(int g, int e) const { return 32 * ch + 8 * g + 2 * q + e; }
 };
 
+// ---- bidirectional op (wkv6_bi_tc.cu): the kernels take a mode BI.
+//   BI_NONE   the ordinary call
+//   BI_CAUSAL the causal direction of wkv6_bi: every batch row has its own length (row_len[b] = p + 1 tokens); tokens
+//             past it are treated as absent and the outputs behind it are written as zeros
+//   BI_REV    the reverse direction: the SAME tiles, read so that the kernel sees the row's first p + 1 tokens in
+//             reversed order.  Chunk c covers reversed positions tau = 64c .. 64c + nv - 1 (nv = 64 but for the last
+//             chunk), i.e. the tile that starts at token max(p + 1 - 64(c+1), 0) -- TMA stores do not take negative
+//             coordinates -- and inside the tile row x holds tau_local = (nv - 1 - x) mod 64; the rows x >= nv of a
+//             short last chunk (tokens the previous chunk already covered) are masked like the padding of a ragged
+//             causal chunk.  ldmatrix / stmatrix take one row address per lane, so reading the raw r, k, w tiles and
+//             writing the output tiles in that row order costs nothing; the tiles the tensor cores read as they
+//             arrive (v, gy) are permuted in place by the compute warps first.  Outputs are ADDED to what the causal
+//             pass stored (cp.reduce.async.bulk.tensor; masked rows add zeros), u = 0.
+enum : int { BI_NONE = 0, BI_CAUSAL = 1, BI_REV = 2 };
+// byte offset inside an 8 KB [64 rows][128 B] swizzled tile -> the same 16-byte chunk of row (r0 - row) mod 64
+__device__ __forceinline__ uint32_t flip_rows(uint32_t off, int r0) {
+    const uint32_t row = off >> 7, row2 = (uint32_t)(r0 - (int)row) & 63u;
+    return (row2 << 7) | ((off & 0x7fu) ^ (((row ^ row2) & 7u) << 4));
+}
+// Reverse the 64 rows of NT 8 KB swizzled tiles in place (row x <-> 63 - x).  Warp w of the 8 compute warps owns rows
+// 4w..4w+3 and their mirror images 60-4w..63-4w: a set closed under the reversal, so no two warps touch the same bytes.
+template <int NT>
+__device__ __forceinline__ void flip_tiles_full(const uint32_t (&tiles)[NT], int warp, int lane) {
+    const int rr = lane & 7, row = rr < 4 ? 4 * warp + rr : 56 - 4 * warp + rr;     // rr 4..7 -> 60-4w .. 63-4w
+    uint32_t x[NT][2][4];
+#pragma unroll
+    for (int t = 0; t < NT; t++)
+#pragma unroll
+        for (int half = 0; half < 2; half++)
+            ldsm_x4(tiles[t] + sw128(row, 16 * ((lane >> 3) + 4 * half)), x[t][half][0], x[t][half][1], x[t][half][2], x[t][half][3]);
+    __syncwarp();
+#pragma unroll
+    for (int t = 0; t < NT; t++)
+#pragma unroll
+        for (int half = 0; half < 2; half++)
+            stsm_x4(tiles[t] + sw128(63 - row, 16 * ((lane >> 3) + 4 * half)), x[t][half][0], x[t][half][1], x[t][half][2], x[t][half][3]);
+}
+// Short last chunk (nv < 64 valid rows): row x -> (nv - 1 - x) mod 64, the rows x >= nv zeroed.  The images of a warp's
+// rows belong to other warps, hence the barrier between reading and writing (all 256 compute threads call this).
+template <int NT>
+__device__ __forceinline__ void flip_tiles_short(const uint32_t (&tiles)[NT], int nv, int warp, int lane) {
+    const int row = 8 * warp + (lane & 7), mine = 8 * warp + (lane >> 2);           // address row / row of my fragment
+    uint32_t x[NT][2][4];
+#pragma unroll
+    for (int t = 0; t < NT; t++)
+#pragma unroll
+        for (int half = 0; half < 2; half++) {
+            ldsm_x4(tiles[t] + sw128(row, 16 * ((lane >> 3) + 4 * half)), x[t][half][0], x[t][half][1], x[t][half][2], x[t][half][3]);
+            if (mine >= nv) x[t][half][0] = x[t][half][1] = x[t][half][2] = x[t][half][3] = 0u;
+        }
+    named_bar_sync<B_SCAN_ID, 256>();
+    const int dst = (nv - 1 - row) & 63;
+#pragma unroll
+    for (int t = 0; t < NT; t++)
+#pragma unroll
+        for (int half = 0; half < 2; half++)
+            stsm_x4(tiles[t] + sw128(dst, 16 * ((lane >> 3) + 4 * half)), x[t][half][0], x[t][half][1], x[t][half][2], x[t][half][3]);
+}
+// zero the rows >= nv of an 8 KB tile (256 threads)
+__device__ __forceinline__ void zero_tile_rows(uint8_t *tile, int nv, int tid) {
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const int u = tid + 256 * k, row = u >> 3;
+        if (row >= nv) *reinterpret_cast<uint4 *>(tile + u * 16) = make_uint4(0, 0, 0, 0);
+    }
+}
+// packed bf16 pair of tokens (t0, t0 + 1): keep what lies before token nv
+__device__ __forceinline__ uint32_t pair_mask(int t0, int nv) { return t0 >= nv ? 0u : t0 + 1 >= nv ? 0xffffu : 0xffffffffu; }
+
 // Hand-offs between the issuer warp and the compute warps go through hardware named barriers
 // (producer: bar.arrive, consumer: bar.sync, 288 threads): nobody spins.  Only lane 0 of the issuer
 // warp ever polls an mbarrier (TMA / tcgen05.commit completion); a compute warp spinning on
 // try_wait would take issue slots from the co-resident CTA that is doing useful work.
-enum : int { B_SCAN = 1, B_RAW, B_PREP, B_M1, B_T1, B_M2, B_T2, B_M3, B_T3, B_T1A, B_T2A, B_BM, B_DR, B_FREE };
+enum : int { B_SCAN = 1, B_RAW, B_PREP, B_M1, B_T1, B_M2, B_T2, B_M3, B_T3, B_T1A, B_T2A, B_BM, B_DR, B_FREE, B_VG };
 template <int ID>
 __device__ __forceinline__ void bar_arrive_all() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(NTHREADS) : "memory"); }
 template <int ID>

@@ -92,6 +92,7 @@ struct Params {
     float lmin;               // floor of the per-token log2-decay (>= -LCLAMP2)
     bf16 *gu, *gs;
     const int *hz_flags;
+    const int *row_len;       // BI modes: tokens of every batch row (p + 1 of wkv6_bi), device int [B]
     long long *dbg;           // nullptr, or [gridDim][NC][8 (32 in the profiling build)] clock64 stamps of warp 0 at the stage boundaries (profiling aid)
 };
 
@@ -100,7 +101,8 @@ __device__ __forceinline__ uint32_t pack_frag(const uint32_t *v, int g, int hh) 
 }
 
 // SEG = false: the ordinary call, its own instantiation (see the forward kernel).
-template <bool SEG>
+// BI: direction of the bidirectional op (tc3_common.cuh); BI_NONE for every other call.
+template <bool SEG, int BI = BI_NONE>
 __global__ void __launch_bounds__(NTHREADS, 2)
 wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_w,
@@ -114,9 +116,11 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
     const int row = blockIdx.x / p.H, h = blockIdx.x % p.H;
     const int b = SEG ? row / p.nseg : row;                                  // batch index inside the [B,T,C] tensors
     const int t_base = SEG ? (row % p.nseg) * p.seg_chunks * L : 0;          // first token of this row's segment
-    const int T = SEG ? min(p.T - t_base, p.seg_chunks * L) : p.T, C = p.H * 64;
+    const int T = BI ? p.row_len[b] : SEG ? min(p.T - t_base, p.seg_chunks * L) : p.T, C = p.H * 64;
     const int NC = (T + L - 1) / L;
-    const int ck_stride = SEG ? p.seg_chunks : NC;                           // checkpoint slots per row
+    const int ck_stride = SEG ? p.seg_chunks : BI ? (p.T + L - 1) / L : NC;  // checkpoint slots per row
+    // first token of chunk c's tile (BI_REV: the tile that ends at token T-1-64c, read backwards; see tc3_common.cuh)
+    auto tok0 = [&](int c) { return BI == BI_REV ? max(T - (c + 1) * L, 0) : t_base + c * L; };
     Frag F;
     F.init();
     const int warp = F.warp, lane = F.lane;
@@ -150,17 +154,17 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         // =====================================================================================
         auto issue_rk = [&](int c) {
             mbar_arrive_expect_tx(&ex.bar_rk, 2 * 8192);
-            tma_load_3d(sm + OFF_R, &map_r, &ex.bar_rk, h * 64, t_base + c * L, b);
-            tma_load_3d(sm + OFF_K, &map_k, &ex.bar_rk, h * 64, t_base + c * L, b);
+            tma_load_3d(sm + OFF_R, &map_r, &ex.bar_rk, h * 64, tok0(c), b);
+            tma_load_3d(sm + OFF_K, &map_k, &ex.bar_rk, h * 64, tok0(c), b);
         };
         auto issue_w = [&](int c) {
             mbar_arrive_expect_tx(&ex.bar_w, 8192);
-            tma_load_3d(sm + OFF_W, &map_w, &ex.bar_w, h * 64, t_base + c * L, b);
+            tma_load_3d(sm + OFF_W, &map_w, &ex.bar_w, h * 64, tok0(c), b);
         };
         auto issue_vg = [&](int c) {
             mbar_arrive_expect_tx(&ex.bar_vg, 2 * 8192);
-            tma_load_3d(sm + OFF_V, &map_v, &ex.bar_vg, h * 64, t_base + c * L, b);
-            tma_load_3d(sm + OFF_GY, &map_gy, &ex.bar_vg, h * 64, t_base + c * L, b);
+            tma_load_3d(sm + OFF_V, &map_v, &ex.bar_vg, h * 64, tok0(c), b);
+            tma_load_3d(sm + OFF_GY, &map_gy, &ex.bar_vg, h * 64, tok0(c), b);
         };
         auto issue_sin = [&](int c) {
             mbar_arrive_expect_tx(&ex.bar_sin, 8192);
@@ -183,6 +187,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         if (lane == 0) {
             mbar_wait(&ex.bar_rk, 0);
             mbar_wait(&ex.bar_w, 0);
+            if (BI) mbar_wait(&ex.bar_vg, 0);                    // the compute warps reverse / mask the V and GY tiles first
         }
         __syncwarp();
         bar_arrive_all<B_RAW>();
@@ -192,6 +197,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             if (lane == 0 && it > 0) tma_store_wait_read<0>();   // every output tile of the previous chunk has left shared memory
             __syncwarp();
             bar_arrive_all<B_FREE>();                            // ... so the preparation may overwrite KT, RP (and T1 DA)
+            if (BI) bar_sync_all<B_VG>();                        // V, GY reversed (BI_REV) / masked behind the row's end (BI_CAUSAL)
             // ---- products that need nothing from the operand preparation run under it
             if (elect_one()) {
                 mbar_wait(&ex.bar_vg, par);
@@ -282,23 +288,51 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             bar_arrive_all<B_M3>();
             bar_sync_all<B_T2>();                                // gv tile written (under M3)
             if (lane == 0) {
-                tma_store_3d(&map_gv, sm + OFF_GVT, h * 64, t_base + c * L, b);
-                tma_store_3d(&map_gr, sm + OFF_GRT, h * 64, t_base + c * L, b);
+                if (BI == BI_REV) {                              // added to what the causal pass stored
+                    tma_reduce_add_3d(&map_gv, sm + OFF_GVT, h * 64, tok0(c), b);
+                    tma_reduce_add_3d(&map_gr, sm + OFF_GRT, h * 64, tok0(c), b);
+                } else {
+                    tma_store_3d(&map_gv, sm + OFF_GVT, h * 64, tok0(c), b);
+                    tma_store_3d(&map_gr, sm + OFF_GRT, h * 64, tok0(c), b);
+                }
                 tma_store_commit();
                 if (c > 0) {                                     // the raw tiles of the next chunk, while T3 runs
                     mbar_wait(&ex.bar_rk, par ^ 1);
                     mbar_wait(&ex.bar_w, par ^ 1);
+                    if (BI) mbar_wait(&ex.bar_vg, par ^ 1);
                 }
             }
             __syncwarp();
             bar_sync_all<B_T3>();                                // gk, gw tiles written
             if (lane == 0) {
-                tma_store_3d(&map_gk, sm + OFF_GKT, h * 64, t_base + c * L, b);
-                tma_store_3d(&map_gw, sm + OFF_GWT, h * 64, t_base + c * L, b);
+                if (BI == BI_REV) {
+                    tma_reduce_add_3d(&map_gk, sm + OFF_GKT, h * 64, tok0(c), b);
+                    tma_reduce_add_3d(&map_gw, sm + OFF_GWT, h * 64, tok0(c), b);
+                } else {
+                    tma_store_3d(&map_gk, sm + OFF_GKT, h * 64, tok0(c), b);
+                    tma_store_3d(&map_gw, sm + OFF_GWT, h * 64, tok0(c), b);
+                }
                 tma_store_commit();
             }
             __syncwarp();
             if (c > 0) bar_arrive_all<B_RAW>();
+        }
+        if (BI == BI_CAUSAL && NC * L < p.T) {                    // all four gradients are 0 behind the row's last chunk
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 16; k++) *reinterpret_cast<uint4 *>(sm + OFF_R + (lane + 32 * k) * 16) = make_uint4(0, 0, 0, 0);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                for (int c = NC; c * L < p.T; c++) {
+                    tma_store_3d(&map_gr, sm + OFF_R, h * 64, c * L, b);
+                    tma_store_3d(&map_gk, sm + OFF_R, h * 64, c * L, b);
+                    tma_store_3d(&map_gv, sm + OFF_R, h * 64, c * L, b);
+                    tma_store_3d(&map_gw, sm + OFF_R, h * 64, c * L, b);
+                }
+                tma_store_commit();
+            }
         }
         if (lane == 0) tma_store_wait_all<0>();
     } else {
@@ -358,14 +392,28 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             bar_sync_all<B_RAW>();
             asm volatile("fence.acq_rel.cta;" ::: "memory");
             STAMP(0);
+            if (BI) {      // the V and GY tiles go to the tensor cores as they lie in shared memory
+                if (BI == BI_REV) {
+                    const uint32_t vt[2] = {sbase + OFF_V, sbase + OFF_GY};
+                    if (nv == L) flip_tiles_full(vt, warp, lane);
+                    else flip_tiles_short(vt, nv, warp, lane);
+                } else if (nv < L) {
+                    zero_tile_rows(sm + OFF_V, nv, threadIdx.x);
+                    zero_tile_rows(sm + OFF_GY, nv, threadIdx.x);
+                }
+                fence_proxy_async();
+                bar_arrive_all<B_VG>();
+            }
+            const int r0 = nv - 1;                  // BI_REV: row x of a tile holds reversed position (r0 - x) mod 64
+            const auto raw = [&](int hh) { return BI == BI_REV ? flip_rows(F.ti(hh), r0) : F.ti(hh); };   // where the raw r, k, w tiles are read
             float lamf[2];                    // Lam (log2 units)
             int irb[2][2], ir0[2], ir3[2];    // block references (integers, log2 units): my two blocks, block 0, block 3
             {   // ---- everything per element lives only inside this block
             float l[2][4][2], exq[2][4];
             {
                 uint32_t wp[2][4];
-                ldsm_x4_t(sbase + OFF_W + F.ti(0), wp[0][0], wp[0][1], wp[0][2], wp[0][3]);
-                ldsm_x4_t(sbase + OFF_W + F.ti(1), wp[1][0], wp[1][1], wp[1][2], wp[1][3]);
+                ldsm_x4_t(sbase + OFF_W + raw(0), wp[0][0], wp[0][1], wp[0][2], wp[0][3]);
+                ldsm_x4_t(sbase + OFF_W + raw(1), wp[1][0], wp[1][1], wp[1][2], wp[1][3]);
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++)
 #pragma unroll
@@ -409,10 +457,18 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             STAMPX(10);
 
             uint32_t rr[2][4], kk[2][4];
-            ldsm_x4_t(sbase + OFF_R + F.ti(0), rr[0][0], rr[0][1], rr[0][2], rr[0][3]);
-            ldsm_x4_t(sbase + OFF_R + F.ti(1), rr[1][0], rr[1][1], rr[1][2], rr[1][3]);
-            ldsm_x4_t(sbase + OFF_K + F.ti(0), kk[0][0], kk[0][1], kk[0][2], kk[0][3]);
-            ldsm_x4_t(sbase + OFF_K + F.ti(1), kk[1][0], kk[1][1], kk[1][2], kk[1][3]);
+            ldsm_x4_t(sbase + OFF_R + raw(0), rr[0][0], rr[0][1], rr[0][2], rr[0][3]);
+            ldsm_x4_t(sbase + OFF_R + raw(1), rr[1][0], rr[1][1], rr[1][2], rr[1][3]);
+            ldsm_x4_t(sbase + OFF_K + raw(0), kk[0][0], kk[0][1], kk[0][2], kk[0][3]);
+            ldsm_x4_t(sbase + OFF_K + raw(1), kk[1][0], kk[1][1], kk[1][2], kk[1][3]);
+            if (BI && nv < L) {              // what lies behind the chunk's nv tokens is real data here, not TMA's zero fill
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const uint32_t m = pair_mask(F.col(g, 0), nv);
+                    rr[0][g] &= m; rr[1][g] &= m;
+                    kk[0][g] &= m; kk[1][g] &= m;
+                }
+            }
             {
                 uint32_t pk[16];
 #pragma unroll
@@ -644,7 +700,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     grp[hh] = f2tobf(f2fma(f2pack(E0, E0 * fast_ex2(__uint_as_float(l4[2 * hh]))), z, ubk));     // E Z + u bd k
                     f2unpacku(f2mul(bf2f2(a4[2 * hh]), z), a4[2 * hh], a4[2 * hh + 1]);    // XA = Rt Z, Rt exactly as the MMAs saw it
                 }
-                stsm_x2_t(sbase + OFF_GRT + ti2_off + 1024u * g, grp[0], grp[1]);
+                stsm_x2_t(sbase + OFF_GRT + (BI == BI_REV ? flip_rows(ti2_off + 1024u * g, r0) : ti2_off + 1024u * g), grp[0], grp[1]);
                 tmem_st_frag1(tPark + PARK_A + 8 * g, a4);
             }
             }
@@ -658,8 +714,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             tc_fence_after();
             tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X1 + 32 * ch), v);
             tmem_wait_ld();
-            stsm_x4(sbase + OFF_GVT + F.rc(0), pack_frag(v, 0, 0), pack_frag(v, 1, 0), pack_frag(v, 2, 0), pack_frag(v, 3, 0));
-            stsm_x4(sbase + OFF_GVT + F.rc(1), pack_frag(v, 0, 1), pack_frag(v, 1, 1), pack_frag(v, 2, 1), pack_frag(v, 3, 1));
+            stsm_x4(sbase + OFF_GVT + (BI == BI_REV ? flip_rows(F.rc(0), r0) : F.rc(0)), pack_frag(v, 0, 0), pack_frag(v, 1, 0), pack_frag(v, 2, 0), pack_frag(v, 3, 0));
+            stsm_x4(sbase + OFF_GVT + (BI == BI_REV ? flip_rows(F.rc(1), r0) : F.rc(1)), pack_frag(v, 0, 1), pack_frag(v, 1, 1), pack_frag(v, 2, 1), pack_frag(v, 3, 1));
             fence_proxy_async();
             tc_fence_before();
             bar_arrive_all<B_T2>();
@@ -723,7 +779,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     runD[hh] += __shfl_sync(0xffffffffu, y, 3, 4);
                     runX[hh] += z1;
                 }
-                stsm_x2_t(sbase + OFF_GKT + ti2_off + 1024u * g, gkp[0], gkp[1]);
+                stsm_x2_t(sbase + OFF_GKT + (BI == BI_REV ? flip_rows(ti2_off + 1024u * g, r0) : ti2_off + 1024u * g), gkp[0], gkp[1]);
                 tmem_st_frag1(tPark + PARK_A + 8 * g, a4);
             }
             }
@@ -777,7 +833,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     }
                     gwp[g] = pack2(gw0, gw1);
                 }
-                stsm_x4_t(sbase + OFF_GWT + F.ti(hh), gwp[0], gwp[1], gwp[2], gwp[3]);
+                stsm_x4_t(sbase + OFF_GWT + (BI == BI_REV ? flip_rows(F.ti(hh), r0) : F.ti(hh)), gwp[0], gwp[1], gwp[2], gwp[3]);
             }
             fence_proxy_async();
             tc_fence_before();
@@ -795,7 +851,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             if (q == 0) atomicAdd(&ex.gu_s[F.row(hh)], x);
         }
         named_bar_sync<B_SCAN, CTHREADS>();
-        if (threadIdx.x < 64) p.gu[(size_t)row * C + h * 64 + threadIdx.x] = __float2bfloat16_rn(ex.gu_s[threadIdx.x]);
+        if (BI != BI_REV && threadIdx.x < 64) p.gu[(size_t)row * C + h * 64 + threadIdx.x] = __float2bfloat16_rn(ex.gu_s[threadIdx.x]);   // (the reverse pass has u = 0)
     }
     tc_fence_before();
     __syncthreads();
@@ -855,9 +911,26 @@ __global__ void __launch_bounds__(256) clamp_gw_kernel(size_t n8, const bf16 *__
 }
 static inline float __logf_host(float x) { return logf(x); }
 
+template <bool SEG, int BI>
+static int launch_bwd_kernel(dim3 grid, cudaStream_t stream, const CUtensorMap *const *m, const Params &p) {
+    static bool attr_done[64] = {};          // function attributes are per device (and per instantiation)
+    int dev = 0;
+    WKV6_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_bwd_kernel<SEG, BI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_bwd_kernel<SEG, BI>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+    wkv6_tc3_bwd_kernel<SEG, BI><<<grid, NTHREADS, SMEM_BYTES, stream>>>(*m[0], *m[1], *m[2], *m[3], *m[4], *m[5], *m[6], *m[7], *m[8], *m[9], p);
+    count_launch();
+    WKV6_CUDA_CHECK(cudaGetLastError());
+    return WKV6_OK;
+}
+
 // one launch of the backward kernel on `a` viewed as given (B rows of T tokens), chunk-start states in ckpt
+// bi / row_len: direction of the bidirectional op (tc3_common.cuh) and the device int [B] row lengths it needs
 static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const float *g_init, int nseg, int seg_chunks,
-                      bool has_s0) {
+                      bool has_s0, int bi = BI_NONE, const int *row_len = nullptr) {
     const int C = a.H * 64;
     if (nseg <= 1) { nseg = 1; seg_chunks = (a.T + L - 1) / L; }
     const size_t NC = (size_t)nseg * seg_chunks;
@@ -887,23 +960,15 @@ static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const f
 #else
     p.dbg = nullptr;
 #endif
-    static bool attr_done[64] = {};          // function attributes are per device
-    int dev = 0;
-    WKV6_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-        const void *kerns[2] = {(const void *)wkv6_tc3_bwd_kernel<false>, (const void *)wkv6_tc3_bwd_kernel<true>};
-        for (const void *kf : kerns) {
-            WKV6_CUDA_CHECK(cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-            WKV6_CUDA_CHECK(cudaFuncSetAttribute(kf, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-        }
-        if (dev >= 0 && dev < 64) attr_done[dev] = true;
-    }
+    p.row_len = row_len;
     const bool clamp = a.lmin > -INFINITY;
     const dim3 grid(a.B * nseg * a.H);
-    if (nseg > 1) wkv6_tc3_bwd_kernel<true><<<grid, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
-    else wkv6_tc3_bwd_kernel<false><<<grid, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, mg, mc, ogr, ogk, ogv, ogw, p);
-    count_launch();
-    WKV6_CUDA_CHECK(cudaGetLastError());
+    int rc;
+    if (bi == BI_CAUSAL) rc = launch_bwd_kernel<false, BI_CAUSAL>(grid, a.stream, maps, p);
+    else if (bi == BI_REV) rc = launch_bwd_kernel<false, BI_REV>(grid, a.stream, maps, p);
+    else if (nseg > 1) rc = launch_bwd_kernel<true, BI_NONE>(grid, a.stream, maps, p);
+    else rc = launch_bwd_kernel<false, BI_NONE>(grid, a.stream, maps, p);
+    if (rc != WKV6_OK) return rc;
     if (clamp) {                       // opt-in decay clamp: a clamped decay no longer depends on w (kept out of the hot kernel)
         const size_t n8 = (size_t)a.B * a.T * C / 8;
         size_t g = (n8 + 255) / 256;
@@ -952,6 +1017,16 @@ static int tc3_backward_segmented(const Args &a, int nseg, int seg_chunks) {
     s.stream_flags = flags;
     s.workspace_bytes = simt_backward_workspace_bytes(a.B, a.T, a.H);
     return simt_backward(s);
+}
+
+// One direction of the bidirectional backward (wkv6_bi_tc.cu): recompute the chunk-start states of that direction
+// (state-only forward in the same mode), then the backward kernel in that mode.  ckpt: bf16 [B*H][ceil(T/64)][64][64].
+int tc3_backward_bi(const Args &a, void *ckpt, int *flags, int bi, const int *row_len) {
+    if (a.B * a.H == 0 || a.T == 0) return WKV6_OK;
+    Args f = a;
+    f.y = nullptr; f.sT = nullptr; f.s0 = nullptr;
+    if (int rc = tc3_forward(f, ckpt, flags, 1, 0, bi, row_len)) return rc;
+    return launch_bwd(a, (const bf16 *)ckpt, flags, nullptr, 1, 0, false, bi, row_len);
 }
 
 int tc3_backward(const Args &a, const Args *exact, bool flags_preset, bool run_fallback) {

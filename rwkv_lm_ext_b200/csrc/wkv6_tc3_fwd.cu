@@ -66,6 +66,7 @@ struct Params {
     // checkpoints are indexed by row; nseg = 1 and seg_chunks = ceil(T/64) for an ordinary call.
     int nseg, seg_chunks;
     float lmin;               // floor of the per-token log2-decay (opt-in clamp; -inf = off)
+    const int *row_len;       // BI modes: tokens of every batch row (p + 1 of wkv6_bi), device int [B]
 };
 
 // 9 warps x 2 CTAs = 5 warps on the fullest SM sub-partition (16384 registers): at most 96 per thread
@@ -73,7 +74,8 @@ struct Params {
 // that the segment arithmetic costs it nothing (with run-time descriptors ptxas scheduled the forward 7 % slower)
 // SO = true: a state-only pass known at compile time (the two extra passes of the segmented routes): no r tile,
 // no Rt / Kt versions, no diag(u) term, no A / Y products -- about half of the operand preparation.
-template <bool SEG, bool SO = false>
+// BI: direction of the bidirectional op (tc3_common.cuh); BI_NONE for every other call.
+template <bool SEG, bool SO = false, int BI = BI_NONE>
 __global__ void __launch_bounds__(NTHREADS, 2)
 wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_w,
@@ -85,9 +87,11 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
     const int row = blockIdx.x / p.H, h = blockIdx.x % p.H;
     const int b = SEG ? row / p.nseg : row;                                  // batch index inside the [B,T,C] tensors
     const int t_base = SEG ? (row % p.nseg) * p.seg_chunks * L : 0;          // first token of this row's segment
-    const int T = SEG ? min(p.T - t_base, p.seg_chunks * L) : p.T;           // tokens of the segment
+    const int T = BI ? p.row_len[b] : SEG ? min(p.T - t_base, p.seg_chunks * L) : p.T;   // tokens of the segment / row
     const int NC = (T + L - 1) / L;
-    const int ck_stride = SEG ? p.seg_chunks : NC;                           // checkpoint slots per row
+    const int ck_stride = SEG ? p.seg_chunks : BI ? (p.T + L - 1) / L : NC;  // checkpoint slots per row
+    // first token of chunk c's tile (BI_REV: the tile that ends at token T-1-64c, read backwards; see tc3_common.cuh)
+    auto tok0 = [&](int c) { return BI == BI_REV ? max(T - (c + 1) * L, 0) : t_base + c * L; };
     Frag F;
     F.init();
     const int warp = F.warp, lane = F.lane;
@@ -116,13 +120,13 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         // =====================================================================================
         auto issue_rkw = [&](int c) {
             mbar_arrive_expect_tx(&ex.bar_rkw, (SO ? 2 : 3) * 8192);
-            if constexpr (!SO) tma_load_3d(sm + OFF_R, &map_r, &ex.bar_rkw, h * 64, t_base + c * L, b);
-            tma_load_3d(sm + OFF_K, &map_k, &ex.bar_rkw, h * 64, t_base + c * L, b);
-            tma_load_3d(sm + OFF_W, &map_w, &ex.bar_rkw, h * 64, t_base + c * L, b);
+            if constexpr (!SO) tma_load_3d(sm + OFF_R, &map_r, &ex.bar_rkw, h * 64, tok0(c), b);
+            tma_load_3d(sm + OFF_K, &map_k, &ex.bar_rkw, h * 64, tok0(c), b);
+            tma_load_3d(sm + OFF_W, &map_w, &ex.bar_rkw, h * 64, tok0(c), b);
         };
         auto issue_v = [&](int c) {
             mbar_arrive_expect_tx(&ex.bar_v, 8192);
-            tma_load_3d(sm + OFF_V, &map_v, &ex.bar_v, h * 64, t_base + c * L, b);
+            tma_load_3d(sm + OFF_V, &map_v, &ex.bar_v, h * 64, tok0(c), b);
         };
         const uint32_t kt = sbase + OFF_KT, rt = sbase + OFF_RT, rh = sbase + OFF_RH, kh = sbase + OFF_KH;
         const uint32_t kl = sbase + OFF_KL, pp = sbase + OFF_P, sb = sbase + OFF_SB, vv = sbase + OFF_V;
@@ -223,8 +227,23 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             }
             bar_sync_all<B_T2>();                                // y tile and the new bf16 S written
             if (lane == 0) {
-                if (!SO && p.has_y) tma_store_3d(&map_y, sm + OFF_YT, h * 64, t_base + c * L, b);
+                if (!SO && p.has_y) {
+                    if (BI == BI_REV) tma_reduce_add_3d(&map_y, sm + OFF_YT, h * 64, tok0(c), b);
+                    else tma_store_3d(&map_y, sm + OFF_YT, h * 64, tok0(c), b);
+                }
                 if (more && p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (blockIdx.x * ck_stride + c + 1) * 64, 0);
+                tma_store_commit();
+            }
+        }
+        if (BI == BI_CAUSAL && !SO && p.has_y && NC * L < p.T) {      // y = 0 behind the row's last chunk
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 16; k++) *reinterpret_cast<uint4 *>(sm + OFF_YT + (lane + 32 * k) * 16) = make_uint4(0, 0, 0, 0);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                for (int c = NC; c * L < p.T; c++) tma_store_3d(&map_y, sm + OFF_YT, h * 64, c * L, b);
                 tma_store_commit();
             }
         }
@@ -279,11 +298,14 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         auto tg = [&](int hh) { return tg_off ^ (hh ? 16u : 0u); };
         auto prepare = [&](int c) {
             const int nv = min(L, T - c * L);
+            // where the RAW r, k, w tiles are read: the same rows, or (BI_REV) row (nv - 1 - x) mod 64
+            const uint32_t tgr_off = BI == BI_REV ? flip_rows(tg_off, nv - 1) : tg_off;
+            auto tgr = [&](int hh) { return tgr_off ^ (hh ? 16u : 0u); };
             float l[2][4][2], exq[2][4];
             {
                 uint32_t wp[2][4];
-                ldsm_x4_t(sbase + OFF_W + tg(0), wp[0][0], wp[0][1], wp[0][2], wp[0][3]);
-                ldsm_x4_t(sbase + OFF_W + tg(1), wp[1][0], wp[1][1], wp[1][2], wp[1][3]);
+                ldsm_x4_t(sbase + OFF_W + tgr(0), wp[0][0], wp[0][1], wp[0][2], wp[0][3]);
+                ldsm_x4_t(sbase + OFF_W + tgr(1), wp[1][0], wp[1][1], wp[1][2], wp[1][3]);
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++)
 #pragma unroll
@@ -313,11 +335,19 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
 
             uint32_t rr[2][4] = {}, kk[2][4];
             if constexpr (!SO) {
-                ldsm_x4_t(sbase + OFF_R + tg(0), rr[0][0], rr[0][1], rr[0][2], rr[0][3]);
-                ldsm_x4_t(sbase + OFF_R + tg(1), rr[1][0], rr[1][1], rr[1][2], rr[1][3]);
+                ldsm_x4_t(sbase + OFF_R + tgr(0), rr[0][0], rr[0][1], rr[0][2], rr[0][3]);
+                ldsm_x4_t(sbase + OFF_R + tgr(1), rr[1][0], rr[1][1], rr[1][2], rr[1][3]);
             }
-            ldsm_x4_t(sbase + OFF_K + tg(0), kk[0][0], kk[0][1], kk[0][2], kk[0][3]);
-            ldsm_x4_t(sbase + OFF_K + tg(1), kk[1][0], kk[1][1], kk[1][2], kk[1][3]);
+            ldsm_x4_t(sbase + OFF_K + tgr(0), kk[0][0], kk[0][1], kk[0][2], kk[0][3]);
+            ldsm_x4_t(sbase + OFF_K + tgr(1), kk[1][0], kk[1][1], kk[1][2], kk[1][3]);
+            if (BI && nv < L) {              // what lies behind the chunk's nv tokens is real data here, not TMA's zero fill
+#pragma unroll
+                for (int g = 0; g < 4; g++) {
+                    const uint32_t m = pair_mask(8 * (2 * g + ch) + 2 * q, nv);
+                    rr[0][g] &= m; rr[1][g] &= m;
+                    kk[0][g] &= m; kk[1][g] &= m;
+                }
+            }
             f2 du2[4];
 #pragma unroll
             for (int g = 0; g < 4; g++) du2[g] = 0ull;
@@ -452,6 +482,13 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     f2unpacku(f2mul(f2packu(v[4 * g + 2 * hh], v[4 * g + 2 * hh + 1]), el2), v[4 * g + 2 * hh], v[4 * g + 2 * hh + 1]);
             }
             tmem_st_frag(tS, v);
+            if (BI == BI_REV) {        // the V tile goes to the tensor cores as it lies in shared memory: reverse its rows
+                mbar_wait(&ex.bar_v, c & 1);                            // (issued a whole chunk ago: landed long since)
+                const int nvc = min(L, T - c * L);
+                const uint32_t vt[1] = {sbase + OFF_V};
+                if (nvc == L) flip_tiles_full(vt, warp, lane);
+                else flip_tiles_short(vt, nvc, warp, lane);
+            }
             tmem_wait_st();
             fence_proxy_async();
             tc_fence_before();
@@ -475,7 +512,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 tmem_wait_ld();
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++)
-                    stsm_x4(sbase + OFF_YT + F.rc(hh), pack2(__uint_as_float(v[0 + 2 * hh]), __uint_as_float(v[1 + 2 * hh])),
+                    stsm_x4(sbase + OFF_YT + (BI == BI_REV ? flip_rows(F.rc(hh), min(L, T - c * L) - 1) : F.rc(hh)), pack2(__uint_as_float(v[0 + 2 * hh]), __uint_as_float(v[1 + 2 * hh])),
                             pack2(__uint_as_float(v[4 + 2 * hh]), __uint_as_float(v[5 + 2 * hh])),
                             pack2(__uint_as_float(v[8 + 2 * hh]), __uint_as_float(v[9 + 2 * hh])),
                             pack2(__uint_as_float(v[12 + 2 * hh]), __uint_as_float(v[13 + 2 * hh])));
@@ -520,10 +557,30 @@ bool tc3_forward_supported(const Args &a) {
 
 // ckpt: nullptr or bf16 [B*H][ceil(T/64)][64 i][64 j] receiving the state at the start of every chunk;
 // hz_flags: device int [B*H], zeroed by the caller; a.y may be nullptr (state-only pass).
-int tc3_forward(const Args &a, void *ckpt, int *hz_flags, int nseg, int seg_chunks) {
+// bi / row_len: direction of the bidirectional op (tc3_common.cuh) and the device int [B] row lengths it needs.
+template <bool SEG, bool SO, int BI>
+static int launch_fwd(dim3 grid, cudaStream_t stream, const CUtensorMap &mr, const CUtensorMap &mk, const CUtensorMap &mv,
+                      const CUtensorMap &mw, const CUtensorMap &my, const CUtensorMap &mc, const Params &p) {
+    static bool attr_done[64] = {};          // function attributes are per device (and per instantiation)
+    int dev = 0;
+    WKV6_CUDA_CHECK(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
+        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<SEG, SO, BI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<SEG, SO, BI>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             cudaSharedmemCarveoutMaxShared));
+        if (dev >= 0 && dev < 64) attr_done[dev] = true;
+    }
+    wkv6_tc3_fwd_kernel<SEG, SO, BI><<<grid, NTHREADS, SMEM_BYTES, stream>>>(mr, mk, mv, mw, my, mc, p);
+    count_launch();
+    WKV6_CUDA_CHECK(cudaGetLastError());
+    return WKV6_OK;
+}
+
+int tc3_forward(const Args &a, void *ckpt, int *hz_flags, int nseg, int seg_chunks, int bi, const int *row_len) {
     if (a.B * a.H == 0 || a.T == 0) return WKV6_OK;
     const int C = a.H * 64;
     if (nseg <= 1) { nseg = 1; seg_chunks = (a.T + L - 1) / L; }
+    if (bi != BI_NONE && (nseg > 1 || !row_len)) { set_error("bidirectional pass: one segment and row lengths required"); return WKV6_EINVAL; }
     const size_t NC = (size_t)nseg * seg_chunks;                 // checkpoint slots per (b,h)
     CUtensorMap mr, mk, mv, mw, my, mc;
     const auto dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -545,32 +602,17 @@ int tc3_forward(const Args &a, void *ckpt, int *hz_flags, int nseg, int seg_chun
     p.hz_flags = hz_flags;
     p.nseg = nseg; p.seg_chunks = seg_chunks;
     p.lmin = tc_lmin_log2(a);
-    static bool attr_done[64] = {};          // function attributes are per device
-    int dev = 0;
-    WKV6_CUDA_CHECK(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                             cudaSharedmemCarveoutMaxShared));
-        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                             cudaSharedmemCarveoutMaxShared));
-        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<true, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                             cudaSharedmemCarveoutMaxShared));
-        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<false, true>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                             cudaSharedmemCarveoutMaxShared));
-        if (dev >= 0 && dev < 64) attr_done[dev] = true;
-    }
+    p.row_len = row_len;
     const dim3 grid(a.B * nseg * a.H);
-    if (nseg > 1 && !p.has_y) wkv6_tc3_fwd_kernel<true, true><<<grid, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
-    else if (nseg > 1) wkv6_tc3_fwd_kernel<true><<<grid, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
-    else if (!p.has_y) wkv6_tc3_fwd_kernel<false, true><<<grid, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
-    else wkv6_tc3_fwd_kernel<false><<<grid, NTHREADS, SMEM_BYTES, a.stream>>>(mr, mk, mv, mw, my, mc, p);
-    count_launch();
-    WKV6_CUDA_CHECK(cudaGetLastError());
-    return WKV6_OK;
+    const bool so = !p.has_y;
+    if (bi == BI_CAUSAL) return so ? launch_fwd<false, true, BI_CAUSAL>(grid, a.stream, mr, mk, mv, mw, my, mc, p)
+                                   : launch_fwd<false, false, BI_CAUSAL>(grid, a.stream, mr, mk, mv, mw, my, mc, p);
+    if (bi == BI_REV) return so ? launch_fwd<false, true, BI_REV>(grid, a.stream, mr, mk, mv, mw, my, mc, p)
+                                : launch_fwd<false, false, BI_REV>(grid, a.stream, mr, mk, mv, mw, my, mc, p);
+    if (nseg > 1) return so ? launch_fwd<true, true, BI_NONE>(grid, a.stream, mr, mk, mv, mw, my, mc, p)
+                            : launch_fwd<true, false, BI_NONE>(grid, a.stream, mr, mk, mv, mw, my, mc, p);
+    return so ? launch_fwd<false, true, BI_NONE>(grid, a.stream, mr, mk, mv, mw, my, mc, p)
+              : launch_fwd<false, false, BI_NONE>(grid, a.stream, mr, mk, mv, mw, my, mc, p);
 }
 
 }  // namespace wkv6

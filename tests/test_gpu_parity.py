@@ -5,7 +5,7 @@ import os
 import pytest
 import torch
 
-from tests.util import (STATE_RELRMS, assert_bf16_close, load_golden, make_inputs, relrms)
+from tests.util import (BF16_MAXABS_REL, STATE_RELRMS, assert_bf16_close, load_golden, make_inputs, relrms)
 
 pytestmark = pytest.mark.gpu
 
@@ -324,9 +324,9 @@ def test_rwkv6_inference_op(M, O, dtype, T):
 # ---------------------------------------------------------------------------------------------
 # bidirectional op
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("decay,T", [("randn", 64), ("model", 64), ("model", 200)])
+@pytest.mark.parametrize("decay,T", [("randn", 64), ("model", 64), ("model", 200), ("randn", 200)])
 def test_wkv6_bi_vs_oracle(M, O, decay, T):
-    """randn decays take the exact SIMT route per stream, model-like ones the two tensor-core passes."""
+    """Both directions run on the tensor-core kernels (BI modes: per-row lengths, in-tile time reversal)."""
     B, H = 4, 2
     C = H * 64
     r, k, v, w, u, gy = make_inputs(B, T, H, seed=21, decay=decay)
@@ -347,6 +347,57 @@ def test_wkv6_bi_vs_oracle(M, O, decay, T):
     assert relrms(y_n, y.detach()) < 1e-6
     for t, key in zip(leaves, ("gr", "gk", "gv", "gw", "gu")):
         assert_bf16_close(t.grad, ref[key], f"bi {key}")
+    assert leaves[0].grad[0, 61:].abs().max().item() == 0.0 and leaves[3].grad[1, 41:].abs().max().item() == 0.0
+
+
+@pytest.mark.parametrize("T", [130, 513])
+def test_wkv6_bi_row_lengths_around_chunk_boundaries(M, O, T):
+    """p on, just before and just behind 64-token chunk boundaries, p = 0, p = T-1 (no masked token), several chunks per
+    row: the reverse direction reads tiles at token offsets p - 64c - 63 (negative for the last one) and mirrors their
+    rows; the causal direction stops at p and writes zeros behind it.  Against the fp64 oracle, per row."""
+    ps = [0, 1, 62, 63, 64, 65, 127, 128, 129, T - 2, T - 1, None]        # None: no masked token at all
+    ps = [p for p in ps if p is None or p < T]
+    B, H = len(ps), 2
+    C = H * 64
+    r, k, v, w, u, gy = make_inputs(B, T, H, seed=33, decay="model")
+    mask = torch.ones(B, T, dtype=torch.int32)
+    for b, p in enumerate(ps):
+        if p is not None:
+            mask[b, p:] = 0
+    ref = O.wkv6_bi_backward(mask, r, k, v, w, u, gy)
+    leaves = [t.clone().to(DEV).requires_grad_(True) for t in (r, k, v, w, u)]
+    y = M.RUN_CUDA_RWKV6_BI(B, T, C, H, mask.to(DEV), *leaves)
+    y.backward(gy.to(DEV))
+    for b, p in enumerate(ps):
+        n = T if p is None else p + 1
+        # y = bf16(bf16(y_causal) + bf16(y_reverse)) like the reference (three roundings, and the two addends may be
+        # larger than their sum): twice the single-rounding max-abs allowance, same rel-RMS bar
+        assert_bf16_close(y[b, :n], ref["y"][b, :n], f"bi y row {b} (p={p})", maxabs_rel=2 * BF16_MAXABS_REL)
+        for t, key in zip(leaves[:4], ("gr", "gk", "gv", "gw")):
+            assert_bf16_close(t.grad[b, :n], ref[key][b, :n], f"bi {key} row {b} (p={p})")
+            assert t.grad[b, n:].abs().sum().item() == 0.0, f"{key} behind p in row {b}"
+        assert y[b, n:].abs().sum().item() == 0.0
+    assert_bf16_close(leaves[4].grad, ref["gu"], "bi gu")
+
+
+def test_wkv6_bi_tensor_core_route_equals_exact_route(M):
+    """Mid-size shape (many streams, 8 chunks): the fused tensor-core route against the exact SIMT bidirectional kernels."""
+    B, T, H = 8, 512, 4
+    C = H * 64
+    r, k, v, w, u, gy = make_inputs(B, T, H, seed=5, decay="model", device=DEV)
+    mask = torch.ones(B, T, dtype=torch.int32, device=DEV)
+    for b, n in enumerate([512, 511, 300, 257, 256, 129, 64, 7]):
+        mask[b, n - 1:] = 0
+    out = {}
+    for impl in ("tc", "simt"):
+        M.set_impl(impl)
+        leaves = [t.clone().requires_grad_(True) for t in (r, k, v, w, u)]
+        y = M.RUN_CUDA_RWKV6_BI(B, T, C, H, mask, *leaves)
+        y.backward(gy)
+        out[impl] = [y.detach()] + [t.grad for t in leaves]
+    M.set_impl("auto")
+    for a, b_, name in zip(out["tc"], out["simt"], ("y", "gr", "gk", "gv", "gw", "gu")):
+        assert_bf16_close(a, b_.float().cpu(), f"bi {name} tc vs simt")
 
 
 # ---------------------------------------------------------------------------------------------
