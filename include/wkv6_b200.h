@@ -108,6 +108,9 @@ WKV6_API int wkv6_backward_raww(int B, int T, int C, int H, const void *r, const
  *       out (may alias s0).  *saved_valid (host int) is set to 1 when `saved` was filled; pass
  *       saved = NULL to wkv6_train_backward otherwise (it then recomputes, needing the larger
  *       workspace of wkv6_backward_workspace_bytes).  gs: NULL iff s0 is NULL, else bf16 [B,H,64,64].
+ *   gu: bf16 [B,C], one row per sample like the reference's launcher (src/model.py:232 then sums over B);
+ *       gu_total: NULL, or bf16 [C] that receives that sum (fp32 accumulation over the bf16 rows, what
+ *       torch.sum(gu, 0) computes) from the backward kernel itself -- the last CTA of every head adds the rows.
  * `saved` is opaque: its layout depends on how the pair schedules the call (few (b,h) streams and T >= 2048:
  * both directions run as time segments, wkv6b200_seg_plan), so it must go to the backward of the same
  * B, T, H and the same library; the workspace then also holds the segmented backward's scratch.
@@ -119,8 +122,8 @@ WKV6_API int wkv6_train_forward(int B, int T, int C, int H, const void *r, const
                        void *sT, int sT_f32, void *y, void *saved, int *saved_valid, void *stream);
 WKV6_API int wkv6_train_backward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
                         const void *w, const void *u, const void *s0, int s0_batched, const void *gy,
-                        void *gr, void *gk, void *gv, void *gw, void *gu, void *gs, const void *saved,
-                        void *workspace, size_t workspace_bytes, void *stream);
+                        void *gr, void *gk, void *gv, void *gw, void *gu, void *gu_total, void *gs,
+                        const void *saved, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * (a3) wkv6state -- cuda/wkv6state_cuda.cu:298-311 bound by cuda/wkv6state_op.cpp:8-21.

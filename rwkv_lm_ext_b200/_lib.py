@@ -30,7 +30,7 @@ SIGNATURES = {
     "wkv6_saved_bytes": (c_sz, _BTCH),
     "wkv6_train_backward_workspace_bytes": (c_sz, _BTCH + [c_i]),
     "wkv6_train_forward": (c_i, _BTCH + [c_p] * 6 + [c_i, c_i, c_p, c_i, c_p, c_p, ctypes.POINTER(c_i), c_p]),
-    "wkv6_train_backward": (c_i, _BTCH + [c_p] * 6 + [c_i] + [c_p] * 9 + [c_sz, c_p]),
+    "wkv6_train_backward": (c_i, _BTCH + [c_p] * 6 + [c_i] + [c_p] * 10 + [c_sz, c_p]),
     "wkv6state_forward": (c_i, _BTCH + [c_p] * 8),
     "wkv6state_backward": (c_i, _BTCH + [c_p] * 14 + [c_sz, c_p]),
     "wkv6infctx_forward": (c_i, _BTCH + [c_p] * 8),
@@ -71,7 +71,7 @@ SIGNATURES = {
 }
 
 _lib = None
-ABI_VERSION = 2   # == wkv6b200_abi_version() of the library this signature table was written for
+ABI_VERSION = 3   # == wkv6b200_abi_version() of the library this signature table was written for
 
 
 class Wkv6B200Error(RuntimeError):

@@ -124,16 +124,17 @@ static int forward3(const Args &a) {
         flags = flag_slice((size_t)a.B * a.H);
         if (!flags) { set_error("cannot get %zu bytes of flag scratch", nb); return WKV6_ECUDA; }
     }
-    WKV6_CUDA_CHECK(cudaMemsetAsync(flags, 0, nb, a.stream));
+    // (the training pair's header has 512 more ints behind the stream flags: per-head arrival counters of the backward's
+    // in-kernel gu reduction when the call is not segmented, per-segment flags when it is)
+    WKV6_CUDA_CHECK(cudaMemsetAsync(flags, 0, a.saved ? nb + 512 * sizeof(int) : nb, a.stream));
     // the training pair segments forward and backward alike (the saved chunk states are in segment-row order)
     int nseg = 1, seg_chunks = 0;
     if (a.saved) seg_plan_train(a.B, a.T, a.H, &nseg, &seg_chunks);
     else seg_plan(a.B, a.T, a.H, &nseg, &seg_chunks);
-    if (int rc = nseg > 1 ? tc3_forward_segmented(a, flags, nseg, seg_chunks, ckpt, a.saved ? flags + (size_t)a.B * a.H : nullptr)
-                          : tc3_forward(a, ckpt, flags)) return rc;
-    Args s = a;                       // exact route, only for the streams the kernel flagged
-    s.stream_flags = flags;
-    return simt_forward(s);
+    // (raw bf16 logits: nothing can raise a flag -- the kernels never do, and there is no fp32 decay to convert -- so
+    // no predicated exact-route launch follows; the zeroed flags only feed the kernels' entry check and the diagnostics)
+    return nseg > 1 ? tc3_forward_segmented(a, flags, nseg, seg_chunks, ckpt, a.saved ? flags + (size_t)a.B * a.H : nullptr)
+                    : tc3_forward(a, ckpt, flags);
 }
 // the same call with the fp32 log-decay converted to raw bf16 logits (tensor-core kernels), exact SIMT
 // kernels on the original values for the streams where that conversion is not lossless
@@ -211,7 +212,7 @@ using namespace wkv6;
 
 extern "C" {
 
-int wkv6b200_abi_version(void) { return 2; }
+int wkv6b200_abi_version(void) { return 3; }
 float wkv6b200_set_decay_clamp(float nats_per_token) {
     const float prev = -decay_clamp_nats();
     g_lmin.store(nats_per_token > 0.f ? -nats_per_token : -INFINITY);
@@ -319,8 +320,8 @@ int wkv6_train_forward(int B, int T, int C, int H, const void *r, const void *k,
 }
 int wkv6_train_backward(int B, int T, int C, int H, const void *r, const void *k, const void *v,
                         const void *w, const void *u, const void *s0, int s0_batched, const void *gy,
-                        void *gr, void *gk, void *gv, void *gw, void *gu, void *gs, const void *saved,
-                        void *workspace, size_t workspace_bytes, void *stream) {
+                        void *gr, void *gk, void *gv, void *gw, void *gu, void *gu_total, void *gs,
+                        const void *saved, void *workspace, size_t workspace_bytes, void *stream) {
     if (int rc = check_shape(B, T, C, H)) return rc;
     if ((size_t)B * T == 0) return WKV6_OK;
     REQUIRE_PTRS(r, k, v, w, u, gy, gr, gk, gv, gw, gu);
@@ -331,7 +332,10 @@ int wkv6_train_backward(int B, int T, int C, int H, const void *r, const void *k
     a.gv = gv; a.gw = gw; a.gu = gu; a.gs = gs; a.workspace = workspace; a.workspace_bytes = workspace_bytes;
     a.saved = const_cast<void *>(saved);
     a.stream = (cudaStream_t)stream;
-    return dispatch_backward(a);
+    a.gu_total = gu_total;
+    const int rc = dispatch_backward(a);
+    if (rc != WKV6_OK || !gu_total || a.gu_total_done) return rc;
+    return seg_sum_gu(1, B, C, gu, gu_total, a.stream);      // routes whose kernels do not add the rows themselves
 }
 
 // ------------------------------------------------------------------------------- wkv6state

@@ -44,6 +44,8 @@ struct Args {
     // backward only
     const void *gy = nullptr;
     void *gr = nullptr, *gk = nullptr, *gv = nullptr, *gw = nullptr, *gu = nullptr, *gs = nullptr;
+    void *gu_total = nullptr;         // training pair only: bf16 [C], sum of gu over the batch rows
+    mutable bool gu_total_done = false;   // set by the route whose kernel added the rows itself
     void *workspace = nullptr;
     size_t workspace_bytes = 0;
     // SIMT kernels only: nullptr, or one device int per (b,h) stream: block `s` runs only when

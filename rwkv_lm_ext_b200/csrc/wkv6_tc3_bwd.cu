@@ -63,6 +63,7 @@ struct Extra {
     float q0p[2][64];         // <S_in, G>_i, partial over each half of j
     float htY[2][64], htX[2][64];   // per token-half totals of D and of X, per channel
     float gu_s[64];
+    int gu_last;
     uint64_t bar_rk, bar_w, bar_vg, bar_sin, bar_bm, bar_m1, bar_dr, bar_m2, bar_m3;
     uint32_t tmem_base;
 };
@@ -91,6 +92,8 @@ struct Params {
     int nseg, seg_chunks;
     float lmin;               // floor of the per-token log2-decay (>= -LCLAMP2)
     bf16 *gu, *gs;
+    bf16 *gu_total;           // nullptr, or bf16 [C]: sum of gu over the grid's rows, added up by the last CTA of every head
+    int *gu_count;            // its arrival counters, int [H], zero before the launch (left zero again)
     const int *hz_flags;
     const int *row_len;       // BI modes: tokens of every batch row (p + 1 of wkv6_bi), device int [B]
     long long *dbg;           // nullptr, or [gridDim][NC][8 (32 in the profiling build)] clock64 stamps of warp 0 at the stage boundaries (profiling aid)
@@ -303,6 +306,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 }
             }
             __syncwarp();
+            if (c > 0) bar_arrive_all<B_RAW>();                  // ... have landed: the compute warps go from T3 straight into the next preparation
             bar_sync_all<B_T3>();                                // gk, gw tiles written
             if (lane == 0) {
                 if (BI == BI_REV) {
@@ -315,7 +319,6 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 tma_store_commit();
             }
             __syncwarp();
-            if (c > 0) bar_arrive_all<B_RAW>();
         }
         if (BI == BI_CAUSAL && NC * L < p.T) {                    // all four gradients are 0 behind the row's last chunk
             if (lane == 0) tma_store_wait_read<0>();
@@ -852,6 +855,22 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         }
         named_bar_sync<B_SCAN, CTHREADS>();
         if (BI != BI_REV && threadIdx.x < 64) p.gu[(size_t)row * C + h * 64 + threadIdx.x] = __float2bfloat16_rn(ex.gu_s[threadIdx.x]);   // (the reverse pass has u = 0)
+        if (!SEG && BI == BI_NONE && p.gu_total) {
+            // sum over the batch rows (src/model.py:232 does it with torch.sum): the last CTA of this head to get here adds
+            // the bf16 rows in fp32, in row order
+            const int rows = gridDim.x / p.H;
+            if (threadIdx.x < 64) __threadfence();
+            named_bar_sync<B_SCAN, CTHREADS>();
+            if (threadIdx.x == 0) ex.gu_last = atomicAdd(&p.gu_count[h], 1) == rows - 1;
+            named_bar_sync<B_SCAN, CTHREADS>();
+            if (ex.gu_last && threadIdx.x < 64) {
+                __threadfence();
+                float acc = 0.f;
+                for (int rb = 0; rb < rows; rb++) acc += __bfloat162float(__ldcg(&p.gu[(size_t)rb * C + h * 64 + threadIdx.x]));
+                p.gu_total[h * 64 + threadIdx.x] = __float2bfloat16_rn(acc);
+                if (threadIdx.x == 0) p.gu_count[h] = 0;
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -955,6 +974,11 @@ static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const f
     p.lmin = tc_lmin_log2(a);
     p.gu = (bf16 *)a.gu; p.gs = (bf16 *)a.gs;
     p.hz_flags = flags;
+    // in-kernel sum of gu over the rows: ordinary call only; the counters sit behind the stream flags (zeroed with them)
+    const bool sum_gu = a.gu_total && nseg == 1 && bi == BI_NONE && a.H <= 512;
+    p.gu_total = sum_gu ? (bf16 *)a.gu_total : nullptr;
+    p.gu_count = const_cast<int *>(flags) + (size_t)a.B * a.H;
+    if (sum_gu) a.gu_total_done = true;
 #ifdef WKV6_FINE_STAMPS
     p.dbg = (long long *)g_tc3_bwd_stamps;
 #else
@@ -1012,11 +1036,7 @@ static int tc3_backward_segmented(const Args &a, int nseg, int seg_chunks) {
     if (rc == WKV6_OK && a.gs)                    // dL/dS_0 is what segment 0 of every sequence produced
         rc = cudaMemcpy2DAsync(a.gs, (size_t)a.H * 4096 * 2, gs_tmp, (size_t)nseg * a.H * 4096 * 2, (size_t)a.H * 4096 * 2, a.B,
                                cudaMemcpyDeviceToDevice, a.stream) == cudaSuccess ? WKV6_OK : WKV6_ECUDA;
-    if (rc != WKV6_OK) return rc;
-    Args s = a;                                   // exact route for the flagged streams, on the call as it was made
-    s.stream_flags = flags;
-    s.workspace_bytes = simt_backward_workspace_bytes(a.B, a.T, a.H);
-    return simt_backward(s);
+    return rc;      // (training pair on raw bf16 logits: no stream is ever flagged, no exact-route launch follows)
 }
 
 // One direction of the bidirectional backward (wkv6_bi_tc.cu): recompute the chunk-start states of that direction
@@ -1047,7 +1067,8 @@ int tc3_backward(const Args &a, const Args *exact, bool flags_preset, bool run_f
     bf16 *ckpt = (bf16 *)(sv + tc3_saved_header(a.B, a.H));
     if (!a.saved) {
         // no training pair: recompute the chunk-start states (and the per-stream hazard flags) first
-        if (!flags_preset) WKV6_CUDA_CHECK(cudaMemsetAsync(flags, 0, (size_t)a.B * a.H * sizeof(int), a.stream));
+        if (!flags_preset) WKV6_CUDA_CHECK(cudaMemsetAsync(flags, 0, ((size_t)a.B * a.H + 512) * sizeof(int), a.stream));
+        else WKV6_CUDA_CHECK(cudaMemsetAsync(flags + (size_t)a.B * a.H, 0, 512 * sizeof(int), a.stream));
         Args f = a;
         f.y = nullptr;
         f.sT = nullptr;
@@ -1055,6 +1076,8 @@ int tc3_backward(const Args &a, const Args *exact, bool flags_preset, bool run_f
     }
     if (int rc = launch_bwd(a, ckpt, flags, nullptr, 1, 0, a.s0 != nullptr)) return rc;
     if (!run_fallback) return WKV6_OK;      // the caller runs its own exact route on the flags in the workspace
+    // Flags are only ever raised by the fp32-decay conversion (flags_preset); a call on raw bf16 logits has none
+    if (!flags_preset && !exact) return WKV6_OK;
     // exact route for the flagged streams only
     Args s = exact ? *exact : a;
     s.workspace = a.workspace;

@@ -205,13 +205,10 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             __syncwarp();
             if (more) {
                 bar_sync_all<B_PA>();                            // Kt / Rt of chunk c+1 written, its raw tiles consumed
-                if (elect_one()) {
-                    tc_fence_after();
-                    issue_A();                                   // queued behind M2 on the tensor pipe
-                    if (c + 2 < NC) issue_rkw(c + 2);
-                }
-                __syncwarp();
+                if (lane == 0 && c + 2 < NC) issue_rkw(c + 2);
             }
+            // M2 ran under the preparation of chunk c+1: release the compute warps (deferred stores, T2) BEFORE spending
+            // a few hundred cycles on issuing A of chunk c+1 -- they wait for nothing else at this point
             if (lane == 0) {
                 mbar_wait(&ex.bar_m2, par);
                 tma_store_wait_read<0>();                        // SB / YT of the previous stores may be rewritten now
@@ -219,6 +216,13 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             __syncwarp();
             bar_arrive_all<B_M2>();
             if (lane == 0 && more) issue_v(c + 1);               // V is free again
+            if (more) {
+                if (elect_one()) {
+                    tc_fence_after();
+                    issue_A();                                   // reads only Kt / Rt, writes only the A columns T1 has consumed
+                }
+                __syncwarp();
+            }
             if (more) {
                 bar_sync_all<B_PB>();
                 if (lane == 0) mbar_wait(&ex.bar_a, par ^ 1);    // A^T of chunk c+1 ran right behind M2

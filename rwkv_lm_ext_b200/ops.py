@@ -77,12 +77,15 @@ class exact_route_report:
 
 
 def _train_backward(ctx, lib, B, T, C, H, r, k, v, w, u, s0, s0_batched, gy, gr, gk, gv, gw, gu, gs):
+    """Returns gu summed over the batch rows (src/model.py:232 `torch.sum(gu, 0)`), computed by the library."""
     saved = ctx.saved_state
     n = lib.wkv6_train_backward_workspace_bytes(B, T, C, H, int(saved is not None))
     ws = torch.empty(max(n, 1), dtype=torch.uint8, device=gy.device)
+    gu_total = torch.empty((C,), device=gy.device, dtype=torch.bfloat16)
     check(lib.wkv6_train_backward(B, T, C, H, ptr(r), ptr(k), ptr(v), ptr(w), ptr(u), ptr(s0), int(s0_batched),
-                                  ptr(gy), ptr(gr), ptr(gk), ptr(gv), ptr(gw), ptr(gu), ptr(gs), ptr(saved),
+                                  ptr(gy), ptr(gr), ptr(gk), ptr(gv), ptr(gw), ptr(gu), ptr(gu_total), ptr(gs), ptr(saved),
                                   ptr(ws), n, stream_of(gy)), "wkv6_train_backward")
+    return gu_total
 
 
 # --------------------------------------------------------------------------------------------
@@ -115,8 +118,8 @@ class WKV_6(torch.autograd.Function):
             gr, gk, gv, gw = (torch.empty((B, T, C), device=gy.device, dtype=torch.bfloat16) for _ in range(4))
             gu = torch.empty((B, C), device=gy.device, dtype=torch.bfloat16)
             lib = _lib.load()
-            _train_backward(ctx, lib, B, T, C, H, r, k, v, w, u, None, False, gy, gr, gk, gv, gw, gu, None)
-            gu = torch.sum(gu, 0).view(H, C // H)          # src/model.py:232
+            gu = _train_backward(ctx, lib, B, T, C, H, r, k, v, w, u, None, False, gy, gr, gk, gv, gw, gu, None)
+            gu = gu.view(H, C // H)                        # src/model.py:232 (the sum over B happens in the library)
             return (None, None, None, None, gr, gk, gv, gw, gu)
 
 
@@ -154,8 +157,8 @@ class WKV_6STATE(torch.autograd.Function):
             gu = torch.empty((B, C), device=gy.device, dtype=torch.bfloat16)
             gs = torch.empty((B, H, C // H, C // H), device=gy.device, dtype=torch.bfloat16)
             lib = _lib.load()
-            _train_backward(ctx, lib, B, T, C, H, r, k, v, w, u, s, False, gy, gr, gk, gv, gw, gu, gs)
-            gu = torch.sum(gu, 0).view(H, C // H)                  # src/model.py:181
+            gu = _train_backward(ctx, lib, B, T, C, H, r, k, v, w, u, s, False, gy, gr, gk, gv, gw, gu, gs)
+            gu = gu.view(H, C // H)                                # src/model.py:181 (summed over B in the library)
             gs = torch.sum(gs, 0).view(H, C // H, C // H)          # src/model.py:182
             return (None, None, None, None, gr, gk, gv, gw, gu, gs)
 
@@ -196,8 +199,8 @@ class WKV_6STATE_INFCTX(torch.autograd.Function):
             gu = torch.empty((B, C), device=gy.device, dtype=torch.bfloat16)
             gs = torch.empty((B, H, C // H, C // H), device=gy.device, dtype=torch.bfloat16)
             lib = _lib.load()
-            _train_backward(ctx, lib, B, T, C, H, r, k, v, w, u, s, True, gy, gr, gk, gv, gw, gu, gs)
-            gu = torch.sum(gu, 0).view(H, C // H)
+            gu = _train_backward(ctx, lib, B, T, C, H, r, k, v, w, u, s, True, gy, gr, gk, gv, gw, gu, gs)
+            gu = gu.view(H, C // H)
             # per-sample state: its gradient is per sample too.  (The reference sums gs over the
             # batch into [H,64,64] even here, src/model.py:128 -- a shape that cannot flow back
             # into a [B,H,64,64] leaf; truncated BPTT: the final state gets no gradient.)
