@@ -51,3 +51,26 @@ if FINE:
     for a, b in zip(order[:-1], order[1:]):
         dd = (s[:, :, b] - s[:, :, a])[:, 2:-2]
         print(f"  -> {label[b]:28s} {dd.mean():8.0f}")
+
+    # per-CTA view: which SM, how many CTAs share it, when it started and how long its 64 chunks took (global timer)
+    smid = s[:, 0, 31].long()
+    t0, t1 = s[:, 0, 30], s[:, -1, 30]
+    dur = (t1 - t0) / 1e3                                     # us from the first to the last chunk start
+    start = (t0 - t0.min()) / 1e3
+    share = torch.bincount(smid, minlength=148)[smid]
+    for n in (1, 2):
+        m = share == n
+        if m.any():
+            d_ = dur[m]
+            print(f"CTAs on SMs with {n} CTA(s): {int(m.sum())}   first->last chunk start: mean {d_.mean():.1f} us  min {d_.min():.1f}  "
+                  f"p50 {d_.median():.1f}  p90 {d_.quantile(0.9):.1f}  max {d_.max():.1f};  start offset max {start[m].max():.1f} us")
+    q = dur[share == 2]
+    if q.numel():
+        slow = torch.argsort(dur, descending=True)[:8]
+        print("slowest CTAs (blockIdx, sm, us):", [(int(i), int(smid[i]), round(float(dur[i]), 1)) for i in slow])
+        per_sm = {}
+        for i in range(len(dur)):
+            per_sm.setdefault(int(smid[i]), []).append(round(float(dur[i]), 1))
+        pairs = sorted(per_sm.items(), key=lambda kv: -max(kv[1]))[:6]
+        print("slowest SMs:", pairs)
+        print("fastest dual SMs:", sorted([kv for kv in per_sm.items() if len(kv[1]) == 2], key=lambda kv: max(kv[1]))[:4])
