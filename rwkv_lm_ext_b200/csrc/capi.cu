@@ -126,26 +126,15 @@ static int forward3(const Args &a) {
     }
     // (the training pair's header has 512 more ints behind the stream flags: per-head arrival counters of the backward's
     // in-kernel gu reduction when the call is not segmented, per-segment flags when it is)
-    WKV6_CUDA_CHECK(cudaMemsetAsync(flags, 0, a.saved ? tc3_saved_header(a.B, a.H) : nb, a.stream));
+    WKV6_CUDA_CHECK(cudaMemsetAsync(flags, 0, a.saved ? nb + 512 * sizeof(int) : nb, a.stream));
     // the training pair segments forward and backward alike (the saved chunk states are in segment-row order)
     int nseg = 1, seg_chunks = 0;
     if (a.saved) seg_plan_train(a.B, a.T, a.H, &nseg, &seg_chunks);
     else seg_plan(a.B, a.T, a.H, &nseg, &seg_chunks);
     // (raw bf16 logits: nothing can raise a flag -- the kernels never do, and there is no fp32 decay to convert -- so
     // no predicated exact-route launch follows; the zeroed flags only feed the kernels' entry check and the diagnostics)
-    if (nseg > 1) return tc3_forward_segmented(a, flags, nseg, seg_chunks, ckpt, a.saved ? flags + (size_t)a.B * a.H : nullptr);
-    // (not when the final state is written over the initial one: the short pieces read s0 while long ones finish)
-    const int n_short = a.saved && a.y && !(a.s0 && a.sT) ? tc3_split_plan(a.B, a.T, a.H) : 0;
-    if (n_short > 0) {
-        // tail split (wkv6_tc3_bwd.cu, tc3_split_plan): state-only pre-pass over the first n_short chunks, then both pieces
-        // of every stream as one grid -- the long ones start from the pre-pass's state
-        float *s1 = tc3_saved_split_state(a.saved, a.B, a.T, a.H);
-        Args f = a;
-        f.y = nullptr; f.sT = s1; f.sT_f32 = 1; f.saved = nullptr;
-        if (int rc = tc3_forward(f, nullptr, flags, 1, 0, 0, nullptr, n_short)) return rc;
-        return tc3_forward(a, ckpt, flags, 1, 0, 0, nullptr, 0, n_short, s1);
-    }
-    return tc3_forward(a, ckpt, flags);
+    return nseg > 1 ? tc3_forward_segmented(a, flags, nseg, seg_chunks, ckpt, a.saved ? flags + (size_t)a.B * a.H : nullptr)
+                    : tc3_forward(a, ckpt, flags);
 }
 // the same call with the fp32 log-decay converted to raw bf16 logits (tensor-core kernels), exact SIMT
 // kernels on the original values for the streams where that conversion is not lossless
@@ -206,7 +195,7 @@ static int dispatch_backward(const Args &a) {
         const size_t base = tc3_backward_workspace_bytes(a.B, a.T, a.H, false), need = base + (size_t)a.B * a.T * a.H * 64 * 2;
         if (!a.workspace || a.workspace_bytes < need) { set_error("workspace too small: need %zu bytes", need); return WKV6_EWORKSPACE; }
         void *w_raw = (uint8_t *)a.workspace + base;
-        int *flags = tc3_backward_flags(a);
+        int *flags = (int *)((uint8_t *)a.workspace + simt_backward_workspace_bytes(a.B, a.T, a.H));
         if (cudaMemsetAsync(flags, 0, (size_t)a.B * a.H * sizeof(int), a.stream) != cudaSuccess) { set_error("cudaMemsetAsync failed"); return WKV6_ECUDA; }
         if (int rc = ew_to_raw_bf16(a.B, a.T, a.H, (const float *)a.w, w_raw, flags, a.stream)) return rc;
         Args t = with_raw_w(a, w_raw);

@@ -70,11 +70,8 @@ size_t simt_backward_workspace_bytes(int B, int T, int H);
 // seg_chunks 64-token chunks (the last may be shorter) that run as separate grid rows; s0 / sT / flags / ckpt
 // are then indexed by row = b*nseg + seg (seg_scan.cu)
 // bi != 0: one direction of the bidirectional op (tc3_common.cuh BI_CAUSAL / BI_REV) with per-row lengths row_len[B]
-// max_chunks > 0: only the first max_chunks chunks (state pre-passes); split / s1: tail split (wkv6_tc3_fwd.cu Params)
 int tc3_forward(const Args &a, void *ckpt, int *hz_flags, int nseg = 1, int seg_chunks = 0, int bi = 0,
-                const int *row_len = nullptr, int max_chunks = 0, int split = 0, const float *s1 = nullptr);
-// Tail split of a call whose B*H streams leave CTA slots idle: chunks given to the short piece of every stream (0 = off)
-int tc3_split_plan(int B, int T, int H);
+                const int *row_len = nullptr);
 bool tc3_forward_supported(const Args &a);
 // role-uniform tcgen05 backward (+ per-stream SIMT fallback, which runs on `exact` when given: the
 // call as the caller made it, e.g. with the fp32 log-decay instead of the converted bf16 logits)
@@ -87,10 +84,8 @@ int bi_backward_tc(const Args &a);
 // fp32 ew = -exp(w) (or decay = exp(-exp(w)) with from_decay) -> raw bf16 logits; raises flags[b*H+h] where the round trip is not exact
 int ew_to_raw_bf16(int B, int T, int H, const float *ew, void *w_raw, int *flags, cudaStream_t stream, int from_decay = 0);
 bool tc3_backward_supported(const Args &a);
-int *tc3_backward_flags(const Args &a);       // flags of a backward without a training pair, inside a.workspace
 size_t tc3_saved_header(int B, int H);
 size_t tc3_saved_bytes(int B, int T, int H);
-float *tc3_saved_split_state(void *saved, int B, int T, int H);   // tail split: fp32 [B,H,64,64] behind the chunk states
 size_t tc3_backward_workspace_bytes(int B, int T, int H, bool has_saved);
 
 void set_error(const char *fmt, ...);

@@ -35,7 +35,6 @@
 // The per-stream flags only mark streams the CALLER routed to the exact SIMT kernels (fp32 decay entries
 // whose values are not bf16 logits); the kernels never raise one.
 #include <cmath>
-#include <stdlib.h>
 #include "common.cuh"
 #include "tc3_common.cuh"
 
@@ -97,14 +96,6 @@ struct Params {
     int *gu_count;            // its arrival counters, int [H], zero before the launch (left zero again)
     const int *hz_flags;
     const int *row_len;       // BI modes: tokens of every batch row (p + 1 of wkv6_bi), device int [B]
-    // tail split (SEG instantiation, split > 0; tc3_split_plan): 2*B*H CTAs.  CTA x < B*H runs chunks [0, split) of stream x
-    // from g_init[x] (dL/dS behind chunk split-1: a state-only pre-pass over the chunks behind it produced it); CTA
-    // B*H + x runs chunks [split, NC) of stream x from G = 0.  Flags, g_init, gs, gu and the checkpoints (slot = stream *
-    // NC + chunk) are indexed by STREAM as in an ordinary call; the two pieces' gu partials meet in gu_part (fp32
-    // [B*H][2][64]) and the piece that arrives second (gu_cnt2, int [B*H], zero before and after) adds them.
-    int split;
-    float *gu_part;
-    int *gu_cnt2;
     long long *dbg;           // nullptr, or [gridDim][NC][8 (32 in the profiling build)] clock64 stamps of warp 0 at the stage boundaries (profiling aid)
 };
 
@@ -121,32 +112,21 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     const __grid_constant__ CUtensorMap map_gy, const __grid_constant__ CUtensorMap map_ck,
                     const __grid_constant__ CUtensorMap map_gr, const __grid_constant__ CUtensorMap map_gk,
                     const __grid_constant__ CUtensorMap map_gv, const __grid_constant__ CUtensorMap map_gw, Params p) {
+    if (p.hz_flags[blockIdx.x] != 0) return;        // the exact (SIMT) route handles this stream
     extern __shared__ __align__(1024) uint8_t sm[];
     Extra &ex = *reinterpret_cast<Extra *>(sm + OFF_TILES_END);
     if ((smem_u32(sm) & 1023u) != 0) __trap();
-    const bool split = SEG && p.split > 0;
-    const bool head = split && (int)blockIdx.x < p.B * p.H;                  // tail split: the long pieces come first in the grid
-    const int rid = split ? (head ? blockIdx.x : blockIdx.x - p.B * p.H) : blockIdx.x;   // row id: flags, checkpoints
-    if (p.hz_flags[rid] != 0) return;               // the exact (SIMT) route handles this stream
-    const int row = rid / p.H, h = rid % p.H;
-    const int b = SEG && !split ? row / p.nseg : row;                        // batch index inside the [B,T,C] tensors
-    const int t_base = split ? (head ? 0 : p.split * L) : SEG ? (row % p.nseg) * p.seg_chunks * L : 0;   // first token of this row's segment
-    const int T = BI ? p.row_len[b] : split ? (head ? p.split * L : p.T - t_base) : SEG ? min(p.T - t_base, p.seg_chunks * L) : p.T, C = p.H * 64;
+    const int row = blockIdx.x / p.H, h = blockIdx.x % p.H;
+    const int b = SEG ? row / p.nseg : row;                                  // batch index inside the [B,T,C] tensors
+    const int t_base = SEG ? (row % p.nseg) * p.seg_chunks * L : 0;          // first token of this row's segment
+    const int T = BI ? p.row_len[b] : SEG ? min(p.T - t_base, p.seg_chunks * L) : p.T, C = p.H * 64;
     const int NC = (T + L - 1) / L;
     const int ck_stride = SEG ? p.seg_chunks : BI ? (p.T + L - 1) / L : NC;  // checkpoint slots per row
-    const int ck_base = split ? rid * ((p.T + L - 1) / L) + t_base / L : rid * ck_stride;
     // first token of chunk c's tile (BI_REV: the tile that ends at token T-1-64c, read backwards; see tc3_common.cuh)
     auto tok0 = [&](int c) { return BI == BI_REV ? max(T - (c + 1) * L, 0) : t_base + c * L; };
     Frag F;
     F.init();
     const int warp = F.warp, lane = F.lane;
-#ifdef WKV6_FINE_STAMPS
-    if (p.dbg && threadIdx.x == 0) {              // slot 28 of the piece's first chunk: global timer at CTA entry
-        unsigned long long gt;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-        p.dbg[(split ? (size_t)ck_base + (NC - 1) : (size_t)blockIdx.x * ck_stride) * 32 + 28] = (long long)gt;
-    }
-#endif
 
     if (threadIdx.x == 0) {
         mbar_init(&ex.bar_rk, 1);
@@ -170,13 +150,6 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
     tc_fence_after();
     const uint32_t tmem = ex.tmem_base;
     const uint32_t sbase = smem_u32(sm);
-#ifdef WKV6_FINE_STAMPS
-    if (p.dbg && threadIdx.x == 0) {              // slot 29: global timer once TMEM is allocated
-        unsigned long long gt;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
-        p.dbg[(split ? (size_t)ck_base + (NC - 1) : (size_t)blockIdx.x * ck_stride) * 32 + 29] = (long long)gt;
-    }
-#endif
 
     if (warp == CWARPS) {
         // =====================================================================================
@@ -198,7 +171,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         };
         auto issue_sin = [&](int c) {
             mbar_arrive_expect_tx(&ex.bar_sin, 8192);
-            tma_load_3d(sm + OFF_SIN, &map_ck, &ex.bar_sin, 0, (ck_base + c) * 64, 0);
+            tma_load_3d(sm + OFF_SIN, &map_ck, &ex.bar_sin, 0, (blockIdx.x * ck_stride + c) * 64, 0);
         };
         if (lane == 0) {
             tma_prefetch_desc(&map_r); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
@@ -389,9 +362,9 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         uint32_t v[16];
 
         // G = dL/dS behind the last token (0, or handed in when this row is a segment)
-        const int seg = split ? (head ? 0 : 1) : SEG ? row % p.nseg : 0;
+        const int seg = SEG ? row % p.nseg : 0;
         const bool first_has_s0 = p.has_s0 || seg > 0;          // a later segment starts from a non-zero state
-        const bool g_is_zero = !SEG || p.g_init == nullptr || seg == (split ? 1 : p.nseg - 1);
+        const bool g_is_zero = !SEG || p.g_init == nullptr || seg == p.nseg - 1;
 #pragma unroll
         for (int x = 0; x < 16; x++) v[x] = 0u;
         if (!g_is_zero) {
@@ -410,8 +383,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
 
 #ifdef WKV6_FINE_STAMPS      // profiling build only (profiles/stage_times.py): 32 clock64 stamps per chunk; the product has none
 #define STAMP_N 32
-#define STAMP_ROW (split ? (size_t)ck_base + (NC - 1 - it) : (size_t)blockIdx.x * ck_stride + it)      /* tail split: indexed by global chunk */
-#define STAMP(k) do { if (p.dbg && threadIdx.x == 0) p.dbg[STAMP_ROW * STAMP_N + (k)] = clock64(); } while (0)
+#define STAMP(k) do { if (p.dbg && threadIdx.x == 0) p.dbg[((size_t)blockIdx.x * ck_stride + it) * STAMP_N + (k)] = clock64(); } while (0)
 #else
 #define STAMP(k) do { } while (0)
 #endif
@@ -428,8 +400,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 unsigned long long gt; unsigned smid;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
                 asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-                p.dbg[STAMP_ROW * STAMP_N + 30] = (long long)gt;
-                p.dbg[STAMP_ROW * STAMP_N + 31] = smid;
+                p.dbg[((size_t)blockIdx.x * ck_stride + it) * STAMP_N + 30] = (long long)gt;
+                p.dbg[((size_t)blockIdx.x * ck_stride + it) * STAMP_N + 31] = smid;
             }
 #endif
             if (BI) {      // the V and GY tiles go to the tensor cores as they lie in shared memory
@@ -831,7 +803,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     ex.htX[ch][F.row(hh)] = runX[hh];
                 }
             }
-            if (c == 0 && p.gs && (!split || head)) {        // after chunk 0, G' 2^rho_0 is dL/dS_0 (the G update of M2 is covered by the M3 commit)
+            if (c == 0 && p.gs) {        // after chunk 0, G' 2^rho_0 is dL/dS_0 (the G update of M2 is covered by the M3 commit)
                 tmem_ld_frag(tG, v);
                 tmem_wait_ld();
 #pragma unroll
@@ -891,29 +863,11 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             if (q == 0) atomicAdd(&ex.gu_s[F.row(hh)], x);
         }
         named_bar_sync<B_SCAN, CTHREADS>();
-        bool stream_done = true;
-        if (split) {      // the piece of this stream that gets here second adds both partials (always seg 0 + seg 1)
-            if (threadIdx.x < 64) {
-                p.gu_part[((size_t)rid * 2 + seg) * 64 + threadIdx.x] = ex.gu_s[threadIdx.x];
-                __threadfence();
-            }
-            named_bar_sync<B_SCAN, CTHREADS>();
-            if (threadIdx.x == 0) ex.gu_last = atomicAdd(&p.gu_cnt2[rid], 1) == 1;
-            named_bar_sync<B_SCAN, CTHREADS>();
-            stream_done = ex.gu_last;
-            if (stream_done && threadIdx.x < 64) {
-                __threadfence();
-                const float a0 = __ldcg(&p.gu_part[((size_t)rid * 2) * 64 + threadIdx.x]), a1 = __ldcg(&p.gu_part[((size_t)rid * 2 + 1) * 64 + threadIdx.x]);
-                p.gu[(size_t)row * C + h * 64 + threadIdx.x] = __float2bfloat16_rn(a0 + a1);
-                if (threadIdx.x == 0) p.gu_cnt2[rid] = 0;
-            }
-            named_bar_sync<B_SCAN, CTHREADS>();       // (ex.gu_last is rewritten below)
-        } else if (BI != BI_REV && threadIdx.x < 64)
-            p.gu[(size_t)row * C + h * 64 + threadIdx.x] = __float2bfloat16_rn(ex.gu_s[threadIdx.x]);   // (the reverse pass has u = 0)
-        if ((!SEG || split) && stream_done && BI == BI_NONE && p.gu_total) {
+        if (BI != BI_REV && threadIdx.x < 64) p.gu[(size_t)row * C + h * 64 + threadIdx.x] = __float2bfloat16_rn(ex.gu_s[threadIdx.x]);   // (the reverse pass has u = 0)
+        if (!SEG && BI == BI_NONE && p.gu_total) {
             // sum over the batch rows (src/model.py:232 does it with torch.sum): the last CTA of this head to get here adds
             // the bf16 rows in fp32, in row order
-            const int rows = p.B;
+            const int rows = gridDim.x / p.H;
             if (threadIdx.x < 64) __threadfence();
             named_bar_sync<B_SCAN, CTHREADS>();
             if (threadIdx.x == 0) ex.gu_last = atomicAdd(&p.gu_count[h], 1) == rows - 1;
@@ -938,42 +892,14 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
 void *g_tc3_bwd_stamps = nullptr;   // profiling build: set through wkv6b200_debug_stamps()
 #endif
 
-// Tail split.  One CTA per stream leaves CTA slots idle when 148 < B*H < 296 (the benchmark shape: 256 streams on 296
-// slots, and the SMs that hold one CTA finish long before those that hold two).  The recurrence is a chain per stream, so
-// the only way to fill the slots is to cut every stream in two: a long piece and a short piece of n chunks whose
-// boundary state comes from a state-only pre-pass over the n chunks in front of it (forward: the first n chunks;
-// backward: dL/dS through the last n chunks, the same recurrence on time-reversed r, gy -- the BI_REV reading).  The
-// 2*B*H pieces run as one grid, long pieces first; the short ones fill the 296 - B*H free slots one after the other.
-// n balances the slots: n ~ NC * (296 - B*H) / 296.  Returns 0 = no split.
-int tc3_split_plan(int B, int T, int H) {
-    static const char *env = getenv("WKV6_B200_SPLIT");     // tuning / A-B aid: chunks of the short piece, 0 = off
-    const int R = B * H, NC = T / L;
-    if (T % L != 0 || NC < 32 || R <= 148 || R >= 290) return 0;
-    if (!env) return 0;      // off by default for now (measured: the block scheduler stops launching the short pieces)
-    int n = atoi(env);
-    if (n > NC / 4) n = NC / 4;
-    return n >= 2 ? n : 0;
-}
-// header: per-stream hazard flags [B*H]; 512 ints (per-segment flags of the time-axis segmentation, at most 296 rows / the
-// per-head arrival counters of the in-kernel gu sum); [B*H] arrival counters of the tail split's gu partials
-size_t tc3_saved_header(int B, int H) { return ((((size_t)2 * B * H + 512) * sizeof(int)) + 1023) / 1024 * 1024; }
-static size_t ckpt_bytes(int B, int T, int H) {
+// per-stream hazard flags [B*H], then (time-axis segmentation, at most 296 segment rows) per-segment flags
+size_t tc3_saved_header(int B, int H) { return ((((size_t)B * H + 512) * sizeof(int)) + 1023) / 1024 * 1024; }
+size_t tc3_saved_bytes(int B, int T, int H) {
     size_t NC = (size_t)(T + L - 1) / L;
     int nseg = 1, seg_chunks = 0;
     seg_plan_train(B, T, H, &nseg, &seg_chunks);           // uneven segments leave a few checkpoint slots unused
     if (nseg > 1) NC = (size_t)nseg * seg_chunks;
-    return (size_t)B * H * NC * 8192;
-}
-// [header][chunk-start states][tail split: fp32 state in front of the long piece, [B,H,64,64]]
-size_t tc3_saved_bytes(int B, int T, int H) {
-    return tc3_saved_header(B, H) + ckpt_bytes(B, T, H) + (tc3_split_plan(B, T, H) ? (size_t)B * H * 4096 * sizeof(float) : 0);
-}
-float *tc3_saved_split_state(void *saved, int B, int T, int H) {
-    return (float *)((uint8_t *)saved + tc3_saved_header(B, H) + ckpt_bytes(B, T, H));
-}
-// tail split of the backward: dL/dS in front of the long piece (fp32 [B,H,64,64]) and the pieces' gu partials
-static size_t split_backward_scratch_bytes(int B, int T, int H) {
-    return tc3_split_plan(B, T, H) ? (size_t)B * H * (4096 + 128) * sizeof(float) + 1024 : 0;
+    return tc3_saved_header(B, H) + (size_t)B * H * NC * 8192;
 }
 // scratch of the time-segmented backward (seg_scan.cu): r, gy, w reversed inside the segments, the segments'
 // own and scanned state gradients, decay sums, per-row gs and gu
@@ -985,8 +911,7 @@ static size_t seg_backward_scratch_bytes(int B, int T, int H) {
     return 3 * n_el * 2 + 2 * st * 4 + Bs * C * 4 + st * 2 + Bs * C * 2 + 1024;
 }
 size_t tc3_backward_workspace_bytes(int B, int T, int H, bool has_saved) {
-    return simt_backward_workspace_bytes(B, T, H) + 1024 + split_backward_scratch_bytes(B, T, H) +
-           (has_saved ? seg_backward_scratch_bytes(B, T, H) : tc3_saved_bytes(B, T, H));
+    return simt_backward_workspace_bytes(B, T, H) + (has_saved ? seg_backward_scratch_bytes(B, T, H) : tc3_saved_bytes(B, T, H));
 }
 bool tc3_backward_supported(const Args &a) {
     return a.io_dtype == WKV6_BF16 && a.w_kind == W_RAW_BF16 && a.mask == nullptr && a.T >= 1 && !a.s0_f32 &&
@@ -1032,9 +957,8 @@ static int launch_bwd_kernel(dim3 grid, cudaStream_t stream, const CUtensorMap *
 
 // one launch of the backward kernel on `a` viewed as given (B rows of T tokens), chunk-start states in ckpt
 // bi / row_len: direction of the bidirectional op (tc3_common.cuh) and the device int [B] row lengths it needs
-// split > 0: tail split (Params), the long piece = chunks [0, split); gu_part = its fp32 scratch [B*H][2][64]
 static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const float *g_init, int nseg, int seg_chunks,
-                      bool has_s0, int bi = BI_NONE, const int *row_len = nullptr, int split = 0, float *gu_part = nullptr) {
+                      bool has_s0, int bi = BI_NONE, const int *row_len = nullptr) {
     const int C = a.H * 64;
     if (nseg <= 1) { nseg = 1; seg_chunks = (a.T + L - 1) / L; }
     const size_t NC = (size_t)nseg * seg_chunks;
@@ -1064,8 +988,6 @@ static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const f
     p.gu_total = sum_gu ? (bf16 *)a.gu_total : nullptr;
     p.gu_count = const_cast<int *>(flags) + (size_t)a.B * a.H;
     if (sum_gu) a.gu_total_done = true;
-    p.split = split; p.gu_part = gu_part;
-    p.gu_cnt2 = const_cast<int *>(flags) + (size_t)a.B * a.H + 512;
 #ifdef WKV6_FINE_STAMPS
     p.dbg = (long long *)g_tc3_bwd_stamps;
 #else
@@ -1073,10 +995,9 @@ static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const f
 #endif
     p.row_len = row_len;
     const bool clamp = a.lmin > -INFINITY;
-    const dim3 grid(a.B * (split > 0 ? 2 : nseg) * a.H);
+    const dim3 grid(a.B * nseg * a.H);
     int rc;
-    if (split > 0) rc = launch_bwd_kernel<true, BI_NONE>(grid, a.stream, maps, p);
-    else if (bi == BI_CAUSAL) rc = launch_bwd_kernel<false, BI_CAUSAL>(grid, a.stream, maps, p);
+    if (bi == BI_CAUSAL) rc = launch_bwd_kernel<false, BI_CAUSAL>(grid, a.stream, maps, p);
     else if (bi == BI_REV) rc = launch_bwd_kernel<false, BI_REV>(grid, a.stream, maps, p);
     else if (nseg > 1) rc = launch_bwd_kernel<true, BI_NONE>(grid, a.stream, maps, p);
     else rc = launch_bwd_kernel<false, BI_NONE>(grid, a.stream, maps, p);
@@ -1137,12 +1058,6 @@ int tc3_backward_bi(const Args &a, void *ckpt, int *flags, int bi, const int *ro
     return launch_bwd(a, (const bf16 *)ckpt, flags, nullptr, 1, 0, false, bi, row_len);
 }
 
-// where tc3_backward keeps the per-stream flags of a call without a training pair (callers that pre-set them)
-int *tc3_backward_flags(const Args &a) {
-    const size_t simt_al = (simt_backward_workspace_bytes(a.B, a.T, a.H) + 1023) / 1024 * 1024;
-    return (int *)((uint8_t *)a.workspace + simt_al + split_backward_scratch_bytes(a.B, a.T, a.H));
-}
-
 int tc3_backward(const Args &a, const Args *exact, bool flags_preset, bool run_fallback) {
     if (a.B * a.H == 0 || a.T == 0) return WKV6_OK;
     const size_t simt_ws = simt_backward_workspace_bytes(a.B, a.T, a.H);
@@ -1156,33 +1071,19 @@ int tc3_backward(const Args &a, const Args *exact, bool flags_preset, bool run_f
         seg_plan_train(a.B, a.T, a.H, &nseg, &seg_chunks);
         if (nseg > 1) return tc3_backward_segmented(a, nseg, seg_chunks);
     }
-    // workspace: [exact-route scratch][tail-split scratch][(no training pair) flags + chunk-start states]
-    const size_t simt_al = (simt_ws + 1023) / 1024 * 1024, split_ws = split_backward_scratch_bytes(a.B, a.T, a.H);
-    uint8_t *sv = a.saved ? (uint8_t *)a.saved : (uint8_t *)tc3_backward_flags(a);
-    (void)split_ws;
+    uint8_t *sv = a.saved ? (uint8_t *)a.saved : (uint8_t *)a.workspace + simt_ws;
     int *flags = (int *)sv;
     bf16 *ckpt = (bf16 *)(sv + tc3_saved_header(a.B, a.H));
     if (!a.saved) {
         // no training pair: recompute the chunk-start states (and the per-stream hazard flags) first
-        const size_t nflag = (size_t)a.B * a.H * sizeof(int);
-        if (!flags_preset) WKV6_CUDA_CHECK(cudaMemsetAsync(flags, 0, tc3_saved_header(a.B, a.H), a.stream));
-        else WKV6_CUDA_CHECK(cudaMemsetAsync((uint8_t *)flags + nflag, 0, tc3_saved_header(a.B, a.H) - nflag, a.stream));
+        if (!flags_preset) WKV6_CUDA_CHECK(cudaMemsetAsync(flags, 0, ((size_t)a.B * a.H + 512) * sizeof(int), a.stream));
+        else WKV6_CUDA_CHECK(cudaMemsetAsync(flags + (size_t)a.B * a.H, 0, 512 * sizeof(int), a.stream));
         Args f = a;
         f.y = nullptr;
         f.sT = nullptr;
         if (int rc = tc3_forward(f, ckpt, flags)) return rc;
     }
-    const int n_short = a.mask ? 0 : tc3_split_plan(a.B, a.T, a.H);
-    if (n_short > 0) {
-        // tail split: dL/dS behind the long piece = the state recurrence on the time-reversed (r, gy, w) of the last
-        // n_short chunks (G_{t-1} = d_t G_t + r_t (x) gy_t), i.e. the state-only forward kernel in its reversed reading
-        float *g_init = (float *)((uint8_t *)a.workspace + simt_al), *gu_part = g_init + (size_t)a.B * a.H * 4096;
-        Args f = a;
-        f.k = a.r; f.v = a.gy; f.y = nullptr; f.s0 = nullptr; f.s0_bstride = 0; f.s0_f32 = 0; f.sT = g_init; f.sT_f32 = 1;
-        f.saved = nullptr; f.gy = nullptr;
-        if (int rc = tc3_forward(f, nullptr, flags, 1, 0, BI_REV, nullptr, n_short)) return rc;
-        if (int rc = launch_bwd(a, ckpt, flags, g_init, 1, 0, a.s0 != nullptr, BI_NONE, nullptr, a.T / L - n_short, gu_part)) return rc;
-    } else if (int rc = launch_bwd(a, ckpt, flags, nullptr, 1, 0, a.s0 != nullptr)) return rc;
+    if (int rc = launch_bwd(a, ckpt, flags, nullptr, 1, 0, a.s0 != nullptr)) return rc;
     if (!run_fallback) return WKV6_OK;      // the caller runs its own exact route on the flags in the workspace
     // Flags are only ever raised by the fp32-decay conversion (flags_preset); a call on raw bf16 logits has none
     if (!flags_preset && !exact) return WKV6_OK;

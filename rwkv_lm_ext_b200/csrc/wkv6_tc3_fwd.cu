@@ -66,14 +66,7 @@ struct Params {
     // checkpoints are indexed by row; nseg = 1 and seg_chunks = ceil(T/64) for an ordinary call.
     int nseg, seg_chunks;
     float lmin;               // floor of the per-token log2-decay (opt-in clamp; -inf = off)
-    const int *row_len;       // BI modes: tokens of every batch row (p + 1 of wkv6_bi), device int [B]; nullptr = T
-    int max_chunks;           // > 0: stop after this many chunks (the state pre-passes of the tail split, wkv6_tc3_bwd.cu)
-    // tail split (SEG instantiation, split > 0; see tc3_split_plan): 2*B*H CTAs.  CTA x < B*H runs chunks [split, NC) of stream
-    // x from the fp32 state s1[x] (a state-only pre-pass over the first `split` chunks produced it) and writes the final
-    // state; CTA B*H + x runs chunks [0, split) of stream x from the caller's s0.  Flags, s0 / sT and the checkpoints
-    // (slot = stream * NC + chunk) are indexed by STREAM, exactly as in an ordinary call.
-    int split;
-    const float *s1;
+    const int *row_len;       // BI modes: tokens of every batch row (p + 1 of wkv6_bi), device int [B]
 };
 
 // 9 warps x 2 CTAs = 5 warps on the fullest SM sub-partition (16384 registers): at most 96 per thread
@@ -87,27 +80,16 @@ __global__ void __launch_bounds__(NTHREADS, 2)
 wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_ck, Params p) {
+    if (p.hz_flags[blockIdx.x] != 0) return;        // flagged before launch (inexact logit conversion): exact route
     extern __shared__ __align__(1024) uint8_t sm[];
     Extra &ex = *reinterpret_cast<Extra *>(sm + OFF_TILES_END);
     if ((smem_u32(sm) & 1023u) != 0) __trap();
-    const bool split = SEG && p.split > 0;
-    const bool tail = split && (int)blockIdx.x < p.B * p.H;                  // tail split: the long pieces come first in the grid
-    const int rid = split ? (tail ? blockIdx.x : blockIdx.x - p.B * p.H) : blockIdx.x;   // row id: flags, checkpoints
-    if (p.hz_flags[rid] != 0) return;               // flagged before launch (inexact logit conversion): exact route
-    const int row = rid / p.H, h = rid % p.H;
-    const int b = SEG && !split ? row / p.nseg : row;                        // batch index inside the [B,T,C] tensors
-    const int t_base = split ? (tail ? p.split * L : 0) : SEG ? (row % p.nseg) * p.seg_chunks * L : 0;   // first token of this row's segment
-    const int T_all = BI ? (p.row_len ? p.row_len[b] : p.T) : split ? (tail ? p.T - t_base : p.split * L)
-                         : SEG ? min(p.T - t_base, p.seg_chunks * L) : p.T;  // tokens of the segment / row
-    const int T = T_all;
-    const int NC = p.max_chunks > 0 ? min((T + L - 1) / L, p.max_chunks) : (T + L - 1) / L;   // (a pre-pass stops early)
+    const int row = blockIdx.x / p.H, h = blockIdx.x % p.H;
+    const int b = SEG ? row / p.nseg : row;                                  // batch index inside the [B,T,C] tensors
+    const int t_base = SEG ? (row % p.nseg) * p.seg_chunks * L : 0;          // first token of this row's segment
+    const int T = BI ? p.row_len[b] : SEG ? min(p.T - t_base, p.seg_chunks * L) : p.T;   // tokens of the segment / row
+    const int NC = (T + L - 1) / L;
     const int ck_stride = SEG ? p.seg_chunks : BI ? (p.T + L - 1) / L : NC;  // checkpoint slots per row
-    const int ck_base = split ? rid * ((p.T + L - 1) / L) + t_base / L : rid * ck_stride;
-    // initial / final state of this CTA
-    const void *s0p = tail ? (const void *)p.s1 : p.s0;
-    const int s0_f32 = tail ? 1 : p.s0_f32;
-    const long long s0_bstride = tail ? (long long)p.H * 4096 : p.s0_bstride;
-    void *sTp = split && !tail ? nullptr : p.sT;
     // first token of chunk c's tile (BI_REV: the tile that ends at token T-1-64c, read backwards; see tc3_common.cuh)
     auto tok0 = [&](int c) { return BI == BI_REV ? max(T - (c + 1) * L, 0) : t_base + c * L; };
     Frag F;
@@ -182,7 +164,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         bar_sync_all<B_PB>();
         bar_sync_all<B_T2>();                                    // initial state in TMEM / shared
         if (lane == 0) {
-            if (p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, ck_base * 64, 0);
+            if (p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (blockIdx.x * ck_stride) * 64, 0);
             tma_store_commit();
         }
         if (lane == 0) mbar_wait(&ex.bar_a, 0);
@@ -253,7 +235,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     if (BI == BI_REV) tma_reduce_add_3d(&map_y, sm + OFF_YT, h * 64, tok0(c), b);
                     else tma_store_3d(&map_y, sm + OFF_YT, h * 64, tok0(c), b);
                 }
-                if (more && p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (ck_base + c + 1) * 64, 0);
+                if (more && p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (blockIdx.x * ck_stride + c + 1) * 64, 0);
                 tma_store_commit();
             }
         }
@@ -289,9 +271,9 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
 #pragma unroll
                 for (int e = 0; e < 2; e++) {
                     float x = 0.f;
-                    if (s0p) {    // caller layout [.,H,64(value j),64(key i)]
-                        const size_t idx = (size_t)row * s0_bstride + ((size_t)h * 64 + F.col(g, e)) * 64 + F.row(hh);
-                        x = s0_f32 ? ((const float *)s0p)[idx] : __bfloat162float(((const bf16 *)s0p)[idx]);
+                    if (p.s0) {   // caller layout [.,H,64(value j),64(key i)]
+                        const size_t idx = (size_t)row * p.s0_bstride + ((size_t)h * 64 + F.col(g, e)) * 64 + F.row(hh);
+                        x = p.s0_f32 ? ((const float *)p.s0)[idx] : __bfloat162float(((const bf16 *)p.s0)[idx]);
                     }
                     v[4 * g + 2 * hh + e] = __float_as_uint(x);
                 }
@@ -547,7 +529,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                         pack2(__uint_as_float(v[4 + 2 * hh]), __uint_as_float(v[5 + 2 * hh])),
                         pack2(__uint_as_float(v[8 + 2 * hh]), __uint_as_float(v[9 + 2 * hh])),
                         pack2(__uint_as_float(v[12 + 2 * hh]), __uint_as_float(v[13 + 2 * hh])));
-            if (c == NC - 1 && sTp) {
+            if (c == NC - 1 && p.sT) {
 #pragma unroll
                 for (int g = 0; g < 4; g++)
 #pragma unroll
@@ -556,8 +538,8 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                         for (int e = 0; e < 2; e++) {
                             const size_t idx = (((size_t)row * p.H + h) * 64 + F.col(g, e)) * 64 + F.row(hh);
                             const float x = __uint_as_float(v[4 * g + 2 * hh + e]);
-                            if (p.sT_f32) ((float *)sTp)[idx] = x;
-                            else ((bf16 *)sTp)[idx] = __float2bfloat16_rn(x);
+                            if (p.sT_f32) ((float *)p.sT)[idx] = x;
+                            else ((bf16 *)p.sT)[idx] = __float2bfloat16_rn(x);
                         }
             }
             fence_proxy_async();
@@ -598,13 +580,11 @@ static int launch_fwd(dim3 grid, cudaStream_t stream, const CUtensorMap &mr, con
     return WKV6_OK;
 }
 
-int tc3_forward(const Args &a, void *ckpt, int *hz_flags, int nseg, int seg_chunks, int bi, const int *row_len,
-                int max_chunks, int split, const float *s1) {
+int tc3_forward(const Args &a, void *ckpt, int *hz_flags, int nseg, int seg_chunks, int bi, const int *row_len) {
     if (a.B * a.H == 0 || a.T == 0) return WKV6_OK;
     const int C = a.H * 64;
     if (nseg <= 1) { nseg = 1; seg_chunks = (a.T + L - 1) / L; }
-    if (bi != BI_NONE && nseg > 1) { set_error("bidirectional pass: one segment required"); return WKV6_EINVAL; }
-    if (split > 0 && (nseg > 1 || bi != BI_NONE || !s1 || !a.y || a.T % L != 0 || split >= a.T / L)) { set_error("tail split: bad arguments"); return WKV6_EINVAL; }
+    if (bi != BI_NONE && (nseg > 1 || !row_len)) { set_error("bidirectional pass: one segment and row lengths required"); return WKV6_EINVAL; }
     const size_t NC = (size_t)nseg * seg_chunks;                 // checkpoint slots per (b,h)
     CUtensorMap mr, mk, mv, mw, my, mc;
     const auto dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -627,8 +607,6 @@ int tc3_forward(const Args &a, void *ckpt, int *hz_flags, int nseg, int seg_chun
     p.nseg = nseg; p.seg_chunks = seg_chunks;
     p.lmin = tc_lmin_log2(a);
     p.row_len = row_len;
-    p.max_chunks = max_chunks; p.split = split; p.s1 = s1;
-    if (split > 0) return launch_fwd<true, false, BI_NONE>(dim3(2 * a.B * a.H), a.stream, mr, mk, mv, mw, my, mc, p);
     const dim3 grid(a.B * nseg * a.H);
     const bool so = !p.has_y;
     if (bi == BI_CAUSAL) return so ? launch_fwd<false, true, BI_CAUSAL>(grid, a.stream, mr, mk, mv, mw, my, mc, p)
