@@ -122,6 +122,42 @@ def run_cpu(steps, warmup, budget_s=20.0):
     return s["B"] * s["T"] / sec, cores, sec, len(ts)
 
 
+def run_reference_python(budget_s=12.0):
+    """The reference's OWN CPU implementation of the recurrence, unmodified: run_rwkv6_forward of
+    src/model_encoder_run.py:31-62 (= tests/test_cpu.py:42-73), from baseline/_ref (placed there by
+    __graft_entry__.build(); git-ignored).  It is forward only (in-place state updates: no autograd) and a Python
+    loop over T x 64, so it is timed on the WKV6 call of BASELINE configs[0] (169M shape: B=8, T=512, H=12, fp32),
+    bounded by `budget_s`.  Returns None when the file is not there."""
+    import importlib.util
+    path = os.path.join(ROOT, "baseline", "_ref", "src", "model_encoder_run.py")
+    if not os.path.isfile(path):
+        return None
+    os.environ.setdefault("RWKV_HEAD_SIZE_A", "64")
+    os.environ["NO_CUDA"] = "1"
+    import torch
+    from rwkv_lm_ext_b200.synthetic import make_inputs
+    spec = importlib.util.spec_from_file_location("_ref_model_encoder_run", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    Br, Tr, Hr = 8, 512, 12
+    r, k, v, w, u, _ = (t.float() for t in make_inputs(Br, Tr, Hr, seed=0, decay="model"))
+    torch.set_num_threads(os.cpu_count() or 1)
+    n = 32                                         # time a prefix first: the loop is linear in T
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        mod.run_rwkv6_forward(r[:, :n].contiguous(), k[:, :n].contiguous(), v[:, :n].contiguous(), w[:, :n].contiguous(), u)
+    per_tok = (time.perf_counter() - t0) / n
+    Tt = int(max(n, min(Tr, budget_s / per_tok)))
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        y = mod.run_rwkv6_forward(r[:, :Tt].contiguous(), k[:, :Tt].contiguous(), v[:, :Tt].contiguous(), w[:, :Tt].contiguous(), u)
+    sec = time.perf_counter() - t0
+    return {"what": "reference run_rwkv6_forward (src/model_encoder_run.py:31-62, unmodified, from baseline/_ref), "
+                    f"forward only, fp32, B={Br} T={Tt} H={Hr} (configs[0] shape{'' if Tt == Tr else ', first ' + str(Tt) + ' tokens'})",
+            "seconds": sec, "tokens_per_s_forward": Br * Tt / sec, "cores": os.cpu_count(), "kind": "reference",
+            "_y": y, "_inputs": (r[:, :Tt].contiguous(), k[:, :Tt].contiguous(), v[:, :Tt].contiguous(), w[:, :Tt].contiguous(), u)}
+
+
 BI = dict(layers=24, D=2048, H=32, ffn=7168, vocab=65536, micro_batch=64, T=512)   # SURVEY.md 8(d) config 3
 
 
@@ -243,6 +279,9 @@ def main():
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
+        rp = run_reference_python(budget_s=20.0)          # the reference's own (forward-only) CPU code, beside the port
+        if rp:
+            line["reference_python"] = {k_: v_ for k_, v_ in rp.items() if not k_.startswith("_")}
         print(json.dumps(line), flush=True)
         return 0
 
@@ -492,6 +531,27 @@ def main():
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"fwd+bwd on B={CPU_SAMPLE['B']} T={CPU_SAMPLE['T']} H={CPU_SAMPLE['H']} "
                                           f"(1/8 of one step's batch), mean of {runs} runs of {sec:.2f} s, {cores} threads"}
+        # BASELINE configs[0]'s recurrence: the reference's own pure-PyTorch CPU path, unmodified, and this library on the
+        # same inputs (bf16) -- a live parity check against the reference's code and the CPU/GPU time of that call
+        rp = run_reference_python()
+        if rp:
+            rr, kk, vv, ww, uu = (t.to(dev).bfloat16().contiguous() for t in rp["_inputs"])
+            Br, Tr, Cr = rr.shape
+            with torch.no_grad():
+                for _ in range(3):
+                    yo = M.RUN_CUDA_RWKV6(Br, Tr, Cr, Cr // 64, rr, kk, vv, ww, uu)
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record()
+                for _ in range(20):
+                    yo = M.RUN_CUDA_RWKV6(Br, Tr, Cr, Cr // 64, rr, kk, vv, ww, uu)
+                b_.record()
+                torch.cuda.synchronize()
+            yr = rp["_y"].double()
+            info = {k_: v_ for k_, v_ in rp.items() if not k_.startswith("_")}
+            info["ours_same_call_ms"] = a_.elapsed_time(b_) / 20
+            info["ours_tokens_per_s_forward"] = Br * Tr / (info["ours_same_call_ms"] * 1e-3)
+            info["relrms_ours_vs_reference"] = float(((yo.double().cpu() - yr).norm() / yr.norm()).item())
+            line["cpu_baseline"]["reference_python"] = info
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
