@@ -106,6 +106,17 @@ def check(rc: int, what: str):
         raise Wkv6B200Error(f"{what} failed with code {rc}: {msg}")
 
 
+def require_current_device(t):
+    """The library takes its stream from the tensor's device but its scratch (flag ring, memory pool, function attributes)
+    from the CURRENT device: a tensor on another device must be used under `torch.cuda.device(t.device)`."""
+    import torch
+    if not t.is_cuda:
+        raise Wkv6B200Error("rwkv_lm_ext_b200 runs on CUDA tensors only (no CPU fallback)")
+    if t.device.index != torch.cuda.current_device():
+        raise Wkv6B200Error(f"tensor on {t.device} but the current CUDA device is cuda:{torch.cuda.current_device()}: "
+                            "wrap the call in `with torch.cuda.device(t.device):`")
+
+
 def ptr(t):
     return None if t is None else t.data_ptr()
 

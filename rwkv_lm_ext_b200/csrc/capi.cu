@@ -80,8 +80,13 @@ static int *flag_slice(size_t n) {
         lock.clear();
         if (!ring[dev]) return nullptr;
     }
-    size_t off = head[dev].fetch_add(n) % RING;
-    if (off + n > RING) off = 0;      // wrap: only collides with a call issued ~1M stream-flags ago
+    // reserve [off, off + n) with a compare-and-swap loop; a slice that would cross the end of the ring starts at 0
+    // and moves the head behind itself, so two live slices only overlap after a full turn of the ring (1M flags)
+    size_t cur = head[dev].load(), off;
+    do {
+        off = cur % RING;
+        if (off + n > RING) off = 0;
+    } while (!head[dev].compare_exchange_weak(cur, cur - cur % RING + (off == 0 && cur % RING != 0 ? RING : 0) + off + n));
     return ring[dev] + off;
 }
 // Forward over `nseg` time segments that run as separate grid rows (seg_scan.cu): state-only pass from zero

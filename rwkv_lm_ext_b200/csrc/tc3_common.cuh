@@ -197,21 +197,23 @@ __device__ __forceinline__ void bar_sync_all() { asm volatile("bar.sync %0, %1;"
 
 // 2^d as a packed bf16 pair for an integer d <= 0 (0 when below the normal range)
 __device__ __forceinline__ uint32_t bfpow2pair(int d) {
-    const uint32_t x = (uint32_t)(max(d, -127) + 127) << 7;
-    return x | (x << 16);
+    return (uint32_t)(max(d, -127) + 127) * 0x00800080u;        // both halves with one multiply: (e << 7) | (e << 23), e < 128
 }
+// the same for -127 <= d <= 0 (no clamp): a single multiply-add
+__device__ __forceinline__ uint32_t bfpow2pair_nc(int d) { return (uint32_t)d * 0x00800080u + 127u * 0x00800080u; }
 // exact scaling of packed bf16 pairs by 2^d, -254 <= d <= 0, as two factors (2^d alone may leave the bf16
-// range although the scaled values do not)
+// range although the scaled values do not).  d is the distance of two neighbouring block references: at most 16
+// tokens x LCLAMP2 = 208 (+ 1 of rounding), so both halves are >= -127 and need no clamp.
 __device__ __forceinline__ void scale1(uint32_t &a, int d) {
-    a = hmul2(hmul2(a, bfpow2pair(d >> 1)), bfpow2pair(d - (d >> 1)));
+    a = hmul2(hmul2(a, bfpow2pair_nc(d >> 1)), bfpow2pair_nc(d - (d >> 1)));
 }
 __device__ __forceinline__ void scale2(uint32_t &a, uint32_t &b, int d) {
-    const uint32_t fa = bfpow2pair(d >> 1), fb = bfpow2pair(d - (d >> 1));
+    const uint32_t fa = bfpow2pair_nc(d >> 1), fb = bfpow2pair_nc(d - (d >> 1));
     a = hmul2(hmul2(a, fa), fb);
     b = hmul2(hmul2(b, fa), fb);
 }
 __device__ __forceinline__ void scale4(uint32_t (&x)[4], int d) {
-    const uint32_t fa = bfpow2pair(d >> 1), fb = bfpow2pair(d - (d >> 1));
+    const uint32_t fa = bfpow2pair_nc(d >> 1), fb = bfpow2pair_nc(d - (d >> 1));
 #pragma unroll
     for (int g = 0; g < 4; g++) x[g] = hmul2(hmul2(x[g], fa), fb);
 }

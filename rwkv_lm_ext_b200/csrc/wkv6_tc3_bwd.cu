@@ -350,6 +350,9 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         uint32_t ti2_off = F.ti1_off ^ ((lane & 8) ? 16u : 0u);
         int dcol = (32 * ch + 2 * q) - (16 * sp + ri);           // column(g, e = 0) - row(hh) at g = hh
         asm volatile("" : "+r"(dcol), "+r"(ti2_off));
+        // where the warp's part of a 64 x 64 (row, column) tile lies: 1 = entirely above the diagonal (column > row), 2 =
+        // entirely below it, 0 = the diagonal runs through it
+        const int tri = 32 * ch - 16 * sp - 15 > 0 ? 1 : 32 * ch + 31 - 16 * sp < 0 ? 2 : 0;
         bool diag_hit[2];                                        // this thread holds the diagonal element of row(hh)
 #pragma unroll
         for (int hh = 0; hh < 2; hh++) {
@@ -604,9 +607,17 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             // branch-free: dcol = (column of e = 0) - row for g = hh; 8 more per group.  The diagonal element (if this
             // thread holds it) is picked with selects and stored once per row half (divergent stores per element were
             // 700 cycles of this stage)
+            // (the warp's part of the tile lies entirely below the diagonal -- kept as it is --, entirely above -- zeros --, or
+            // on it: `tri`)
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
                 uint32_t pk[4];
+                if (tri == 2) {
+#pragma unroll
+                    for (int g = 0; g < 4; g++) pk[g] = pack2(__uint_as_float(v[4 * g + 2 * hh]), __uint_as_float(v[4 * g + 2 * hh + 1]));
+                } else if (tri == 1) {
+                    pk[0] = pk[1] = pk[2] = pk[3] = 0u;
+                } else {
                 float dv = 0.f;
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
@@ -615,8 +626,9 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     pk[g] = pack2(d < 0 ? a0 : 0.f, d < -1 ? a1 : 0.f);
                     dv = sel_eq(d, 0, a0, sel_eq(d, -1, a1, dv));
                 }
-                stsm_x4(sbase + OFF_DA + F.rc(hh), pk[0], pk[1], pk[2], pk[3]);
                 if (diag_hit[hh]) ex.bd[F.row(hh)] = dv;
+                }
+                stsm_x4(sbase + OFF_DA + F.rc(hh), pk[0], pk[1], pk[2], pk[3]);
             }
             STAMPX(25);
             fence_proxy_async();
@@ -661,14 +673,21 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             STAMPX(18);
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
+                uint32_t pk[4];
+                if (tri == 1) {
+#pragma unroll
+                    for (int g = 0; g < 4; g++) pk[g] = pack2(__uint_as_float(v[4 * g + 2 * hh]), __uint_as_float(v[4 * g + 2 * hh + 1]));
+                } else if (tri == 2) {
+                    pk[0] = pk[1] = pk[2] = pk[3] = 0u;
+                } else {
                 const int sr = F.row(hh);
                 const float dg = (ex.pdu[0][sr] + ex.pdu[1][sr]) + (ex.pdu[2][sr] + ex.pdu[3][sr]);
-                uint32_t pk[4];
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
                     const int d = dcol + 8 * (g - hh);                    // (t - s) for e = 0
                     const float a0 = __uint_as_float(v[4 * g + 2 * hh]), a1 = __uint_as_float(v[4 * g + 2 * hh + 1]);
                     pk[g] = pack2(d > 0 ? a0 : (d == 0 ? dg : 0.f), d > -1 ? a1 : (d == -1 ? dg : 0.f));
+                }
                 }
                 stsm_x4(sbase + OFF_PT + F.rc(hh), pk[0], pk[1], pk[2], pk[3]);
             }

@@ -261,6 +261,9 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         const uint32_t tS = tmem_addr(tmem, 32 * sp, TM_S + 32 * ch);
         int dcol = (32 * ch + 2 * q) - (16 * sp + F.ri);           // column(g, e = 0) - row(hh) at g = hh
         asm volatile("" : "+r"(dcol));
+        // where the warp's part of a 64 x 64 (row, column) tile lies: 1 = entirely above the diagonal (column > row), 2 =
+        // entirely below it, 0 = the diagonal runs through it
+        const int tri = 32 * ch - 16 * sp - 15 > 0 ? 1 : 32 * ch + 31 - 16 * sp < 0 ? 2 : 0;
         uint32_t v[16];
 
         // ---- initial state -> TMEM (fp32 master, [i][j]) and shared (bf16 operand copy)
@@ -459,21 +462,33 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             bar_sync_all<B_A>();
             tc_fence_after();
             if (!SO && p.has_y) {
+            // The warp's 16 x 32 part of A^T (rows s = 16sp.., columns t = 32ch..) lies entirely above the diagonal for
+            // (sp 0,1; ch 1): kept as it is; entirely below for (sp 2,3; ch 0): zeros, no TMEM load; the other four warps mask
+            if (tri == 2) {
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) stsm_x4_t(sbase + OFF_P + F.ti(hh), 0u, 0u, 0u, 0u);
+            } else {
             tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_A + 32 * ch), v);
             tmem_wait_ld();
             // branch-free: dcol = (t of e = 0) - s at g = hh; 8 more per column group
 #pragma unroll
             for (int hh = 0; hh < 2; hh++) {
+                uint32_t pk[4];
+                if (tri == 1) {
+#pragma unroll
+                    for (int g = 0; g < 4; g++) pk[g] = pack2(__uint_as_float(v[4 * g + 2 * hh]), __uint_as_float(v[4 * g + 2 * hh + 1]));
+                } else {
                 const int sr = F.row(hh);
                 const float dg = (ex.pdu[0][sr] + ex.pdu[1][sr]) + (ex.pdu[2][sr] + ex.pdu[3][sr]);
-                uint32_t pk[4];
 #pragma unroll
                 for (int g = 0; g < 4; g++) {
                     const int d = dcol + 8 * (g - hh);                    // (t - s) for e = 0
                     const float a0 = __uint_as_float(v[4 * g + 2 * hh]), a1 = __uint_as_float(v[4 * g + 2 * hh + 1]);
                     pk[g] = pack2(d > 0 ? a0 : (d == 0 ? dg : 0.f), d > -1 ? a1 : (d == -1 ? dg : 0.f));
                 }
+                }
                 stsm_x4_t(sbase + OFF_P + F.ti(hh), pk[0], pk[1], pk[2], pk[3]);       // P[t][s]
+            }
             }
             }
             tmem_ld_frag(tS, v);

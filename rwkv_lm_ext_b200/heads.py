@@ -10,8 +10,7 @@ from ._lib import check, ptr, stream_of
 
 
 def _cuda(t):
-    if not t.is_cuda:
-        raise _lib.Wkv6B200Error("rwkv_lm_ext_b200 kernels run on CUDA tensors only (no CPU fallback)")
+    _lib.require_current_device(t)
 
 
 def _bf16_param(t):

@@ -26,8 +26,7 @@ def _assert_bf16_contig(*ts):
 
 
 def _require_cuda(t):
-    if not t.is_cuda:
-        raise _lib.Wkv6B200Error("rwkv_lm_ext_b200 operators run on CUDA tensors only (no CPU fallback)")
+    _lib.require_current_device(t)
 
 
 def _workspace(lib, B, T, C, H, device):
