@@ -172,26 +172,32 @@ __global__ void __launch_bounds__(256) ddlerp_mix_kernel(int B, int T, int C, co
     }
 }
 
-// xxx = x + (shift(x) - x) * maa_x
+// xxx = x + (shift(x) - x) * maa_x.  One block per (b, 16 token rows): a thread keeps its 8 channels of maa_x and of the previous token in
+// registers and walks 16 token rows -- every x element is read once (plus one row per 16), no index arithmetic per vector.
+constexpr int SHIFT_ROWS = 16;
 __global__ void __launch_bounds__(256) shift_lerp_kernel(int B, int T, int C, const bf16 *__restrict__ x,
                                                          const bf16 *__restrict__ shift, const bf16 *__restrict__ maa_x,
                                                          bf16 *__restrict__ out) {
-    const size_t nvec = (size_t)B * T * C / 8;
-    const int cv = C / 8;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t row = i / cv;
-        const int c = (int)(i % cv) * 8, t = (int)(row % T), b = (int)(row / T);
-        float xf[8], pf[8], af[8], o[8];
-        unpack8(ld8(x + i * 8), xf);
-        if (t > 0) unpack8(ld8(x + i * 8 - C), pf);
+    const int nt = (T + SHIFT_ROWS - 1) / SHIFT_ROWS;
+    const int b = blockIdx.x / nt, t0 = (blockIdx.x % nt) * SHIFT_ROWS, t1 = min(T, t0 + SHIFT_ROWS);
+    for (int c = threadIdx.x * 8; c < C; c += blockDim.x * 8) {
+        float pf[8], af[8];
+        unpack8(ld8(maa_x + c), af);
+        if (t0 > 0) unpack8(ld8(x + ((size_t)b * T + t0 - 1) * C + c), pf);
         else if (shift) unpack8(ld8(shift + (size_t)b * C + c), pf);
         else
             for (int e = 0; e < 8; e++) pf[e] = 0.f;
-        unpack8(ld8(maa_x + c), af);
+        const bf16 *src = x + ((size_t)b * T + t0) * C + c;
+        bf16 *dst = out + ((size_t)b * T + t0) * C + c;
+        for (int t = t0; t < t1; t++, src += C, dst += C) {
+            float xf[8], o[8];
+            unpack8(ld8(src), xf);
 #pragma unroll
-        for (int e = 0; e < 8; e++) o[e] = xf[e] + rb(rb(pf[e] - xf[e]) * af[e]);
-        st8(out + i * 8, pack8(o));
+            for (int e = 0; e < 8; e++) { o[e] = xf[e] + rb(rb(pf[e] - xf[e]) * af[e]); pf[e] = xf[e]; }
+            st8(dst, pack8(o));
+        }
     }
+    (void)B;
 }
 
 // GroupNorm over 64-channel groups, then * g.  8 lanes (8 channels each) per group.
@@ -379,7 +385,7 @@ int tmix_shift_lerp_bf16(int B, int T, int C, const void *x, const void *shift_s
     if (B < 0 || T < 0 || C <= 0 || (C & 7)) { set_error("tmix_shift_lerp_bf16: need C %% 8 == 0"); return WKV6_EINVAL; }
     if ((size_t)B * T == 0) return WKV6_OK;
     if (!x || !maa_x || !out) { set_error("tmix_shift_lerp_bf16: null pointer"); return WKV6_EINVAL; }
-    shift_lerp_kernel<<<grid_for((size_t)B * T * C / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+    shift_lerp_kernel<<<(unsigned)((size_t)B * ((T + SHIFT_ROWS - 1) / SHIFT_ROWS)), 256, 0, (cudaStream_t)stream>>>(
         B, T, C, (const bf16 *)x, (const bf16 *)shift_state, (const bf16 *)maa_x, (bf16 *)out);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());

@@ -284,30 +284,28 @@ __global__ void __launch_bounds__(256) gn_gate_bwd_kernel(long long BT, int C, f
 // ------------------------------------------------------------------------------------------------
 // pooling backward: gx[b,t,:] = gout[b,:] * wgt(t) / L  inside the pooled range, 0 outside.
 // ------------------------------------------------------------------------------------------------
+// Write-only: gx[b,t,:] = gout[b,:] * weight(t).  One block per (b, 16 token rows): a thread keeps its 8 channels of gout[b] in registers
+// and walks 16 token rows, so there is no index arithmetic per store and the weight is one value per row.
+constexpr int POOL_ROWS = 16;
 __global__ void __launch_bounds__(256) pooling_bwd_kernel(int kind, int B, int T, int D,
                                                           const int64_t *__restrict__ alen, int add_one,
                                                           const float *__restrict__ gout, bf16 *__restrict__ gx) {
-    const int dv = D / 8;
-    const size_t nvec = (size_t)B * T * dv;
-    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += (size_t)gridDim.x * blockDim.x) {
-        const size_t row = i / dv;
-        const int d = (int)(i % dv) * 8, t = (int)(row % T), b = (int)(row / T);
-        const long long L64 = alen[b] + add_one;
-        const float Lf = (float)L64;
-        const long long tend = (kind == 0) ? L64 + 1 : L64;
-        float o[8];
-        if (t < tend) {
-            const float wgt = ((kind == 0) ? (float)(t + 1) / Lf : 1.0f) / Lf;
-            const float4 a = *reinterpret_cast<const float4 *>(gout + (size_t)b * D + d);
-            const float4 c = *reinterpret_cast<const float4 *>(gout + (size_t)b * D + d + 4);
-            o[0] = a.x * wgt; o[1] = a.y * wgt; o[2] = a.z * wgt; o[3] = a.w * wgt;
-            o[4] = c.x * wgt; o[5] = c.y * wgt; o[6] = c.z * wgt; o[7] = c.w * wgt;
-        } else {
-#pragma unroll
-            for (int e = 0; e < 8; e++) o[e] = 0.f;
+    const int nt = (T + POOL_ROWS - 1) / POOL_ROWS;
+    const int b = blockIdx.x / nt, t0 = (blockIdx.x % nt) * POOL_ROWS, t1 = min(T, t0 + POOL_ROWS);
+    const long long L64 = alen[b] + add_one;
+    const float Lf = (float)L64, inv = 1.0f / Lf;
+    const long long tend = (kind == 0) ? L64 + 1 : L64;
+    for (int d = threadIdx.x * 8; d < D; d += blockDim.x * 8) {
+        const float4 a = *reinterpret_cast<const float4 *>(gout + (size_t)b * D + d);
+        const float4 c = *reinterpret_cast<const float4 *>(gout + (size_t)b * D + d + 4);
+        bf16 *dst = gx + ((size_t)b * T + t0) * D + d;
+        for (int t = t0; t < t1; t++, dst += D) {
+            const float wgt = t < tend ? ((kind == 0) ? (float)(t + 1) / Lf : 1.0f) / Lf : 0.f;
+            float o[8] = {a.x * wgt, a.y * wgt, a.z * wgt, a.w * wgt, c.x * wgt, c.y * wgt, c.z * wgt, c.w * wgt};
+            st8(dst, pack8(o));
         }
-        st8(gx + i * 8, pack8(o));
     }
+    (void)inv; (void)B;
 }
 
 // gx[b,t,:] = (t == pos[b]) ? gout[b,:] : 0      (gradient of gather_rows)
@@ -494,7 +492,7 @@ int pooling_backward_bf16(int kind, int variant, int B, int T, int D, const int6
     if (B < 0 || T <= 0 || D <= 0 || (D & 7) || (kind != 0 && kind != 2)) { set_error("pooling_backward_bf16: bad arguments (D %% 8 == 0, kind 0 or 2)"); return WKV6_EINVAL; }
     if (B == 0) return WKV6_OK;
     if (!actual_len || !gout_f32 || !gx) { set_error("pooling_backward_bf16: null pointer"); return WKV6_EINVAL; }
-    pooling_bwd_kernel<<<grid_for((size_t)B * T * D / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+    pooling_bwd_kernel<<<(unsigned)((size_t)B * ((T + POOL_ROWS - 1) / POOL_ROWS)), 256, 0, (cudaStream_t)stream>>>(
         kind, B, T, D, actual_len, (kind == 0 && variant == 1) ? 1 : 0, gout_f32, (bf16 *)gx);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());

@@ -795,26 +795,30 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     f2unpack(x2, x0, x1);
                     f2unpack(nd2, nd0, nd1);
                     f2unpack(xa, xa0, xa1);
-                    // exclusive prefix of -D over the 4 lanes of the group; total of X
+                    // exclusive prefix of -D over the 4 lanes of the group; X is only needed as a total: per-lane sums
+                    // here, one reduction over the 4 lanes behind the loop
                     const float pd = nd0 + nd1;
-                    float y = pd, z1 = x0 + x1, tmp;
+                    float y = pd, tmp;
                     tmp = __shfl_up_sync(0xffffffffu, y, 1, 4);
                     if (q >= 1) y += tmp;
-                    z1 += __shfl_xor_sync(0xffffffffu, z1, 1);
                     tmp = __shfl_up_sync(0xffffffffu, y, 2, 4);
                     if (q >= 2) y += tmp;
-                    z1 += __shfl_xor_sync(0xffffffffu, z1, 2);
                     const float ex0 = runD[hh] + (y - pd);                     // sum_{s<t} (-D_s) for e = 0
                     a4[2 * hh] = __float_as_uint(ex0 + xa0);                   // gl_t = base - (this)
                     a4[2 * hh + 1] = __float_as_uint(ex0 + nd0 + xa1);
                     runD[hh] += __shfl_sync(0xffffffffu, y, 3, 4);
-                    runX[hh] += z1;
+                    runX[hh] += x0 + x1;
                 }
                 stsm_x2_t(sbase + OFF_GKT + (BI == BI_REV ? flip_rows(ti2_off + 1024u * g, r0) : ti2_off + 1024u * g), gkp[0], gkp[1]);
                 tmem_st_frag1(tPark + PARK_A + 8 * g, a4);
             }
             }
             STAMPX(20);
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                runX[hh] += __shfl_xor_sync(0xffffffffu, runX[hh], 1);
+                runX[hh] += __shfl_xor_sync(0xffffffffu, runX[hh], 2);
+            }
             if (q == 0) {
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++) {
