@@ -57,7 +57,7 @@ __host__ __device__ constexpr uint32_t rp_ver(int p) { return p == 0 ? 0u : p ==
 constexpr uint32_t OFF_GRT = OFF_KT + 8192, OFF_GVT = OFF_KT, OFF_GKT = OFF_DA, OFF_GWT = OFF_RP;
 
 struct Extra {
-    float gtot[8][64];        // decay total of every 8-token group, per channel (log2 units)
+    float gtot[64][8];        // decay total of every 8-token group, per channel (log2 units): one 32-byte row per channel
     float pdu[4][64];         // per channel-quarter partial sums of r u k, per token
     float bd[64];             // Bm[t,t]
     float q0p[2][64];         // <S_in, G>_i, partial over each half of j
@@ -451,7 +451,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                         y = __shfl_up_sync(0xffffffffu, x, 2, 4);
                         if (q >= 2) x += y;
                         exq[hh][g] = x - ps;
-                        if (q == 3) ex.gtot[4 * ch + g][F.row(hh)] = x;
+                        if (q == 3) ex.gtot[F.row(hh)][4 * ch + g] = x;
                     }
             }
             {   // park l in the shadow lanes (fragment order [4g + 2h + e])
@@ -504,11 +504,13 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             for (int hh = 0; hh < 2; hh++) {
                 float run = 0.f, gb[4];
                 int ir[4];
+                const float4 gt0 = *reinterpret_cast<const float4 *>(&ex.gtot[F.row(hh)][0]), gt1 = *reinterpret_cast<const float4 *>(&ex.gtot[F.row(hh)][4]);
+                const float gt[8] = {gt0.x, gt0.y, gt0.z, gt0.w, gt1.x, gt1.y, gt1.z, gt1.w};
 #pragma unroll
                 for (int x8 = 0; x8 < 8; x8++) {
                     if (x8 & 1) ir[x8 >> 1] = __float2int_rn(run);        // middle of block x8/2, integer log2 grid
                     if ((x8 >> 2) == ch) gb[x8 & 3] = run;
-                    run += ex.gtot[x8][F.row(hh)];
+                    run += gt[x8];
                 }
                 lamf[hh] = run;
                 irb[hh][0] = ch ? ir[2] : ir[0];                           // my groups 0,1 are block 2ch, groups 2,3 block 2ch+1

@@ -40,7 +40,7 @@ __host__ __device__ constexpr uint32_t kt_ver(int q) { return q == 3 ? 0u : q ==
 constexpr uint32_t OFF_RT = 53248, OFF_P = 61440, OFF_RH = 69632, OFF_KH = 77824, OFF_KL = 86016, OFF_SB = 94208, OFF_YT = 102400;
 constexpr uint32_t OFF_TILES_END = 110592;
 struct Extra {
-    float gtot[8][64];        // decay total of every 8-token group, per channel (log2 units)
+    float gtot[64][8];        // decay total of every 8-token group, per channel (log2 units): one 32-byte row per channel
     float pdu[4][64];         // per channel-quarter partial sums of r u k, per token
     uint64_t bar_rkw, bar_v, bar_a, bar_m2;
     uint32_t tmem_base;
@@ -335,7 +335,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                         y = __shfl_up_sync(0xffffffffu, x, 2, 4);
                         if (q >= 2) x += y;
                         exq[hh][g] = x - ps;
-                        if (q == 3) ex.gtot[2 * g + ch][F.row(hh)] = x;
+                        if (q == 3) ex.gtot[F.row(hh)][2 * g + ch] = x;
                     }
             }
             named_bar_sync<B_SCAN, CTHREADS>();
@@ -363,11 +363,13 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 // prefix over the 8 groups of this channel: start of my groups, the four block references, total
                 float run = 0.f, gb[4];
                 int ir[4];
+                const float4 gt0 = *reinterpret_cast<const float4 *>(&ex.gtot[F.row(hh)][0]), gt1 = *reinterpret_cast<const float4 *>(&ex.gtot[F.row(hh)][4]);
+                const float gt[8] = {gt0.x, gt0.y, gt0.z, gt0.w, gt1.x, gt1.y, gt1.z, gt1.w};
 #pragma unroll
                 for (int x8 = 0; x8 < 8; x8++) {
                     if (x8 & 1) ir[x8 >> 1] = __float2int_rn(run);        // middle of block x8/2, integer log2 grid
                     if ((x8 & 1) == ch) gb[x8 >> 1] = run;
-                    run += ex.gtot[x8][F.row(hh)];
+                    run += gt[x8];
                 }
                 const float lam = run;
                 elam_nx[hh] = fast_ex2(lam);
