@@ -327,17 +327,23 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     launches0 = M.launch_count()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     t_start.record()
     for i in range(args.steps):
-        step(r, k, v, w, u, gy, evs[i])
+        step(r, k, v, w, u, gy)
     t_end.record()
     barrier()
     clocks = sampler.stop()
     launches = M.launch_count() - launches0
     ms = t_start.elapsed_time(t_end) / args.steps
+    # forward / backward split (the roofline's per-launch duration): the same steps again with an event between the two
+    # calls -- kept out of the timed region above, which holds exactly K steps and nothing else
+    n_split = max(3, min(args.steps, 20))
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(n_split)]
+    for i in range(n_split):
+        step(r, k, v, w, u, gy, evs[i])
+    barrier()
     fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
     bwd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
     if world > 1:
@@ -483,7 +489,7 @@ def main():
     impl_name = {0: "auto", 1: "simt", 2: "tc"}[M.load().wkv6b200_get_impl()]
     traffic = None
     try:      # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the committed ncu --set full capture
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r1_dram_traffic.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r2_dram_traffic.json")))
         traffic = tj["wkv6_tc3_bwd_kernel" if dom_is_bwd else "wkv6_tc3_fwd_kernel"]["dram_bytes_per_launch"]
     except Exception:
         pass

@@ -70,13 +70,14 @@ size_t simt_backward_workspace_bytes(int B, int T, int H);
 // seg_chunks 64-token chunks (the last may be shorter) that run as separate grid rows; s0 / sT / flags / ckpt
 // are then indexed by row = b*nseg + seg (seg_scan.cu)
 // bi != 0: one direction of the bidirectional op (tc3_common.cuh BI_CAUSAL / BI_REV) with per-row lengths row_len[B]
+// (+ row_order[B]: the batch rows sorted by length, longest first)
 int tc3_forward(const Args &a, void *ckpt, int *hz_flags, int nseg = 1, int seg_chunks = 0, int bi = 0,
-                const int *row_len = nullptr);
+                const int *row_len = nullptr, const int *row_order = nullptr);
 bool tc3_forward_supported(const Args &a);
 // role-uniform tcgen05 backward (+ per-stream SIMT fallback, which runs on `exact` when given: the
 // call as the caller made it, e.g. with the fp32 log-decay instead of the converted bf16 logits)
 int tc3_backward(const Args &a, const Args *exact = nullptr, bool flags_preset = false, bool run_fallback = true);
-int tc3_backward_bi(const Args &a, void *ckpt, int *flags, int bi, const int *row_len);
+int tc3_backward_bi(const Args &a, void *ckpt, int *flags, int bi, const int *row_len, const int *row_order);
 // wkv6_bi forward as two launches of the chunked forward kernel around a reverse-gather / combine pair
 int bi_forward_tc(const Args &a, int *flags);
 bool bi_forward_tc_supported(const Args &a);

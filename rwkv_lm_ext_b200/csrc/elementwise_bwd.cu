@@ -208,12 +208,22 @@ __global__ void __launch_bounds__(256) gn_gate_bwd_kernel(long long BT, int C, f
     unpack8(ld8(lw + c), wf);
     unpack8(ld8(lb + c), bfv);
 
+    // one row ahead: the three 16-byte loads of row + 1 are in flight while row is reduced (a row is 12 shuffles deep)
+    bf16x8 ny, ng, ngo;
+    if (r0 < r1) {
+        const size_t off0 = (size_t)r0 * C + c;
+        ny = ld8(y + off0); ng = ld8(g + off0); ngo = ld8(gout + off0);
+    }
     for (long long row = r0; row < r1; row++) {          // warp-uniform bounds: shuffles are safe
         const size_t off = (size_t)row * C + c;
         float f[8], gf[8], go[8];
-        unpack8(ld8(y + off), f);
-        unpack8(ld8(g + off), gf);
-        unpack8(ld8(gout + off), go);
+        unpack8(ny, f);
+        unpack8(ng, gf);
+        unpack8(ngo, go);
+        if (row + 1 < r1) {
+            const size_t offn = off + C;
+            ny = ld8(y + offn); ng = ld8(g + offn); ngo = ld8(gout + offn);
+        }
         float s = 0.f;
 #pragma unroll
         for (int e = 0; e < 8; e++) s += f[e];

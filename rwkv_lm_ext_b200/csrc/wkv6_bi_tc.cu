@@ -37,6 +37,20 @@ __global__ void __launch_bounds__(256) bi_last_kernel(int T, const int *__restri
     if (threadIdx.x == 0) p[blockIdx.x] = (best >= T ? T - 1 : best) + 1;       // row length p + 1
 }
 
+// order[rank] = b with the rows ranked by length, longest first (ties by index): the CTAs of long rows start first, so
+// the last wave of the grid is made of short rows.  One block; B is a batch size.
+__global__ void __launch_bounds__(256) bi_order_kernel(int B, const int *__restrict__ len, int *__restrict__ order) {
+    for (int b = threadIdx.x; b < B; b += blockDim.x) {
+        const int lb = len[b];
+        int rank = 0;
+        for (int j = 0; j < B; j++) {
+            const int lj = len[j];
+            rank += (lj > lb) | ((lj == lb) & (j < b));
+        }
+        order[rank] = b;
+    }
+}
+
 }  // namespace
 
 // WKV6_B200_SYNC_DEBUG=1: synchronise after every step of the bidirectional op and name the one that failed
@@ -62,11 +76,11 @@ int bi_forward_tc(const Args &a, int *flags) {
     const size_t n = (size_t)a.B * a.T * C * sizeof(bf16);
     const bool convert = a.w_kind == W_LOG_F32;
     // stream-ordered scratch: zero u, row lengths, (raw logits when the caller passed fp32 -exp(w))
-    const size_t usz = ((size_t)a.H * N * sizeof(bf16) + 255) / 256 * 256, lsz = ((size_t)a.B * sizeof(int) + 255) / 256 * 256;
+    const size_t usz = ((size_t)a.H * N * sizeof(bf16) + 255) / 256 * 256, lsz = ((size_t)2 * a.B * sizeof(int) + 255) / 256 * 256;
     uint8_t *sc = nullptr;
     WKV6_CUDA_CHECK(cudaMallocAsync((void **)&sc, usz + lsz + (convert ? n : 0), a.stream));
     bf16 *u0 = (bf16 *)sc;
-    int *row_len = (int *)(sc + usz);
+    int *row_len = (int *)(sc + usz), *row_order = row_len + a.B;
     const void *w_raw = a.w;
     int rc = WKV6_OK;
     if (convert) {
@@ -76,17 +90,18 @@ int bi_forward_tc(const Args &a, int *flags) {
     if (rc == WKV6_OK && cudaMemsetAsync(u0, 0, (size_t)a.H * N * sizeof(bf16), a.stream) != cudaSuccess) rc = WKV6_ECUDA;
     if (rc == WKV6_OK) {
         bi_last_kernel<<<a.B, 256, 0, a.stream>>>(a.T, a.mask, row_len);
-        count_launch();
+        bi_order_kernel<<<1, 256, 0, a.stream>>>(a.B, row_len, row_order);
+        count_launch(2);
         if (cudaGetLastError() != cudaSuccess) { set_error("wkv6_bi row-length launch failed"); rc = WKV6_ECUDA; }
     }
     if (rc == WKV6_OK) {
         Args f = a;                       // causal direction: stores y (zeros behind p)
         f.mask = nullptr; f.w = w_raw; f.w_kind = W_RAW_BF16;
-        rc = tc3_forward(f, nullptr, flags, 1, 0, tc3::BI_CAUSAL, row_len);
+        rc = tc3_forward(f, nullptr, flags, 1, 0, tc3::BI_CAUSAL, row_len, row_order);
         if (rc == WKV6_OK) rc = dbg_sync(a.stream, "forward, causal direction");
         if (rc == WKV6_OK) {              // reverse direction: u = 0, adds to y
             f.u = u0;
-            rc = tc3_forward(f, nullptr, flags, 1, 0, tc3::BI_REV, row_len);
+            rc = tc3_forward(f, nullptr, flags, 1, 0, tc3::BI_REV, row_len, row_order);
         }
         if (rc == WKV6_OK) rc = dbg_sync(a.stream, "forward, reverse direction");
     }
@@ -110,12 +125,12 @@ int bi_backward_tc(const Args &a) {
     const size_t base = tc3_backward_workspace_bytes(a.B, a.T, a.H, false);
     if (!a.workspace || a.workspace_bytes < base) { set_error("workspace too small: need %zu bytes", base); return WKV6_EWORKSPACE; }
     const size_t nflag = (size_t)a.B * a.H * sizeof(int);
-    const size_t usz = ((size_t)a.H * N * sizeof(bf16) + 255) / 256 * 256, lsz = ((size_t)a.B * sizeof(int) + 255) / 256 * 256;
+    const size_t usz = ((size_t)a.H * N * sizeof(bf16) + 255) / 256 * 256, lsz = ((size_t)2 * a.B * sizeof(int) + 255) / 256 * 256;
     const size_t gsz = ((size_t)a.B * C * sizeof(bf16) + 255) / 256 * 256, fsz = (nflag + 255) / 256 * 256;
     uint8_t *sc = nullptr;
     WKV6_CUDA_CHECK(cudaMallocAsync((void **)&sc, usz + lsz + gsz + fsz + (convert ? n : 0), a.stream));
     bf16 *u0 = (bf16 *)sc;
-    int *row_len = (int *)(sc + usz);
+    int *row_len = (int *)(sc + usz), *row_order = row_len + a.B;
     bf16 *gu2 = (bf16 *)(sc + usz + lsz);
     int *allflags = (int *)(sc + usz + lsz + gsz);
     const void *w_raw = a.w;
@@ -131,16 +146,17 @@ int bi_backward_tc(const Args &a) {
     if (rc == WKV6_OK && convert) rc = ew_to_raw_bf16(a.B, a.T, a.H, (const float *)a.w, const_cast<void *>(w_raw), wsflags, a.stream);
     if (rc == WKV6_OK) {
         bi_last_kernel<<<a.B, 256, 0, a.stream>>>(a.T, a.mask, row_len);
-        count_launch();
+        bi_order_kernel<<<1, 256, 0, a.stream>>>(a.B, row_len, row_order);
+        count_launch(2);
         ck(cudaGetLastError());
     }
     Args d = a;
     d.mask = nullptr; d.w = w_raw; d.w_kind = W_RAW_BF16; d.stream_flags = nullptr;
-    if (rc == WKV6_OK) rc = tc3_backward_bi(d, ckpt, wsflags, tc3::BI_CAUSAL, row_len);
+    if (rc == WKV6_OK) rc = tc3_backward_bi(d, ckpt, wsflags, tc3::BI_CAUSAL, row_len, row_order);
     if (rc == WKV6_OK) rc = dbg_sync(a.stream, "backward, causal direction");
     if (rc == WKV6_OK) {
         d.u = u0; d.gu = gu2;
-        rc = tc3_backward_bi(d, ckpt, wsflags, tc3::BI_REV, row_len);
+        rc = tc3_backward_bi(d, ckpt, wsflags, tc3::BI_REV, row_len, row_order);
     }
     if (rc == WKV6_OK) rc = dbg_sync(a.stream, "backward, reverse direction");
     if (rc == WKV6_OK) ck(cudaMemcpyAsync(allflags, wsflags, nflag, cudaMemcpyDeviceToDevice, a.stream));

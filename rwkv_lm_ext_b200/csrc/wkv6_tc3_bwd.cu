@@ -96,6 +96,7 @@ struct Params {
     int *gu_count;            // its arrival counters, int [H], zero before the launch (left zero again)
     const int *hz_flags;
     const int *row_len;       // BI modes: tokens of every batch row (p + 1 of wkv6_bi), device int [B]
+    const int *row_order;     // BI modes: batch rows sorted by length, longest first, device int [B]
     long long *dbg;           // nullptr, or [gridDim][NC][8 (32 in the profiling build)] clock64 stamps of warp 0 at the stage boundaries (profiling aid)
 };
 
@@ -112,11 +113,13 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     const __grid_constant__ CUtensorMap map_gy, const __grid_constant__ CUtensorMap map_ck,
                     const __grid_constant__ CUtensorMap map_gr, const __grid_constant__ CUtensorMap map_gk,
                     const __grid_constant__ CUtensorMap map_gv, const __grid_constant__ CUtensorMap map_gw, Params p) {
-    if (p.hz_flags[blockIdx.x] != 0) return;        // the exact (SIMT) route handles this stream
+    const int h = blockIdx.x % p.H;
+    const int row = BI ? p.row_order[blockIdx.x / p.H] : blockIdx.x / p.H;
+    const int rid = BI ? row * p.H + h : blockIdx.x;     // row id: flags, checkpoints
+    if (p.hz_flags[rid] != 0) return;               // the exact (SIMT) route handles this stream
     extern __shared__ __align__(1024) uint8_t sm[];
     Extra &ex = *reinterpret_cast<Extra *>(sm + OFF_TILES_END);
     if ((smem_u32(sm) & 1023u) != 0) __trap();
-    const int row = blockIdx.x / p.H, h = blockIdx.x % p.H;
     const int b = SEG ? row / p.nseg : row;                                  // batch index inside the [B,T,C] tensors
     const int t_base = SEG ? (row % p.nseg) * p.seg_chunks * L : 0;          // first token of this row's segment
     const int T = BI ? p.row_len[b] : SEG ? min(p.T - t_base, p.seg_chunks * L) : p.T, C = p.H * 64;
@@ -171,7 +174,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         };
         auto issue_sin = [&](int c) {
             mbar_arrive_expect_tx(&ex.bar_sin, 8192);
-            tma_load_3d(sm + OFF_SIN, &map_ck, &ex.bar_sin, 0, (blockIdx.x * ck_stride + c) * 64, 0);
+            tma_load_3d(sm + OFF_SIN, &map_ck, &ex.bar_sin, 0, (rid * ck_stride + c) * 64, 0);
         };
         if (lane == 0) {
             tma_prefetch_desc(&map_r); tma_prefetch_desc(&map_k); tma_prefetch_desc(&map_v);
@@ -337,7 +340,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 tma_store_commit();
             }
         }
-        if (lane == 0) tma_store_wait_all<0>();
+        if (lane == 0) tma_store_wait_read<0>();          // shared memory has been read; the writes complete with the grid
     } else {
         // =====================================================================================
         // compute warps
@@ -983,7 +986,7 @@ static int launch_bwd_kernel(dim3 grid, cudaStream_t stream, const CUtensorMap *
 // one launch of the backward kernel on `a` viewed as given (B rows of T tokens), chunk-start states in ckpt
 // bi / row_len: direction of the bidirectional op (tc3_common.cuh) and the device int [B] row lengths it needs
 static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const float *g_init, int nseg, int seg_chunks,
-                      bool has_s0, int bi = BI_NONE, const int *row_len = nullptr) {
+                      bool has_s0, int bi = BI_NONE, const int *row_len = nullptr, const int *row_order = nullptr) {
     const int C = a.H * 64;
     if (nseg <= 1) { nseg = 1; seg_chunks = (a.T + L - 1) / L; }
     const size_t NC = (size_t)nseg * seg_chunks;
@@ -1018,7 +1021,7 @@ static int launch_bwd(const Args &a, const bf16 *ckpt, const int *flags, const f
 #else
     p.dbg = nullptr;
 #endif
-    p.row_len = row_len;
+    p.row_len = row_len; p.row_order = row_order;
     const bool clamp = a.lmin > -INFINITY;
     const dim3 grid(a.B * nseg * a.H);
     int rc;
@@ -1075,12 +1078,12 @@ static int tc3_backward_segmented(const Args &a, int nseg, int seg_chunks) {
 
 // One direction of the bidirectional backward (wkv6_bi_tc.cu): recompute the chunk-start states of that direction
 // (state-only forward in the same mode), then the backward kernel in that mode.  ckpt: bf16 [B*H][ceil(T/64)][64][64].
-int tc3_backward_bi(const Args &a, void *ckpt, int *flags, int bi, const int *row_len) {
+int tc3_backward_bi(const Args &a, void *ckpt, int *flags, int bi, const int *row_len, const int *row_order) {
     if (a.B * a.H == 0 || a.T == 0) return WKV6_OK;
     Args f = a;
     f.y = nullptr; f.sT = nullptr; f.s0 = nullptr;
-    if (int rc = tc3_forward(f, ckpt, flags, 1, 0, bi, row_len)) return rc;
-    return launch_bwd(a, (const bf16 *)ckpt, flags, nullptr, 1, 0, false, bi, row_len);
+    if (int rc = tc3_forward(f, ckpt, flags, 1, 0, bi, row_len, row_order)) return rc;
+    return launch_bwd(a, (const bf16 *)ckpt, flags, nullptr, 1, 0, false, bi, row_len, row_order);
 }
 
 int tc3_backward(const Args &a, const Args *exact, bool flags_preset, bool run_fallback) {

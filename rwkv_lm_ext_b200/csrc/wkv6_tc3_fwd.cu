@@ -67,6 +67,7 @@ struct Params {
     int nseg, seg_chunks;
     float lmin;               // floor of the per-token log2-decay (opt-in clamp; -inf = off)
     const int *row_len;       // BI modes: tokens of every batch row (p + 1 of wkv6_bi), device int [B]
+    const int *row_order;     // BI modes: batch rows sorted by length, longest first (CTAs of long rows start first), device int [B]
 };
 
 // 9 warps x 2 CTAs = 5 warps on the fullest SM sub-partition (16384 registers): at most 96 per thread
@@ -80,11 +81,13 @@ __global__ void __launch_bounds__(NTHREADS, 2)
 wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_w,
                     const __grid_constant__ CUtensorMap map_y, const __grid_constant__ CUtensorMap map_ck, Params p) {
-    if (p.hz_flags[blockIdx.x] != 0) return;        // flagged before launch (inexact logit conversion): exact route
+    const int h = blockIdx.x % p.H;
+    const int row = BI ? p.row_order[blockIdx.x / p.H] : blockIdx.x / p.H;
+    const int rid = BI ? row * p.H + h : blockIdx.x;     // row id: flags, checkpoints
+    if (p.hz_flags[rid] != 0) return;               // flagged before launch (inexact logit conversion): exact route
     extern __shared__ __align__(1024) uint8_t sm[];
     Extra &ex = *reinterpret_cast<Extra *>(sm + OFF_TILES_END);
     if ((smem_u32(sm) & 1023u) != 0) __trap();
-    const int row = blockIdx.x / p.H, h = blockIdx.x % p.H;
     const int b = SEG ? row / p.nseg : row;                                  // batch index inside the [B,T,C] tensors
     const int t_base = SEG ? (row % p.nseg) * p.seg_chunks * L : 0;          // first token of this row's segment
     const int T = BI ? p.row_len[b] : SEG ? min(p.T - t_base, p.seg_chunks * L) : p.T;   // tokens of the segment / row
@@ -164,7 +167,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         bar_sync_all<B_PB>();
         bar_sync_all<B_T2>();                                    // initial state in TMEM / shared
         if (lane == 0) {
-            if (p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (blockIdx.x * ck_stride) * 64, 0);
+            if (p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (rid * ck_stride) * 64, 0);
             tma_store_commit();
         }
         if (lane == 0) mbar_wait(&ex.bar_a, 0);
@@ -235,7 +238,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     if (BI == BI_REV) tma_reduce_add_3d(&map_y, sm + OFF_YT, h * 64, tok0(c), b);
                     else tma_store_3d(&map_y, sm + OFF_YT, h * 64, tok0(c), b);
                 }
-                if (more && p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (blockIdx.x * ck_stride + c + 1) * 64, 0);
+                if (more && p.has_ckpt) tma_store_3d(&map_ck, sm + OFF_SB, 0, (rid * ck_stride + c + 1) * 64, 0);
                 tma_store_commit();
             }
         }
@@ -251,7 +254,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 tma_store_commit();
             }
         }
-        if (lane == 0) tma_store_wait_all<0>();
+        if (lane == 0) tma_store_wait_read<0>();          // shared memory has been read; the writes complete with the grid
     } else {
         // =====================================================================================
         // compute warps
@@ -597,11 +600,12 @@ static int launch_fwd(dim3 grid, cudaStream_t stream, const CUtensorMap &mr, con
     return WKV6_OK;
 }
 
-int tc3_forward(const Args &a, void *ckpt, int *hz_flags, int nseg, int seg_chunks, int bi, const int *row_len) {
+int tc3_forward(const Args &a, void *ckpt, int *hz_flags, int nseg, int seg_chunks, int bi, const int *row_len,
+                const int *row_order) {
     if (a.B * a.H == 0 || a.T == 0) return WKV6_OK;
     const int C = a.H * 64;
     if (nseg <= 1) { nseg = 1; seg_chunks = (a.T + L - 1) / L; }
-    if (bi != BI_NONE && (nseg > 1 || !row_len)) { set_error("bidirectional pass: one segment and row lengths required"); return WKV6_EINVAL; }
+    if (bi != BI_NONE && (nseg > 1 || !row_len || !row_order)) { set_error("bidirectional pass: one segment and row lengths required"); return WKV6_EINVAL; }
     const size_t NC = (size_t)nseg * seg_chunks;                 // checkpoint slots per (b,h)
     CUtensorMap mr, mk, mv, mw, my, mc;
     const auto dt = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -623,7 +627,7 @@ int tc3_forward(const Args &a, void *ckpt, int *hz_flags, int nseg, int seg_chun
     p.hz_flags = hz_flags;
     p.nseg = nseg; p.seg_chunks = seg_chunks;
     p.lmin = tc_lmin_log2(a);
-    p.row_len = row_len;
+    p.row_len = row_len; p.row_order = row_order;
     const dim3 grid(a.B * nseg * a.H);
     const bool so = !p.has_y;
     if (bi == BI_CAUSAL) return so ? launch_fwd<false, true, BI_CAUSAL>(grid, a.stream, mr, mk, mv, mw, my, mc, p)
