@@ -380,6 +380,81 @@ def test_wkv6_bi_row_lengths_around_chunk_boundaries(M, O, T):
     assert_bf16_close(leaves[4].grad, ref["gu"], "bi gu")
 
 
+def test_wkv6_bi_native_entry_with_an_inexact_stream(M, O):
+    """cuda/wkv6_bi_op.cpp surface (fp32 -exp(w)): a stream whose decays are not bf16 logits is recomputed by the exact
+    SIMT bidirectional kernels (bit-identical to impl="simt"), the others run both directions on the tensor-core
+    kernels -- in one call, forward and backward."""
+    B, T, H = 3, 200, 2
+    C = H * 64
+    r, k, v, w, u, gy = make_inputs(B, T, H, seed=41, decay="model")
+    ew = -torch.exp(w.float())
+    ew[1, :, 64:] = -torch.exp(w.float()[1, :, 64:] + 0.001)        # stream (1,1): not representable as bf16 logits
+    mask = torch.ones(B, T, dtype=torch.int32)
+    mask[0, 150:] = 0
+    mask[1, 77:] = 0
+    dv = lambda t: t.to(DEV).contiguous()
+    rd, kd, vd, ud, gyd, ewd, md = map(dv, (r, k, v, u, gy, ew, mask))
+    out = {}
+    for impl in ("auto", "simt"):
+        M.set_impl(impl)
+        try:
+            y = torch.empty_like(rd)
+            M.wkv6_bi_cuda.forward(B, T, C, H, md, rd, kd, vd, ewd, ud, y)
+            g = [torch.empty_like(rd) for _ in range(4)]
+            gu = torch.empty(B, C, device=DEV, dtype=torch.bfloat16)
+            M.wkv6_bi_cuda.backward(B, T, C, H, md, rd, kd, vd, ewd, ud, gyd, *g, gu)
+        finally:
+            M.set_impl("auto")
+        out[impl] = [y] + g
+    y_ref = O.wkv6_bi_forward(mask, r, k, v, ew, u, w_is_log_decay=True) if "w_is_log_decay" in O.wkv6_bi_forward.__code__.co_varnames else None
+    for a, b_, name in zip(out["auto"], out["simt"], ("y", "gr", "gk", "gv", "gw")):
+        assert torch.equal(a[1, :, 64:], b_[1, :, 64:]), f"{name}: the inexact stream must come from the exact kernels"
+        assert_bf16_close(a, b_.float().cpu(), f"bi native {name} auto vs simt", maxabs_rel=2 * BF16_MAXABS_REL)
+    if y_ref is not None:
+        assert_bf16_close(out["auto"][0], y_ref, "bi native y vs oracle", maxabs_rel=2 * BF16_MAXABS_REL)
+
+
+def test_gu_total_is_the_row_sum(M):
+    """The training pair's backward adds the per-sample gu rows over the batch in the kernel (last CTA of every head):
+    the result must be what torch.sum(gu, 0) gives (src/model.py:232) -- fp32 accumulation of the bf16 rows."""
+    from rwkv_lm_ext_b200 import _lib
+    lib = _lib.load()
+    B, T, H = 5, 192, 3
+    C = H * 64
+    r, k, v, w, u, gy = make_inputs(B, T, H, seed=9, decay="model", device=DEV)
+    st = torch.cuda.current_stream().cuda_stream
+    y = torch.empty_like(r)
+    saved = torch.empty(lib.wkv6_saved_bytes(B, T, C, H), dtype=torch.uint8, device=DEV)
+    import ctypes
+    valid = ctypes.c_int(0)
+    p = lambda t: t.data_ptr()
+    assert lib.wkv6_train_forward(B, T, C, H, p(r), p(k), p(v), p(w), p(u), None, 0, 0, None, 0, p(y), p(saved), ctypes.byref(valid), st) == 0
+    assert valid.value == 1
+    n = lib.wkv6_train_backward_workspace_bytes(B, T, C, H, 1)
+    ws = torch.empty(n, dtype=torch.uint8, device=DEV)
+    g = [torch.empty_like(r) for _ in range(4)]
+    gu = torch.empty(B, C, device=DEV, dtype=torch.bfloat16)
+    for _ in range(2):                       # twice on the same saved buffer: the arrival counters return to zero
+        gu_total = torch.full((C,), float("nan"), device=DEV, dtype=torch.bfloat16)
+        assert lib.wkv6_train_backward(B, T, C, H, p(r), p(k), p(v), p(w), p(u), None, 0, p(gy), *(p(t) for t in g), p(gu),
+                                       p(gu_total), None, p(saved), p(ws), n, st) == 0
+        assert torch.equal(gu_total, torch.sum(gu.float(), 0).bfloat16())
+    # and the Python surface returns it
+    leaves = [t.clone().requires_grad_(True) for t in (r, k, v, w, u)]
+    M.RUN_CUDA_RWKV6(B, T, C, H, *leaves).backward(gy)
+    assert torch.equal(leaves[4].grad.reshape(-1), gu_total)
+
+
+def test_tensor_on_another_device_is_refused(M):
+    """The library takes scratch from the CURRENT device: a tensor on a different one must raise, not misbehave."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from rwkv_lm_ext_b200._lib import Wkv6B200Error
+    r, k, v, w, u, _ = make_inputs(1, 64, 1, seed=0, decay="model", device=torch.device("cuda", 1))
+    with torch.cuda.device(0), pytest.raises(Wkv6B200Error):
+        M.RUN_CUDA_RWKV6(1, 64, 64, 1, r, k, v, w, u)
+
+
 def test_wkv6_bi_tensor_core_route_equals_exact_route(M):
     """Mid-size shape (many streams, 8 chunks): the fused tensor-core route against the exact SIMT bidirectional kernels."""
     B, T, H = 8, 512, 4
