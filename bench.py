@@ -213,7 +213,8 @@ def run_bi_encoder(args, M, torch, dist, dev, rank, world, barrier):
     for _ in range(2):
         step_e2e()
     ems = timed(step_e2e, steps)
-    lin_flops = 2 * Bm * T * c["layers"] * (2 * 5 * D * D + 2 * D * c["ffn"] + D * D)   # Linears (time-mix ones run twice)
+    # Linears per layer: r, k, v for both directions, gate and output once (time mix); key, value, receptance (channel mix)
+    lin_flops = 2 * Bm * T * c["layers"] * (8 * D * D + 2 * D * c["ffn"] + D * D)
     res = {"metric": "bi-encoder passages/s (1B6 shape)", "value": world * Bm / (ms * 1e-3), "unit": "passages/s",
            "ms_per_step": ms, "steps": steps, "micro_batch_per_gpu": [Bm, T], "global_batch": world * Bm,
            "model": f"RWKV-6 1B6 shape L{c['layers']} D{D} H{c['H']} FFN{c['ffn']}, random init, bf16",

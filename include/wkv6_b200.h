@@ -216,6 +216,10 @@ WKV6_API int create_mask_rev_idx(int B, int T, const int64_t *idx, int64_t emb_i
 /* out[b,t,:] = x[b,rev_idx[b,t],:]  (reverse_x, src/model_ext.py:418-419); bf16 [B,T,D]. */
 WKV6_API int gather_tokens_bf16(int B, int T, int D, const void *x, const int64_t *rev_idx, void *out,
                        void *stream);
+/* out [2B,T,D]: out[b] = x[b], out[B + b] = reverse_x(x)[b] -- the plain and the reversed sequences of
+ * bi_att_forward_batch (src/model_encoder_run.py:64-75) stacked as one batch, one read of x.  D % 8 == 0. */
+WKV6_API int stack_reversed_bf16(int B, int T, int D, const void *x, const int64_t *rev_idx, void *out,
+                        void *stream);
 
 /* (a7) token-shift + ddlerp of RWKV_Tmix_x060.jit_func (src/model.py:437-449), mixing stage:
  * given x [B,T,C], the five data-dependent coefficients m [5,B,T,C] (output of the rank-R LoRA

@@ -47,6 +47,7 @@ SIGNATURES = {
     "pooling_bf16": (c_i, [c_i, c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "create_mask_rev_idx": (c_i, [c_i, c_i, c_p, c_i64, c_i64, c_p, c_p, c_p]),
     "gather_tokens_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "stack_reversed_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
     "tmix_ddlerp_mix_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p]),
     "tmix_ddlerp_lora_bf16": (c_i, [c_i, c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p, c_p, c_p]),
     "tmix_shift_lerp_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),

@@ -74,6 +74,23 @@ __global__ void gather_tokens_kernel(int BT, int T, int D, const bf16 *__restric
     }
 }
 
+// out[b,t,:] = x[b,t,:] and out[B + b,t,:] = x[b,rev[b,t],:]: the plain and the reversed sequences stacked as one batch of
+// 2B rows (what the bidirectional encoders feed their projections), one read of x
+__global__ void stack_reversed_kernel(int BT, int T, int D, const bf16 *__restrict__ x, const int64_t *__restrict__ rev,
+                                      bf16 *__restrict__ out) {
+    const int warps = (gridDim.x * blockDim.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    for (int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < BT; row += warps) {
+        const int b = row / T;
+        const bf16 *src = x + (size_t)row * D, *srcr = x + ((size_t)b * T + (size_t)rev[row]) * D;
+        bf16 *dst = out + (size_t)row * D, *dstr = dst + (size_t)BT * D;
+        for (int d = lane * 8; d < D; d += 256) {
+            st8(dst + d, ld8(src + d));
+            st8(dstr + d, ld8(srcr + d));
+        }
+    }
+}
+
 // mask + reverse index, one block per row
 __global__ void mask_rev_kernel(int T, const int64_t *__restrict__ idx, int64_t emb, int64_t pad,
                                 int32_t *__restrict__ mask, int64_t *__restrict__ rev) {
@@ -363,6 +380,17 @@ int gather_tokens_bf16(int B, int T, int D, const void *x, const int64_t *rev_id
     const int BT = B * T;
     gather_tokens_kernel<<<grid_for((size_t)BT * 32, 256), 256, 0, (cudaStream_t)stream>>>(
         BT, T, D, (const bf16 *)x, rev_idx, (bf16 *)out);
+    count_launch();
+    WKV6_CUDA_CHECK(cudaGetLastError());
+    return WKV6_OK;
+}
+
+int stack_reversed_bf16(int B, int T, int D, const void *x, const int64_t *rev_idx, void *out, void *stream) {
+    if (B < 0 || T < 0 || D <= 0 || (D & 7)) { set_error("stack_reversed_bf16: need D %% 8 == 0"); return WKV6_EINVAL; }
+    if ((size_t)B * T == 0) return WKV6_OK;
+    if (!x || !rev_idx || !out) { set_error("stack_reversed_bf16: null pointer"); return WKV6_EINVAL; }
+    const int BT = B * T;
+    stack_reversed_kernel<<<grid_for((size_t)BT * 32, 256), 256, 0, (cudaStream_t)stream>>>(BT, T, D, (const bf16 *)x, rev_idx, (bf16 *)out);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
     return WKV6_OK;

@@ -32,10 +32,13 @@ def bi_tmix_forward(att, x, rev_idx):
     """bi_att_forward_batch (src/model_encoder_run.py:64-75, :77-93) on the fused kernels."""
     B, T, C = x.shape
     H = att.time_faaaa.shape[0]
-    r, k, v, g, w = tmix.tmix_x060_project(att, x)
-    rr, rk, rv, _, rw = tmix.tmix_x060_project(att, heads.reverse_x(x, rev_idx))
-    y = ops.RUN_CUDA_RWKV6(B, T, C, H, r, k, v, w, att.time_faaaa)
-    ry = ops.RUN_CUDA_RWKV6(B, T, C, H, rr, rk, rv, rw, att.time_faaaa)       # still in reversed token order
+    # both directions as ONE batch of 2B rows (the reversed sequences behind the plain ones): every kernel and every
+    # Linear of the projection runs once on twice the rows, the recurrence as one launch of 2*B*H streams; the gate is
+    # only needed for the plain direction (the reference computes and drops the reversed one)
+    xx = heads.stack_reversed(x, rev_idx)
+    r, k, v, g, w = tmix.tmix_x060_project(att, xx, gate_rows=B)
+    y2 = ops.RUN_CUDA_RWKV6(2 * B, T, C, H, r, k, v, w, att.time_faaaa)
+    y, ry = y2[:B], y2[B:]                                                       # ry: still in reversed token order
     z = heads.groupnorm_gate_pair(y, ry, rev_idx, g, att.ln_x.weight, att.ln_x.bias, H, att.ln_x.eps, gate_act="silu")
     return att.output(z)
 

@@ -164,6 +164,20 @@ class _ReverseX(torch.autograd.Function):
         return gx, None
 
 
+def stack_reversed(x: torch.Tensor, rev_idx: torch.Tensor) -> torch.Tensor:
+    """cat([x, reverse_x(x, rev_idx)], 0)  [2B,T,D]: both directions of a bidirectional encoder layer as one batch.
+    One kernel (x read once) when no gradient is needed; the differentiable pieces otherwise."""
+    _cuda(x)
+    if _needs_grad(x) or x.shape[-1] % 8 != 0:
+        return torch.cat([x, reverse_x(x, rev_idx)], 0)
+    assert x.dtype == torch.bfloat16 and x.dim() == 3 and rev_idx.dtype == torch.int64 and rev_idx.shape == x.shape[:2]
+    x, rev_idx = x.contiguous(), rev_idx.contiguous()
+    B, T, D = x.shape
+    out = torch.empty((2 * B, T, D), device=x.device, dtype=x.dtype)
+    check(_lib.load().stack_reversed_bf16(B, T, D, ptr(x), ptr(rev_idx), ptr(out), stream_of(x)), "stack_reversed_bf16")
+    return out
+
+
 def reverse_x(x: torch.Tensor, rev_idx: torch.Tensor) -> torch.Tensor:
     """== torch.gather(x, 1, rev_idx[..., None].expand(-1, -1, D))  (src/model_ext.py:418-419).
     Differentiable w.r.t. x when rev_idx is a per-row permutation (what reverse_x_idx builds)."""

@@ -32,9 +32,11 @@ def _maa5(layer):
                       layer.time_maa_r.view(1, C), layer.time_maa_g.view(1, C)], 0)
 
 
-def tmix_x060_project(layer, x, shift_state=None):
+def tmix_x060_project(layer, x, shift_state=None, gate_rows=None):
     """jit_func (src/model.py:434-459 / :738-762): x [B,T,C] bf16 -> r, k, v, g_raw, w (each [B,T,C]);
-    g_raw is the gate Linear's output BEFORE silu (tmix_x060_finish applies it in-kernel)."""
+    g_raw is the gate Linear's output BEFORE silu (tmix_x060_finish applies it in-kernel).
+    gate_rows: compute the gate for the first `gate_rows` batch rows only (the bidirectional encoders stack the reversed
+    sequences behind the plain ones and never use their gate)."""
     B, T, C = x.shape
     bf = heads._bf16_param          # fp32 parameters (mixed-precision modules) are cast, never reinterpreted
     xxx = heads.tmix_shift_lerp(x, layer.time_maa_x, shift_state)
@@ -43,7 +45,7 @@ def tmix_x060_project(layer, x, shift_state=None):
     r = layer.receptance(xr)
     k = layer.key(xk)
     v = layer.value(xv)
-    g = layer.gate(xg)                      # raw: silu is applied inside the GroupNorm*gate kernel
+    g = layer.gate(xg if gate_rows is None else xg[:gate_rows])      # raw: silu is applied inside the GroupNorm*gate kernel
     # time_decay + tanh(xw @ W1) @ W2 with the bias add as the GEMM epilogue
     w = torch.addmm(bf(layer.time_decay).view(-1), torch.tanh(xw.view(B * T, C) @ bf(layer.time_decay_w1)),
                     bf(layer.time_decay_w2)).view(B, T, -1)

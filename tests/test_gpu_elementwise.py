@@ -63,6 +63,12 @@ def test_gather_and_reverse_bit_exact(M):
     got = M.reverse_x(x, rev)
     assert torch.equal(got, want)
     assert torch.equal(M.reverse_x(got, rev), x)        # the permutation is an involution
+    # both directions stacked as one batch of 2B rows (the bidirectional encoders' input), one kernel
+    from rwkv_lm_ext_b200 import heads
+    assert torch.equal(heads.stack_reversed(x, rev), torch.cat([x, want], 0))
+    xg = x.clone().requires_grad_(True)                  # under autograd: the differentiable pieces
+    heads.stack_reversed(xg, rev).sum().backward()
+    assert torch.equal(xg.grad, torch.full_like(x, 2.0))
     # odd D falls back to scalar copies
     x2 = torch.randn(2, 5, 13, generator=g).bfloat16().to(DEV)
     p2 = torch.tensor([4, 0], device=DEV)
