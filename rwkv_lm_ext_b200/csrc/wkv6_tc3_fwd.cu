@@ -496,6 +496,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             }
             }
             }
+            if (c == 0) {              // S *= 2^Lam of the first chunk (every later chunk: T2 of the chunk before it, below)
             tmem_ld_frag(tS, v);
             tmem_wait_ld();
 #pragma unroll
@@ -506,6 +507,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     f2unpacku(f2mul(f2packu(v[4 * g + 2 * hh], v[4 * g + 2 * hh + 1]), el2), v[4 * g + 2 * hh], v[4 * g + 2 * hh + 1]);
             }
             tmem_st_frag(tS, v);
+            }
             if (BI == BI_REV) {        // the V tile goes to the tensor cores as it lies in shared memory: reverse its rows
                 mbar_wait(&ex.bar_v, c & 1);                            // (issued a whole chunk ago: landed long since)
                 const int nvc = min(L, T - c * L);
@@ -561,6 +563,17 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                             if (p.sT_f32) ((float *)p.sT)[idx] = x;
                             else ((bf16 *)p.sT)[idx] = __float2bfloat16_rn(x);
                         }
+            }
+            if (more) {                // the state is in registers anyway: decay it for the next chunk here (elam is already
+#pragma unroll                 // the next chunk's), so T1 no longer loads, scales and stores it
+                for (int hh = 0; hh < 2; hh++) {
+                    const f2 el2 = f2bcast(elam[hh]);
+#pragma unroll
+                    for (int g = 0; g < 4; g++)
+                        f2unpacku(f2mul(f2packu(v[4 * g + 2 * hh], v[4 * g + 2 * hh + 1]), el2), v[4 * g + 2 * hh], v[4 * g + 2 * hh + 1]);
+                }
+                tmem_st_frag(tS, v);
+                tmem_wait_st();
             }
             fence_proxy_async();
             tc_fence_before();
