@@ -38,7 +38,7 @@ class _ShiftLerp2(torch.autograd.Function):
         check(lib.cmix_shift_lerp2_backward_bf16(B, T, C, ptr(x), ptr(shift_state), ptr(maa_kr), ptr(gxk), ptr(gxr), ptr(gx),
                                                  ptr(gmaa), ptr(gshift), ptr(ws), ws.numel(), stream_of(x)),
               "cmix_shift_lerp2_backward_bf16")
-        return gx, gshift, gmaa.to(maa_kr.dtype)
+        return gx, gshift, (gmaa.to(maa_kr.dtype) if ctx.needs_input_grad[2] else None)
 
 
 def _shift_lerp2_fwd(x, shift_state, maa_kr):
@@ -55,7 +55,7 @@ def cmix_shift_lerp2(x, maa_k, maa_r, shift_state=None):
     assert x.dtype == torch.bfloat16
     x = x.contiguous()
     C = x.shape[-1]
-    maa_kr = _bf16_param(torch.cat([maa_k.reshape(1, C), maa_r.reshape(1, C)], 0))
+    maa_kr = _bf16_param(torch.cat([maa_k.reshape(1, C), maa_r.reshape(1, C)], 0))      # (two [C] rows: a 3 us launch)
     shift_state = _bf16_param(shift_state)
     if _needs_grad(x, maa_kr, shift_state):
         return _ShiftLerp2.apply(x, shift_state, maa_kr)

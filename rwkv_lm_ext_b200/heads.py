@@ -215,7 +215,7 @@ class _ShiftLerp(torch.autograd.Function):
         ws = _ws(lib, B, T, C, 1, x.device)
         check(lib.tmix_shift_lerp_backward_bf16(B, T, C, ptr(x), ptr(shift_state), ptr(maa_x), ptr(gout), ptr(gx), ptr(gmaa),
                                                 ptr(gshift), ptr(ws), ws.numel(), stream_of(x)), "tmix_shift_lerp_backward_bf16")
-        return gx, gshift, gmaa.to(maa_x.dtype)
+        return gx, gshift, (gmaa.to(maa_x.dtype) if ctx.needs_input_grad[2] else None)     # frozen parameter: no cast
 
 
 def tmix_shift_lerp(x, maa_x, shift_state=None):
@@ -263,7 +263,7 @@ class _DdlerpMix(torch.autograd.Function):
         check(lib.tmix_ddlerp_mix_backward_bf16(B, T, C, ptr(x), ptr(shift_state), ptr(maa), ptr(m), *[ptr(g) for g in gouts],
                                                 ptr(gx), ptr(gm), ptr(gmaa), ptr(gshift), ptr(ws), ws.numel(), stream_of(x)),
               "tmix_ddlerp_mix_backward_bf16")
-        return gx, gshift, gmaa.to(maa.dtype), gm
+        return gx, gshift, (gmaa.to(maa.dtype) if ctx.needs_input_grad[2] else None), gm
 
 
 def tmix_ddlerp_mix(x, maa_wkvrg, m, shift_state=None):
@@ -307,9 +307,10 @@ class _DdlerpLora(torch.autograd.Function):
                                                 ptr(gx), ptr(gm), ptr(gmaa), ptr(gshift), ptr(ws), ws.numel(), stream_of(x)),
               "tmix_ddlerp_mix_backward_bf16")
         gm5 = gm.view(5, B * T, C)
-        gh = torch.bmm(gm5, w2.transpose(1, 2)).transpose(0, 1).reshape(B * T, 5 * R)
-        gw2 = torch.bmm(h5.transpose(1, 2), gm5)
-        return gx, gshift, gmaa.to(maa.dtype), gh.view_as(h), gw2
+        need = ctx.needs_input_grad                                  # frozen parameters (LoRA SFT): no cast, no bmm
+        gh = torch.bmm(gm5, w2.transpose(1, 2)).transpose(0, 1).reshape(B * T, 5 * R).view_as(h) if need[3] else None
+        gw2 = torch.bmm(h5.transpose(1, 2), gm5) if need[4] else None
+        return gx, gshift, (gmaa.to(maa.dtype) if need[2] else None), gh, gw2
 
 
 def _ddlerp_lora_fwd(x, shift_state, maa, h, w2):
@@ -373,7 +374,8 @@ class _GroupNormGate(torch.autograd.Function):
         check(lib.groupnorm_gate_backward_bf16(B * T, C, H, float(eps), act, ptr(y), ptr(g), ptr(ln_w), ptr(ln_b), ptr(gout),
                                                ptr(gy), ptr(gg), ptr(gw), ptr(gb), ptr(ws), ws.numel(), stream_of(y)),
               "groupnorm_gate_backward_bf16")
-        return gy, gg, gw.to(ln_w.dtype), gb.to(ln_b.dtype), None, None, None
+        need = ctx.needs_input_grad
+        return gy, gg, (gw.to(ln_w.dtype) if need[2] else None), (gb.to(ln_b.dtype) if need[3] else None), None, None, None
 
 
 def groupnorm_gate(y, g, ln_w, ln_b, H, eps, gate_act=None):

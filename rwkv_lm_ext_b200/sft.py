@@ -64,9 +64,63 @@ class LoraLinear(nn.Module):
         self.weight.data = (w - lora_B @ lora_A).to(self.weight.dtype)
 
     def forward(self, x):
-        if self.pissa:
-            return F.linear(x, self.weight) + F.linear(F.linear(x, self.lora_A), self.lora_B)
-        return F.linear(x, self.weight) + self.scaling * F.linear(F.linear(self.lora_dropout(x), self.lora_A), self.lora_B)
+        if self.training and self.lora_dropout.p > 0:          # dropout on the adapter input: the eager chain
+            if self.pissa:
+                return F.linear(x, self.weight) + F.linear(F.linear(x, self.lora_A), self.lora_B)
+            return F.linear(x, self.weight) + self.scaling * F.linear(F.linear(self.lora_dropout(x), self.lora_A), self.lora_B)
+        return _LoraFn.apply(x, self.weight, self.lora_A, self.lora_B, 1.0 if self.pissa else self.scaling)
+
+
+# id(parameter) -> callable(parameter), registered by GradBuckets: a backward pass that finds its parameter here adds
+# the gradient straight into the flat buffer (GEMM with beta = 1) and reports it, instead of returning a tensor that
+# autograd would add with one more elementwise kernel per parameter
+_GRAD_SINKS = {}
+
+
+def _param_grad(p, m1, m2, alpha):
+    """alpha * m1 @ m2 as the gradient of parameter p: accumulated in place when p's gradient lives in a GradBuckets
+    buffer (returns None: autograd has nothing left to do), a new tensor otherwise."""
+    sink = _GRAD_SINKS.get(id(p))
+    if sink is not None and p.grad is not None:
+        p.grad.addmm_(m1, m2, alpha=alpha)
+        sink(p)
+        return None
+    return torch.addmm(p, m1, m2, beta=0, alpha=alpha)
+
+
+class _LoraFn(torch.autograd.Function):
+    """x W^T + s (x A^T) B^T (src/rwkvLinear.py:94-96) with the scaling and both additions folded into the GEMMs:
+    forward 3 launches (eager: 3 GEMMs + mul + add), backward 5 (eager: 5 GEMMs + mul + add + 2 accumulations)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, A, B, scaling):
+        x2 = x.reshape(-1, x.shape[-1])
+        xa = x2 @ A.t()                                          # [N, r]
+        out = x2 @ weight.t()
+        out.addmm_(xa, B.t(), alpha=scaling)
+        ctx.save_for_backward(x2, weight, A, B, xa)
+        ctx.scaling, ctx.x_shape = scaling, x.shape
+        return out.view(*x.shape[:-1], weight.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, weight, A, B, xa = ctx.saved_tensors
+        s = ctx.scaling
+        need_x, need_w, need_a, need_b = ctx.needs_input_grad[:4]
+        gy2 = gy.reshape(-1, gy.shape[-1])
+        gx = gw = ga = gb = None
+        gxa = gy2 @ B if (need_x or need_a) else None            # [N, r], unscaled
+        if need_b:
+            gb = _param_grad(B, gy2.t(), xa, s)
+        if need_a:
+            ga = _param_grad(A, gxa.t(), x2, s)
+        if need_x:
+            gx = gy2 @ weight
+            gx.addmm_(gxa, A, alpha=s)
+            gx = gx.view(ctx.x_shape)
+        if need_w:
+            gw = gy2.t() @ x2
+        return gx, gw, ga, gb, None
 
 
 def _linear(i, o, lora):
@@ -347,10 +401,16 @@ class GradBuckets:
             self.buckets.append((cur_lo, off, cur_cnt))
         self._pending = [c for _, _, c in self.buckets]
         self._handles = []
+        self._seen = set()
         self.bytes = total * self.flat.element_size()
         self._hooks = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params]
+        for p in self.params:                                  # backward passes that write into the buffer themselves
+            _GRAD_SINKS[id(p)] = self._hook
 
     def _hook(self, p):
+        if id(p) in self._seen:                        # reported by the backward pass itself (_param_grad) and by autograd
+            return
+        self._seen.add(id(p))
         b = self._bucket_of[id(p)]
         self._pending[b] -= 1
         if self._pending[b] == 0 and self.world > 1:
@@ -369,6 +429,7 @@ class GradBuckets:
             self.flat.div_(self.world)
         self._handles = []
         self._pending = [c for _, _, c in self.buckets]
+        self._seen = set()
         return self.flat
 
     def zero(self):
@@ -377,6 +438,9 @@ class GradBuckets:
     def remove(self):
         for h in self._hooks:
             h.remove()
+        for p in self.params:
+            if _GRAD_SINKS.get(id(p)) == self._hook:
+                del _GRAD_SINKS[id(p)]
 
 
 class SftTrainer:

@@ -28,8 +28,17 @@ from . import heads, ops
 
 def _maa5(layer):
     C = layer.time_maa_w.shape[-1]
-    return torch.cat([layer.time_maa_w.view(1, C), layer.time_maa_k.view(1, C), layer.time_maa_v.view(1, C),
-                      layer.time_maa_r.view(1, C), layer.time_maa_g.view(1, C)], 0)
+    ps = (layer.time_maa_w, layer.time_maa_k, layer.time_maa_v, layer.time_maa_r, layer.time_maa_g)
+    if any(p.requires_grad for p in ps) and torch.is_grad_enabled():
+        return torch.cat([p.view(1, C) for p in ps], 0)
+    # frozen (inference, LoRA SFT): the stacked bf16 copy is kept until a parameter is written or moved
+    key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
+    hit = layer.__dict__.get("_maa5_cache")
+    if hit is None or hit[0] != key:
+        with torch.no_grad():
+            hit = (key, heads._bf16_param(torch.cat([p.detach().view(1, C) for p in ps], 0)))
+        layer.__dict__["_maa5_cache"] = hit
+    return hit[1]
 
 
 def tmix_x060_project(layer, x, shift_state=None, gate_rows=None):

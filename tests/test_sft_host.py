@@ -68,6 +68,44 @@ def test_lora_linear_matches_the_reference_formulas():
     assert (m.lora_B.data @ m.lora_A.data).norm() >= 0.9 * S[:4].norm()
 
 
+def test_lora_linear_fused_backward_equals_the_eager_chain():
+    """_LoraFn folds the scaling and both additions into the GEMMs; with a GradBuckets buffer the adapter gradients are
+    accumulated in place (no tensor returned to autograd) and the bucket bookkeeping is told."""
+    torch.manual_seed(3)
+    for pissa in (False, True):
+        m = sft.LoraLinear(24, 16, r=4, alpha=32).double()
+        m.pissa = pissa
+        with torch.no_grad():
+            m.lora_B.normal_()
+        x = torch.randn(3, 5, 24, dtype=torch.float64, requires_grad=True)
+        gy = torch.randn(3, 5, 16, dtype=torch.float64)
+        s = 1.0 if pissa else 32 / 4
+        ref = F.linear(x, m.weight) + s * F.linear(F.linear(x, m.lora_A), m.lora_B)
+        want = torch.autograd.grad(ref, (x, m.weight, m.lora_A, m.lora_B), gy)
+        out = m(x)
+        assert out.shape == ref.shape and torch.allclose(out, ref, atol=1e-12)
+        got = torch.autograd.grad(out, (x, m.weight, m.lora_A, m.lora_B), gy)
+        for a, b in zip(got, want):
+            assert torch.allclose(a, b, atol=1e-10)
+        # frozen weight, gradients straight into the flat buffer: two backward passes accumulate, the hooks fire once each
+        m.weight.requires_grad = False
+        gbk = sft.GradBuckets([m.lora_A, m.lora_B], n_buckets=1)
+        try:
+            for rep in (1, 2):
+                m(x).backward(gy)
+                assert gbk._pending == [0]
+                gbk._pending, gbk._seen = [2], set()           # what finish() does, without dividing
+                assert torch.allclose(m.lora_A.grad, rep * want[2], atol=1e-10) and torch.allclose(m.lora_B.grad, rep * want[3], atol=1e-10)
+                assert m.lora_A.grad.data_ptr() >= gbk.flat.data_ptr()                  # still views of the flat buffer
+            assert torch.allclose(x.grad, 2 * want[0], atol=1e-10) and m.weight.grad is None
+        finally:
+            gbk.remove()
+        assert not sft._GRAD_SINKS
+        m.train()
+        m.lora_dropout.p = 0.5                                   # dropout: the eager chain (different mask per call)
+        assert m(x).shape == ref.shape
+
+
 def test_trainable_checkpoint_format(tmp_path):
     model = sft.RwkvSft(layers=1, D=64, H=1, ffn=96, vocab=50, lora_r=2, lora_alpha=4)
     train = model.mark_trainable()
