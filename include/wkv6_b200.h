@@ -266,7 +266,8 @@ WKV6_API int tmix_ddlerp_mix_backward_bf16(int B, int T, int C, const void *x, c
 WKV6_API int tmix_shift_lerp_backward_bf16(int B, int T, int C, const void *x, const void *shift_state,
                                   const void *maa_x, const void *gout, void *gx, float *gmaa_x,
                                   void *gshift, void *ws, size_t ws_bytes, void *stream);
-/* gy, gg bf16 [B*T,C]; gln_w, gln_b fp32 [C]. */
+/* gy, gg bf16 [B*T,C]; gln_w, gln_b fp32 [C], or both NULL (frozen affine parameters: their reduction is skipped;
+ * the same holds for gmaa / gmaa_x / gmaa_kr of the other backward entries). */
 WKV6_API int groupnorm_gate_backward_bf16(int BT, int C, int H, float eps, int gate_act, const void *y,
                                  const void *g, const void *ln_w, const void *ln_b, const void *gout, void *gy, void *gg,
                                  float *gln_w, float *gln_b, void *ws, size_t ws_bytes, void *stream);
@@ -310,6 +311,20 @@ WKV6_API int relu_sq_backward_bf16(size_t n, const void *x, const void *gy, void
 WKV6_API int sigmoid_mul_bf16(size_t n, const void *r, const void *kv, void *out, void *stream);
 WKV6_API int sigmoid_mul_backward_bf16(size_t n, const void *r, const void *kv, const void *gout, void *gr,
                               void *gkv, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * SFT loss (src/model.py:1244-1283 `training_step`, my_qa_mask == 0 branch, + `L2Wrap` src/model.py:960-974) on bf16
+ * logits [rows, V] (rows = B*T, V % 8 == 0, V <= 65536), fp32 arithmetic:
+ *   mean_out[0] = mean over the rows with target != ignore_index of  logsumexp(x_row) - x_row[target];  mean_out[1] = their number
+ *   row_stats fp32 [3][rows] (row loss, logsumexp, maximum) and row_argmax int [rows] are kept for the backward
+ *   glogits[r,j] = gloss[0] * (softmax(x_r)_j - [j == target_r]) / mean_out[1]   (0 for an ignored row)
+ *                  + [j == row_argmax[r]] * maximum_r * l2_factor                 (L2Wrap: l2_factor = 1e-4 / rows)
+ * gloss: device fp32 scalar (the gradient arriving at the loss). */
+WKV6_API int cross_entropy_l2wrap_bf16(long long rows, int V, const void *logits, const int64_t *targets, long long ignore_index,
+                              float *row_stats, int *row_argmax, float *mean_out, void *stream);
+WKV6_API int cross_entropy_l2wrap_backward_bf16(long long rows, int V, const void *logits, const int64_t *targets,
+                                       long long ignore_index, const float *row_stats, const int *row_argmax,
+                                       const float *mean_out, const float *gloss, float l2_factor, void *glogits, void *stream);
 
 #ifdef __cplusplus
 }

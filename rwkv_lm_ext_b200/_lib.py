@@ -69,10 +69,12 @@ SIGNATURES = {
     "sigmoid_mul_bf16": (c_i, [c_sz, c_p, c_p, c_p, c_p]),
     "sigmoid_mul_backward_bf16": (c_i, [c_sz, c_p, c_p, c_p, c_p, c_p, c_p]),
     "scatter_tokens_bf16": (c_i, [c_i, c_i, c_i, c_p, c_p, c_p, c_p]),
+    "cross_entropy_l2wrap_bf16": (c_i, [ctypes.c_longlong, c_i, c_p, c_p, ctypes.c_longlong, c_p, c_p, c_p, c_p]),
+    "cross_entropy_l2wrap_backward_bf16": (c_i, [ctypes.c_longlong, c_i, c_p, c_p, ctypes.c_longlong, c_p, c_p, c_p, c_p, c_f, c_p, c_p]),
 }
 
 _lib = None
-ABI_VERSION = 3   # == wkv6b200_abi_version() of the library this signature table was written for
+ABI_VERSION = 4   # == wkv6b200_abi_version() of the library this signature table was written for
 
 
 class Wkv6B200Error(RuntimeError):

@@ -32,13 +32,13 @@ class _ShiftLerp2(torch.autograd.Function):
         gxk = torch.zeros_like(x) if gxk is None else gxk.contiguous()
         gxr = torch.zeros_like(x) if gxr is None else gxr.contiguous()
         gx = torch.empty_like(x)
-        gmaa = torch.empty(2, C, dtype=torch.float32, device=x.device)
+        gmaa = torch.empty(2, C, dtype=torch.float32, device=x.device) if ctx.needs_input_grad[2] else None
         gshift = torch.empty_like(shift_state) if shift_state is not None else None
         ws = _ws(lib, B, T, C, 3, x.device)
         check(lib.cmix_shift_lerp2_backward_bf16(B, T, C, ptr(x), ptr(shift_state), ptr(maa_kr), ptr(gxk), ptr(gxr), ptr(gx),
                                                  ptr(gmaa), ptr(gshift), ptr(ws), ws.numel(), stream_of(x)),
               "cmix_shift_lerp2_backward_bf16")
-        return gx, gshift, (gmaa.to(maa_kr.dtype) if ctx.needs_input_grad[2] else None)
+        return gx, gshift, (gmaa.to(maa_kr.dtype) if gmaa is not None else None)
 
 
 def _shift_lerp2_fwd(x, shift_state, maa_kr):

@@ -217,7 +217,7 @@ using namespace wkv6;
 
 extern "C" {
 
-int wkv6b200_abi_version(void) { return 3; }
+int wkv6b200_abi_version(void) { return 4; }
 float wkv6b200_set_decay_clamp(float nats_per_token) {
     const float prev = -decay_clamp_nats();
     g_lmin.store(nats_per_token > 0.f ? -nats_per_token : -INFINITY);

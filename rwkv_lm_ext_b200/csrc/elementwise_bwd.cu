@@ -400,7 +400,7 @@ int tmix_ddlerp_mix_backward_bf16(int B, int T, int C, const void *x, const void
     if (B < 0 || T < 0 || C <= 0 || (C & 7)) { set_error("tmix_ddlerp_mix_backward_bf16: need C %% 8 == 0"); return WKV6_EINVAL; }
     const long long BT = (long long)B * T;
     if (BT == 0) return WKV6_OK;
-    if (!x || !maa || !m || !gxw || !gxk || !gxv || !gxr || !gxg || !gx || !gm || !gmaa || !ws) {
+    if (!x || !maa || !m || !gxw || !gxk || !gxv || !gxr || !gxg || !gx || !gm || !ws) {
         set_error("tmix_ddlerp_mix_backward_bf16: null pointer");
         return WKV6_EINVAL;
     }
@@ -415,8 +415,8 @@ int tmix_ddlerp_mix_backward_bf16(int B, int T, int C, const void *x, const void
                                            (float *)ws, &slots, (cudaStream_t)stream);
         if (rc <= 0) {
             if (rc < 0) return rc;
-            sum_partials_kernel<<<(5 * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(slots, 5 * C, (size_t)5 * C, (const float *)ws, gmaa);
-            count_launch();
+            if (gmaa) sum_partials_kernel<<<(5 * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(slots, 5 * C, (size_t)5 * C, (const float *)ws, gmaa);
+            if (gmaa) count_launch();
             WKV6_CUDA_CHECK(cudaGetLastError());
             return WKV6_OK;
         }
@@ -426,8 +426,8 @@ int tmix_ddlerp_mix_backward_bf16(int B, int T, int C, const void *x, const void
     ddlerp_bwd_kernel<5, true, DD_V><<<grid, 256, 0, (cudaStream_t)stream>>>(
         B, T, C, split_of(BT, S, DD_LANES), (const bf16 *)x, (const bf16 *)shift_state, (const bf16 *)maa, (const bf16 *)m,
         gout, (bf16 *)gx, (bf16 *)gm, shift_state ? (bf16 *)gshift : nullptr, (float *)ws);
-    sum_partials_kernel<<<(5 * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(S, 5 * C, (size_t)5 * C, (const float *)ws, gmaa);
-    count_launch(2);
+    if (gmaa) sum_partials_kernel<<<(5 * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(S, 5 * C, (size_t)5 * C, (const float *)ws, gmaa);
+    count_launch(gmaa ? 2 : 1);
     WKV6_CUDA_CHECK(cudaGetLastError());
     return WKV6_OK;
 }
@@ -438,7 +438,7 @@ int tmix_shift_lerp_backward_bf16(int B, int T, int C, const void *x, const void
     if (B < 0 || T < 0 || C <= 0 || (C & 7)) { set_error("tmix_shift_lerp_backward_bf16: need C %% 8 == 0"); return WKV6_EINVAL; }
     const long long BT = (long long)B * T;
     if (BT == 0) return WKV6_OK;
-    if (!x || !maa_x || !gout || !gx || !gmaa_x || !ws) { set_error("tmix_shift_lerp_backward_bf16: null pointer"); return WKV6_EINVAL; }
+    if (!x || !maa_x || !gout || !gx || !ws) { set_error("tmix_shift_lerp_backward_bf16: null pointer"); return WKV6_EINVAL; }
     Ptr5 g1;
     for (int i = 0; i < 5; i++) g1.p[i] = (const bf16 *)gout;
     if (ws_bytes < elementwise_backward_workspace_bytes(B, T, C, 1)) { set_error("tmix_shift_lerp_backward_bf16: workspace too small"); return WKV6_EINVAL; }
@@ -449,8 +449,8 @@ int tmix_shift_lerp_backward_bf16(int B, int T, int C, const void *x, const void
                                            shift_state ? gshift : nullptr, (float *)ws, &slots, (cudaStream_t)stream);
         if (rc <= 0) {
             if (rc < 0) return rc;
-            sum_partials_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(slots, C, (size_t)C, (const float *)ws, gmaa_x);
-            count_launch();
+            if (gmaa_x) sum_partials_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(slots, C, (size_t)C, (const float *)ws, gmaa_x);
+            if (gmaa_x) count_launch();
             WKV6_CUDA_CHECK(cudaGetLastError());
             return WKV6_OK;
         }
@@ -460,8 +460,8 @@ int tmix_shift_lerp_backward_bf16(int B, int T, int C, const void *x, const void
     ddlerp_bwd_kernel<1, false, DD_V><<<grid, 256, 0, (cudaStream_t)stream>>>(
         B, T, C, split_of(BT, S, DD_LANES), (const bf16 *)x, (const bf16 *)shift_state, (const bf16 *)maa_x, nullptr,
         g1, (bf16 *)gx, nullptr, shift_state ? (bf16 *)gshift : nullptr, (float *)ws);
-    sum_partials_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(S, C, (size_t)C, (const float *)ws, gmaa_x);
-    count_launch(2);
+    if (gmaa_x) sum_partials_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(S, C, (size_t)C, (const float *)ws, gmaa_x);
+    count_launch(gmaa_x ? 2 : 1);
     WKV6_CUDA_CHECK(cudaGetLastError());
     return WKV6_OK;
 }
@@ -471,7 +471,7 @@ int groupnorm_gate_backward_bf16(int BT, int C, int H, float eps, int gate_act, 
                                  float *gln_w, float *gln_b, void *ws, size_t ws_bytes, void *stream) {
     if (BT < 0 || H <= 0 || C != H * 64) { set_error("groupnorm_gate_backward_bf16: need C == H*64"); return WKV6_EINVAL; }
     if (BT == 0) return WKV6_OK;
-    if (!y || !g || !ln_w || !ln_b || !gout || !gy || !gg || !gln_w || !gln_b || !ws) {
+    if (!y || !g || !ln_w || !ln_b || !gout || !gy || !gg || (!gln_w != !gln_b) || !ws) {
         set_error("groupnorm_gate_backward_bf16: null pointer");
         return WKV6_EINVAL;
     }
@@ -490,9 +490,9 @@ int groupnorm_gate_backward_bf16(int BT, int C, int H, float eps, int gate_act, 
         gn_gate_bwd_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(
             BT, C, eps, split_of(BT, S), (const bf16 *)y, (const bf16 *)g, (const bf16 *)ln_w, (const bf16 *)ln_b,
             (const bf16 *)gout, (bf16 *)gy, (bf16 *)gg, partial);
-    sum_partials_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(S, C, (size_t)2 * C, partial, gln_w);
-    sum_partials_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(S, C, (size_t)2 * C, partial + C, gln_b);
-    count_launch(3);
+    if (gln_w) sum_partials_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(S, C, (size_t)2 * C, partial, gln_w);
+    if (gln_b) sum_partials_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(S, C, (size_t)2 * C, partial + C, gln_b);
+    count_launch(gln_w ? 3 : 1);
     WKV6_CUDA_CHECK(cudaGetLastError());
     return WKV6_OK;
 }
@@ -539,7 +539,7 @@ int cmix_shift_lerp2_backward_bf16(int B, int T, int C, const void *x, const voi
     if (B < 0 || T < 0 || C <= 0 || (C & 7)) { set_error("cmix_shift_lerp2_backward_bf16: need C %% 8 == 0"); return WKV6_EINVAL; }
     const long long BT = (long long)B * T;
     if (BT == 0) return WKV6_OK;
-    if (!x || !maa_kr || !gxk || !gxr || !gx || !gmaa_kr || !ws) { set_error("cmix_shift_lerp2_backward_bf16: null pointer"); return WKV6_EINVAL; }
+    if (!x || !maa_kr || !gxk || !gxr || !gx || !ws) { set_error("cmix_shift_lerp2_backward_bf16: null pointer"); return WKV6_EINVAL; }
     if (ws_bytes < elementwise_backward_workspace_bytes(B, T, C, 3)) { set_error("cmix_shift_lerp2_backward_bf16: workspace too small"); return WKV6_EINVAL; }
     const void *gs[2] = {gxk, gxr};
     int slots = 0;
@@ -559,8 +559,8 @@ int cmix_shift_lerp2_backward_bf16(int B, int T, int C, const void *x, const voi
             ddlerp_bwd_kernel<1, false, DD_V><<<grid, 256, 0, (cudaStream_t)stream>>>(
                 B, T, C, split_of(BT, S, DD_LANES), (const bf16 *)x, (const bf16 *)shift_state, (const bf16 *)maa_kr + (size_t)n * C,
                 nullptr, g1, n == 0 ? (bf16 *)gx : tmp, nullptr, shift_state ? (n == 0 ? (bf16 *)gshift : tmp_shift) : nullptr, part);
-            sum_partials_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(S, C, (size_t)C, part, gmaa_kr + (size_t)n * C);
-            count_launch(2);
+            if (gmaa_kr) sum_partials_kernel<<<(C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(S, C, (size_t)C, part, gmaa_kr + (size_t)n * C);
+            count_launch(gmaa_kr ? 2 : 1);
         }
         add_bf16_kernel<<<1184, 256, 0, (cudaStream_t)stream>>>((size_t)BT * C, (bf16 *)gx, tmp);
         if (shift_state) add_bf16_kernel<<<64, 256, 0, (cudaStream_t)stream>>>((size_t)B * C, (bf16 *)gshift, tmp_shift);
@@ -569,8 +569,8 @@ int cmix_shift_lerp2_backward_bf16(int B, int T, int C, const void *x, const voi
         cudaFreeAsync(tmp, (cudaStream_t)stream);
         return WKV6_OK;
     }
-    sum_partials_kernel<<<(2 * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(slots, 2 * C, (size_t)2 * C, (const float *)ws, gmaa_kr);
-    count_launch();
+    if (gmaa_kr) sum_partials_kernel<<<(2 * C + 255) / 256, 256, 0, (cudaStream_t)stream>>>(slots, 2 * C, (size_t)2 * C, (const float *)ws, gmaa_kr);
+    if (gmaa_kr) count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
     return WKV6_OK;
 }

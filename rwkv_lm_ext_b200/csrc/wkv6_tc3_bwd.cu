@@ -399,7 +399,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             const int nv = min(L, T - c * L);
             // ================================================================== P: operand preparation
             bar_sync_all<B_RAW>();
-            asm volatile("fence.acq_rel.cta;" ::: "memory");
+            asm volatile("fence.acq_rel.cta;" ::: "memory");     // (measured: free -- 0.598 ms with and without it)
             STAMP(0);
 #ifdef WKV6_FINE_STAMPS
             if (p.dbg && threadIdx.x == 0) {          // slots 30 / 31: global timer (ns) and the SM this CTA runs on

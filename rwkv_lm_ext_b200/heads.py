@@ -210,12 +210,12 @@ class _ShiftLerp(torch.autograd.Function):
         B, T, C = x.shape
         gout = gout.contiguous()
         gx = torch.empty_like(x)
-        gmaa = torch.empty(C, dtype=torch.float32, device=x.device)
+        gmaa = torch.empty(C, dtype=torch.float32, device=x.device) if ctx.needs_input_grad[2] else None   # frozen: no reduction
         gshift = torch.empty_like(shift_state) if shift_state is not None else None
         ws = _ws(lib, B, T, C, 1, x.device)
         check(lib.tmix_shift_lerp_backward_bf16(B, T, C, ptr(x), ptr(shift_state), ptr(maa_x), ptr(gout), ptr(gx), ptr(gmaa),
                                                 ptr(gshift), ptr(ws), ws.numel(), stream_of(x)), "tmix_shift_lerp_backward_bf16")
-        return gx, gshift, (gmaa.to(maa_x.dtype) if ctx.needs_input_grad[2] else None)     # frozen parameter: no cast
+        return gx, gshift, (gmaa.to(maa_x.dtype) if gmaa is not None else None)
 
 
 def tmix_shift_lerp(x, maa_x, shift_state=None):
@@ -257,13 +257,13 @@ class _DdlerpMix(torch.autograd.Function):
         B, T, C = x.shape
         gouts = [torch.zeros_like(x) if g is None else g.contiguous() for g in gouts]
         gx, gm = torch.empty_like(x), torch.empty_like(m)
-        gmaa = torch.empty(5, C, dtype=torch.float32, device=x.device)
+        gmaa = torch.empty(5, C, dtype=torch.float32, device=x.device) if ctx.needs_input_grad[2] else None
         gshift = torch.empty_like(shift_state) if shift_state is not None else None
         ws = _ws(lib, B, T, C, 5, x.device)
         check(lib.tmix_ddlerp_mix_backward_bf16(B, T, C, ptr(x), ptr(shift_state), ptr(maa), ptr(m), *[ptr(g) for g in gouts],
                                                 ptr(gx), ptr(gm), ptr(gmaa), ptr(gshift), ptr(ws), ws.numel(), stream_of(x)),
               "tmix_ddlerp_mix_backward_bf16")
-        return gx, gshift, (gmaa.to(maa.dtype) if ctx.needs_input_grad[2] else None), gm
+        return gx, gshift, (gmaa.to(maa.dtype) if gmaa is not None else None), gm
 
 
 def tmix_ddlerp_mix(x, maa_wkvrg, m, shift_state=None):
@@ -300,7 +300,7 @@ class _DdlerpLora(torch.autograd.Function):
         m = torch.bmm(h5, w2).view(5, B, T, C)
         gouts = [torch.zeros_like(x) if g is None else g.contiguous() for g in gouts]
         gx, gm = torch.empty_like(x), torch.empty_like(m)
-        gmaa = torch.empty(5, C, dtype=torch.float32, device=x.device)
+        gmaa = torch.empty(5, C, dtype=torch.float32, device=x.device) if ctx.needs_input_grad[2] else None
         gshift = torch.empty_like(shift_state) if shift_state is not None else None
         ws = _ws(lib, B, T, C, 5, x.device)
         check(lib.tmix_ddlerp_mix_backward_bf16(B, T, C, ptr(x), ptr(shift_state), ptr(maa), ptr(m), *[ptr(g) for g in gouts],
@@ -310,7 +310,7 @@ class _DdlerpLora(torch.autograd.Function):
         need = ctx.needs_input_grad                                  # frozen parameters (LoRA SFT): no cast, no bmm
         gh = torch.bmm(gm5, w2.transpose(1, 2)).transpose(0, 1).reshape(B * T, 5 * R).view_as(h) if need[3] else None
         gw2 = torch.bmm(h5.transpose(1, 2), gm5) if need[4] else None
-        return gx, gshift, (gmaa.to(maa.dtype) if need[2] else None), gh, gw2
+        return gx, gshift, (gmaa.to(maa.dtype) if gmaa is not None else None), gh, gw2
 
 
 def _ddlerp_lora_fwd(x, shift_state, maa, h, w2):
@@ -368,14 +368,14 @@ class _GroupNormGate(torch.autograd.Function):
         B, T, C = y.shape
         gout = gout.contiguous()
         gy, gg = torch.empty_like(y), torch.empty_like(g)
-        gw = torch.empty(C, dtype=torch.float32, device=y.device)
-        gb = torch.empty(C, dtype=torch.float32, device=y.device)
+        need_p = ctx.needs_input_grad[2] or ctx.needs_input_grad[3]                       # frozen affine: no reduction
+        gw = torch.empty(C, dtype=torch.float32, device=y.device) if need_p else None
+        gb = torch.empty(C, dtype=torch.float32, device=y.device) if need_p else None
         ws = _ws(lib, B, T, C, 2, y.device)
         check(lib.groupnorm_gate_backward_bf16(B * T, C, H, float(eps), act, ptr(y), ptr(g), ptr(ln_w), ptr(ln_b), ptr(gout),
                                                ptr(gy), ptr(gg), ptr(gw), ptr(gb), ptr(ws), ws.numel(), stream_of(y)),
               "groupnorm_gate_backward_bf16")
-        need = ctx.needs_input_grad
-        return gy, gg, (gw.to(ln_w.dtype) if need[2] else None), (gb.to(ln_b.dtype) if need[3] else None), None, None, None
+        return gy, gg, (gw.to(ln_w.dtype) if need_p else None), (gb.to(ln_b.dtype) if need_p else None), None, None, None
 
 
 def groupnorm_gate(y, g, ln_w, ln_b, H, eps, gate_act=None):

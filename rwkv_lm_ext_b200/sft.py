@@ -234,9 +234,47 @@ class _L2Wrap(torch.autograd.Function):             # src/model.py:960-974
         return grad_output, gy
 
 
+class _FusedLoss(torch.autograd.Function):
+    """Cross entropy + L2Wrap on bf16 logits in two kernels (csrc/cross_entropy.cu): the forward reads the [B*T, V]
+    matrix once, the backward reads it once and writes the gradient once (the eager chain moves it nine times)."""
+
+    @staticmethod
+    def forward(ctx, logits, targets):
+        from . import _lib
+        from ._lib import check, ptr, stream_of
+        V = logits.shape[-1]
+        rows = logits.numel() // V
+        dev = logits.device
+        stats = torch.empty(3, rows, dtype=torch.float32, device=dev)
+        amax = torch.empty(rows, dtype=torch.int32, device=dev)
+        mean = torch.empty(2, dtype=torch.float32, device=dev)
+        check(_lib.load().cross_entropy_l2wrap_bf16(rows, V, ptr(logits), ptr(targets), -100, ptr(stats), ptr(amax), ptr(mean),
+                                                    stream_of(logits)), "cross_entropy_l2wrap_bf16")
+        ctx.save_for_backward(logits, targets, stats, amax, mean)
+        return mean[0]
+
+    @staticmethod
+    def backward(ctx, gloss):
+        from . import _lib
+        from ._lib import check, ptr, stream_of
+        logits, targets, stats, amax, mean = ctx.saved_tensors
+        V = logits.shape[-1]
+        rows = logits.numel() // V
+        g = torch.empty_like(logits)
+        gloss = gloss.to(torch.float32).contiguous()
+        check(_lib.load().cross_entropy_l2wrap_backward_bf16(rows, V, ptr(logits), ptr(targets), -100, ptr(stats), ptr(amax), ptr(mean),
+                                                             ptr(gloss), 1e-4 / rows, ptr(g), stream_of(logits)),
+              "cross_entropy_l2wrap_backward_bf16")
+        return g, None
+
+
 def sft_loss(logits, targets):
-    """src/model.py:1244-1283 (my_qa_mask == 0 branch): mean cross entropy over the tokens whose label is not -100."""
-    loss = F.cross_entropy(logits.view(-1, logits.size(-1)).float(), targets.reshape(-1))
+    """src/model.py:1244-1283 (my_qa_mask == 0 branch): mean cross entropy over the tokens whose label is not -100,
+    wrapped in L2Wrap (src/model.py:960-974).  bf16 logits on the GPU take the fused kernels (fp32 arithmetic inside)."""
+    V = logits.size(-1)
+    if logits.is_cuda and logits.dtype == torch.bfloat16 and logits.dim() == 3 and V % 8 == 0 and V <= 65536:
+        return _FusedLoss.apply(logits.contiguous(), targets.reshape(-1).contiguous())
+    loss = F.cross_entropy(logits.view(-1, V).float(), targets.reshape(-1))
     return _L2Wrap.apply(loss, logits)
 
 

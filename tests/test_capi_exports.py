@@ -24,7 +24,7 @@ def test_header_and_library_agree():
     assert declared <= exported, declared - exported
     # ... and nothing else: no test kernels, no profiling hooks in the product library
     assert exported <= declared, exported - declared
-    assert lib.wkv6b200_abi_version() == 3
+    assert lib.wkv6b200_abi_version() == 4
 
 
 def test_argument_validation_without_gpu():

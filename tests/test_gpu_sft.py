@@ -45,6 +45,53 @@ def test_lora_sft_loss_goes_down_over_length_buckets():
             assert torch.equal(p, frozen[n]), n                  # base weights are frozen
 
 
+@pytest.mark.parametrize("shape", [(2, 37, 65536), (3, 5, 1000), (1, 1, 8)])
+def test_fused_loss_equals_the_eager_chain(shape):
+    """csrc/cross_entropy.cu against F.cross_entropy on the fp32 copy + L2Wrap (src/model.py:960-974, 1244-1283): loss
+    to fp32 accuracy, gradient to bf16 rounding; ignored rows, an upstream gradient != 1, a tied maximum."""
+    import torch.nn.functional as F
+    from rwkv_lm_ext_b200 import sft
+    B, T, V = shape
+    g = torch.Generator(device="cpu").manual_seed(B * 1000 + V)
+    logits = (torch.randn(B, T, V, generator=g) * 2).to(torch.bfloat16)
+    top = torch.randint(0, V, (B, T), generator=g)
+    logits.scatter_(-1, top.unsqueeze(-1), 12.0)                 # a unique maximum per row (bf16 ties are likely otherwise)
+    tgt = torch.randint(0, V, (B, T), generator=g)
+    if T > 2:
+        tgt[0, :2] = -100
+    logits, tgt = logits.to(DEV), tgt.to(DEV)
+    x1, x2 = logits.clone().requires_grad_(), logits.clone().requires_grad_()
+    loss = sft.sft_loss(x1, tgt)
+    ref = sft._L2Wrap.apply(F.cross_entropy(x2.view(-1, V).float(), tgt.view(-1)), x2)
+    assert loss.dtype == torch.float32 and abs(loss.item() - ref.item()) <= 2e-6 * abs(ref.item()) + 1e-6
+    (loss * 0.5).backward()
+    (ref * 0.5).backward()
+    # reference gradient in fp32 (the eager chain rounds the two terms to bf16 separately)
+    p = torch.softmax(logits.float().view(-1, V), -1)
+    valid = (tgt.view(-1) != -100)
+    onehot = torch.zeros_like(p).scatter_(-1, tgt.view(-1).clamp(min=0).unsqueeze(-1), 1.0)
+    want = (p - onehot) * (valid.float() * 0.5 / valid.sum()).unsqueeze(-1)
+    want.scatter_add_(-1, top.to(DEV).view(-1, 1), torch.full((B * T, 1), 12.0 * 1e-4 / (B * T), device=DEV))
+    got = x1.grad.float().view(-1, V)
+    assert (got - want).abs().max().item() <= 2.0 ** -8 * want.abs().max().item()
+    assert ((got - want).abs() <= 2.0 ** -8 * want.abs() + 1e-12).all()
+    assert (got - x2.grad.float().view(-1, V)).abs().max().item() <= 2.0 ** -6 * want.abs().max().item()   # the eager bf16 chain
+    assert (got[~valid] != 0).sum().item() == (~valid).sum().item()                                         # ignored rows: the L2Wrap term only
+    # a tied maximum goes to the lowest index; every label ignored -> nan like torch
+    tie = torch.zeros(1, 2, V, dtype=torch.bfloat16, device=DEV)
+    tie[0, 0, 3:5] = 4.0
+    tie[0, 1, V - 1] = 4.0
+    tie.requires_grad_()
+    sft.sft_loss(tie, torch.tensor([[1, 0]], device=DEV)).backward()
+    l2 = 4.0 * 1e-4 / 2
+    gt = tie.grad.float()
+    pmax = torch.softmax(tie.detach().float(), -1)
+    assert abs(gt[0, 0, 3].item() - (pmax[0, 0, 3].item() / 2 + l2)) <= 2.0 ** -8 * (pmax[0, 0, 3].item() / 2 + l2)
+    assert abs(gt[0, 0, 4].item() - pmax[0, 0, 4].item() / 2) <= 2.0 ** -8 * pmax[0, 0, 4].item()
+    none = sft.sft_loss(logits, torch.full_like(tgt, -100))
+    assert none.isnan().item()
+
+
 def test_cuda_graph_step_equals_eager_step():
     from rwkv_lm_ext_b200 import sft
     torch.manual_seed(0)
