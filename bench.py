@@ -101,25 +101,43 @@ class ClockSampler(threading.Thread):
                 "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
-def run_cpu(steps, warmup, budget_s=20.0):
-    """The oracle's C port on host cores, on CPU_SAMPLE: up to `steps` runs of the sample, stopping
-    early once `budget_s` seconds of CPU work are spent.  Returns (tokens/s, cores, s/run, runs)."""
+def run_cpu(steps, warmup, budget_s=20.0, exact_steps=False):
+    """The oracle's C port on host cores, on CPU_SAMPLE.  Default (the `cpu_baseline` leg of our own arm): up to `steps`
+    runs of the sample, stopping early once `budget_s` seconds of CPU work are spent.  exact_steps (the reference arm):
+    `warmup` untimed and EXACTLY `steps` timed runs; if they would not fit in `budget_s`, the sample's T is halved until
+    they do.  Returns (tokens/s, cores, s/run, runs, T of the sample)."""
     from oracle import c_oracle
     from rwkv_lm_ext_b200.synthetic import make_inputs
     s = CPU_SAMPLE
     r, k, v, w, u, gy = (t.float() for t in make_inputs(s["B"], s["T"], s["H"], seed=0, decay="model"))
     cores = c_oracle.use_all_cores()
-    for _ in range(warmup):
-        c_oracle.forward(r[:, :256], k[:, :256], v[:, :256], w[:, :256], u)
-        c_oracle.backward(r[:, :256], k[:, :256], v[:, :256], w[:, :256], u, gy[:, :256])
-    ts = []
-    while len(ts) < steps and (not ts or sum(ts) < budget_s):
+    Ts = s["T"]
+
+    def one(n):
+        c_oracle.forward(r[:, :n], k[:, :n], v[:, :n], w[:, :n], u)
+        c_oracle.backward(r[:, :n], k[:, :n], v[:, :n], w[:, :n], u, gy[:, :n])
+
+    if exact_steps:
+        one(256)
         t0 = time.perf_counter()
-        c_oracle.forward(r, k, v, w, u)
-        c_oracle.backward(r, k, v, w, u, gy)
+        one(Ts)
+        est = time.perf_counter() - t0
+        while Ts > 256 and est * (steps + warmup) > budget_s:
+            Ts //= 2
+            est /= 2
+        r, k, v, w, gy = (t[:, :Ts].contiguous() for t in (r, k, v, w, gy))
+        for _ in range(warmup):
+            one(Ts)
+    else:
+        for _ in range(warmup):
+            one(256)
+    ts = []
+    while len(ts) < steps and (exact_steps or not ts or sum(ts) < budget_s):
+        t0 = time.perf_counter()
+        one(Ts)
         ts.append(time.perf_counter() - t0)
     sec = sum(ts) / len(ts)
-    return s["B"] * s["T"] / sec, cores, sec, len(ts)
+    return s["B"] * Ts / sec, cores, sec, len(ts), Ts
 
 
 def run_reference_python(budget_s=12.0):
@@ -270,11 +288,15 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
-        val, cores, sec, steps = run_cpu(max(1, args.steps), min(args.warmup, 1), budget_s=30.0)
-        sample = (f"fwd+bwd on B={CPU_SAMPLE['B']} T={CPU_SAMPLE['T']} H={CPU_SAMPLE['H']} "
-                  f"(1/8 of one step's batch), mean of {steps} runs, {sec:.2f} s each, {cores} threads")
+        # same K and W as our arm; a step = one bounded sample of the workload (one batch row of the 8, shortened if K of
+        # them would not fit in two minutes), timed as it is -- ms_per_step is the sample's own time, not an extrapolation
+        warm = max(args.warmup, 3)
+        val, cores, sec, steps, Ts = run_cpu(max(1, args.steps), warm, budget_s=120.0, exact_steps=True)
+        sample = (f"fwd+bwd on B={CPU_SAMPLE['B']} T={Ts} H={CPU_SAMPLE['H']} per step "
+                  f"({CPU_SAMPLE['B'] * Ts} of the workload's {B * T} tokens), mean of {steps} steps, {sec:.3f} s each, {cores} threads")
         line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
-                "steps": steps, "warmup": min(args.warmup, 1), "ms_per_step": sec * 1e3 * (B / CPU_SAMPLE["B"]),
+                "steps": steps, "warmup": warm, "ms_per_step": sec * 1e3, "tokens_per_step": CPU_SAMPLE["B"] * Ts,
+                "full_step_ms_extrapolated": sec * 1e3 * (B * T) / (CPU_SAMPLE["B"] * Ts),
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                 "data": "synthetic", "config": config(args.gpus),
                 "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
@@ -499,7 +521,9 @@ def main():
                 "kernel": ("wkv6 backward" if dom_is_bwd else "wkv6 forward") + f" ({impl_name})",
                 "algorithmic_bytes_per_launch": dom_bytes, "launch_ms": dom_ms,
                 "fwd_ms": fwd_ms, "bwd_ms": bwd_ms,
-                "step_frac": elems * (BYTES_FWD + BYTES_BWD) / ((fwd_ms + bwd_ms) * 1e-3) / 1e9 / peak}
+                # the whole step against the roofline: the 28 B/element of forward + backward over the timed region itself
+                # (fwd_ms / bwd_ms come from the split run behind it, whose extra events cost a few microseconds per step)
+                "step_frac": elems * (BYTES_FWD + BYTES_BWD) / (ms * 1e-3) / 1e9 / peak}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -534,7 +558,7 @@ def main():
         line["reference_cuda"] = {"unavailable": f"{type(e).__name__}: {e}"}
 
     if world == 1 and not args.no_cpu_baseline:
-        val, cores, sec, runs = run_cpu(1000, 1, budget_s=12.0)
+        val, cores, sec, runs, _ = run_cpu(1000, 1, budget_s=12.0)
         line["cpu_baseline"] = {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": f"fwd+bwd on B={CPU_SAMPLE['B']} T={CPU_SAMPLE['T']} H={CPU_SAMPLE['H']} "
                                           f"(1/8 of one step's batch), mean of {runs} runs of {sec:.2f} s, {cores} threads"}
