@@ -9,7 +9,7 @@ from .ops import (HEAD_SIZE, RUN_CUDA_RWKV6, RUN_CUDA_RWKV6_BI, RUN_CUDA_RWKV6_S
 from .heads import (add_layernorm, create_mask_and_rev_idx, eos_gather, eos_index, gather_rows, groupnorm_gate, groupnorm_gate_pair, pooling,  # noqa: F401
                     reverse_x, tmix_ddlerp_lora, tmix_ddlerp_mix, tmix_shift_lerp)
 from .cmix import cmix_shift_lerp2, cmix_x060_forward, relu_sq, sigmoid_mul  # noqa: F401
-from .encoders import (bi_encoder_encode, bi_encoder_hidden, bi_tmix_forward, blocks_forward, causal_hidden, classification_logits,  # noqa: F401
+from .encoders import (GraphedForward, bi_encoder_encode, bi_encoder_hidden, bi_tmix_forward, blocks_forward, causal_hidden, classification_logits,  # noqa: F401
                        cross_encoder_rows, encode_corpus, length_buckets, sequence_embedding)
 from .infctx import BlockState, BlockStateList, ChannelMixState, TimeMixState  # noqa: F401
 from .tmix import Tmix_x060, tmix_x060_finish, tmix_x060_forward, tmix_x060_project  # noqa: F401

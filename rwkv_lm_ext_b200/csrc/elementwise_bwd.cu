@@ -17,8 +17,21 @@ namespace {
 
 typedef __nv_bfloat16 bf16;
 struct alignas(16) bf16x8 { __nv_bfloat162 v[4]; };
-__device__ __forceinline__ bf16x8 ld8(const bf16 *p) { return *reinterpret_cast<const bf16x8 *>(p); }
-__device__ __forceinline__ void st8(bf16 *p, const bf16x8 &x) { *reinterpret_cast<bf16x8 *>(p) = x; }
+// ONE 128-bit access each way (copying the struct itself is compiled to four 32-bit accesses: __nv_bfloat162 has its own
+// copy operations)
+__device__ __forceinline__ bf16x8 ld8(const bf16 *p) {
+    const uint4 u = *reinterpret_cast<const uint4 *>(p);
+    bf16x8 r;
+    r.v[0] = *reinterpret_cast<const __nv_bfloat162 *>(&u.x);
+    r.v[1] = *reinterpret_cast<const __nv_bfloat162 *>(&u.y);
+    r.v[2] = *reinterpret_cast<const __nv_bfloat162 *>(&u.z);
+    r.v[3] = *reinterpret_cast<const __nv_bfloat162 *>(&u.w);
+    return r;
+}
+__device__ __forceinline__ void st8(bf16 *p, const bf16x8 &x) {
+    *reinterpret_cast<uint4 *>(p) = make_uint4(*reinterpret_cast<const uint32_t *>(&x.v[0]), *reinterpret_cast<const uint32_t *>(&x.v[1]),
+                                                *reinterpret_cast<const uint32_t *>(&x.v[2]), *reinterpret_cast<const uint32_t *>(&x.v[3]));
+}
 __device__ __forceinline__ void unpack8(const bf16x8 &x, float *f) {
 #pragma unroll
     for (int i = 0; i < 4; i++) { float2 t = __bfloat1622float2(x.v[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }

@@ -172,3 +172,35 @@ def encode_corpus(model, sequences, fn=None, max_tokens=32768, end_id=1, pad_id=
         for r, i in enumerate(members):
             out[i] = res[r]
     return torch.stack(out)
+
+
+class GraphedForward:
+    """`fn(model, idx)` for ONE input shape as a CUDA-graph replay: the forwards above make ~130 launches per layer, a
+    third of them a few microseconds long, and launched eagerly the GPU waits for the host between them (1B6 bi-encoder,
+    64 x 512 tokens: ~10 % of the step).  Every kernel of the path takes its scratch from torch's allocator or from
+    stream-ordered allocations and nothing synchronises with the host, so the whole forward captures.
+
+        enc = GraphedForward(bi_encoder_encode, model, idx)      # warms up, captures
+        emb = enc(idx2)                                          # idx2.shape == idx.shape; emb is overwritten by the next call
+
+    Inference only (captured under no_grad).  Parameters are read in place: weight updates are seen by later replays."""
+
+    def __init__(self, fn, model, example_idx, warmup=2):
+        assert example_idx.is_cuda
+        self.fn, self.model = fn, model
+        self.static_idx = example_idx.clone()
+        side = torch.cuda.Stream(device=example_idx.device)
+        side.wait_stream(torch.cuda.current_stream(example_idx.device))
+        with torch.cuda.stream(side), torch.no_grad():
+            for _ in range(warmup):
+                fn(model, self.static_idx)
+        torch.cuda.current_stream(example_idx.device).wait_stream(side)
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.no_grad(), torch.cuda.graph(self.graph):
+            self.static_out = fn(model, self.static_idx)
+
+    def __call__(self, idx):
+        assert idx.shape == self.static_idx.shape and idx.dtype == self.static_idx.dtype, "one graph per input shape"
+        self.static_idx.copy_(idx, non_blocking=True)
+        self.graph.replay()
+        return self.static_out

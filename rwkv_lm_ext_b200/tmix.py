@@ -31,7 +31,10 @@ def _maa5(layer):
     ps = (layer.time_maa_w, layer.time_maa_k, layer.time_maa_v, layer.time_maa_r, layer.time_maa_g)
     if any(p.requires_grad for p in ps) and torch.is_grad_enabled():
         return torch.cat([p.view(1, C) for p in ps], 0)
-    # frozen (inference, LoRA SFT): the stacked bf16 copy is kept until a parameter is written or moved
+    if ps[0].is_cuda and torch.cuda.is_current_stream_capturing():
+        # inside a CUDA-graph capture the stacking has to be part of the graph: replays must read the live parameters
+        return heads._bf16_param(torch.cat([p.detach().view(1, C) for p in ps], 0))
+    # frozen (inference, LoRA SFT), eager: the stacked bf16 copy is kept until a parameter is written or moved
     key = tuple((p.data_ptr(), p._version, p.dtype) for p in ps)
     hit = layer.__dict__.get("_maa5_cache")
     if hit is None or hit[0] != key:

@@ -79,3 +79,27 @@ def test_bi_encoder_is_differentiable():
     emb.float().pow(2).sum().backward()
     for name, p in model.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), name
+
+
+def test_graphed_forward_replays_the_eager_forward():
+    """GraphedForward: the whole bi-encoder forward captured once per input shape; replays on new ids (device or pinned
+    host) give bit-identical embeddings to the eager call, and a weight update is seen by later replays."""
+    import rwkv_lm_ext_b200 as M
+    from rwkv_lm_ext_b200.synthetic import make_bi_encoder, make_passages
+    model = make_bi_encoder(2, 128, 2, 448, 512, seed=0, device=DEV)
+    a = make_passages(6, T=96, vocab=512, seed=1, min_len=20).to(DEV)
+    b = make_passages(6, T=96, vocab=512, seed=2, min_len=20)
+    enc = M.GraphedForward(M.bi_encoder_encode, model, a)
+    with torch.no_grad():
+        want_a, want_b = M.bi_encoder_encode(model, a), M.bi_encoder_encode(model, b.to(DEV))
+    assert torch.equal(enc(a), want_a)
+    assert torch.equal(enc(b.pin_memory()), want_b)                  # ids straight from pinned host memory
+    assert torch.equal(enc(a).clone(), want_a)
+    with torch.no_grad():
+        model.blocks[0].att.time_maa_k.add_(0.25)                    # a frozen-parameter cache (tmix._maa5) must notice
+        model.blocks[1].ffn.value.weight.mul_(0.5)
+        want2 = M.bi_encoder_encode(model, a)
+    assert not torch.equal(want2, want_a)
+    assert torch.equal(enc(a), want2)
+    with pytest.raises(AssertionError):
+        enc(a[:, :64])
