@@ -27,6 +27,20 @@ typedef __nv_bfloat16 bf16;
 constexpr int ROWS = 8, COLS = 256, NS = 3;
 
 struct alignas(16) bf16x8 { __nv_bfloat162 v[4]; };
+// ONE 128-bit access each way, global or shared (copying the struct itself is compiled to four 32-bit accesses)
+__device__ __forceinline__ bf16x8 ld8(const void *p) {
+    const uint4 u = *reinterpret_cast<const uint4 *>(p);
+    bf16x8 r;
+    r.v[0] = *reinterpret_cast<const __nv_bfloat162 *>(&u.x);
+    r.v[1] = *reinterpret_cast<const __nv_bfloat162 *>(&u.y);
+    r.v[2] = *reinterpret_cast<const __nv_bfloat162 *>(&u.z);
+    r.v[3] = *reinterpret_cast<const __nv_bfloat162 *>(&u.w);
+    return r;
+}
+__device__ __forceinline__ void st8(void *p, const bf16x8 &x) {
+    *reinterpret_cast<uint4 *>(p) = make_uint4(*reinterpret_cast<const uint32_t *>(&x.v[0]), *reinterpret_cast<const uint32_t *>(&x.v[1]),
+                                                *reinterpret_cast<const uint32_t *>(&x.v[2]), *reinterpret_cast<const uint32_t *>(&x.v[3]));
+}
 __device__ __forceinline__ void unpack8(const bf16x8 &x, float *f) {
 #pragma unroll
     for (int i = 0; i < 4; i++) { float2 t = __bfloat1622float2(x.v[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
@@ -111,8 +125,8 @@ ddlerp_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
 #pragma unroll
             for (int n = 0; n < NOUT; n++) {
                 float gf[8], cf[8];
-                unpack8(*reinterpret_cast<const bf16x8 *>(gout.p[n] + off), gf);
-                if (HAS_M) unpack8(*reinterpret_cast<const bf16x8 *>(m + n * plane + off), cf);
+                unpack8(ld8(gout.p[n] + off), gf);
+                if (HAS_M) unpack8(ld8(m + n * plane + off), cf);
 #pragma unroll
                 for (int e = 0; e < 8; e++) {
                     const float a = maas[n * COLS + lane * 8 + e];
@@ -138,18 +152,18 @@ ddlerp_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
         mbar_wait(&full[s], (i / NS) & 1);
 
         float xf[8], pf[8], xx[8], gxx[8], gsum[8];
-        unpack8(*reinterpret_cast<const bf16x8 *>(st + ((row + 1) * COLS + lane * 8) * 2), xf);
-        if (t == 0 && shift != nullptr && clive) unpack8(*reinterpret_cast<const bf16x8 *>(shift + (size_t)b * C + c), pf);
-        else unpack8(*reinterpret_cast<const bf16x8 *>(st + (row * COLS + lane * 8) * 2), pf);
+        unpack8(ld8(st + ((row + 1) * COLS + lane * 8) * 2), xf);
+        if (t == 0 && shift != nullptr && clive) unpack8(ld8(shift + (size_t)b * C + c), pf);
+        else unpack8(ld8(st + (row * COLS + lane * 8) * 2), pf);
 #pragma unroll
         for (int e = 0; e < 8; e++) { xx[e] = rb(pf[e] - xf[e]); gxx[e] = 0.f; gsum[e] = 0.f; }
         const size_t off = ((size_t)b * T + t) * C + c;
 #pragma unroll
         for (int n = 0; n < NOUT; n++) {
             float gf[8], cf[8], gmv[8];
-            unpack8(*reinterpret_cast<const bf16x8 *>(st + S::X_BYTES + n * S::T_BYTES + (row * COLS + lane * 8) * 2), gf);
+            unpack8(ld8(st + S::X_BYTES + n * S::T_BYTES + (row * COLS + lane * 8) * 2), gf);
             if (HAS_M)
-                unpack8(*reinterpret_cast<const bf16x8 *>(st + S::X_BYTES + (NOUT + n) * S::T_BYTES + (row * COLS + lane * 8) * 2), cf);
+                unpack8(ld8(st + S::X_BYTES + (NOUT + n) * S::T_BYTES + (row * COLS + lane * 8) * 2), cf);
             const float4 a0 = *reinterpret_cast<const float4 *>(maas + n * COLS + lane * 8);
             const float4 a1 = *reinterpret_cast<const float4 *>(maas + n * COLS + lane * 8 + 4);
             const float af[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
@@ -161,7 +175,7 @@ ddlerp_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
                 gmv[e] = gf[e] * xx[e];
                 acc[n][e] += gmv[e];                       // rows past the split arrive as zeros
             }
-            if (HAS_M && live) *reinterpret_cast<bf16x8 *>(gm + n * plane + off) = pack8(gmv);
+            if (HAS_M && live) st8(gm + n * plane + off, pack8(gmv));
         }
         *reinterpret_cast<float4 *>(gxs + row * COLS + lane * 8) = make_float4(gxx[0], gxx[1], gxx[2], gxx[3]);
         *reinterpret_cast<float4 *>(gxs + row * COLS + lane * 8 + 4) = make_float4(gxx[4], gxx[5], gxx[6], gxx[7]);
@@ -172,8 +186,8 @@ ddlerp_bwd_tma_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_co
             const float o[8] = {gsum[0] - gxx[0] + n0.x, gsum[1] - gxx[1] + n0.y, gsum[2] - gxx[2] + n0.z,
                                 gsum[3] - gxx[3] + n0.w, gsum[4] - gxx[4] + n1.x, gsum[5] - gxx[5] + n1.y,
                                 gsum[6] - gxx[6] + n1.z, gsum[7] - gxx[7] + n1.w};
-            *reinterpret_cast<bf16x8 *>(gx + off) = pack8(o);
-            if (t == 0 && gshift != nullptr) *reinterpret_cast<bf16x8 *>(gshift + (size_t)b * C + c) = pack8(gxx);
+            st8(gx + off, pack8(o));
+            if (t == 0 && gshift != nullptr) st8(gshift + (size_t)b * C + c, pack8(gxx));
         }
         __syncthreads();                                   // gxs and stage s are free again
         if (row == 0) {

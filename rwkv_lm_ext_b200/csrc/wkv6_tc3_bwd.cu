@@ -347,8 +347,12 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         // =====================================================================================
         const int sp = F.sp, ch = F.ch, q = F.q, ri = F.ri;
         const float u_h[2] = {__bfloat162float(p.u[h * 64 + F.row(0)]), __bfloat162float(p.u[h * 64 + F.row(1)])};
-        const uint32_t tG = tmem_addr(tmem, 32 * sp, TM_G + 32 * ch);
-        const uint32_t tPark = tmem_addr(tmem, 32 * sp + 16, 32 * ch);
+        // the warp's TMEM window (sub-partition sp, column half ch), kept in a register: re-derived from SR_TID in front of
+        // every TMEM access it cost an S2R round trip + 6 instructions at the start of each stage
+        uint32_t tb = tmem_addr(tmem, 32 * sp, 32 * ch);
+        asm volatile("" : "+r"(tb));
+        const uint32_t tG = tb + TM_G;
+        const uint32_t tPark = tb + (16u << 16);
         // x2 transposing stores of one 8-token group: lanes 0-7 address the rows of channel half 0, lanes 8-15 of half 1
         uint32_t ti2_off = F.ti1_off ^ ((lane & 8) ? 16u : 0u);
         int dcol = (32 * ch + 2 * q) - (16 * sp + ri);           // column(g, e = 0) - row(hh) at g = hh
@@ -605,7 +609,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             STAMP(2);
             // ---- Bm[t rows][s cols] -> dA[t][s] = Bm for s < t; bd[t] = Bm[t,t]   (G is fetched along with it)
             uint32_t vg[16];
-            tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch), v);
+            tmem_ld_frag(tb + TM_X0, v);
             tmem_ld_frag(tG, vg);
             tmem_wait_ld();
             STAMPX(14);
@@ -673,7 +677,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             tc_fence_after();
             STAMPX(17);
             // ---- A^T[s rows][t cols] -> P^T[s][t] = A^T for t > s, diag = sum_i r u k
-            tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X1 + 32 * ch), v);
+            tmem_ld_frag(tb + TM_X1, v);
             tmem_wait_ld();
             STAMPX(18);
 #pragma unroll
@@ -713,8 +717,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             {
             uint32_t tb[2][5][4];
             auto t2_load = [&](int g, uint32_t (&b)[5][4]) {
-                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch + 8 * g), b[0]);
-                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 8 * g), b[1]);
+                tmem_ld_frag1(tb + TM_X0 + 8 * g, b[0]);
+                tmem_ld_frag1(tb + TM_X2 + 8 * g, b[1]);
                 tmem_ld_frag1(tPark + PARK_A + 8 * g, b[2]);
                 tmem_ld_frag1(tPark + PARK_B + 8 * g, b[3]);
                 tmem_ld_frag1(tPark + PARK_L + 8 * g, b[4]);
@@ -748,7 +752,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             // ---- gv rows -> tile (runs while the tensor cores work on M3)
             bar_sync_all<B_M2>();
             tc_fence_after();
-            tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X1 + 32 * ch), v);
+            tmem_ld_frag(tb + TM_X1, v);
             tmem_wait_ld();
             stsm_x4(sbase + OFF_GVT + (BI == BI_REV ? flip_rows(F.rc(0), r0) : F.rc(0)), pack_frag(v, 0, 0), pack_frag(v, 1, 0), pack_frag(v, 2, 0), pack_frag(v, 3, 0));
             stsm_x4(sbase + OFF_GVT + (BI == BI_REV ? flip_rows(F.rc(1), r0) : F.rc(1)), pack_frag(v, 0, 1), pack_frag(v, 1, 1), pack_frag(v, 2, 1), pack_frag(v, 3, 1));
@@ -768,8 +772,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             {
             uint32_t tb[2][6][4];
             auto t3_load = [&](int g, uint32_t (&b)[6][4]) {
-                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch + 8 * g), b[0]);
-                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 8 * g), b[1]);
+                tmem_ld_frag1(tb + TM_X0 + 8 * g, b[0]);
+                tmem_ld_frag1(tb + TM_X2 + 8 * g, b[1]);
                 tmem_ld_frag1(tPark + PARK_A + 8 * g, b[2]);
                 tmem_ld_frag1(tPark + PARK_B + 8 * g, b[3]);
                 tmem_ld_frag1(tPark + PARK_C + 8 * g, b[4]);
