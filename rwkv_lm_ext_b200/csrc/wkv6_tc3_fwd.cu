@@ -263,9 +263,9 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         const float u_h[2] = {__bfloat162float(p.u[h * 64 + F.row(0)]), __bfloat162float(p.u[h * 64 + F.row(1)])};
         // the warp's TMEM window (sub-partition sp, column half ch), kept in a register: re-derived from SR_TID in front of
         // every TMEM access it cost an S2R round trip + 6 instructions at the start of each stage
-        uint32_t tb = tmem_addr(tmem, 32 * sp, 32 * ch);
-        asm volatile("" : "+r"(tb));
-        const uint32_t tS = tb + TM_S;
+        uint32_t twin = tmem_addr(tmem, 32 * sp, 32 * ch);
+        asm volatile("" : "+r"(twin));
+        const uint32_t tS = twin + TM_S;
         int dcol = (32 * ch + 2 * q) - (16 * sp + F.ri);           // column(g, e = 0) - row(hh) at g = hh
         asm volatile("" : "+r"(dcol));
         // where the warp's part of a 64 x 64 (row, column) tile lies: 1 = entirely above the diagonal (column > row), 2 =
@@ -477,7 +477,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++) stsm_x4_t(sbase + OFF_P + F.ti(hh), 0u, 0u, 0u, 0u);
             } else {
-            tmem_ld_frag(tb + TM_A, v);
+            tmem_ld_frag(twin + TM_A, v);
             tmem_wait_ld();
             // branch-free: dcol = (t of e = 0) - s at g = hh; 8 more per column group
 #pragma unroll
@@ -538,7 +538,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             }
             // ================================================================== T2: y tile, new bf16 S
             if (!SO && p.has_y) {
-                tmem_ld_frag(tb + TM_Y, v);
+                tmem_ld_frag(twin + TM_Y, v);
                 tmem_wait_ld();
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++)
