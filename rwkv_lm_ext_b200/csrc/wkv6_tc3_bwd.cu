@@ -345,16 +345,15 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
         // =====================================================================================
         const int sp = F.sp, ch = F.ch, q = F.q, ri = F.ri;
         const float u_h[2] = {__bfloat162float(p.u[h * 64 + F.row(0)]), __bfloat162float(p.u[h * 64 + F.row(1)])};
-        // the warp's TMEM window (sub-partition sp, column half ch), kept in a register: re-derived from SR_TID in front of
-        // every TMEM access it cost an S2R round trip + 6 instructions at the start of each stage
-        uint32_t twin = tmem_addr(tmem, 32 * sp, 32 * ch);
-        // (the forward pins this value in a register -- asm volatile("" : "+r"(twin)) -- which removes the S2R + 6 instructions the
-        // compiler otherwise re-derives in front of every TMEM access: forward 0.2193 -> 0.2167 ms.  Here, at the 96-register
-        // limit, the extra live register spills 48 bytes and gains nothing.  setmaxnreg (issuer warp down to 32 registers,
-        // compute warps up to 104: no spills, no re-derivation, ptxas accepts it) deadlocks in USETMAXREG.TRY_ALLOC on this
-        // 9-warp CTA -- the register pool works per warpgroup-aligned sub-partition -- so it is not used.)
-        const uint32_t tG = twin + TM_G;
-        const uint32_t tPark = twin + (16u << 16);
+        // (The forward pins its TMEM window address in a register, which removes the S2R + 6 instructions the compiler
+        // otherwise re-derives in front of every TMEM access: forward 0.2193 -> 0.2167 ms.  Here, at the 96-register limit, one
+        // more live register spills 48 bytes and gains nothing.  More registers for the compute warps through setmaxnreg were
+        // tried both ways: the issuer warp alone down to 32 / compute warps up to 104 deadlocks in USETMAXREG.TRY_ALLOC (the
+        // pool is per sub-partition: only a whole warpgroup, one warp on each, can feed it); with three full warpgroups (384
+        // threads, launch at 80 registers, warps 9-11 idle) it runs and is exact, but slower -- forward 0.2166 -> 0.2192 ms,
+        // backward 0.3825 -> 0.411 ms: the 32-register issuer path spills.)
+        const uint32_t tG = tmem_addr(tmem, 32 * sp, TM_G + 32 * ch);
+        const uint32_t tPark = tmem_addr(tmem, 32 * sp + 16, 32 * ch);
         // x2 transposing stores of one 8-token group: lanes 0-7 address the rows of channel half 0, lanes 8-15 of half 1
         uint32_t ti2_off = F.ti1_off ^ ((lane & 8) ? 16u : 0u);
         int dcol = (32 * ch + 2 * q) - (16 * sp + ri);           // column(g, e = 0) - row(hh) at g = hh
@@ -611,7 +610,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             STAMP(2);
             // ---- Bm[t rows][s cols] -> dA[t][s] = Bm for s < t; bd[t] = Bm[t,t]   (G is fetched along with it)
             uint32_t vg[16];
-            tmem_ld_frag(twin + TM_X0, v);
+            tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch), v);
             tmem_ld_frag(tG, vg);
             tmem_wait_ld();
             STAMPX(14);
@@ -679,7 +678,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             tc_fence_after();
             STAMPX(17);
             // ---- A^T[s rows][t cols] -> P^T[s][t] = A^T for t > s, diag = sum_i r u k
-            tmem_ld_frag(twin + TM_X1, v);
+            tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X1 + 32 * ch), v);
             tmem_wait_ld();
             STAMPX(18);
 #pragma unroll
@@ -719,8 +718,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             {
             uint32_t tb[2][5][4];
             auto t2_load = [&](int g, uint32_t (&b)[5][4]) {
-                tmem_ld_frag1(twin + TM_X0 + 8 * g, b[0]);
-                tmem_ld_frag1(twin + TM_X2 + 8 * g, b[1]);
+                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch + 8 * g), b[0]);
+                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 8 * g), b[1]);
                 tmem_ld_frag1(tPark + PARK_A + 8 * g, b[2]);
                 tmem_ld_frag1(tPark + PARK_B + 8 * g, b[3]);
                 tmem_ld_frag1(tPark + PARK_L + 8 * g, b[4]);
@@ -754,7 +753,7 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             // ---- gv rows -> tile (runs while the tensor cores work on M3)
             bar_sync_all<B_M2>();
             tc_fence_after();
-            tmem_ld_frag(twin + TM_X1, v);
+            tmem_ld_frag(tmem_addr(tmem, 32 * sp, TM_X1 + 32 * ch), v);
             tmem_wait_ld();
             stsm_x4(sbase + OFF_GVT + (BI == BI_REV ? flip_rows(F.rc(0), r0) : F.rc(0)), pack_frag(v, 0, 0), pack_frag(v, 1, 0), pack_frag(v, 2, 0), pack_frag(v, 3, 0));
             stsm_x4(sbase + OFF_GVT + (BI == BI_REV ? flip_rows(F.rc(1), r0) : F.rc(1)), pack_frag(v, 0, 1), pack_frag(v, 1, 1), pack_frag(v, 2, 1), pack_frag(v, 3, 1));
@@ -774,8 +773,8 @@ wkv6_tc3_bwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
             {
             uint32_t tb[2][6][4];
             auto t3_load = [&](int g, uint32_t (&b)[6][4]) {
-                tmem_ld_frag1(twin + TM_X0 + 8 * g, b[0]);
-                tmem_ld_frag1(twin + TM_X2 + 8 * g, b[1]);
+                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X0 + 32 * ch + 8 * g), b[0]);
+                tmem_ld_frag1(tmem_addr(tmem, 32 * sp, TM_X2 + 32 * ch + 8 * g), b[1]);
                 tmem_ld_frag1(tPark + PARK_A + 8 * g, b[2]);
                 tmem_ld_frag1(tPark + PARK_B + 8 * g, b[3]);
                 tmem_ld_frag1(tPark + PARK_C + 8 * g, b[4]);
