@@ -76,7 +76,11 @@ struct Params {
 // SO = true: a state-only pass known at compile time (the two extra passes of the segmented routes): no r tile,
 // no Rt / Kt versions, no diag(u) term, no A / Y products -- about half of the operand preparation.
 // BI: direction of the bidirectional op (tc3_common.cuh); BI_NONE for every other call.
-template <bool SEG, bool SO = false, int BI = BI_NONE>
+// KLO: split Kh into bf16 hi + lo for the state update.  Needed where the fp32 state leaves the kernel (sT: infctx /
+// inference / the segment passes): without it the final state drifts by 1.5e-3 rel-RMS over 64 chunks.  Where only y and
+// the bf16 chunk-start states are produced it changes y by 1.4 % of its own bf16 error (3.25e-3 -> 3.29e-3 against the fp64
+// oracle at T = 4096, tests/tc_emulation.py) and costs 5 % of the forward: those calls run without it.
+template <bool SEG, bool SO = false, int BI = BI_NONE, bool KLO = true>
 __global__ void __launch_bounds__(NTHREADS, 2)
 wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_k,
                     const __grid_constant__ CUtensorMap map_v, const __grid_constant__ CUtensorMap map_w,
@@ -199,6 +203,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 for (int k = 0; k < 4; k++)                      // S[i,j] += Kh^T V  (hi, then lo)
                     mma_bf16_ss(tmem + TM_S, smem_desc_sw128(kh + 2048 * k, 8192, 1024),
                                 smem_desc_sw128(vv + 2048 * k, 8192, 1024), ID_MM, 1);
+                if constexpr (KLO)
 #pragma unroll
                 for (int k = 0; k < 4; k++)
                     mma_bf16_ss(tmem + TM_S, smem_desc_sw128(kl + 2048 * k, 8192, 1024),
@@ -301,7 +306,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
 
         // Operand preparation of chunk c: Kt (both versions) and Rt go to shared memory at once; Rh, Kh (hi,
         // lo) and 2^Lam stay in registers until the MMAs of the previous chunk no longer read those tiles.
-        uint32_t rhp[2][4], khp[2][4], klp[2][4];
+        uint32_t rhp[2][4], khp[2][4], klp[KLO ? 2 : 1][4];
         float elam_nx[2];
         // Token groups of the operand preparation: thread (ch, lane) owns the 8-token groups 2g + ch, g = 0..3, i.e.
         // ONE group of each 16-token reference block (block g = groups 2g and 2g + 1).  With the natural mapping
@@ -399,7 +404,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                     }
                     const f2 kh = f2mul(kf, el);                          // Kh = k * 2^(Lam - cum)
                     khp[hh][g] = f2tobf(kh);
-                    klp[hh][g] = f2tobf(f2sub(kh, bf2f2(khp[hh][g])));
+                    if constexpr (KLO) klp[hh][g] = f2tobf(f2sub(kh, bf2f2(khp[hh][g])));
                 }
                 if constexpr (!SO) {
                 const uint32_t ti = tg(hh), t1 = tg1_off ^ (hh ? 16u : 0u);
@@ -454,7 +459,7 @@ wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_cons
                 const uint32_t ti = tg(hh);
                 if constexpr (!SO) stsm_x4_t(sbase + OFF_RH + ti, rhp[hh][0], rhp[hh][1], rhp[hh][2], rhp[hh][3]);
                 stsm_x4_t(sbase + OFF_KH + ti, khp[hh][0], khp[hh][1], khp[hh][2], khp[hh][3]);
-                stsm_x4_t(sbase + OFF_KL + ti, klp[hh][0], klp[hh][1], klp[hh][2], klp[hh][3]);
+                if constexpr (KLO) stsm_x4_t(sbase + OFF_KL + ti, klp[hh][0], klp[hh][1], klp[hh][2], klp[hh][3]);
             }
             fence_proxy_async();
             bar_arrive_all<B_PB>();
@@ -599,19 +604,19 @@ bool tc3_forward_supported(const Args &a) {
 // ckpt: nullptr or bf16 [B*H][ceil(T/64)][64 i][64 j] receiving the state at the start of every chunk;
 // hz_flags: device int [B*H], zeroed by the caller; a.y may be nullptr (state-only pass).
 // bi / row_len: direction of the bidirectional op (tc3_common.cuh) and the device int [B] row lengths it needs.
-template <bool SEG, bool SO, int BI>
+template <bool SEG, bool SO, int BI, bool KLO>
 static int launch_fwd(dim3 grid, cudaStream_t stream, const CUtensorMap &mr, const CUtensorMap &mk, const CUtensorMap &mv,
                       const CUtensorMap &mw, const CUtensorMap &my, const CUtensorMap &mc, const Params &p) {
     static bool attr_done[64] = {};          // function attributes are per device (and per instantiation)
     int dev = 0;
     WKV6_CUDA_CHECK(cudaGetDevice(&dev));
     if (dev < 0 || dev >= 64 || !attr_done[dev]) {
-        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<SEG, SO, BI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<SEG, SO, BI>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<SEG, SO, BI, KLO>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        WKV6_CUDA_CHECK(cudaFuncSetAttribute(wkv6_tc3_fwd_kernel<SEG, SO, BI, KLO>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                              cudaSharedmemCarveoutMaxShared));
         if (dev >= 0 && dev < 64) attr_done[dev] = true;
     }
-    wkv6_tc3_fwd_kernel<SEG, SO, BI><<<grid, NTHREADS, SMEM_BYTES, stream>>>(mr, mk, mv, mw, my, mc, p);
+    wkv6_tc3_fwd_kernel<SEG, SO, BI, KLO><<<grid, NTHREADS, SMEM_BYTES, stream>>>(mr, mk, mv, mw, my, mc, p);
     count_launch();
     WKV6_CUDA_CHECK(cudaGetLastError());
     return WKV6_OK;
@@ -647,14 +652,15 @@ int tc3_forward(const Args &a, void *ckpt, int *hz_flags, int nseg, int seg_chun
     p.row_len = row_len; p.row_order = row_order;
     const dim3 grid(a.B * nseg * a.H);
     const bool so = !p.has_y;
-    if (bi == BI_CAUSAL) return so ? launch_fwd<false, true, BI_CAUSAL>(grid, a.stream, mr, mk, mv, mw, my, mc, p)
-                                   : launch_fwd<false, false, BI_CAUSAL>(grid, a.stream, mr, mk, mv, mw, my, mc, p);
-    if (bi == BI_REV) return so ? launch_fwd<false, true, BI_REV>(grid, a.stream, mr, mk, mv, mw, my, mc, p)
-                                : launch_fwd<false, false, BI_REV>(grid, a.stream, mr, mk, mv, mw, my, mc, p);
-    if (nseg > 1) return so ? launch_fwd<true, true, BI_NONE>(grid, a.stream, mr, mk, mv, mw, my, mc, p)
-                            : launch_fwd<true, false, BI_NONE>(grid, a.stream, mr, mk, mv, mw, my, mc, p);
-    return so ? launch_fwd<false, true, BI_NONE>(grid, a.stream, mr, mk, mv, mw, my, mc, p)
-              : launch_fwd<false, false, BI_NONE>(grid, a.stream, mr, mk, mv, mw, my, mc, p);
+    const bool klo = so || a.sT != nullptr;          // the fp32 state leaves the kernel: keep the hi + lo split of Kh
+#define FWD(SEG_, BI_) (so ? launch_fwd<SEG_, true, BI_, true>(grid, a.stream, mr, mk, mv, mw, my, mc, p) \
+                        : klo ? launch_fwd<SEG_, false, BI_, true>(grid, a.stream, mr, mk, mv, mw, my, mc, p) \
+                              : launch_fwd<SEG_, false, BI_, false>(grid, a.stream, mr, mk, mv, mw, my, mc, p))
+    if (bi == BI_CAUSAL) return FWD(false, BI_CAUSAL);
+    if (bi == BI_REV) return FWD(false, BI_REV);
+    if (nseg > 1) return FWD(true, BI_NONE);
+    return FWD(false, BI_NONE);
+#undef FWD
 }
 
 }  // namespace wkv6
