@@ -173,7 +173,9 @@ static int forward3_ew(const Args &a) {
     cudaFreeAsync(w_raw, a.stream);
     return rc;
 }
-static int dispatch_forward(const Args &a) {
+static int dispatch_forward(const Args &a0) {
+    Args a = a0;
+    if (a.hi_lo < 0) a.hi_lo = a.sT != nullptr;      // one precision class for every internal pass of this call
     const int impl = current_impl();
     if (impl != WKV6_IMPL_SIMT && tc3_forward_supported(a)) return forward3(a);
     if (impl != WKV6_IMPL_SIMT && ew_convertible(a) && !a.saved) return forward3_ew(a);

@@ -39,6 +39,10 @@ struct Args {
     void *sT = nullptr;
     int sT_f32 = 0;
     void *y = nullptr;
+    // tensor-core forward: split Kh into bf16 hi + lo for the state update (wkv6_tc3_fwd.cu, KLO).  -1: decided by
+    // whether THIS pass returns a state (sT); the forward entry points fix it for the whole call (every internal pass of
+    // a segmented call then rounds like the unsegmented one).
+    int hi_lo = -1;
     // bidirectional (wkv6_bi): mask int32 [B,T]; nullptr = plain causal op
     const int *mask = nullptr;
     // backward only

@@ -652,10 +652,14 @@ int tc3_forward(const Args &a, void *ckpt, int *hz_flags, int nseg, int seg_chun
     p.row_len = row_len; p.row_order = row_order;
     const dim3 grid(a.B * nseg * a.H);
     const bool so = !p.has_y;
-    const bool klo = so || a.sT != nullptr;          // the fp32 state leaves the kernel: keep the hi + lo split of Kh
-#define FWD(SEG_, BI_) (so ? launch_fwd<SEG_, true, BI_, true>(grid, a.stream, mr, mk, mv, mw, my, mc, p) \
-                        : klo ? launch_fwd<SEG_, false, BI_, true>(grid, a.stream, mr, mk, mv, mw, my, mc, p) \
-                              : launch_fwd<SEG_, false, BI_, false>(grid, a.stream, mr, mk, mv, mw, my, mc, p))
+    // the fp32 state leaves the kernel: keep the hi + lo split of Kh.  (A state-only pass that only recomputes the bf16
+    // chunk-start states -- the backward without a training pair -- runs without it, like the forward whose states it
+    // reproduces bit for bit.)
+    const bool klo = a.hi_lo >= 0 ? a.hi_lo != 0 : a.sT != nullptr;
+#define FWD(SEG_, BI_) (so ? (klo ? launch_fwd<SEG_, true, BI_, true>(grid, a.stream, mr, mk, mv, mw, my, mc, p) \
+                                  : launch_fwd<SEG_, true, BI_, false>(grid, a.stream, mr, mk, mv, mw, my, mc, p)) \
+                        : (klo ? launch_fwd<SEG_, false, BI_, true>(grid, a.stream, mr, mk, mv, mw, my, mc, p) \
+                               : launch_fwd<SEG_, false, BI_, false>(grid, a.stream, mr, mk, mv, mw, my, mc, p)))
     if (bi == BI_CAUSAL) return FWD(false, BI_CAUSAL);
     if (bi == BI_REV) return FWD(false, BI_REV);
     if (nseg > 1) return FWD(true, BI_NONE);
