@@ -79,7 +79,7 @@ struct Params {
 // KLO: split Kh into bf16 hi + lo for the state update.  Needed where the fp32 state leaves the kernel (sT: infctx /
 // inference / the segment passes): without it the final state drifts by 1.5e-3 rel-RMS over 64 chunks.  Where only y and
 // the bf16 chunk-start states are produced it changes y by 1.4 % of its own bf16 error (3.25e-3 -> 3.29e-3 against the fp64
-// oracle at T = 4096, tests/tc_emulation.py) and costs 5 % of the forward: those calls run without it.
+// recurrence at T = 4096, tests/tc_emulation.py) and costs 5 % of the forward: those calls run without it.
 template <bool SEG, bool SO = false, int BI = BI_NONE, bool KLO = true>
 __global__ void __launch_bounds__(NTHREADS, 2)
 wkv6_tc3_fwd_kernel(const __grid_constant__ CUtensorMap map_r, const __grid_constant__ CUtensorMap map_k,
