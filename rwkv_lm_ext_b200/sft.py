@@ -272,7 +272,8 @@ def sft_loss(logits, targets):
     """src/model.py:1244-1283 (my_qa_mask == 0 branch): mean cross entropy over the tokens whose label is not -100,
     wrapped in L2Wrap (src/model.py:960-974).  bf16 logits on the GPU take the fused kernels (fp32 arithmetic inside)."""
     V = logits.size(-1)
-    if logits.is_cuda and logits.dtype == torch.bfloat16 and logits.dim() == 3 and V % 8 == 0 and V <= 65536:
+    if (logits.is_cuda and logits.dtype == torch.bfloat16 and logits.dim() == 3 and V % 8 == 0 and V <= 65536
+            and targets.device == logits.device and targets.dtype == torch.long):
         return _FusedLoss.apply(logits.contiguous(), targets.reshape(-1).contiguous())
     loss = F.cross_entropy(logits.view(-1, V).float(), targets.reshape(-1))
     return _L2Wrap.apply(loss, logits)
