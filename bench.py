@@ -386,7 +386,7 @@ def main():
                 y_static = M.RUN_CUDA_RWKV6(B, T, C, H, *static)
                 y_static.backward(gy)
             launches_per_step = M.launch_count() - n0
-            for _ in range(3):
+            for _ in range(max(args.warmup, 10)):     # W untimed warm-up steps of the thing that is timed
                 graph.replay()
         except Exception as e:                       # capture refused: time the eager step
             sys.stderr.write(f"bench: CUDA-graph capture of the step failed ({type(e).__name__}: {e}); timing eager steps\n")
